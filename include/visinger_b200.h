@@ -1,0 +1,169 @@
+/*
+ * visinger_b200.h -- C ABI of the B200-native VISinger inference hot path.
+ *
+ * The reference (jisang93/VISinger) is pure Python/PyTorch and has NO FFI, plugin or
+ * operator interface of its own: the drop-in boundary is its nn.Module surface
+ * (SURVEY.md section 8b).  This header is the C boundary underneath our mirror of that
+ * surface; each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - activations are the reference's own tensors: fp32, [B, C, T] contiguous
+ *     (time fastest), resident on the pack's CUDA device; `mask` is [B, 1, T] in {0,1};
+ *     `g` is the speaker condition [B, gin, 1] or NULL (modules/visinger/flow.py:33,
+ *     modules/visinger/decoder.py:40);
+ *   - weights enter as the reference's state-dict entries (HOST fp32 pointers, the
+ *     names and shapes of SURVEY.md Appendix A, either `weight_g`+`weight_v` or a
+ *     plain `weight` after remove_weight_norm); vsg_pack_create folds weight-norm and
+ *     the Flip permutations, re-lays the weights out for the kernels and uploads them;
+ *   - the caller owns every input, output and workspace buffer; the library allocates
+ *     device memory only inside vsg_pack_create and frees it in vsg_pack_destroy.
+ *     No call synchronises the host or allocates: all run calls are asynchronous on
+ *     `stream` (a cudaStream_t passed as void*) and CUDA-graph capturable;
+ *   - every function returns 0 on success or a negative VSG_E* code and never throws;
+ *     vsg_last_error() returns a thread-local, human readable message for the last
+ *     failing call;
+ *   - a VsgPack is immutable after creation and may be shared by several streams of
+ *     its device; calls that share one workspace must be stream-ordered.
+ */
+#ifndef VISINGER_B200_H_
+#define VISINGER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSG_ABI_VERSION 1
+
+enum {
+  VSG_OK = 0,
+  VSG_EINVAL = -1,   /* bad argument / shape / missing weight             */
+  VSG_ECUDA = -2,    /* a CUDA runtime or driver call failed               */
+  VSG_ENOMEM = -3,   /* workspace too small / allocation failed            */
+  VSG_EUNSUPPORTED = -4 /* configuration outside what the kernels implement */
+};
+
+/* Arithmetic mode of a run call. */
+enum {
+  VSG_PRECISION_FP32 = 0, /* fp32 storage, fp32 FFMA accumulate: the parity mode
+                             (waveform max-abs <= 1e-4, flow z <= 1e-5 vs the reference) */
+  VSG_PRECISION_BF16 = 1  /* bf16 operands + storage, fp32 accumulate on tcgen05 tensor
+                             cores (TMEM accumulators, TMA-fed): the throughput mode     */
+};
+
+#define VSG_MAX_UPS 8
+#define VSG_MAX_RESBLOCK_KERNELS 4
+#define VSG_MAX_RESBLOCK_DILATIONS 4
+
+/* Constructor arguments of the two reference modules.  A part with n_flows == 0 /
+ * n_ups == 0 is absent from the pack. */
+typedef struct VsgConfig {
+  /* ResidualCouplingBlock(channels, hidden_channels, kernel_size, dilation_rate,
+   * n_layers, n_flows, gin_channels)            modules/visinger/flow.py:16-31 */
+  int32_t flow_channels;
+  int32_t flow_hidden;
+  int32_t flow_kernel_size;
+  int32_t flow_dilation_rate;
+  int32_t flow_n_layers;
+  int32_t flow_n_flows;
+  int32_t flow_gin;
+  /* Generator(initial_channel, resblock, resblock_kernel_sizes, resblock_dilation_sizes,
+   * upsample_rates, upsample_initial_channel, upsample_kernel_sizes, gin_channels)
+   *                                             modules/visinger/decoder.py:14-38 */
+  int32_t dec_initial_channel;
+  int32_t dec_resblock;      /* 1 = ResBlock1, 2 = ResBlock2 */
+  int32_t dec_n_kernels;     /* len(resblock_kernel_sizes) */
+  int32_t dec_resblock_kernel_sizes[VSG_MAX_RESBLOCK_KERNELS];
+  int32_t dec_n_dilations[VSG_MAX_RESBLOCK_KERNELS];
+  int32_t dec_resblock_dilations[VSG_MAX_RESBLOCK_KERNELS][VSG_MAX_RESBLOCK_DILATIONS];
+  int32_t dec_n_ups;         /* len(upsample_rates) */
+  int32_t dec_upsample_rates[VSG_MAX_UPS];
+  int32_t dec_upsample_kernel_sizes[VSG_MAX_UPS];
+  int32_t dec_upsample_initial_channel;
+  int32_t dec_gin;
+} VsgConfig;
+
+/* One state-dict entry (host memory, fp32, contiguous). */
+typedef struct VsgTensor {
+  const char* name;   /* e.g. "flow.flows.0.enc.in_layers.2.weight_v", "decoder.ups.0.bias" */
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} VsgTensor;
+
+typedef struct VsgPack VsgPack;
+
+/* ABI version of the loaded library (== VSG_ABI_VERSION of the header it was built from). */
+int vsg_abi_version(void);
+
+/* Thread-local message of the last failing call ("" if none). */
+const char* vsg_last_error(void);
+
+/*
+ * One-time weight pre-pack.  Replaces what the reference does implicitly on every
+ * forward: the weight_norm pre-hook (torch.nn.utils.weight_norm at
+ * modules/visinger/encoder.py:147,154,164 and modules/visinger/decoder.py:24-26,72-87)
+ * and Flip (modules/visinger/flow.py:88-95, folded into channel permutations of
+ * pre/post).  `weights` uses the key layout of the reference checkpoint
+ * ["state_dict"]["model"] (utils/commons/ckpt_utils.py:37-56) restricted to the two
+ * modules: flow weights under prefix `flow_prefix`, decoder weights under `dec_prefix`
+ * (e.g. "flow." / "decoder.", or "" when packing a stand-alone module).
+ */
+int vsg_pack_create(const VsgConfig* cfg, const VsgTensor* weights, int32_t n_weights,
+                    const char* flow_prefix, const char* dec_prefix, int32_t device, VsgPack** out);
+void vsg_pack_destroy(VsgPack* pack);
+
+/* Bytes of caller-provided scratch each run call needs for (B, T) in `precision`
+ * (the max over the three run calls).  0 on invalid arguments. */
+size_t vsg_workspace_bytes(const VsgPack* pack, int32_t B, int32_t T, int32_t precision);
+
+/*
+ * Prior sampling, models/visinger.py:107:
+ *   z_p = (mu_p + noise * exp(logs_p)) * mask         all [B, C, T], mask [B, 1, T]
+ * `noise` is injected by the caller (the reference draws torch.randn_like(mu_p)).
+ */
+int vsg_prior_sample(const float* mu_p, const float* logs_p, const float* noise, const float* mask,
+                     float* z_p, int32_t B, int32_t C, int32_t T, void* stream);
+
+/*
+ * ResidualCouplingBlock.forward(x, x_mask, g, reverse)   modules/visinger/flow.py:33-40
+ * (coupling layers flow.py:66-85, WaveNet modules/visinger/encoder.py:167-195 with
+ * fused_add_tanh_sigmoid_multiply encoder.py:206-213).  x, y: [B, channels, T]; y may
+ * alias x.  `g` NULL iff flow_gin == 0.  reverse != 0 is the inference direction.
+ */
+int vsg_flow_forward(const VsgPack* pack, const float* x, const float* mask, const float* g, float* y,
+                     int32_t B, int32_t T, int32_t reverse, int32_t precision,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Generator.forward(x, g)                                 modules/visinger/decoder.py:40-59
+ * z: [B, initial_channel, T] -> wav: [B, 1, T * prod(upsample_rates)].
+ */
+int vsg_generator_forward(const VsgPack* pack, const float* z, const float* g, float* wav,
+                          int32_t B, int32_t T, int32_t precision,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The whole inference hot path, models/visinger.py:107-111:
+ *   z_p = (mu_p + noise*exp(logs_p))*mask ; z_q = flow(z_p, mask, g, reverse=True)*mask ;
+ *   wav = decoder(z_q*mask, g)
+ * `z_q_out` (may be NULL) receives z_q [B, channels, T].
+ */
+int vsg_infer(const VsgPack* pack, const float* mu_p, const float* logs_p, const float* noise,
+              const float* mask, const float* g, float* wav, float* z_q_out,
+              int32_t B, int32_t T, int32_t precision,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Samples produced per latent frame (prod(upsample_rates)); 0 if the pack has no decoder. */
+int32_t vsg_hop_size(const VsgPack* pack);
+
+/* Number of kernels launched by the most recent run call on this thread (bench bookkeeping). */
+int32_t vsg_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISINGER_B200_H_ */

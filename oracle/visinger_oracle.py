@@ -1,0 +1,314 @@
+"""CPU oracle for the VISinger inference hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a from-scratch *restatement* of the reference's algorithm for
+
+    prior sampling -> ResidualCouplingBlock (reverse / forward) -> HiFi-GAN Generator
+
+written as pure functions over a state-dict (name -> tensor).  It exists so that
+`tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference`
+legs of `bench.py` have something to check / time the CUDA path against.  Nothing
+under `visinger_b200/` may import it; the product path has no CPU fallback.
+
+Arithmetic provenance: the reference's arithmetic lives in an un-vendored
+third-party dependency, PyTorch (reference README pins torch==1.11.0+cu113; this
+image has torch 2.11.0).  The primitives used below (`F.conv1d`,
+`F.conv_transpose1d`, tanh, sigmoid, leaky_relu) are the very ATen CPU kernels the
+reference's own `nn.Conv1d` / `nn.ConvTranspose1d` modules dispatch to, so the
+fp32 oracle is bit-comparable with the reference run on CPU.  Weight-norm
+(`w = g * v / ||v||`, recomputed on every forward by the reference's
+`torch.nn.utils.weight_norm` pre-hook) is restated explicitly in `_eff_weight`.
+
+Parity pinning: the reference ships NO tests, golden vectors or fixtures
+(SURVEY.md section 4).  The oracle is therefore pinned against outputs of the
+reference modules themselves, imported unmodified from /root/reference in the
+build container by `tests/golden/make_golden.py`; the resulting fixtures live in
+`tests/golden/*.npz` and `tests/test_oracle_golden.py` checks this file against
+them (bit-exact in fp32 on the same torch build, <=1e-6 otherwise).
+
+Reference citations are `path:line` relative to the reference repository root.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+LRELU_SLOPE = 0.1  # modules/visinger/decoder.py:10
+
+StateDict = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------------------
+# weight handling
+# --------------------------------------------------------------------------------------
+def _eff_weight(sd: StateDict, prefix: str) -> torch.Tensor:
+    """Effective conv weight for `prefix` ("...conv_name").
+
+    Old-style weight norm (torch.nn.utils.weight_norm, dim=0) stores `weight_g`
+    [D0,1,1] and `weight_v` [D0,D1,k] and recomputes w = v * (g / ||v||_{dims 1,2})
+    before every forward (applied at modules/visinger/encoder.py:147,154,164 and
+    modules/visinger/decoder.py:24-26,72-87,117-120).  For ConvTranspose1d dim 0 is
+    C_in, so the norm runs over (C_out, k) -- SURVEY.md 7.2-7.  After
+    `remove_weight_norm` only `.weight` exists; both spellings are accepted.
+    """
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"]
+    g = sd[prefix + ".weight_g"]
+    v = sd[prefix + ".weight_v"]
+    # torch._weight_norm(v, g, 0) == v * (g / ||v||_{dims 1,2}); it is the ATen primitive the
+    # reference's pre-hook calls, used here so the fp32 oracle reproduces its rounding exactly.
+    return torch._weight_norm(v, g, 0)
+
+
+def _bias(sd: StateDict, prefix: str) -> Optional[torch.Tensor]:
+    return sd.get(prefix + ".bias")
+
+
+def get_padding(kernel_size: int, dilation: int = 1) -> int:
+    """modules/commons/utils.py:109-110."""
+    return int((kernel_size * dilation - dilation) / 2)
+
+
+# --------------------------------------------------------------------------------------
+# a1: prior sampling
+# --------------------------------------------------------------------------------------
+def prior_sample(mu_p, logs_p, noise, mask):
+    """models/visinger.py:107 : z_p = (mu_p + randn_like(mu_p) * exp(logs_p)) * mask.
+
+    The noise tensor is injected: CPU and CUDA generators differ.
+    """
+    return (mu_p + noise * torch.exp(logs_p)) * mask
+
+
+# --------------------------------------------------------------------------------------
+# a5/a6: WaveNet with the fused gate
+# --------------------------------------------------------------------------------------
+def gate(a, b, n_channels: int):
+    """modules/visinger/encoder.py:206-213 fused_add_tanh_sigmoid_multiply."""
+    s = a + b
+    return torch.tanh(s[:, :n_channels]) * torch.sigmoid(s[:, n_channels:])
+
+
+def wavenet(sd: StateDict, prefix: str, x, x_mask, g, *, hidden: int, kernel_size: int,
+            dilation_rate: int, n_layers: int):
+    """modules/visinger/encoder.py:167-195 WaveNet.forward (eval mode: dropout is identity)."""
+    out = torch.zeros_like(x)
+    if g is not None:
+        g = F.conv1d(g, _eff_weight(sd, prefix + "cond_layer"), _bias(sd, prefix + "cond_layer"))
+    for i in range(n_layers):
+        dil = dilation_rate ** i
+        pad = int((kernel_size * dil - dil) / 2)
+        x_in = F.conv1d(x, _eff_weight(sd, f"{prefix}in_layers.{i}"), _bias(sd, f"{prefix}in_layers.{i}"),
+                        dilation=dil, padding=pad)
+        if g is not None:
+            g_l = g[:, i * 2 * hidden:(i + 1) * 2 * hidden, :]
+        else:
+            g_l = torch.zeros_like(x_in)
+        acts = gate(x_in, g_l, hidden)
+        rs = F.conv1d(acts, _eff_weight(sd, f"{prefix}res_skip_layers.{i}"),
+                      _bias(sd, f"{prefix}res_skip_layers.{i}"))
+        if i < n_layers - 1:
+            x = (x + rs[:, :hidden]) * x_mask
+            out = out + rs[:, hidden:]
+        else:
+            out = out + rs
+    return out * x_mask
+
+
+# --------------------------------------------------------------------------------------
+# a2/a3/a4: residual coupling block
+# --------------------------------------------------------------------------------------
+def coupling_layer(sd: StateDict, prefix: str, x, x_mask, g, reverse: bool, *, channels: int, hidden: int,
+                   kernel_size: int, dilation_rate: int, n_layers: int):
+    """modules/visinger/flow.py:66-85 ResidualCouplingLayer.forward with mean_only=True
+    (the only way ResidualCouplingBlock builds it, flow.py:29-30): logs == 0."""
+    half = channels // 2
+    x0, x1 = x[:, :half], x[:, half:]
+    h = F.conv1d(x0, sd[prefix + "pre.weight"], sd[prefix + "pre.bias"]) * x_mask
+    h = wavenet(sd, prefix + "enc.", h, x_mask, g, hidden=hidden, kernel_size=kernel_size,
+                dilation_rate=dilation_rate, n_layers=n_layers)
+    m = F.conv1d(h, sd[prefix + "post.weight"], sd[prefix + "post.bias"]) * x_mask
+    if not reverse:
+        x1 = m + x1 * x_mask          # flow.py:78 with exp(logs) == 1
+    else:
+        x1 = (x1 - m) * x_mask        # flow.py:83 with exp(-logs) == 1
+    return torch.cat([x0, x1], 1)
+
+
+def flow(sd: StateDict, x, x_mask, g=None, reverse: bool = False, *, channels: int = 192, hidden: int = 192,
+         kernel_size: int = 5, dilation_rate: int = 1, n_layers: int = 4, n_flows: int = 4, prefix: str = ""):
+    """modules/visinger/flow.py:33-40 ResidualCouplingBlock.forward.
+
+    flows[2i] is a coupling layer, flows[2i+1] a Flip (torch.flip over channels,
+    flow.py:88-95).  Forward applies them in order, reverse in reversed order; both
+    return only the tensor (logdet discarded at flow.py:36).
+    """
+    kw = dict(channels=channels, hidden=hidden, kernel_size=kernel_size, dilation_rate=dilation_rate,
+              n_layers=n_layers)
+    if not reverse:
+        for i in range(n_flows):
+            x = coupling_layer(sd, f"{prefix}flows.{2 * i}.", x, x_mask, g, False, **kw)
+            x = torch.flip(x, [1])
+    else:
+        for i in reversed(range(n_flows)):
+            x = torch.flip(x, [1])
+            x = coupling_layer(sd, f"{prefix}flows.{2 * i}.", x, x_mask, g, True, **kw)
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# a7/a8/a9: HiFi-GAN generator
+# --------------------------------------------------------------------------------------
+def resblock1(sd: StateDict, prefix: str, x, kernel_size: int, dilations: Sequence[int]):
+    """modules/visinger/decoder.py:91-104 ResBlock1.forward with x_mask=None (the only way
+    Generator.forward calls it, decoder.py:51-53)."""
+    for i, d in enumerate(dilations):
+        xt = F.leaky_relu(x, LRELU_SLOPE)
+        xt = F.conv1d(xt, _eff_weight(sd, f"{prefix}convs1.{i}"), _bias(sd, f"{prefix}convs1.{i}"),
+                      dilation=d, padding=get_padding(kernel_size, d))
+        xt = F.leaky_relu(xt, LRELU_SLOPE)
+        xt = F.conv1d(xt, _eff_weight(sd, f"{prefix}convs2.{i}"), _bias(sd, f"{prefix}convs2.{i}"),
+                      dilation=1, padding=get_padding(kernel_size, 1))
+        x = xt + x
+    return x
+
+
+def resblock2(sd: StateDict, prefix: str, x, kernel_size: int, dilations: Sequence[int]):
+    """modules/visinger/decoder.py:124-133 ResBlock2.forward with x_mask=None."""
+    for i, d in enumerate(dilations):
+        xt = F.leaky_relu(x, LRELU_SLOPE)
+        xt = F.conv1d(xt, _eff_weight(sd, f"{prefix}convs.{i}"), _bias(sd, f"{prefix}convs.{i}"),
+                      dilation=d, padding=get_padding(kernel_size, d))
+        x = xt + x
+    return x
+
+
+def generator(sd: StateDict, x, g=None, *, resblock: str = "1", resblock_kernel_sizes=(3, 7, 11),
+              resblock_dilation_sizes=((1, 3, 5), (1, 3, 5), (1, 3, 5)), upsample_rates=(5, 5, 3, 2, 2),
+              upsample_kernel_sizes=(11, 11, 7, 4, 4), prefix: str = ""):
+    """modules/visinger/decoder.py:40-59 Generator.forward."""
+    nk = len(resblock_kernel_sizes)
+    x = F.conv1d(x, sd[prefix + "conv_pre.weight"], sd[prefix + "conv_pre.bias"], padding=3)
+    if g is not None:
+        x = x + F.conv1d(g, sd[prefix + "cond.weight"], sd[prefix + "cond.bias"])
+    rb = resblock1 if resblock == "1" else resblock2
+    for i, (u, k) in enumerate(zip(upsample_rates, upsample_kernel_sizes)):
+        x = F.leaky_relu(x, LRELU_SLOPE)
+        x = F.conv_transpose1d(x, _eff_weight(sd, f"{prefix}ups.{i}"), _bias(sd, f"{prefix}ups.{i}"),
+                               stride=u, padding=(k - u) // 2)
+        xs = None
+        for j in range(nk):
+            r = rb(sd, f"{prefix}resblocks.{i * nk + j}.", x, resblock_kernel_sizes[j],
+                   resblock_dilation_sizes[j])
+            xs = r if xs is None else xs + r
+        x = xs / nk
+    x = F.leaky_relu(x, LRELU_SLOPE)          # slope 0.1 here too (decoder.py:55)
+    x = F.conv1d(x, sd[prefix + "conv_post.weight"], None, padding=3)
+    return torch.tanh(x)
+
+
+# --------------------------------------------------------------------------------------
+# the whole hot path (models/visinger.py:105-111)
+# --------------------------------------------------------------------------------------
+def infer_hot_path(sd: StateDict, mu_p, logs_p, noise, mask, g, *, flow_kw=None, dec_kw=None,
+                   flow_prefix: str = "flow.", dec_prefix: str = "decoder."):
+    """models/visinger.py:107-111: sample, flow reverse, decode.  Returns (wav [B, L], z_q)."""
+    z_p = prior_sample(mu_p, logs_p, noise, mask)
+    z_q = flow(sd, z_p, mask, g=g, reverse=True, prefix=flow_prefix, **(flow_kw or {})) * mask
+    wav = generator(sd, z_q * mask, g=g, prefix=dec_prefix, **(dec_kw or {})).squeeze(1)
+    return wav, z_q
+
+
+# --------------------------------------------------------------------------------------
+# deterministic synthetic weights (used by tests, smoke and bench on both sides)
+# --------------------------------------------------------------------------------------
+def flow_param_shapes(channels=192, hidden=192, kernel_size=5, n_layers=4, n_flows=4, gin=256):
+    """State-dict layout of ResidualCouplingBlock."""
+    shapes = {}
+    half = channels // 2
+    for f in range(n_flows):
+        p = f"flows.{2 * f}."
+        shapes[p + "pre.weight"] = (hidden, half, 1)
+        shapes[p + "pre.bias"] = (hidden,)
+        if gin:
+            shapes[p + "enc.cond_layer.bias"] = (2 * hidden * n_layers,)
+            shapes[p + "enc.cond_layer.weight_g"] = (2 * hidden * n_layers, 1, 1)
+            shapes[p + "enc.cond_layer.weight_v"] = (2 * hidden * n_layers, gin, 1)
+        for i in range(n_layers):
+            shapes[p + f"enc.in_layers.{i}.bias"] = (2 * hidden,)
+            shapes[p + f"enc.in_layers.{i}.weight_g"] = (2 * hidden, 1, 1)
+            shapes[p + f"enc.in_layers.{i}.weight_v"] = (2 * hidden, hidden, kernel_size)
+            rs = 2 * hidden if i < n_layers - 1 else hidden
+            shapes[p + f"enc.res_skip_layers.{i}.bias"] = (rs,)
+            shapes[p + f"enc.res_skip_layers.{i}.weight_g"] = (rs, 1, 1)
+            shapes[p + f"enc.res_skip_layers.{i}.weight_v"] = (rs, hidden, 1)
+        shapes[p + "post.weight"] = (half, hidden, 1)
+        shapes[p + "post.bias"] = (half,)
+    return shapes
+
+
+def generator_param_shapes(initial_channel=192, resblock="1", resblock_kernel_sizes=(3, 7, 11),
+                           resblock_dilation_sizes=((1, 3, 5),) * 3, upsample_rates=(5, 5, 3, 2, 2),
+                           upsample_initial_channel=512, upsample_kernel_sizes=(11, 11, 7, 4, 4), gin=256):
+    """State-dict layout of Generator."""
+    shapes = {"conv_pre.weight": (upsample_initial_channel, initial_channel, 7),
+              "conv_pre.bias": (upsample_initial_channel,)}
+    ch = upsample_initial_channel
+    nk = len(resblock_kernel_sizes)
+    for i, (u, k) in enumerate(zip(upsample_rates, upsample_kernel_sizes)):
+        cin, ch = upsample_initial_channel // 2 ** i, upsample_initial_channel // 2 ** (i + 1)
+        shapes[f"ups.{i}.bias"] = (ch,)
+        shapes[f"ups.{i}.weight_g"] = (cin, 1, 1)
+        shapes[f"ups.{i}.weight_v"] = (cin, ch, k)
+        for j, (rk, rd) in enumerate(zip(resblock_kernel_sizes, resblock_dilation_sizes)):
+            p = f"resblocks.{i * nk + j}."
+            names = ("convs1", "convs2") if resblock == "1" else ("convs",)
+            for nm in names:
+                for q in range(len(rd)):
+                    shapes[p + f"{nm}.{q}.bias"] = (ch,)
+                    shapes[p + f"{nm}.{q}.weight_g"] = (ch, 1, 1)
+                    shapes[p + f"{nm}.{q}.weight_v"] = (ch, ch, rk)
+    shapes["conv_post.weight"] = (1, ch, 7)
+    if gin:
+        shapes["cond.weight"] = (upsample_initial_channel, gin, 1)
+        shapes["cond.bias"] = (upsample_initial_channel,)
+    return shapes
+
+
+def synth_state_dict(shapes: Dict[str, tuple], seed: int) -> StateDict:
+    """Deterministic random weights keyed by name.
+
+    Mimics the reference's effective default init (kaiming-uniform v, g ~ ||v||,
+    small uniform bias) and -- unlike the reference init
+    (flow.py:63-64 zeroes `post`) -- makes every coupling layer non-trivial
+    (SURVEY.md Appendix B-2).  Tensors are drawn in
+    sorted-name order from one torch.Generator so both sides of a parity test can
+    rebuild identical weights from the seed alone.
+    """
+    gen = torch.Generator().manual_seed(seed)
+    sd: StateDict = {}
+    for name in sorted(shapes):
+        shp = shapes[name]
+        if name.endswith("weight_g"):
+            continue  # derived from v below
+        if name.endswith(".bias"):
+            sd[name] = (torch.rand(shp, generator=gen) * 2 - 1) * 0.05
+        elif ".post." in name:
+            # SURVEY.md 8(c) patch (2): re-randomise the zero-initialised `post` at std 0.05
+            sd[name] = (torch.rand(shp, generator=gen) * 2 - 1) * (0.05 * 3 ** 0.5)
+        else:
+            # PyTorch's default conv init: kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)),
+            # fan_in = shape[1] * k (which for ConvTranspose1d is C_out * k, as torch computes it)
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            bound = (1.0 / fan_in) ** 0.5
+            sd[name] = (torch.rand(shp, generator=gen) * 2 - 1) * bound
+    for name in sorted(shapes):
+        if name.endswith("weight_g"):
+            v = sd[name[:-1] + "v"]
+            norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(shapes[name])
+            # g = ||v|| * (1 +- 10 %): exercises the weight-norm fold without changing the scale
+            sd[name] = norm * (0.9 + 0.2 * torch.rand(shapes[name], generator=gen))
+    return sd

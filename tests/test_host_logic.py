@@ -1,0 +1,61 @@
+"""CPU: host-side mirror of the reference interface (constructor signatures, state-dict contract,
+loud failure without CUDA)."""
+import pytest
+import torch
+
+from oracle import visinger_oracle as O
+from helpers import FLOW_FULL, GEN_FULL, flow_shapes, gen_shapes
+
+
+def test_flow_state_dict_contract():
+    from visinger_b200 import ResidualCouplingBlock
+    m = ResidualCouplingBlock(192, 192, 5, 1, 4, gin_channels=256)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == flow_shapes(FLOW_FULL)
+    # reference zero-initialises `post` (flow.py:63-64)
+    assert float(m.flows[0].post.weight.abs().max()) == 0.0
+    sd = O.synth_state_dict(flow_shapes(FLOW_FULL), 3)
+    m.load_state_dict(sd)   # strict
+    assert len(m.flows) == 8 and not list(m.flows[1].parameters())
+
+
+def test_generator_state_dict_contract_and_remove_weight_norm():
+    from visinger_b200 import Generator
+    m = Generator(192, "1", [3, 7, 11], [[1, 3, 5]] * 3, [5, 5, 3, 2, 2], 512, [11, 11, 7, 4, 4], gin_channels=256)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == gen_shapes(GEN_FULL)
+    assert m.hop_size == 300
+    # ConvTranspose1d weight-norm is over dim 0 = C_in
+    assert got["ups.0.weight_g"] == (512, 1, 1) and got["ups.0.weight_v"] == (512, 256, 11)
+    m.load_state_dict(O.synth_state_dict(gen_shapes(GEN_FULL), 4))
+    m.remove_weight_norm()
+    keys = set(m.state_dict().keys())
+    assert "ups.0.weight" in keys and "ups.0.weight_g" not in keys
+    assert "resblocks.0.convs1.0.weight" in keys
+
+
+def test_resblock2_layout():
+    from visinger_b200 import Generator
+    cfg = dict(initial_channel=8, resblock="2", rk=[3, 5], rd=[[1, 3], [1, 3]], ur=[4, 2], uic=16, uk=[8, 4], gin=0)
+    m = Generator(8, "2", cfg["rk"], cfg["rd"], cfg["ur"], 16, cfg["uk"], gin_channels=0)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == gen_shapes(cfg)
+
+
+def test_cpu_tensors_fail_loudly_no_fallback():
+    from visinger_b200 import ResidualCouplingBlock, Generator
+    f = ResidualCouplingBlock(8, 16, 5, 1, 2, gin_channels=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        f(torch.zeros(1, 8, 10), torch.ones(1, 1, 10))
+    g = Generator(8, "1", [3], [[1, 3, 5]], [2], 16, [4], gin_channels=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        g(torch.zeros(1, 8, 10))
+
+
+def test_product_package_does_not_import_the_oracle():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dp, _, files in os.walk(os.path.join(root, "visinger_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("no CPU or", ""), f"{f} mentions the oracle"

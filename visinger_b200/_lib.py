@@ -1,0 +1,251 @@
+"""ctypes binding of the C-ABI library (include/visinger_b200.h).
+
+The library is built IN-TREE with nvcc for sm_100a (`visinger_b200/lib/libvisinger_b200.so`) and
+loaded with ctypes: no torch types cross the boundary, only raw device pointers, sizes and the
+CUDA stream handle.  PyTorch is used for device memory and streams only.  There is no CPU or
+eager fallback: if the library cannot be built or loaded, or a tensor is not on a CUDA device,
+the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import os
+import shutil
+import subprocess
+import threading
+from typing import Dict, Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_LIBDIR = os.path.join(_HERE, "lib")
+_LIBPATH = os.path.join(_LIBDIR, "libvisinger_b200.so")
+_HEADER = os.path.join(os.path.dirname(_HERE), "include", "visinger_b200.h")
+_SOURCES = ["api.cu", "pack.cu", "run_f32.cu", "run_tc.cu"]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+
+PRECISION_FP32 = 0
+PRECISION_BF16 = 1
+_PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16}
+
+VSG_MAX_UPS = 8
+VSG_MAX_RESBLOCK_KERNELS = 4
+VSG_MAX_RESBLOCK_DILATIONS = 4
+
+
+def precision_code(p) -> int:
+    if isinstance(p, int):
+        return p
+    try:
+        return _PRECISIONS[str(p).lower()]
+    except KeyError:
+        raise ValueError(f"unknown precision {p!r}; use 'fp32' or 'bf16'") from None
+
+
+class VsgConfig(ctypes.Structure):
+    _fields_ = [
+        ("flow_channels", ctypes.c_int32), ("flow_hidden", ctypes.c_int32), ("flow_kernel_size", ctypes.c_int32),
+        ("flow_dilation_rate", ctypes.c_int32), ("flow_n_layers", ctypes.c_int32), ("flow_n_flows", ctypes.c_int32),
+        ("flow_gin", ctypes.c_int32),
+        ("dec_initial_channel", ctypes.c_int32), ("dec_resblock", ctypes.c_int32), ("dec_n_kernels", ctypes.c_int32),
+        ("dec_resblock_kernel_sizes", ctypes.c_int32 * VSG_MAX_RESBLOCK_KERNELS),
+        ("dec_n_dilations", ctypes.c_int32 * VSG_MAX_RESBLOCK_KERNELS),
+        ("dec_resblock_dilations", (ctypes.c_int32 * VSG_MAX_RESBLOCK_DILATIONS) * VSG_MAX_RESBLOCK_KERNELS),
+        ("dec_n_ups", ctypes.c_int32),
+        ("dec_upsample_rates", ctypes.c_int32 * VSG_MAX_UPS),
+        ("dec_upsample_kernel_sizes", ctypes.c_int32 * VSG_MAX_UPS),
+        ("dec_upsample_initial_channel", ctypes.c_int32), ("dec_gin", ctypes.c_int32),
+    ]
+
+
+class VsgTensor(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.c_void_p), ("ndim", ctypes.c_int32),
+                ("shape", ctypes.c_int64 * 4)]
+
+
+def _source_files():
+    files = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    return files + [_HEADER]
+
+
+def _source_hash() -> str:
+    h = hashlib.sha256()
+    for f in _source_files():
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _nvcc() -> Optional[str]:
+    cand = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+    return cand if os.path.exists(cand) else shutil.which("nvcc")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into the in-tree shared library (no GPU needed)."""
+    os.makedirs(_LIBDIR, exist_ok=True)
+    want = _source_hash()
+    stamp = _LIBPATH + ".hash"
+    if not force and os.path.exists(_LIBPATH) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return _LIBPATH
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("visinger_b200: libvisinger_b200.so is missing or stale and nvcc was not found; "
+                           "there is no fallback path")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", _LIBPATH + ".tmp"] + [os.path.join(_CSRC, s) for s in _SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd), flush=True)
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("visinger_b200: nvcc failed\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stdout + proc.stderr, flush=True)
+    os.replace(_LIBPATH + ".tmp", _LIBPATH)
+    with open(stamp, "w") as fh:
+        fh.write(want)
+    return _LIBPATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> ctypes.CDLL:
+    """Load (building first if stale) the C-ABI library.  Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = build()
+        L = ctypes.CDLL(path)
+        vp, i32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t
+        L.vsg_abi_version.restype = ctypes.c_int
+        L.vsg_last_error.restype = ctypes.c_char_p
+        L.vsg_last_launch_count.restype = i32
+        L.vsg_pack_create.restype = ctypes.c_int
+        L.vsg_pack_create.argtypes = [ctypes.POINTER(VsgConfig), ctypes.POINTER(VsgTensor), i32, ctypes.c_char_p,
+                                      ctypes.c_char_p, i32, ctypes.POINTER(vp)]
+        L.vsg_pack_destroy.restype = None
+        L.vsg_pack_destroy.argtypes = [vp]
+        L.vsg_workspace_bytes.restype = sz
+        L.vsg_workspace_bytes.argtypes = [vp, i32, i32, i32]
+        L.vsg_hop_size.restype = i32
+        L.vsg_hop_size.argtypes = [vp]
+        L.vsg_prior_sample.restype = ctypes.c_int
+        L.vsg_prior_sample.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
+        L.vsg_flow_forward.restype = ctypes.c_int
+        L.vsg_flow_forward.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]
+        L.vsg_generator_forward.restype = ctypes.c_int
+        L.vsg_generator_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+        L.vsg_infer.restype = ctypes.c_int
+        L.vsg_infer.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+        if L.vsg_abi_version() != 1:
+            raise RuntimeError("visinger_b200: ABI version mismatch between _lib.py and the shared library")
+        _lib = L
+        return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().vsg_last_error().decode(errors="replace")
+        raise RuntimeError(f"visinger_b200: {what} failed ({rc}): {msg}")
+
+
+def last_launch_count() -> int:
+    return int(lib().vsg_last_launch_count())
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"visinger_b200: {name} is on {t.device}; the B200 path has no CPU fallback "
+                           "(move the module and its inputs to a CUDA device)")
+
+
+def as_f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class Pack:
+    """Owner of a VsgPack* (device-resident pre-packed weights)."""
+
+    def __init__(self, cfg: VsgConfig, state_dict: Dict[str, torch.Tensor], flow_prefix: str, dec_prefix: str,
+                 device: torch.device):
+        self._h = ctypes.c_void_p()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("visinger_b200: weights must live on a CUDA device; there is no CPU fallback")
+        L = lib()
+        host = {}
+        for k, v in state_dict.items():
+            if (flow_prefix is not None and k.startswith(flow_prefix)) or \
+               (dec_prefix is not None and k.startswith(dec_prefix)):
+                host[k] = v.detach().to("cpu", torch.float32).contiguous()
+        arr = (VsgTensor * len(host))()
+        keep = []
+        for i, (k, v) in enumerate(host.items()):
+            nm = k.encode()
+            keep.append(nm)
+            arr[i].name = nm
+            arr[i].data = v.data_ptr()
+            arr[i].ndim = v.dim()
+            for d in range(v.dim()):
+                arr[i].shape[d] = v.shape[d]
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        rc = L.vsg_pack_create(ctypes.byref(cfg), arr, len(host), (flow_prefix or "").encode(),
+                               (dec_prefix or "").encode(), idx, ctypes.byref(self._h))
+        check(rc, "vsg_pack_create")
+        self.index = idx
+        self.hop = int(L.vsg_hop_size(self._h))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def workspace_bytes(self, B: int, T: int, precision: int) -> int:
+        return int(lib().vsg_workspace_bytes(self._h, B, T, precision))
+
+    def __del__(self):
+        try:
+            if self._h and _lib is not None:
+                _lib.vsg_pack_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+_ws_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream); allocated through torch's caching allocator."""
+    stream = torch.cuda.current_stream(device)
+    key = (device.index, stream.cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _ws_cache.pop(key, None)
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    _ws_cache.clear()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

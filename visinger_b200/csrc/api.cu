@@ -1,0 +1,125 @@
+// extern "C" entry points of include/visinger_b200.h: argument validation and dispatch.
+#include "vsg_common.cuh"
+#include "run.cuh"
+
+using namespace vsg;
+
+namespace {
+
+int check_common(const VsgPack* pack, int B, int T, int precision) {
+  if (!pack) return fail(VSG_EINVAL, "pack is NULL");
+  if (B < 0 || T < 0) return fail(VSG_EINVAL, "negative batch (%d) or length (%d)", B, T);
+  if (B > 65535) return fail(VSG_EUNSUPPORTED, "batch %d exceeds 65535", B);
+  if (precision != VSG_PRECISION_FP32 && precision != VSG_PRECISION_BF16)
+    return fail(VSG_EINVAL, "unknown precision %d", precision);
+  return VSG_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+size_t flow_ws(const VsgPack* p, int B, int T, int prec) {
+  if (!p->has_flow) return 0;
+  return prec == VSG_PRECISION_FP32 ? flow_ws_bytes_f32(p, B, T) : flow_ws_bytes_tc(p, B, T);
+}
+size_t dec_ws(const VsgPack* p, int B, int T, int prec) {
+  if (!p->has_dec) return 0;
+  return prec == VSG_PRECISION_FP32 ? dec_ws_bytes_f32(p, B, T) : dec_ws_bytes_tc(p, B, T);
+}
+
+}  // namespace
+
+extern "C" size_t vsg_workspace_bytes(const VsgPack* pack, int32_t B, int32_t T, int32_t precision) {
+  if (check_common(pack, B, T, precision) != VSG_OK) return 0;
+  const size_t z = pack->has_flow ? align256((size_t)B * pack->cfg.flow_channels * T * sizeof(float))
+                                  : align256((size_t)B * pack->cfg.dec_initial_channel * T * sizeof(float));
+  return z + std::max(flow_ws(pack, B, T, precision), dec_ws(pack, B, T, precision)) + 1024;
+}
+
+extern "C" int vsg_prior_sample(const float* mu_p, const float* logs_p, const float* noise, const float* mask,
+                                float* z_p, int32_t B, int32_t C, int32_t T, void* stream) {
+  g_launches = 0;
+  if (B < 0 || C < 0 || T < 0) return fail(VSG_EINVAL, "negative dimension");
+  if ((long long)B * C * T == 0) return VSG_OK;
+  if (!mu_p || !logs_p || !noise || !mask || !z_p) return fail(VSG_EINVAL, "null pointer");
+  return prior_sample(mu_p, logs_p, noise, mask, z_p, B, C, T, (cudaStream_t)stream);
+}
+
+extern "C" int vsg_flow_forward(const VsgPack* pack, const float* x, const float* mask, const float* g, float* y,
+                                int32_t B, int32_t T, int32_t reverse, int32_t precision, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  VSG_TRY(check_common(pack, B, T, precision));
+  if (!pack->has_flow) return fail(VSG_EINVAL, "pack has no flow");
+  if (B == 0 || T == 0) return VSG_OK;
+  if (!x || !mask || !y) return fail(VSG_EINVAL, "null pointer");
+  if (!workspace) return fail(VSG_ENOMEM, "workspace is NULL");
+  DeviceGuard dg(pack->device);
+  if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
+  Workspace ws(workspace, workspace_bytes);
+  if (precision == VSG_PRECISION_FP32)
+    return flow_forward_f32(pack, x, mask, g, y, B, T, reverse, ws, (cudaStream_t)stream);
+  return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, (cudaStream_t)stream);
+}
+
+extern "C" int vsg_generator_forward(const VsgPack* pack, const float* z, const float* g, float* wav, int32_t B,
+                                     int32_t T, int32_t precision, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  g_launches = 0;
+  VSG_TRY(check_common(pack, B, T, precision));
+  if (!pack->has_dec) return fail(VSG_EINVAL, "pack has no decoder");
+  if (B == 0 || T == 0) return VSG_OK;
+  if (!z || !wav) return fail(VSG_EINVAL, "null pointer");
+  if (!workspace) return fail(VSG_ENOMEM, "workspace is NULL");
+  if ((long long)T * pack->hop > 0x7fffffffLL / 4) return fail(VSG_EUNSUPPORTED, "sequence too long (%d frames)", T);
+  DeviceGuard dg(pack->device);
+  if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
+  Workspace ws(workspace, workspace_bytes);
+  if (precision == VSG_PRECISION_FP32)
+    return generator_forward_f32(pack, z, g, wav, B, T, ws, (cudaStream_t)stream);
+  return generator_forward_tc(pack, z, g, wav, B, T, ws, (cudaStream_t)stream);
+}
+
+extern "C" int vsg_infer(const VsgPack* pack, const float* mu_p, const float* logs_p, const float* noise,
+                         const float* mask, const float* g, float* wav, float* z_q_out, int32_t B, int32_t T,
+                         int32_t precision, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  VSG_TRY(check_common(pack, B, T, precision));
+  if (!pack->has_flow || !pack->has_dec) return fail(VSG_EINVAL, "vsg_infer needs a pack with both flow and decoder");
+  if (pack->cfg.flow_channels != pack->cfg.dec_initial_channel)
+    return fail(VSG_EINVAL, "flow channels (%d) != decoder initial_channel (%d)", pack->cfg.flow_channels,
+                pack->cfg.dec_initial_channel);
+  if (B == 0 || T == 0) return VSG_OK;
+  if (!mu_p || !logs_p || !noise || !mask || !wav) return fail(VSG_EINVAL, "null pointer");
+  if (!workspace) return fail(VSG_ENOMEM, "workspace is NULL");
+  DeviceGuard dg(pack->device);
+  if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = pack->cfg.flow_channels;
+  Workspace ws(workspace, workspace_bytes);
+  float* z = ws.take<float>((size_t)B * C * T);
+  if (ws.overflow) return fail(VSG_ENOMEM, "workspace too small");
+  const size_t mark = ws.off;
+  int launches = 0;
+  // z_p = (mu_p + noise * exp(logs_p)) * mask                       models/visinger.py:107
+  VSG_TRY(prior_sample(mu_p, logs_p, noise, mask, z, B, C, T, st));
+  // z_q = flow(z_p, mask, g, reverse=True) * mask                    models/visinger.py:109
+  if (precision == VSG_PRECISION_FP32) VSG_TRY(flow_forward_f32(pack, z, mask, g, z, B, T, 1, ws, st));
+  else VSG_TRY(flow_forward_tc(pack, z, mask, g, z, B, T, 1, ws, st));
+  VSG_TRY(mask_mul(z, mask, z, B, C, T, st));
+  if (z_q_out)
+    VSG_CUDA_TRY(cudaMemcpyAsync(z_q_out, z, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // wav = decoder(z_q * mask, g)                                      models/visinger.py:111
+  ws.off = mark;   // the flow scratch is dead; the decoder reuses it
+  if (precision == VSG_PRECISION_FP32) VSG_TRY(generator_forward_f32(pack, z, g, wav, B, T, ws, st));
+  else VSG_TRY(generator_forward_tc(pack, z, g, wav, B, T, ws, st));
+  (void)launches;
+  return VSG_OK;
+}

@@ -1,0 +1,326 @@
+// vsg_pack_create / vsg_pack_destroy: the one-time weight pre-pack.
+//
+// What the reference recomputes on every forward is folded here, once:
+//   * weight-norm  w = v * (g / ||v||)   (torch.nn.utils.weight_norm pre-hook; applied at
+//     modules/visinger/encoder.py:147,154,164 and modules/visinger/decoder.py:24-26,72-87,117-120);
+//     for ConvTranspose1d the norm runs over dim 0 = C_in;
+//   * Flip (modules/visinger/flow.py:88-95) -> channel-reversed copies of pre / post;
+//   * the gate's tanh/sigmoid halves (encoder.py:206-213) -> interleaved output channels of
+//     in_layers and cond_layer so one thread owns both halves of a channel;
+//   * ConvTranspose1d -> `stride` polyphase dense sub-convolutions.
+#include "vsg_common.cuh"
+#include "pack_tc.cuh"
+
+#include <math.h>
+
+namespace vsg {
+
+thread_local char g_err[1024] = {0};
+thread_local int g_launches = 0;
+
+namespace {
+
+struct HostTensor {
+  const float* data;
+  std::vector<int64_t> shape;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+struct Loader {
+  std::map<std::string, HostTensor> m;
+  VsgPack* pack;
+
+  const HostTensor* find(const std::string& k) const {
+    auto it = m.find(k);
+    return it == m.end() ? nullptr : &it->second;
+  }
+
+  // Effective weight of conv `prefix` as a flat vector in its stored [D0][D1][k] order.
+  int eff_weight(const std::string& prefix, int64_t d0, int64_t d1, int64_t k, std::vector<float>& out) const {
+    const int64_t n = d0 * d1 * k;
+    out.resize(n);
+    if (const HostTensor* w = find(prefix + ".weight")) {
+      if (w->numel() != n) return fail(VSG_EINVAL, "%s.weight has %lld elements, expected %lld", prefix.c_str(),
+                                       (long long)w->numel(), (long long)n);
+      memcpy(out.data(), w->data, n * sizeof(float));
+      return VSG_OK;
+    }
+    const HostTensor* g = find(prefix + ".weight_g");
+    const HostTensor* v = find(prefix + ".weight_v");
+    if (!g || !v) return fail(VSG_EINVAL, "missing weight for %s (.weight or .weight_g/.weight_v)", prefix.c_str());
+    if (v->numel() != n || g->numel() != d0)
+      return fail(VSG_EINVAL, "%s: weight_v has %lld elements (expected %lld), weight_g %lld (expected %lld)",
+                  prefix.c_str(), (long long)v->numel(), (long long)n, (long long)g->numel(), (long long)d0);
+    const int64_t inner = d1 * k;
+    for (int64_t r = 0; r < d0; ++r) {
+      double ss = 0.0;
+      for (int64_t i = 0; i < inner; ++i) { double t = v->data[r * inner + i]; ss += t * t; }
+      const float norm = (float)sqrt(ss);
+      const float scale = g->data[r] / norm;
+      for (int64_t i = 0; i < inner; ++i) out[r * inner + i] = v->data[r * inner + i] * scale;
+    }
+    return VSG_OK;
+  }
+
+  int bias(const std::string& prefix, int64_t n, std::vector<float>& out, bool required) const {
+    out.assign(n, 0.f);
+    const HostTensor* b = find(prefix + ".bias");
+    if (!b) return required ? fail(VSG_EINVAL, "missing %s.bias", prefix.c_str()) : VSG_OK;
+    if (b->numel() != n) return fail(VSG_EINVAL, "%s.bias has %lld elements, expected %lld", prefix.c_str(),
+                                     (long long)b->numel(), (long long)n);
+    memcpy(out.data(), b->data, n * sizeof(float));
+    return VSG_OK;
+  }
+
+  template <typename T>
+  int upload(const std::vector<T>& h, T** d) const {
+    void* p = nullptr;
+    VSG_CUDA_TRY(cudaMalloc(&p, h.size() * sizeof(T) + 256));
+    pack->allocs.push_back(p);
+    VSG_CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *d = (T*)p;
+    return VSG_OK;
+  }
+};
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Conv1d weight W[co][ci][j] -> fp32 pack [ci][j][CoutP], output channel co stored at perm(co).
+template <typename Perm>
+int pack_conv_f32(const Loader& L, const std::vector<float>& W, const std::vector<float>& b, int Cout, int Cin, int k,
+                  Perm perm, ConvW32* out) {
+  out->Cin = Cin; out->Cout = Cout; out->ktaps = k; out->CoutP = round_up(Cout, 64);
+  std::vector<float> wp((size_t)Cin * k * out->CoutP, 0.f), bp(out->CoutP, 0.f);
+  for (int co = 0; co < Cout; ++co) {
+    const int pc = perm(co);
+    bp[pc] = b[co];
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int j = 0; j < k; ++j) wp[((size_t)ci * k + j) * out->CoutP + pc] = W[((size_t)co * Cin + ci) * k + j];
+  }
+  VSG_TRY(L.upload(wp, &out->w));
+  VSG_TRY(L.upload(bp, &out->bias));
+  return VSG_OK;
+}
+
+struct Identity { int operator()(int c) const { return c; } };
+struct GateInterleave { int H; int operator()(int c) const { return c < H ? 2 * c : 2 * (c - H) + 1; } };
+
+int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
+  const VsgConfig& c = P->cfg;
+  const int C = c.flow_channels, H = c.flow_hidden, K = c.flow_kernel_size, NL = c.flow_n_layers, half = C / 2;
+  if (C % 2 || C <= 0 || H <= 0 || NL <= 0 || K % 2 == 0 || c.flow_dilation_rate < 1)
+    return fail(VSG_EINVAL, "bad flow config (channels %d hidden %d kernel %d layers %d)", C, H, K, NL);
+  P->flow_layers.resize(c.flow_n_flows);
+  std::vector<float> W, b;
+  for (int f = 0; f < c.flow_n_flows; ++f) {
+    FlowLayer& fl = P->flow_layers[f];
+    const std::string p = pre + "flows." + std::to_string(2 * f) + ".";
+    // pre: Conv1d(half -> H, 1)       flow.py:60
+    VSG_TRY(L.eff_weight(p + "pre", H, half, 1, W));
+    VSG_TRY(L.bias(p + "pre", H, b, true));
+    VSG_TRY(pack_conv_f32(L, W, b, H, half, 1, Identity{}, &fl.pre[0]));
+    {
+      std::vector<float> Wf(W.size());
+      for (int co = 0; co < H; ++co)
+        for (int ci = 0; ci < half; ++ci) Wf[(size_t)co * half + ci] = W[(size_t)co * half + (half - 1 - ci)];
+      VSG_TRY(pack_conv_f32(L, Wf, b, H, half, 1, Identity{}, &fl.pre[1]));
+    }
+    // post: Conv1d(H -> half, 1)      flow.py:62 (mean_only)
+    VSG_TRY(L.eff_weight(p + "post", half, H, 1, W));
+    VSG_TRY(L.bias(p + "post", half, b, true));
+    VSG_TRY(pack_conv_f32(L, W, b, half, H, 1, Identity{}, &fl.post[0]));
+    {
+      std::vector<float> Wf(W.size()), bf(b.size());
+      for (int co = 0; co < half; ++co) {
+        bf[co] = b[half - 1 - co];
+        for (int ci = 0; ci < H; ++ci) Wf[(size_t)co * H + ci] = W[(size_t)(half - 1 - co) * H + ci];
+      }
+      VSG_TRY(pack_conv_f32(L, Wf, bf, half, H, 1, Identity{}, &fl.post[1]));
+    }
+    // WaveNet                        encoder.py:131-165
+    fl.in_layers.resize(NL);
+    fl.res_skip.resize(NL);
+    for (int i = 0; i < NL; ++i) {
+      const std::string pi = p + "enc.in_layers." + std::to_string(i);
+      VSG_TRY(L.eff_weight(pi, 2 * H, H, K, W));
+      VSG_TRY(L.bias(pi, 2 * H, b, true));
+      VSG_TRY(pack_conv_f32(L, W, b, 2 * H, H, K, GateInterleave{H}, &fl.in_layers[i]));
+      const int rs = (i < NL - 1) ? 2 * H : H;
+      const std::string pr = p + "enc.res_skip_layers." + std::to_string(i);
+      VSG_TRY(L.eff_weight(pr, rs, H, 1, W));
+      VSG_TRY(L.bias(pr, rs, b, true));
+      VSG_TRY(pack_conv_f32(L, W, b, rs, H, 1, Identity{}, &fl.res_skip[i]));
+    }
+    if (c.flow_gin > 0) {
+      const int O = 2 * H * NL, I = c.flow_gin;
+      VSG_TRY(L.eff_weight(p + "enc.cond_layer", O, I, 1, W));
+      VSG_TRY(L.bias(p + "enc.cond_layer", O, b, true));
+      std::vector<float> Wp(W.size()), bp(b.size());
+      GateInterleave gi{H};
+      for (int l = 0; l < NL; ++l)
+        for (int cc = 0; cc < 2 * H; ++cc) {
+          const int src = l * 2 * H + cc, dst = l * 2 * H + gi(cc);
+          bp[dst] = b[src];
+          memcpy(&Wp[(size_t)dst * I], &W[(size_t)src * I], I * sizeof(float));
+        }
+      VSG_TRY(L.upload(Wp, &fl.cond_w));
+      VSG_TRY(L.upload(bp, &fl.cond_b));
+    }
+  }
+  P->has_flow = true;
+  return VSG_OK;
+}
+
+int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
+  const VsgConfig& c = P->cfg;
+  const int C0 = c.dec_initial_channel, UIC = c.dec_upsample_initial_channel;
+  if (c.dec_n_ups > VSG_MAX_UPS || c.dec_n_kernels > VSG_MAX_RESBLOCK_KERNELS || c.dec_n_kernels <= 0 ||
+      (c.dec_resblock != 1 && c.dec_resblock != 2) || C0 <= 0 || UIC <= 0 || (UIC >> c.dec_n_ups) <= 0)
+    return fail(VSG_EINVAL, "bad decoder config");
+  std::vector<float> W, b;
+  // conv_pre: Conv1d(C0 -> UIC, 7, padding 3), no weight norm   decoder.py:19
+  VSG_TRY(L.eff_weight(pre + "conv_pre", UIC, C0, 7, W));
+  VSG_TRY(L.bias(pre + "conv_pre", UIC, b, true));
+  VSG_TRY(pack_conv_f32(L, W, b, UIC, C0, 7, Identity{}, &P->conv_pre));
+  VSG_TRY(pack_conv_tc(P, W, b, UIC, C0, 7, &P->conv_pre_tc));
+  if (c.dec_gin > 0) {   // cond: Conv1d(gin -> UIC, 1)            decoder.py:37-38
+    VSG_TRY(L.eff_weight(pre + "cond", UIC, c.dec_gin, 1, W));
+    VSG_TRY(L.bias(pre + "cond", UIC, b, true));
+    VSG_TRY(L.upload(W, &P->dec_cond_w));
+    VSG_TRY(L.upload(b, &P->dec_cond_b));
+  }
+  P->ups.resize(c.dec_n_ups);
+  P->hop = 1;
+  int ch = UIC;
+  for (int i = 0; i < c.dec_n_ups; ++i) {
+    UpStage& st = P->ups[i];
+    st.rate = c.dec_upsample_rates[i];
+    st.kernel = c.dec_upsample_kernel_sizes[i];
+    st.Cin = UIC >> i;
+    st.Cout = UIC >> (i + 1);
+    st.pad = (st.kernel - st.rate) / 2;
+    if (st.rate < 1 || st.kernel < st.rate || (st.kernel - st.rate) % 2)
+      return fail(VSG_EUNSUPPORTED, "ups.%d: kernel %d / stride %d needs kernel >= stride and (kernel - stride) even",
+                  i, st.kernel, st.rate);
+    P->hop *= st.rate;
+    ch = st.Cout;
+    // ConvTranspose1d weight [Cin][Cout][k], weight-norm over dim 0 = Cin   decoder.py:24-26
+    const std::string pu = pre + "ups." + std::to_string(i);
+    VSG_TRY(L.eff_weight(pu, st.Cin, st.Cout, st.kernel, W));
+    VSG_TRY(L.bias(pu, st.Cout, b, true));
+    // polyphase split: y[q*s + r] = sum_{jj} sum_ci x[ci, q + in_off0 + jj] * W[ci][co][j0 + s*(n_r-1-jj)]
+    st.phases.resize(st.rate);
+    for (int r = 0; r < st.rate; ++r) {
+      const int s = st.rate, k = st.kernel, p = st.pad;
+      const int j0 = (r + p) % s;
+      const int nr = (k - 1 - j0) / s + 1;
+      const int cr = (r + p - j0) / s;
+      UpsPhase& ph = st.phases[r];
+      ph.in_off0 = cr - nr + 1;
+      std::vector<float> Wc((size_t)st.Cout * st.Cin * nr);   // as a Conv1d weight [co][ci][jj]
+      for (int co = 0; co < st.Cout; ++co)
+        for (int ci = 0; ci < st.Cin; ++ci)
+          for (int jj = 0; jj < nr; ++jj)
+            Wc[((size_t)co * st.Cin + ci) * nr + jj] = W[((size_t)ci * st.Cout + co) * k + j0 + s * (nr - 1 - jj)];
+      VSG_TRY(pack_conv_f32(L, Wc, b, st.Cout, st.Cin, nr, Identity{}, &ph.f32));
+      VSG_TRY(pack_conv_tc(P, Wc, b, st.Cout, st.Cin, nr, &ph.tc));
+    }
+    // resblocks                                                            decoder.py:28-32
+    st.blocks.resize(c.dec_n_kernels);
+    for (int j = 0; j < c.dec_n_kernels; ++j) {
+      ResBlockPack& rb = st.blocks[j];
+      rb.kernel = c.dec_resblock_kernel_sizes[j];
+      if (rb.kernel % 2 == 0) return fail(VSG_EUNSUPPORTED, "even resblock kernel size %d", rb.kernel);
+      const int nd = c.dec_n_dilations[j];
+      if (nd <= 0 || nd > VSG_MAX_RESBLOCK_DILATIONS) return fail(VSG_EINVAL, "bad dilation count");
+      rb.dilations.assign(c.dec_resblock_dilations[j], c.dec_resblock_dilations[j] + nd);
+      const std::string pb = pre + "resblocks." + std::to_string(i * c.dec_n_kernels + j) + ".";
+      rb.c1.resize(nd); rb.c1_tc.resize(nd);
+      if (c.dec_resblock == 1) { rb.c2.resize(nd); rb.c2_tc.resize(nd); }
+      for (int q = 0; q < nd; ++q) {
+        const std::string n1 = pb + (c.dec_resblock == 1 ? "convs1." : "convs.") + std::to_string(q);
+        VSG_TRY(L.eff_weight(n1, ch, ch, rb.kernel, W));
+        VSG_TRY(L.bias(n1, ch, b, true));
+        VSG_TRY(pack_conv_f32(L, W, b, ch, ch, rb.kernel, Identity{}, &rb.c1[q]));
+        VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_tc[q]));
+        if (c.dec_resblock == 1) {
+          const std::string n2 = pb + "convs2." + std::to_string(q);
+          VSG_TRY(L.eff_weight(n2, ch, ch, rb.kernel, W));
+          VSG_TRY(L.bias(n2, ch, b, true));
+          VSG_TRY(pack_conv_f32(L, W, b, ch, ch, rb.kernel, Identity{}, &rb.c2[q]));
+          VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_tc[q]));
+        }
+      }
+    }
+  }
+  // conv_post: Conv1d(ch -> 1, 7, padding 3, bias=False)                    decoder.py:34
+  VSG_TRY(L.eff_weight(pre + "conv_post", 1, ch, 7, W));
+  VSG_TRY(L.upload(W, &P->conv_post_w));
+  P->conv_post_k = 7;
+  P->has_dec = true;
+  return VSG_OK;
+}
+
+}  // namespace
+}  // namespace vsg
+
+using namespace vsg;
+
+extern "C" int vsg_abi_version(void) { return VSG_ABI_VERSION; }
+extern "C" const char* vsg_last_error(void) { return vsg::g_err; }
+extern "C" int32_t vsg_last_launch_count(void) { return vsg::g_launches; }
+extern "C" int32_t vsg_hop_size(const VsgPack* p) { return (p && p->has_dec) ? p->hop : 0; }
+
+extern "C" int vsg_pack_create(const VsgConfig* cfg, const VsgTensor* weights, int32_t n_weights,
+                               const char* flow_prefix, const char* dec_prefix, int32_t device, VsgPack** out) {
+  if (!cfg || !out || (!weights && n_weights > 0)) return fail(VSG_EINVAL, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  VSG_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(VSG_EINVAL, "device %d out of range (%d visible)", device, ndev);
+  int prev = 0;
+  VSG_CUDA_TRY(cudaGetDevice(&prev));
+  VSG_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VSG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(VSG_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  VsgPack* P = new VsgPack();
+  P->cfg = *cfg;
+  P->device = device;
+  P->sm_count = prop.multiProcessorCount;
+  Loader L;
+  L.pack = P;
+  for (int i = 0; i < n_weights; ++i) {
+    if (!weights[i].name || !weights[i].data || weights[i].ndim < 0 || weights[i].ndim > 4) {
+      delete P;
+      return fail(VSG_EINVAL, "weight table entry %d is malformed", i);
+    }
+    HostTensor t;
+    t.data = weights[i].data;
+    t.shape.assign(weights[i].shape, weights[i].shape + weights[i].ndim);
+    L.m[weights[i].name] = t;
+  }
+  int rc = VSG_OK;
+  if (cfg->flow_n_flows > 0) rc = pack_flow(L, flow_prefix ? flow_prefix : "", P);
+  if (rc == VSG_OK && cfg->dec_n_ups > 0) rc = pack_decoder(L, dec_prefix ? dec_prefix : "", P);
+  if (rc == VSG_OK && !P->has_flow && !P->has_dec) rc = fail(VSG_EINVAL, "config selects neither flow nor decoder");
+  cudaSetDevice(prev);
+  if (rc != VSG_OK) {
+    vsg_pack_destroy(P);
+    return rc;
+  }
+  *out = P;
+  return VSG_OK;
+}
+
+extern "C" void vsg_pack_destroy(VsgPack* pack) {
+  if (!pack) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(pack->device);
+  for (void* p : pack->allocs) cudaFree(p);
+  cudaSetDevice(prev);
+  delete pack;
+}

@@ -1,0 +1,28 @@
+// Internal declarations shared by the run drivers and the C-ABI entry points.
+#pragma once
+#include "vsg_common.cuh"
+
+namespace vsg {
+
+int launch_cond(const float* W, const float* bias, const float* g, float* out, int O, int I, int B, cudaStream_t st);
+int prior_sample(const float* mu, const float* logs, const float* noise, const float* mask, float* z, int B, int C,
+                 int T, cudaStream_t st);
+int mask_mul(const float* x, const float* mask, float* y, int B, int C, int T, cudaStream_t st);
+
+// fp32 parity mode (run_f32.cu)
+size_t flow_ws_bytes_f32(const VsgPack* P, int B, int T);
+size_t dec_ws_bytes_f32(const VsgPack* P, int B, int T);
+int flow_forward_f32(const VsgPack* P, const float* x, const float* mask, const float* g, float* y, int B, int T,
+                     int reverse, Workspace& ws, cudaStream_t st);
+int generator_forward_f32(const VsgPack* P, const float* z, const float* g, float* wav, int B, int T, Workspace& ws,
+                          cudaStream_t st);
+
+// bf16 tensor-core mode (run_tc.cu)
+size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T);
+size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T);
+int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, float* y, int B, int T,
+                    int reverse, Workspace& ws, cudaStream_t st);
+int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float* wav, int B, int T, Workspace& ws,
+                         cudaStream_t st);
+
+}  // namespace vsg

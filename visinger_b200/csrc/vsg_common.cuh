@@ -1,0 +1,135 @@
+// Shared host-side plumbing of the C-ABI library: error reporting, the pack object,
+// the workspace bump allocator.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/visinger_b200.h"
+
+namespace vsg {
+
+extern thread_local char g_err[1024];
+extern thread_local int g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define VSG_CUDA_TRY(expr)                                                                         \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::vsg::fail(VSG_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define VSG_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != VSG_OK) return _r; \
+  } while (0)
+
+#define VSG_LAUNCH_CHECK(what)                                                                    \
+  do {                                                                                            \
+    ++::vsg::g_launches;                                                                          \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess)                                                                        \
+      return ::vsg::fail(VSG_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e));     \
+  } while (0)
+
+// ---- packed weights -----------------------------------------------------------------------------
+// fp32 path: [Cin][ktaps][CoutP] + bias[CoutP]
+struct ConvW32 {
+  float* w = nullptr;
+  float* bias = nullptr;
+  int Cin = 0, Cout = 0, CoutP = 0, ktaps = 0;
+};
+
+// bf16 tensor-core path: [ktaps][CoutT][CinT] bf16 (K-major rows of CinT channels), bias fp32 [CoutT]
+struct ConvWTC {
+  __nv_bfloat16* w = nullptr;
+  float* bias = nullptr;
+  int Cin = 0, Cout = 0, CinT = 0, CoutT = 0, ktaps = 0;
+  CUtensorMap tmap;     // 2-D map over [ktaps*CoutT rows][CinT]
+  bool has_tmap = false;
+};
+
+struct UpsPhase {
+  ConvW32 f32;
+  ConvWTC tc;
+  int in_off0 = 0;
+};
+
+struct FlowLayer {
+  ConvW32 pre[2], post[2];          // [0] = as stored, [1] = Flip folded in
+  std::vector<ConvW32> in_layers;   // gate-interleaved output channels
+  std::vector<ConvW32> res_skip;
+  float* cond_w = nullptr;          // [2H*n_layers][gin], rows gate-interleaved per layer
+  float* cond_b = nullptr;
+};
+
+struct ResBlockPack {
+  int kernel = 0;
+  std::vector<int> dilations;
+  std::vector<ConvW32> c1, c2;      // ResBlock2 uses c1 only
+  std::vector<ConvWTC> c1_tc, c2_tc;
+};
+
+struct UpStage {
+  int rate = 0, kernel = 0, Cin = 0, Cout = 0, pad = 0;
+  std::vector<UpsPhase> phases;
+  std::vector<ResBlockPack> blocks;
+};
+
+}  // namespace vsg
+
+struct VsgPack {
+  VsgConfig cfg;
+  int device = 0;
+  int hop = 0;
+  int sm_count = 148;
+  bool has_flow = false, has_dec = false;
+  std::vector<void*> allocs;
+  // flow
+  std::vector<vsg::FlowLayer> flow_layers;
+  // decoder
+  vsg::ConvW32 conv_pre;
+  vsg::ConvWTC conv_pre_tc;
+  float* dec_cond_w = nullptr;   // [uic][gin]
+  float* dec_cond_b = nullptr;
+  std::vector<vsg::UpStage> ups;
+  float* conv_post_w = nullptr;  // [C_last][k]
+  int conv_post_k = 7;
+};
+
+namespace vsg {
+
+struct Workspace {
+  char* base;
+  size_t cap, off = 0;
+  bool overflow = false;
+  Workspace(void* p, size_t bytes) : base((char*)p), cap(bytes) {}
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    if (off + bytes > cap) { overflow = true; off += bytes; return nullptr; }
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+};
+
+inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+}  // namespace vsg
