@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds synthesised per wall-second on the VISinger inference hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--precision bf16|fp32] [--impl reference]
+
+A "step" is one pass of the hot path (models/visinger.py:107-111 of the reference: prior sampling ->
+ResidualCouplingBlock reverse -> HiFi-GAN Generator) over one batch of synthetic input: B=16 utterances
+x T=1000 latent frames = 200 s of 24 kHz audio per GPU per step (BASELINE.json configs[1]+[2], the shapes
+the metric's roofline is quoted on), random weights of config/models/visinger.yaml shape.
+
+  value     device-resident throughput: inputs already in HBM, CUDA events around K steps, max over ranks
+  e2e       the same through the public module API with pinned HOST buffers: H2D of (mu_p, logs_p, noise,
+            mask, g) and D2H of the waveform inside the timed region, every step
+  roofline  decoder convolutions (the dominant kernels): algorithmic FLOPs (SURVEY.md 8d:
+            333 911 680 FLOP per latent frame) / CUDA-event time of the generator region
+  cpu_baseline  the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1 only)
+
+Multi-GPU: utterances are independent, so ranks shard by utterance with no collective on the data path
+(weak scaling: every rank runs the same per-GPU batch); torch.distributed is used only for the barrier
+and the max-over-ranks of the device-measured time.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FRAME_SEC = 300.0 / 24000.0                 # hop_size / sample_rate (preprocess.yaml:9,11)
+DEC_FLOP_PER_FRAME = 333_911_680
+FLOW_FLOP_PER_FRAME = 14_155_776
+METRIC = "audio-sec synthesized per wall-sec"
+UNIT = "audio-s/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("VSG_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_sustained=d.get("bf16_tflops_sustained", 1390.4), bf16_burst=d.get("bf16_tflops", 1674.5),
+                    hbm=d.get("hbm_gbs", 6549.8), src="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def oracle_hot_path_time(B, T, reps, threads):
+    """Times the oracle port of the reference CPU path (flow reverse + generator, fp32, eval, no_grad)."""
+    import torch
+    from oracle import visinger_oracle as O
+    from helpers import FLOW_FULL, GEN_FULL, flow_shapes, gen_shapes, make_inputs
+    torch.set_num_threads(threads)
+    fsd = O.synth_state_dict(flow_shapes(FLOW_FULL), 1234)
+    gsd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
+    sd = {"flow." + k: v for k, v in fsd.items()}
+    sd.update({"decoder." + k: v for k, v in gsd.items()})
+    x, mask, g = make_inputs(0, B, 192, T, 256)
+    logs = torch.full_like(x, -1.0)
+    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(1))
+    times = []
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.infer_hot_path(sd, x, logs, noise, mask, g)
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference is
+    Python and cannot travel to the GPU box) on all host threads, each step a bounded sample."""
+    import torch
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    Bs, Ts = 1, args.frames     # bounded sample of the arm's workload: one of its B utterances per step
+    times = oracle_hot_path_time(Bs, Ts, args.warmup + args.steps, cores)[args.warmup:]
+    audio = Bs * Ts * FRAME_SEC
+    tot = sum(times)
+    val = audio * len(times) / tot
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "hot path (prior sample -> flow reverse -> HiFi-GAN generator), oracle port of the "
+                                   "reference CPU path; bounded sample per step: 1 of the " + str(args.batch) + f" utterances of the B={args.batch} x T={Ts} workload ({Ts * FRAME_SEC:.1f} s audio)",
+                       "threads": torch.get_num_threads()},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps of 1 utterance x T={Ts} frames ({Ts * FRAME_SEC:.1f} s audio each), fp32, all host threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from oracle import visinger_oracle as O            # weights generator only (shared with the tests)
+    from helpers import FLOW_FULL, GEN_FULL, flow_shapes, gen_shapes, make_inputs
+    from visinger_b200.models.visinger import HotPath
+    import visinger_b200
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = args.batch, args.frames
+    audio_per_step = B * T * FRAME_SEC
+
+    fsd = O.synth_state_dict(flow_shapes(FLOW_FULL), 1234)
+    gsd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
+    hp = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, dev, precision=args.precision)
+
+    x, mask, g = make_inputs(rank, B, 192, T, 256)
+    logs = torch.full_like(x, -1.0)
+    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + rank))
+    host = [t.pin_memory() for t in (x, logs, noise, mask, g)]
+    devin = [t.to(dev) for t in host]
+    wav_host = torch.empty(B, T * 300, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * 4 for t in host)
+    d2h = wav_host.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    def step_resident():
+        hp.infer(*devin)
+
+    def step_e2e():
+        d = [t.to(dev, non_blocking=True) for t in host]
+        wav, _ = hp.infer(*d)
+        wav_host.copy_(wav.view(B, -1), non_blocking=True)
+
+    def step_decoder():
+        hp.decode(devin[0], devin[4])
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches_per_step = hp.last_launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(step_resident, args.steps)
+    sampler.stop_flag = True
+    sampler.join()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    for _ in range(2):
+        step_decoder()
+    ms_dec = timed(step_decoder, args.steps)
+
+    if rank == 0:
+        pk = peaks()
+        value = world * audio_per_step * args.steps / (ms * 1e-3)
+        e2e_value = world * audio_per_step * args.steps / (ms_e2e * 1e-3)
+        dec_tflops = DEC_FLOP_PER_FRAME * B * T * args.steps / (ms_dec * 1e-3) / 1e12
+        peak = pk["bf16_sustained"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"hot path: prior sample -> ResidualCouplingBlock.reverse -> HiFi-GAN Generator; "
+                                   f"B={B} utterances x T={T} latent frames ({audio_per_step:.0f} s audio) per GPU per step; "
+                                   "config/models/visinger.yaml shapes, random weights",
+                       "precision_mode": args.precision, "sharding": f"by utterance, {world} replica(s), no collective",
+                       "l2": "no explicit flush: each step streams >1 GB of activations, far beyond the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": dec_tflops / peak, "traffic": None,
+                         "kernel": "decoder convolutions (vsg_generator_forward region)",
+                         "algorithmic": f"{DEC_FLOP_PER_FRAME} FLOP/frame x {B * T} frames",
+                         "ms": ms_dec / args.steps, "peak_source": pk["src"] + ", sustained bf16"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = len(os.sched_getaffinity(0))
+            ts = oracle_hot_path_time(1, T, 4, cores)[1:]
+            line["cpu_baseline"] = {"value": T * FRAME_SEC / min(ts), "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"1 of the {B} utterances (T={T} frames, {T * FRAME_SEC:.1f} s audio), best of 3 "
+                                              "after 1 warm-up, fp32, oracle port of the reference CPU path on all host threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -163,6 +163,21 @@ int32_t vsg_hop_size(const VsgPack* pack);
 /* Number of kernels launched by the most recent run call on this thread (bench bookkeeping). */
 int32_t vsg_last_launch_count(void);
 
+/*
+ * Per-layer parity hook (tests and tuning only; it allocates and synchronises, unlike the run calls):
+ * one Conv1d on the bf16 tcgen05 kernel, the unit the reference dispatches as nn.Conv1d -> F.conv1d
+ * (modules/visinger/decoder.py:72-87).
+ *   x_bf16: device bf16 [B, L, Cin] channels-last; w: HOST fp32 [Cout][Cin][k]; bias: HOST fp32 [Cout] or NULL;
+ *   out: device fp32 [B, L, Cout] = conv1d(x, w, dilation, padding = (k-1)*dilation/2) + bias.
+ *   flags bit 0: HALO mode (one activation box per channel chunk, taps through row-shifted UMMA
+ *   descriptors); bit 1: fill the UMMA descriptor base_offset field from the start address.
+ */
+int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias, float* out, int32_t B, int32_t L,
+                          int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t flags, int32_t device);
+
+/* Process-wide default for the activation-operand feeding mode of the tensor-core convolutions. */
+int vsg_set_tc_options(int32_t halo_mode, int32_t desc_base_offset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,6 +149,10 @@ def lib() -> ctypes.CDLL:
         L.vsg_generator_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
         L.vsg_infer.restype = ctypes.c_int
         L.vsg_infer.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+        L.vsg_debug_conv1d_bf16.restype = ctypes.c_int
+        L.vsg_debug_conv1d_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32]
+        L.vsg_set_tc_options.restype = ctypes.c_int
+        L.vsg_set_tc_options.argtypes = [i32, i32]
         if L.vsg_abi_version() != 1:
             raise RuntimeError("visinger_b200: ABI version mismatch between _lib.py and the shared library")
         _lib = L
@@ -245,6 +249,27 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 def release_workspaces() -> None:
     _ws_cache.clear()
+
+
+def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int, flags: int = 0) -> torch.Tensor:
+    """Per-layer parity hook: one Conv1d on the tcgen05 kernel.  x_bld: CUDA bf16 [B, L, Cin] channels-last;
+    w: [Cout, Cin, k] fp32 (any device); returns CUDA fp32 [B, L, Cout]."""
+    require_cuda(x_bld, "x")
+    assert x_bld.dtype == torch.bfloat16 and x_bld.is_contiguous()
+    B, Lx, Cin = x_bld.shape
+    Cout, _, k = w.shape
+    wh = w.detach().to("cpu", torch.float32).contiguous()
+    bh = bias.detach().to("cpu", torch.float32).contiguous() if bias is not None else None
+    out = torch.empty(B, Lx, Cout, dtype=torch.float32, device=x_bld.device)
+    torch.cuda.synchronize(x_bld.device)
+    rc = lib().vsg_debug_conv1d_bf16(x_bld.data_ptr(), wh.data_ptr(), bh.data_ptr() if bh is not None else None,
+                                     out.data_ptr(), B, Lx, Cin, Cout, k, dilation, flags, x_bld.device.index or 0)
+    check(rc, "vsg_debug_conv1d_bf16")
+    return out
+
+
+def set_tc_options(halo_mode: int, desc_base_offset: int = 0) -> None:
+    check(lib().vsg_set_tc_options(int(halo_mode), int(desc_base_offset)), "vsg_set_tc_options")
 
 
 def stream_ptr(device: torch.device) -> int:

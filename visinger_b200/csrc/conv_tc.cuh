@@ -1,0 +1,440 @@
+// bf16 tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma with TMEM accumulators, operands
+// staged in shared memory by TMA, warp-specialised and persistent.
+//
+// Activations are channels-last bf16 [B, L, C]; one CTA tile is 128 time steps (GEMM M = UMMA M = 128,
+// one TMEM lane per time step) x N_TILE output channels (GEMM N <= 256) of one utterance.  The GEMM K
+// dimension runs over (input-channel chunk, tap):
+//     D[t, co] = sum_{chunk, tap} X[t + in_off0 + tap*dil, chunk] . W[tap][co, chunk]^T
+//   * A operand: a [rows x KC] K-major box of X fetched by a 3-D TMA map (C, L, B).  Rows outside
+//     [0, L) are zero-filled by the TMA unit -- that IS the convolution's zero padding and it also keeps
+//     utterances of a batch apart.  In HALO mode one box of 128 + (ktaps-1)*dil rows is loaded per
+//     channel chunk and every tap re-reads it through a row-shifted UMMA descriptor (A traffic / ktaps);
+//     in RELOAD mode a fresh 128-row box is fetched per (chunk, tap).
+//   * B operand: the pre-packed weights [tap][Cout][Cin] (K-major rows) through a 2-D TMA map.
+//   * swizzle = KC*2 bytes (128B / 64B / 32B) on both operands, identical in the TMA map and the UMMA
+//     shared-memory descriptor.
+// ConvTranspose1d runs as `stride` polyphase launches of the same kernel (out_stride / out_phase).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane), warps 2..5 = epilogue (TMEM -> registers -> fused bias / residual / resblock-sum / leaky_relu ->
+// bf16 global stores).  The accumulator is double-buffered in TMEM (2 x N_TILE columns) so the epilogue of
+// tile i overlaps the main loop of tile i+1.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+
+namespace vsg {
+
+struct ConvTC {
+  int B, Lq, Lout;              // q positions per utterance, output length
+  int n_cchunks, KC, ktaps, dil, in_off0;
+  int Cout, n_tile, n_ntiles, CoutT;   // CoutT: rows per tap in the packed weight matrix
+  int out_stride, out_phase;
+  int m_tiles_per_b, total_tiles;
+  int halo_mode;                // 1: one A box per channel chunk, taps via row-shifted descriptors
+  int desc_base_offset;         // 1: fill the UMMA descriptor base_offset field from the start address
+  int a_rows;                   // rows per A box
+  int stages_a, stages_w;
+  uint32_t a_stage_bytes, w_stage_bytes, a_box_bytes, w_box_bytes;
+  uint32_t tmem_cols;
+  uint32_t swizzle_code;        // UMMA layout type: 2 = 128B, 4 = 64B, 6 = 32B
+  uint32_t sbo_bytes;           // 8 rows * row bytes
+  // epilogue
+  const float* bias;            // [Cout] or null
+  const float* bcond; int bcond_bs;   // [B][bcond_bs] or null
+  const __nv_bfloat16* add0;    // same geometry as the output, or null (residual)
+  const __nv_bfloat16* add1;    // same geometry as the output, or null (running resblock sum)
+  float scale;                  // applied after the adds
+  float slope;                  // leaky_relu slope for out_act
+  __nv_bfloat16* out_raw;       // value as is, or null
+  __nv_bfloat16* out_act;       // leaky_relu(value), or null
+  float* out_f32;               // optional fp32 copy of the raw value [B, Lout, Cout] (debug / parity hook)
+  int* error_flag;              // set to 1 if a barrier wait times out
+};
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (error_flag) atomicExch(error_flag, 1);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// tcgen05.commit: arrive on `bar` once every MMA issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M = 128.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major; 1)
+//   [32,46) stride byte offset >> 4 (distance between 8-row groups) | [46,48) version = 1
+//   [49,52) base offset | [61,64) layout type (2 = SWIZZLE_128B, 4 = 64B, 6 = 32B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1u << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)(base_off & 7u) << 49;
+  d |= (uint64_t)(layout & 7u) << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
+// both operands K-major, N >> 3 at [17,23), M >> 4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+
+}  // namespace tc
+
+__global__ void __launch_bounds__(tc::kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvTC p) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up: [A stages][W stages][barriers][tmem base]
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t w_base = a_base + p.stages_a * p.a_stage_bytes;
+  const uint32_t bar_base = w_base + p.stages_w * p.w_stage_bytes;
+  // barrier slots (8 bytes each)
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (3 * kMaxStages + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (4 * kMaxStages + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (4 * kMaxStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (4 * kMaxStages + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < p.stages_a; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.stages_w; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int n_kblocks = p.n_cchunks * p.ktaps;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_ntiles;
+        const int mt = (tile / p.n_ntiles) % p.m_tiles_per_b;
+        const int b = tile / (p.n_ntiles * p.m_tiles_per_b);
+        const int row0 = mt * 128 + p.in_off0;
+        for (int c = 0; c < p.n_cchunks; ++c) {
+          if (p.halo_mode) {
+            mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);
+            mbar_expect_tx(a_full(sa), p.a_box_bytes);
+            tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), c * p.KC, row0, b);
+            if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+          }
+          for (int j = 0; j < p.ktaps; ++j) {
+            if (!p.halo_mode) {
+              mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);
+              mbar_expect_tx(a_full(sa), p.a_box_bytes);
+              tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), c * p.KC, row0 + j * p.dil, b);
+              if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+            }
+            mbar_wait(w_empty(sw), pw ^ 1, p.error_flag);
+            mbar_expect_tx(w_full(sw), p.w_box_bytes);
+            tma_load_2d(w_base + sw * p.w_stage_bytes, &tmW, w_full(sw), c * p.KC, j * p.CoutT + nt * p.n_tile);
+            if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.n_tile);
+      const uint32_t row_bytes = (uint32_t)p.KC * 2u;
+      const int kk_n = p.KC / 16;
+      int sa = 0, sw = 0, as = 0;
+      uint32_t pa = 0, pw = 0, pacc = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(acc_empty(as), pacc ^ 1, p.error_flag);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.n_tile);
+        uint32_t accumulate = 0;
+        for (int c = 0; c < p.n_cchunks; ++c) {
+          if (p.halo_mode) { mbar_wait(a_full(sa), pa, p.error_flag); }
+          for (int j = 0; j < p.ktaps; ++j) {
+            if (!p.halo_mode) { mbar_wait(a_full(sa), pa, p.error_flag); }
+            mbar_wait(w_full(sw), pw, p.error_flag);
+            fence_after_sync();
+            const uint32_t a_addr = a_base + sa * p.a_stage_bytes + (p.halo_mode ? (uint32_t)(j * p.dil) * row_bytes : 0u);
+            const uint32_t w_addr = w_base + sw * p.w_stage_bytes;
+            for (int kk = 0; kk < kk_n; ++kk) {
+              const uint32_t aa = a_addr + kk * 32u, ww = w_addr + kk * 32u;
+              const uint32_t boff_a = p.desc_base_offset ? ((aa >> 7) & 7u) : 0u;
+              umma_bf16(d_tmem, make_desc(aa, p.sbo_bytes, p.swizzle_code, boff_a),
+                        make_desc(ww, p.sbo_bytes, p.swizzle_code, 0u), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(w_empty(sw));
+            if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
+            if (!p.halo_mode) {
+              umma_commit(a_empty(sa));
+              if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+            }
+          }
+          if (p.halo_mode) {
+            umma_commit(a_empty(sa));
+            if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+          }
+        }
+        umma_commit(acc_full(as));
+        if (++as == 2) { as = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int quarter = warp & 3;          // tcgen05.ld: warp w may only touch lanes 32*(w%4) .. +31
+    int as = 0;
+    uint32_t pacc = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_ntiles;
+      const int mt = (tile / p.n_ntiles) % p.m_tiles_per_b;
+      const int b = tile / (p.n_ntiles * p.m_tiles_per_b);
+      mbar_wait(acc_full(as), pacc, p.error_flag);
+      fence_after_sync();
+      const int q = mt * 128 + quarter * 32 + lane;
+      const int n = q * p.out_stride + p.out_phase;
+      const bool row_ok = (q < p.Lq) && (n < p.Lout);
+      const long long row_off = ((long long)b * p.Lout + n) * p.Cout;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.n_tile);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);          // warp-collective: executed by every lane
+        const int ch = nt * p.n_tile + c0;
+        if (row_ok && ch < p.Cout) {
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch + i));
+              v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+            }
+          }
+          if (p.bcond) {
+            const float* bc = p.bcond + (long long)b * p.bcond_bs + ch;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bc + i));
+              v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+            }
+          }
+          if (p.add0) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.add0 + row_off + ch);
+            float f[8];
+            unpack_bf16x8(src[0], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += f[i];
+            unpack_bf16x8(src[1], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+          }
+          if (p.add1) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.add1 + row_off + ch);
+            float f[8];
+            unpack_bf16x8(src[0], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += f[i];
+            unpack_bf16x8(src[1], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+          }
+          if (p.scale != 1.0f) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= p.scale;
+          }
+          if (p.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + row_off + ch);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (p.out_raw) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_raw + row_off + ch);
+            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          }
+          if (p.out_act) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+            uint4* dst = reinterpret_cast<uint4*>(p.out_act + row_off + ch);
+            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(as));
+      if (++as == 2) { as = 0; pacc ^= 1; }
+    }
+  }
+
+  // ---- teardown: everyone done with TMEM before the allocating warp frees it ----
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---- glue kernels of the bf16 path --------------------------------------------------------------
+
+// [B, C, T] fp32 (reference layout) -> [B, T, C] bf16 (channels-last), optional leaky_relu.  32x32 smem tile.
+__global__ void transpose_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? x[((long long)b * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < T && c < C) y[((long long)b * T + t) * C + c] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+// conv_post on the channels-last bf16 stream: input is already leaky_relu'd (out_act of the last stage).
+// wav[b, n] = tanh(sum_{j, c} w[c][j] * x[b, n + j - pad, c]).  One thread per sample.
+__global__ void conv_post_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[C][k]*/,
+                                      float* __restrict__ wav, int C, int L, int k) {
+  extern __shared__ float wsm[];   // [k][C]
+  for (int i = threadIdx.x; i < C * k; i += blockDim.x) {
+    const int c = i / k, j = i - c * k;
+    wsm[j * C + c] = w[i];
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (n >= L) return;
+  const int pad = (k - 1) / 2;
+  float s = 0.f;
+  for (int j = 0; j < k; ++j) {
+    const int pos = n + j - pad;
+    if (pos < 0 || pos >= L) continue;
+    const uint4* row = reinterpret_cast<const uint4*>(x + ((long long)b * L + pos) * C);
+    for (int c8 = 0; c8 < C / 8; ++c8) {
+      float f[8];
+      tc::unpack_bf16x8(__ldg(row + c8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(wsm[j * C + c8 * 8 + i], f[i], s);
+    }
+  }
+  wav[(long long)b * L + n] = tanhf(s);
+}
+
+}  // namespace vsg

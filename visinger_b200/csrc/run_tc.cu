@@ -1,11 +1,339 @@
-// placeholder until the tcgen05 path lands
+// bf16 tensor-core mode: weight pre-pack, TMA tensor maps, launch logic and the Generator driver.
 #include "vsg_common.cuh"
 #include "run.cuh"
 #include "pack_tc.cuh"
+#include "conv_tc.cuh"
+
+#include <algorithm>
+#include <mutex>
+
 namespace vsg {
-int pack_conv_tc(VsgPack*, const std::vector<float>&, const std::vector<float>&, int, int, int, ConvWTC*) { return VSG_OK; }
+
+namespace {
+
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+int pick_kc(int cin) { return cin % 64 == 0 ? 64 : cin % 32 == 0 ? 32 : cin % 16 == 0 ? 16 : 0; }
+int pick_ntile(int cout) {
+  for (int n : {256, 128, 64, 32, 16})
+    if (cout % n == 0) return n;
+  return 0;
+}
+
+int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows,
+              int kc) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(VSG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VSG_ECUDA, "cuTensorMapEncodeTiled(2d) failed with %d", (int)r);
+  return VSG_OK;
+}
+
+int encode_3d(CUtensorMap* m, const void* base, uint64_t C, uint64_t L, uint64_t B, uint32_t box_c, uint32_t box_rows,
+              int kc) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(VSG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {C, L, B};
+  cuuint64_t strides[2] = {C * 2, C * L * 2};
+  cuuint32_t box[3] = {box_c, box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VSG_ECUDA, "cuTensorMapEncodeTiled(3d) failed with %d", (int)r);
+  return VSG_OK;
+}
+
+constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kSmemMax = 227 * 1024;
+
+struct EpiTC {
+  const float* bias = nullptr;
+  const float* bcond = nullptr; int bcond_bs = 0;
+  const __nv_bfloat16* add0 = nullptr;
+  const __nv_bfloat16* add1 = nullptr;
+  float scale = 1.f;
+  __nv_bfloat16* out_raw = nullptr;
+  __nv_bfloat16* out_act = nullptr;
+  float* out_f32 = nullptr;
+};
+
+struct TCOptions { int halo_mode = 0; int desc_base_offset = 0; };
+
+TCOptions g_default_opts;
+
+// One convolution launch.  x: [B, Lin, Cin] bf16 channels-last; outputs: [B, Lout, Cout].
+int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, int B, int Lin, int in_off0, int dil,
+                   int Lq, int out_stride, int out_phase, int Lout, const EpiTC& e, const TCOptions& opt, int* error_flag,
+                   cudaStream_t st) {
+  if (!w.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 16 "
+                                                 "(conv %d -> %d)", w.Cin, w.Cout);
+  if (Lq <= 0 || B <= 0) return VSG_OK;
+  const int KC = pick_kc(w.Cin), NT = pick_ntile(w.Cout);
+  ConvTC p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Lq = Lq; p.Lout = Lout;
+  p.KC = KC; p.n_cchunks = w.Cin / KC; p.ktaps = w.ktaps; p.dil = dil; p.in_off0 = in_off0;
+  p.Cout = w.Cout; p.n_tile = NT; p.n_ntiles = w.Cout / NT; p.CoutT = w.CoutT;
+  p.out_stride = out_stride; p.out_phase = out_phase;
+  p.m_tiles_per_b = (Lq + 127) / 128;
+  p.total_tiles = p.m_tiles_per_b * p.n_ntiles * B;
+  const int halo = (w.ktaps - 1) * dil;
+  p.halo_mode = (opt.halo_mode && w.ktaps > 1 && 128 + halo <= 256) ? 1 : 0;
+  p.desc_base_offset = opt.desc_base_offset;
+  p.a_rows = p.halo_mode ? 128 + halo : 128;
+  p.a_box_bytes = (uint32_t)p.a_rows * KC * 2;
+  p.w_box_bytes = (uint32_t)NT * KC * 2;
+  p.a_stage_bytes = (p.a_box_bytes + 1023u) & ~1023u;
+  p.w_stage_bytes = (p.w_box_bytes + 1023u) & ~1023u;
+  if (p.halo_mode) {
+    p.stages_a = 2;
+    p.stages_w = (int)std::min<size_t>(tc::kMaxStages, (kSmemBudget - 2 * p.a_stage_bytes) / p.w_stage_bytes);
+  } else {
+    p.stages_a = p.stages_w = (int)std::min<size_t>(tc::kMaxStages, kSmemBudget / (p.a_stage_bytes + p.w_stage_bytes));
+  }
+  if (p.stages_a < 2 || p.stages_w < 2) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
+  p.tmem_cols = (uint32_t)std::max(32, 2 * NT);
+  p.swizzle_code = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
+  p.sbo_bytes = 8u * KC * 2u;
+  p.bias = e.bias; p.bcond = e.bcond; p.bcond_bs = e.bcond_bs;
+  p.add0 = e.add0; p.add1 = e.add1; p.scale = e.scale; p.slope = 0.1f;
+  p.out_raw = e.out_raw; p.out_act = e.out_act; p.out_f32 = e.out_f32;
+  p.error_flag = error_flag;
+
+  CUtensorMap tmA;
+  VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.Cin, (uint64_t)Lin, (uint64_t)B, (uint32_t)KC, (uint32_t)p.a_rows, KC));
+  const size_t smem = 1024 + (size_t)p.stages_a * p.a_stage_bytes + (size_t)p.stages_w * p.w_stage_bytes + 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    attr_set = true;
+  }
+  const int grid = std::min(p.total_tiles, P->sm_count);
+  conv_tc_kernel<<<grid, tc::kThreads, smem, st>>>(tmA, w.tmap, p);
+  VSG_LAUNCH_CHECK("conv_tc_kernel");
+  return VSG_OK;
+}
+
+size_t dec_max_elems(const VsgPack* P, int B, int T) {
+  size_t m = (size_t)B * P->cfg.dec_upsample_initial_channel * T;
+  long long L = T;
+  for (const UpStage& st : P->ups) {
+    L *= st.rate;
+    m = std::max(m, (size_t)B * st.Cout * (size_t)L);
+  }
+  return m;
+}
+
+}  // namespace
+
+// Conv1d-style weight W[co][ci][j] -> bf16 [j][co][ci] (K-major rows) + its 2-D TMA map.
+int pack_conv_tc(VsgPack* P, const std::vector<float>& W, const std::vector<float>& b, int Cout, int Cin, int k,
+                 ConvWTC* out) {
+  out->Cin = Cin; out->Cout = Cout; out->CinT = Cin; out->CoutT = Cout; out->ktaps = k;
+  out->has_tmap = false;
+  const int KC = pick_kc(Cin), NT = pick_ntile(Cout);
+  if (KC == 0 || NT == 0 || k < 1) return VSG_OK;   // not representable on the tensor-core path; fp32 mode still works
+  std::vector<__nv_bfloat16> wp((size_t)k * Cout * Cin);
+  for (int j = 0; j < k; ++j)
+    for (int co = 0; co < Cout; ++co)
+      for (int ci = 0; ci < Cin; ++ci)
+        wp[((size_t)j * Cout + co) * Cin + ci] = __float2bfloat16(W[((size_t)co * Cin + ci) * k + j]);
+  void* dw = nullptr;
+  VSG_CUDA_TRY(cudaMalloc(&dw, wp.size() * sizeof(__nv_bfloat16) + 256));
+  P->allocs.push_back(dw);
+  VSG_CUDA_TRY(cudaMemcpy(dw, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  out->w = (__nv_bfloat16*)dw;
+  void* db = nullptr;
+  VSG_CUDA_TRY(cudaMalloc(&db, (size_t)Cout * sizeof(float) + 256));
+  P->allocs.push_back(db);
+  VSG_CUDA_TRY(cudaMemcpy(db, b.data(), (size_t)Cout * sizeof(float), cudaMemcpyHostToDevice));
+  out->bias = (float*)db;
+  VSG_TRY(encode_2d(&out->tmap, dw, (uint64_t)Cin, (uint64_t)k * Cout, (uint32_t)KC, (uint32_t)NT, KC));
+  out->has_tmap = true;
+  return VSG_OK;
+}
+
 size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T) { return flow_ws_bytes_f32(P, B, T); }
-size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T) { return dec_ws_bytes_f32(P, B, T); }
-int flow_forward_tc(const VsgPack*, const float*, const float*, const float*, float*, int, int, int, Workspace&, cudaStream_t) { return fail(VSG_EUNSUPPORTED, "bf16 path not built"); }
-int generator_forward_tc(const VsgPack*, const float*, const float*, float*, int, int, Workspace&, cudaStream_t) { return fail(VSG_EUNSUPPORTED, "bf16 path not built"); }
+
+int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, float* y, int B, int T,
+                    int reverse, Workspace& ws, cudaStream_t st) {
+  // The flow is 4 % of the path's FLOPs; until its tensor-core kernels land it runs the fp32 kernels in both modes.
+  return flow_forward_f32(P, x, mask, g, y, B, T, reverse, ws, st);
+}
+
+size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T) {
+  const size_t E = dec_max_elems(P, B, T);
+  return align256((size_t)B * T * P->cfg.dec_initial_channel * 2) + align256((size_t)B * P->cfg.dec_upsample_initial_channel * 4) +
+         8 * align256(E * 2) + 256;
+}
+
+// Generator.forward (modules/visinger/decoder.py:40-59) on the tensor-core kernels.
+int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float* wav, int B, int T, Workspace& ws,
+                         cudaStream_t st) {
+  const VsgConfig& c = P->cfg;
+  const int C0 = c.dec_initial_channel, UIC = c.dec_upsample_initial_channel, NK = c.dec_n_kernels;
+  const size_t E = dec_max_elems(P, B, T);
+  typedef __nv_bfloat16 bf;
+  bf* zt = ws.take<bf>((size_t)B * T * C0);
+  float* cond = ws.take<float>((size_t)B * UIC);
+  bf* bIn = ws.take<bf>(E);   // leaky_relu'd stage input (what ups / conv_post consume)
+  bf* bU = ws.take<bf>(E);    // upsampled x (residual for the first pair of every resblock)
+  bf* bUA = ws.take<bf>(E);   // leaky_relu(x)
+  bf* bR = ws.take<bf>(E);    // resblock running x
+  bf* bRA = ws.take<bf>(E);   // leaky_relu of it
+  bf* bT = ws.take<bf>(E);    // leaky_relu(conv1 output)  (ResBlock2: ping-pong partner of bR)
+  bf* bTA = ws.take<bf>(E);   // (ResBlock2 only)
+  bf* bS = ws.take<bf>(E);    // running sum over the NK resblocks
+  int* err = ws.take<int>(1);
+  if (ws.overflow) return fail(VSG_ENOMEM, "generator workspace too small: need %zu bytes", ws.off);
+  VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+  const TCOptions opt = g_default_opts;
+
+  if (c.dec_gin > 0) {
+    if (!g) return fail(VSG_EINVAL, "generator was built with gin_channels=%d but g is NULL", c.dec_gin);
+    VSG_TRY(launch_cond(P->dec_cond_w, P->dec_cond_b, g, cond, UIC, c.dec_gin, B, st));
+  }
+  {  // boundary: [B, C, T] fp32 -> [B, T, C] bf16, once
+    dim3 grid((T + 31) / 32, (C0 + 31) / 32, B), block(32, 8);
+    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(z, zt, C0, T);
+    VSG_LAUNCH_CHECK("transpose_to_bf16_kernel");
+  }
+  {  // x = conv_pre(z) + cond(g); only leaky_relu(x) is ever consumed (decoder.py:41-45)
+    EpiTC e;
+    e.bias = P->conv_pre_tc.bias;
+    if (c.dec_gin > 0) { e.bcond = cond; e.bcond_bs = UIC; }
+    e.out_act = bIn;
+    VSG_TRY(launch_conv_tc(P, P->conv_pre_tc, zt, B, T, -3, 1, T, 1, 0, T, e, opt, err, st));
+  }
+  int L = T, ch = UIC;
+  for (int i = 0; i < c.dec_n_ups; ++i) {
+    const UpStage& us = P->ups[i];
+    const int Lout = L * us.rate;
+    for (int r = 0; r < us.rate; ++r) {   // ConvTranspose1d as polyphase convolutions (decoder.py:46)
+      EpiTC e;
+      e.bias = us.phases[r].tc.bias;
+      e.out_raw = bU; e.out_act = bUA;
+      const int Lq = (Lout - r + us.rate - 1) / us.rate;
+      VSG_TRY(launch_conv_tc(P, us.phases[r].tc, bIn, B, L, us.phases[r].in_off0, 1, Lq, us.rate, r, Lout, e, opt, err, st));
+    }
+    ch = us.Cout; L = Lout;
+    for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
+      const ResBlockPack& rb = us.blocks[j];
+      const int nd = (int)rb.dilations.size(), k = rb.kernel;
+      const bf* cur = bU; const bf* curA = bUA;
+      for (int q = 0; q < nd; ++q) {
+        const bool last = (q == nd - 1);
+        const int d = rb.dilations[q];
+        EpiTC e2;
+        e2.add0 = cur;
+        if (last) {
+          e2.add1 = (j > 0) ? bS : nullptr;
+          if (j == NK - 1) { e2.scale = 1.0f / (float)NK; e2.out_act = bIn; }
+          else e2.out_raw = bS;
+        }
+        if (c.dec_resblock == 1) {        // ResBlock1 (decoder.py:91-104)
+          EpiTC e1;
+          e1.bias = rb.c1_tc[q].bias; e1.out_act = bT;
+          VSG_TRY(launch_conv_tc(P, rb.c1_tc[q], curA, B, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
+          e2.bias = rb.c2_tc[q].bias;
+          if (!last) { e2.out_raw = bR; e2.out_act = bRA; }
+          VSG_TRY(launch_conv_tc(P, rb.c2_tc[q], bT, B, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
+          cur = bR; curA = bRA;
+        } else {                           // ResBlock2 (decoder.py:124-133)
+          e2.bias = rb.c1_tc[q].bias;
+          bf* nr = (cur == bR) ? bT : bR;
+          bf* nra = (cur == bR) ? bTA : bRA;
+          if (!last) { e2.out_raw = nr; e2.out_act = nra; }
+          VSG_TRY(launch_conv_tc(P, rb.c1_tc[q], curA, B, L, -((k * d - d) / 2), d, L, 1, 0, L, e2, opt, err, st));
+          cur = nr; curA = nra;
+        }
+      }
+    }
+  }
+  {  // wav = tanh(conv_post(leaky_relu(x)))   (decoder.py:55-57); bIn already holds leaky_relu(x)
+    dim3 grid((L + 255) / 256, B);
+    conv_post_bf16_kernel<<<grid, 256, (size_t)ch * P->conv_post_k * sizeof(float), st>>>(bIn, P->conv_post_w, wav, ch, L,
+                                                                                           P->conv_post_k);
+    VSG_LAUNCH_CHECK("conv_post_bf16_kernel");
+  }
+  return VSG_OK;
+}
+
+}  // namespace vsg
+
+using namespace vsg;
+
+// Per-layer parity hook (tests only; allocates and synchronises): one bf16 tensor-core Conv1d.
+//   x: device bf16 [B, L, Cin] channels-last; w: host fp32 [Cout][Cin][k]; bias: host fp32 [Cout] or NULL;
+//   out: device fp32 [B, L, Cout] = conv1d(x, w, dilation, padding = (k-1)*dilation/2) + bias.
+//   flags bit 0: HALO mode (one A box per channel chunk), bit 1: fill the UMMA descriptor base_offset field.
+extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias, float* out, int32_t B,
+                                     int32_t L, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t flags,
+                                     int32_t device) {
+  g_launches = 0;
+  if (!x_bf16 || !w || !out) return fail(VSG_EINVAL, "null pointer");
+  VSG_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VSG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  VsgPack tmp;
+  tmp.device = device;
+  tmp.sm_count = prop.multiProcessorCount;
+  std::vector<float> W(w, w + (size_t)Cout * Cin * k), bz(Cout, 0.f);
+  if (bias) bz.assign(bias, bias + Cout);
+  ConvWTC wt;
+  int rc = pack_conv_tc(&tmp, W, bz, Cout, Cin, k, &wt);
+  int* err = nullptr;
+  if (rc == VSG_OK && cudaMalloc(&err, sizeof(int)) != cudaSuccess) rc = fail(VSG_ECUDA, "cudaMalloc failed");
+  if (rc == VSG_OK) {
+    cudaMemset(err, 0, sizeof(int));
+    EpiTC e;
+    e.bias = wt.bias;
+    e.out_f32 = out;
+    TCOptions opt;
+    opt.halo_mode = flags & 1;
+    opt.desc_base_offset = (flags >> 1) & 1;
+    rc = launch_conv_tc(&tmp, wt, (const __nv_bfloat16*)x_bf16, B, L, -((k - 1) * dilation / 2), dilation, L, 1, 0, L, e,
+                        opt, err, 0);
+    if (rc == VSG_OK) {
+      cudaError_t ce = cudaDeviceSynchronize();
+      if (ce != cudaSuccess) rc = fail(VSG_ECUDA, "conv_tc_kernel execution failed: %s", cudaGetErrorString(ce));
+    }
+  }
+  if (err) cudaFree(err);
+  for (void* q : tmp.allocs) cudaFree(q);
+  return rc;
+}
+
+// Select the default A-operand feeding mode of the tensor-core convolutions (process-wide; tests and tuning).
+extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t desc_base_offset) {
+  g_default_opts.halo_mode = halo_mode;
+  g_default_opts.desc_base_offset = desc_base_offset;
+  return VSG_OK;
 }
