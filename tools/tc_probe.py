@@ -15,7 +15,7 @@ from visinger_b200 import _lib
 CASES = [  # Cin, Cout, k, dil, B, L
     (64, 64, 3, 1, 1, 128), (64, 64, 3, 1, 2, 300), (256, 256, 3, 1, 2, 300), (256, 256, 11, 5, 2, 300),
     (128, 128, 7, 3, 2, 700), (64, 64, 11, 1, 3, 129), (32, 32, 3, 3, 2, 300), (32, 32, 11, 5, 1, 1000),
-    (16, 16, 7, 5, 2, 300), (16, 16, 3, 1, 1, 4000), (192, 512, 7, 1, 2, 100), (512, 256, 2, 1, 2, 200),
+    (16, 16, 7, 5, 2, 300), (16, 16, 3, 1, 1, 4000), (192, 512, 7, 1, 2, 100), (512, 256, 3, 1, 2, 200),
     (96, 192, 1, 1, 2, 300), (192, 384, 5, 1, 2, 300),
 ]
 
