@@ -165,18 +165,22 @@ int32_t vsg_last_launch_count(void);
 
 /*
  * Per-layer parity hook (tests and tuning only; it allocates and synchronises, unlike the run calls):
- * one Conv1d on the bf16 tcgen05 kernel, the unit the reference dispatches as nn.Conv1d -> F.conv1d
- * (modules/visinger/decoder.py:72-87).
+ * one Conv1d on the bf16 tcgen05 kernel with its fused epilogue -- the unit the reference dispatches as
+ * nn.Conv1d -> F.conv1d followed by the residual add / leaky_relu (modules/visinger/decoder.py:91-104).
  *   x_bf16: device bf16 [B, L, Cin] channels-last; w: HOST fp32 [Cout][Cin][k]; bias: HOST fp32 [Cout] or NULL;
- *   out: device fp32 [B, L, Cout] = conv1d(x, w, dilation, padding = (k-1)*dilation/2) + bias.
- *   flags bit 0: HALO mode (one activation box per channel chunk, taps through row-shifted UMMA
- *   descriptors); bit 1: fill the UMMA descriptor base_offset field from the start address.
+ *   add0/add1: device bf16 [B, L, Cout] or NULL;
+ *   v = (conv1d(x, w, dilation, padding = (k-1)*dilation/2) + bias + add0 + add1) * scale
+ *   out_f32 (device fp32 [B, L, Cout] or NULL) = v; out_raw_bf16 = bf16(v); out_act_bf16 = bf16(leaky_relu(v, 0.1)).
+ *   flags bit 0: HALO mode (one activation box per channel chunk, taps through row-shifted UMMA descriptors);
+ *   bit 1: keep the weights resident in shared memory.
  */
-int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias, float* out, int32_t B, int32_t L,
-                          int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t flags, int32_t device);
+int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias, const void* add0_bf16,
+                          const void* add1_bf16, float scale, float* out_f32, void* out_raw_bf16, void* out_act_bf16,
+                          int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t flags,
+                          int32_t device);
 
-/* Process-wide default for the activation-operand feeding mode of the tensor-core convolutions. */
-int vsg_set_tc_options(int32_t halo_mode, int32_t desc_base_offset);
+/* Process-wide defaults of the tensor-core convolutions: activation-operand feeding mode, resident weights. */
+int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident);
 
 #ifdef __cplusplus
 }

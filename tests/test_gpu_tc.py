@@ -13,21 +13,52 @@ pytestmark = pytest.mark.gpu
 CONV_TOL = 2e-3
 
 
-@pytest.mark.parametrize("cin,cout,k,dil,B,L", [
+CASES = [
     (64, 64, 3, 1, 1, 128), (256, 256, 3, 1, 2, 300), (256, 256, 11, 5, 2, 300), (128, 128, 7, 3, 2, 700),
     (64, 64, 11, 1, 3, 129), (32, 32, 3, 3, 2, 300), (16, 16, 7, 5, 2, 300), (192, 512, 7, 1, 2, 100),
     (512, 256, 3, 1, 2, 200), (96, 192, 1, 1, 2, 300), (192, 384, 5, 1, 2, 300), (16, 16, 3, 1, 1, 20000),
-])
-def test_tc_conv1d_matches_fconv1d(cuda_device, cin, cout, k, dil, B, L):
-    from visinger_b200 import _lib
+    (32, 32, 11, 5, 1, 5000), (128, 128, 3, 5, 1, 1000),
+]
+
+
+def _case(cin, cout, k, dil, B, L):
     gen = torch.Generator().manual_seed(cin + cout + k + dil)
     x = torch.randn(B, L, cin, generator=gen).to(torch.bfloat16)
     w = (torch.randn(cout, cin, k, generator=gen) / (cin * k) ** 0.5).to(torch.bfloat16).float()
     b = torch.randn(cout, generator=gen) * 0.1
     ref = F.conv1d(x.float().transpose(1, 2).double(), w.double(), b.double(), dilation=dil,
                    padding=(k - 1) * dil // 2).transpose(1, 2)
-    got = _lib.debug_conv1d_bf16(x.to(cuda_device).contiguous(), w, b, dil, flags=0).cpu()
+    return x, w, b, ref, gen
+
+
+@pytest.mark.parametrize("flags", [0, 1, 3], ids=["reload", "halo", "halo+resident"])
+@pytest.mark.parametrize("cin,cout,k,dil,B,L", CASES)
+def test_tc_conv1d_matches_fconv1d(cuda_device, cin, cout, k, dil, B, L, flags):
+    """A-operand feeding modes: per-tap reload, halo (row-shifted UMMA descriptors), halo + resident weights."""
+    from visinger_b200 import _lib
+    x, w, b, ref, _ = _case(cin, cout, k, dil, B, L)
+    got = _lib.debug_conv1d_bf16(x.to(cuda_device).contiguous(), w, b, dil, flags=flags).cpu()
     assert maxabs(got, ref) <= CONV_TOL
+
+
+@pytest.mark.parametrize("cin,cout,k,dil,B,L", [(256, 256, 3, 1, 2, 300), (128, 128, 7, 3, 1, 333), (64, 64, 11, 5, 2, 257),
+                                                (32, 32, 7, 1, 2, 1000), (16, 16, 3, 1, 3, 4100), (16, 16, 11, 5, 1, 70)])
+def test_tc_conv1d_fused_epilogue(cuda_device, cin, cout, k, dil, B, L):
+    """Residual + running-sum adds (TMA-loaded), scale, and the two bf16 outputs (TMA-stored): what the
+    reference does as `x = xt + x`, `xs += ...`, `x = xs / 3`, `F.leaky_relu` (decoder.py:48-54,93-102)."""
+    from visinger_b200 import _lib
+    x, w, b, ref, gen = _case(cin, cout, k, dil, B, L)
+    add0 = torch.randn(B, L, cout, generator=gen).to(torch.bfloat16)
+    add1 = torch.randn(B, L, cout, generator=gen).to(torch.bfloat16)
+    want = (ref + add0.double() + add1.double()) / 3.0
+    d = cuda_device
+    out, raw, act = _lib.debug_conv1d_bf16(x.to(d).contiguous(), w, b, dil, flags=3, add0=add0.to(d).contiguous(),
+                                           add1=add1.to(d).contiguous(), scale=1.0 / 3.0, want_bf16=True)
+    assert maxabs(out.cpu(), want) <= CONV_TOL
+    assert maxabs(raw.cpu().double(), want) <= 2e-2          # bf16 rounding of O(1) values
+    assert maxabs(act.cpu().double(), F.leaky_relu(want, 0.1)) <= 2e-2
+    # bf16 outputs are exactly the rounded fp32 result (the TMA store path moves bytes, it does not compute)
+    assert torch.equal(raw.cpu(), out.cpu().to(torch.bfloat16))
 
 
 @pytest.mark.parametrize("B,T", [(1, 7), (2, 64), (3, 150)])

@@ -150,7 +150,8 @@ def lib() -> ctypes.CDLL:
         L.vsg_infer.restype = ctypes.c_int
         L.vsg_infer.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
         L.vsg_debug_conv1d_bf16.restype = ctypes.c_int
-        L.vsg_debug_conv1d_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32]
+        L.vsg_debug_conv1d_bf16.argtypes = [vp, vp, vp, vp, vp, ctypes.c_float, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
+                                            i32]
         L.vsg_set_tc_options.restype = ctypes.c_int
         L.vsg_set_tc_options.argtypes = [i32, i32]
         if L.vsg_abi_version() != 1:
@@ -251,25 +252,35 @@ def release_workspaces() -> None:
     _ws_cache.clear()
 
 
-def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int, flags: int = 0) -> torch.Tensor:
-    """Per-layer parity hook: one Conv1d on the tcgen05 kernel.  x_bld: CUDA bf16 [B, L, Cin] channels-last;
-    w: [Cout, Cin, k] fp32 (any device); returns CUDA fp32 [B, L, Cout]."""
+def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int, flags: int = 0, add0=None,
+                      add1=None, scale: float = 1.0, want_bf16: bool = False):
+    """Per-layer parity hook: one Conv1d (+ fused epilogue) on the tcgen05 kernel.
+    x_bld / add0 / add1: CUDA bf16 [B, L, C] channels-last; w: [Cout, Cin, k] fp32 (any device).
+    Returns out_f32 [B, L, Cout], or (out_f32, out_raw_bf16, out_act_bf16) when want_bf16."""
     require_cuda(x_bld, "x")
     assert x_bld.dtype == torch.bfloat16 and x_bld.is_contiguous()
     B, Lx, Cin = x_bld.shape
     Cout, _, k = w.shape
     wh = w.detach().to("cpu", torch.float32).contiguous()
     bh = bias.detach().to("cpu", torch.float32).contiguous() if bias is not None else None
-    out = torch.empty(B, Lx, Cout, dtype=torch.float32, device=x_bld.device)
-    torch.cuda.synchronize(x_bld.device)
+    dev = x_bld.device
+    out = torch.empty(B, Lx, Cout, dtype=torch.float32, device=dev)
+    raw = torch.zeros(B, Lx, Cout, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    act = torch.zeros(B, Lx, Cout, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    for t in (add0, add1):
+        assert t is None or (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous())
+    torch.cuda.synchronize(dev)
     rc = lib().vsg_debug_conv1d_bf16(x_bld.data_ptr(), wh.data_ptr(), bh.data_ptr() if bh is not None else None,
-                                     out.data_ptr(), B, Lx, Cin, Cout, k, dilation, flags, x_bld.device.index or 0)
+                                     add0.data_ptr() if add0 is not None else None,
+                                     add1.data_ptr() if add1 is not None else None, float(scale), out.data_ptr(),
+                                     raw.data_ptr() if want_bf16 else None, act.data_ptr() if want_bf16 else None,
+                                     B, Lx, Cin, Cout, k, dilation, flags, dev.index or 0)
     check(rc, "vsg_debug_conv1d_bf16")
-    return out
+    return (out, raw, act) if want_bf16 else out
 
 
-def set_tc_options(halo_mode: int, desc_base_offset: int = 0) -> None:
-    check(lib().vsg_set_tc_options(int(halo_mode), int(desc_base_offset)), "vsg_set_tc_options")
+def set_tc_options(halo_mode: int, w_resident: int = 1) -> None:
+    check(lib().vsg_set_tc_options(int(halo_mode), int(w_resident)), "vsg_set_tc_options")
 
 
 def stream_ptr(device: torch.device) -> int:

@@ -13,12 +13,18 @@
 //   * B operand: the pre-packed weights [tap][Cout][Cin] (K-major rows) through a 2-D TMA map.
 //   * swizzle = KC*2 bytes (128B / 64B / 32B) on both operands, identical in the TMA map and the UMMA
 //     shared-memory descriptor.
+//   * small convolutions (all (chunk, tap) weight tiles <= ~100 KB) keep their weights RESIDENT in shared
+//     memory for the whole persistent kernel: one TMA burst at start, no per-tap barrier round trips.
 // ConvTranspose1d runs as `stride` polyphase launches of the same kernel (out_stride / out_phase).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
-// lane), warps 2..5 = epilogue (TMEM -> registers -> fused bias / residual / resblock-sum / leaky_relu ->
-// bf16 global stores).  The accumulator is double-buffered in TMEM (2 x N_TILE columns) so the epilogue of
-// tile i overlaps the main loop of tile i+1.
+// lane), warps 2..5 = epilogue.  The accumulator is double-buffered in TMEM (2 x N_TILE columns) so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+// Epilogue: each warp owns 32 rows (its TMEM lane quarter) and walks the tile in chunks of `cw` channels:
+// tcgen05.ld -> + bias (+ speaker condition) -> + residual / running resblock sum (TMA-loaded into swizzled
+// shared memory, prefetched n_add_bufs-1 chunks ahead, across tiles) -> x scale -> write the raw value and
+// leaky_relu(value) as bf16 into swizzled staging buffers -> TMA store.  All global traffic of the kernel
+// is bulk TMA: no per-thread global loads or stores on the hot path.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -34,22 +40,24 @@ struct ConvTC {
   int out_stride, out_phase;
   int m_tiles_per_b, total_tiles;
   int halo_mode;                // 1: one A box per channel chunk, taps via row-shifted descriptors
-  int desc_base_offset;         // 1: fill the UMMA descriptor base_offset field from the start address
   int a_rows;                   // rows per A box
+  int w_resident;               // 1: all (chunk, tap) weight tiles are loaded once and stay in shared memory
   int stages_a, stages_w;
   uint32_t a_stage_bytes, w_stage_bytes, a_box_bytes, w_box_bytes;
+  uint32_t w_off, e_off, bar_off;      // shared-memory carve-up, relative to the 1024-aligned base (A ring at 0)
   uint32_t tmem_cols;
   uint32_t swizzle_code;        // UMMA layout type: 2 = 128B, 4 = 64B, 6 = 32B
   uint32_t sbo_bytes;           // 8 rows * row bytes
-  // epilogue
+  // epilogue: per warp, 32 rows x cw channels per chunk, staged in swizzled shared memory, moved by TMA
+  int cw, n_echunks;
+  uint32_t e_buf_bytes, e_warp_bytes, e_swz_mask;
+  int n_add_bufs;
+  int has_add0, has_add1;       // residual / running resblock sum: same geometry as the output, TMA-loaded
+  int has_raw, has_act;         // outputs: value as is / leaky_relu(value), TMA-stored
   const float* bias;            // [Cout] or null
   const float* bcond; int bcond_bs;   // [B][bcond_bs] or null
-  const __nv_bfloat16* add0;    // same geometry as the output, or null (residual)
-  const __nv_bfloat16* add1;    // same geometry as the output, or null (running resblock sum)
   float scale;                  // applied after the adds
   float slope;                  // leaky_relu slope for out_act
-  __nv_bfloat16* out_raw;       // value as is, or null
-  __nv_bfloat16* out_act;       // leaky_relu(value), or null
   float* out_f32;               // optional fp32 copy of the raw value [B, Lout, Cout] (debug / parity hook)
   int* error_flag;              // set to 1 if a barrier wait times out
 };
@@ -152,18 +160,16 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+// 16 consecutive fp32 accumulator columns of this thread's TMEM lane (no wait: pair with tmem_wait_ld).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -178,28 +184,216 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
   }
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// TMA / UMMA swizzle: XOR the 16-byte-chunk index (address bits 4..6) with address bits 7..9 (masked by mode).
+__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
+constexpr int kMaxAddBufs = 4;
+constexpr int kMaxCW = 64;
+// barrier slots
+constexpr int kBarAFull = 0, kBarAEmpty = kMaxStages, kBarWFull = 2 * kMaxStages, kBarWEmpty = 3 * kMaxStages;
+constexpr int kBarAccFull = 4 * kMaxStages, kBarAccEmpty = kBarAccFull + 2, kBarAdd = kBarAccEmpty + 2;
+constexpr int kNumBars = kBarAdd + 4 * kMaxAddBufs;
 
 }  // namespace tc
 
+template <int CW>
+__device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, const CUtensorMap& tmAdd1,
+                                                 const CUtensorMap& tmRaw, const CUtensorMap& tmAct, const ConvTC& p,
+                                                 uint32_t smem_base, uint32_t bar_base, uint32_t tmem_base, int warp,
+                                                 int lane) {
+  using namespace tc;
+  const int ew = warp - 2;               // staging-buffer owner index 0..3
+  const int quarter = warp & 3;          // tcgen05.ld: warp w may only touch TMEM lanes 32*(w%4) .. +31
+  const uint32_t e_base = smem_base + p.e_off + (uint32_t)ew * p.e_warp_bytes;
+  const uint32_t add0_b = e_base;
+  const uint32_t add1_b = add0_b + (p.has_add0 ? (uint32_t)p.n_add_bufs * p.e_buf_bytes : 0u);
+  const uint32_t raw_b = add1_b + (p.has_add1 ? (uint32_t)p.n_add_bufs * p.e_buf_bytes : 0u);
+  const uint32_t act_b = raw_b + (p.has_raw ? 2u * p.e_buf_bytes : 0u);
+  const bool has_add = p.has_add0 || p.has_add1;
+  const bool has_out = p.has_raw || p.has_act;
+  const uint32_t add_bytes = (uint32_t)(p.has_add0 + p.has_add1) * 32u * CW * 2u;
+  auto add_bar = [&](int buf) { return bar_base + 8u * (kBarAdd + ew * kMaxAddBufs + buf); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (kBarAccFull + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (kBarAccEmpty + s); };
+
+  const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_items = my_tiles * p.n_echunks;
+
+  // (tile, chunk) item -> TMA coordinates of this warp's 32-row slab
+  auto issue_add = [&](int item) {   // lane 0 only
+    const int ti = item / p.n_echunks, cc = item % p.n_echunks;
+    const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+    const int nt = tile % p.n_ntiles;
+    const int mt = (tile / p.n_ntiles) % p.m_tiles_per_b;
+    const int b = tile / (p.n_ntiles * p.m_tiles_per_b);
+    const int buf = item % p.n_add_bufs;
+    const int ch = nt * p.n_tile + cc * CW, row = mt * 128 + quarter * 32;
+    mbar_expect_tx(add_bar(buf), add_bytes);
+    if (p.has_add0) tma_load_3d(add0_b + buf * p.e_buf_bytes, &tmAdd0, add_bar(buf), ch, row, b);
+    if (p.has_add1) tma_load_3d(add1_b + buf * p.e_buf_bytes, &tmAdd1, add_bar(buf), ch, row, b);
+  };
+  if (has_add && lane == 0) {
+    for (int i = 0; i < n_items && i < p.n_add_bufs - 1; ++i) issue_add(i);
+  }
+
+  int as = 0;
+  uint32_t pacc = 0, add_phase = 0, out_count = 0;
+  int item = 0;
+  const uint32_t row_off = (uint32_t)lane * (CW * 2);   // this lane's row inside a staging buffer
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int nt = tile % p.n_ntiles;
+    const int mt = (tile / p.n_ntiles) % p.m_tiles_per_b;
+    const int b = tile / (p.n_ntiles * p.m_tiles_per_b);
+    mbar_wait(acc_full(as), pacc, p.error_flag);
+    fence_after_sync();
+    const int row0 = mt * 128 + quarter * 32;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.n_tile);
+    for (int cc = 0; cc < p.n_echunks; ++cc, ++item) {
+      if (has_add && lane == 0) {
+        const int nxt = item + p.n_add_bufs - 1;
+        if (nxt < n_items) issue_add(nxt);   // its buffer was last read at item-1 (warp-synced below)
+      }
+      const int ch = nt * p.n_tile + cc * CW;
+      float v[CW];
+      {
+        uint32_t r[CW];
+#pragma unroll
+        for (int i = 0; i < CW / 16; ++i) tmem_ld16_nowait(taddr + (uint32_t)(cc * CW + i * 16), r + 16 * i);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+      }
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < CW; i += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch + i));
+          v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+        }
+      }
+      if (p.bcond) {
+        const float* bc = p.bcond + (long long)b * p.bcond_bs + ch;
+#pragma unroll
+        for (int i = 0; i < CW; i += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(bc + i));
+          v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+        }
+      }
+      if (has_add) {
+        const int buf = item % p.n_add_bufs;
+        mbar_wait(add_bar(buf), (add_phase >> buf) & 1u, p.error_flag);
+        add_phase ^= 1u << buf;
+        if (p.has_add0) {
+          const uint32_t base = add0_b + buf * p.e_buf_bytes;
+#pragma unroll
+          for (int c = 0; c < CW / 8; ++c) {
+            float f[8];
+            unpack_bf16x8(lds128(base + swz(row_off + c * 16, p.e_swz_mask)), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * c + i] += f[i];
+          }
+        }
+        if (p.has_add1) {
+          const uint32_t base = add1_b + buf * p.e_buf_bytes;
+#pragma unroll
+          for (int c = 0; c < CW / 8; ++c) {
+            float f[8];
+            unpack_bf16x8(lds128(base + swz(row_off + c * 16, p.e_swz_mask)), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * c + i] += f[i];
+          }
+        }
+      }
+      if (p.scale != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) v[i] *= p.scale;
+      }
+      if (p.out_f32) {   // debug / parity hook only: plain per-thread stores
+        const int q = row0 + lane, n = q * p.out_stride + p.out_phase;
+        if (q < p.Lq && n < p.Lout && ch < p.Cout) {
+          float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((long long)b * p.Lout + n) * p.Cout + ch);
+#pragma unroll
+          for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+      if (has_out) {
+        const uint32_t ob = (out_count & 1u) * p.e_buf_bytes;
+        if (lane == 0) bulk_wait_read<1>();   // the store that last used this buffer (2 groups ago) has drained
+        __syncwarp();
+        if (p.has_raw) {
+#pragma unroll
+          for (int c = 0; c < CW / 8; ++c) {
+            const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                                       pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+            sts128(raw_b + ob + swz(row_off + c * 16, p.e_swz_mask), u);
+          }
+        }
+        if (p.has_act) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+#pragma unroll
+          for (int c = 0; c < CW / 8; ++c) {
+            const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                                       pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+            sts128(act_b + ob + swz(row_off + c * 16, p.e_swz_mask), u);
+          }
+        }
+        fence_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          if (p.has_raw) tma_store_3d(&tmRaw, raw_b + ob, ch, row0, b);
+          if (p.has_act) tma_store_3d(&tmAct, act_b + ob, ch, row0, b);
+          bulk_commit();
+        }
+        ++out_count;
+      }
+      __syncwarp();   // every lane is done with this item's add buffer before lane 0 refills it
+    }
+    fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty(as));
+    if (++as == 2) { as = 0; pacc ^= 1; }
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
 __global__ void __launch_bounds__(tc::kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvTC p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmAdd0, const __grid_constant__ CUtensorMap tmAdd1,
+               const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmAct, const ConvTC p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up: [A stages][W stages][barriers][tmem base]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t w_base = a_base + p.stages_a * p.a_stage_bytes;
-  const uint32_t bar_base = w_base + p.stages_w * p.w_stage_bytes;
-  // barrier slots (8 bytes each)
-  auto a_full = [&](int s) { return bar_base + 8u * s; };
-  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  auto w_full = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
-  auto w_empty = [&](int s) { return bar_base + 8u * (3 * kMaxStages + s); };
-  auto acc_full = [&](int s) { return bar_base + 8u * (4 * kMaxStages + s); };
-  auto acc_empty = [&](int s) { return bar_base + 8u * (4 * kMaxStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (4 * kMaxStages + 4);
+  const uint32_t w_base = smem_base + p.w_off;
+  const uint32_t bar_base = smem_base + p.bar_off;
+  auto a_full = [&](int s) { return bar_base + 8u * (kBarAFull + s); };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kBarAEmpty + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (kBarWFull + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (kBarWEmpty + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (kBarAccFull + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (kBarAccEmpty + s); };
+  const uint32_t tmem_slot = bar_base + 8u * kNumBars;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -207,9 +401,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
-    for (int s = 0; s < p.stages_a; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < p.stages_w; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    if (p.has_add0) prefetch_tmap(&tmAdd0);
+    if (p.has_add1) prefetch_tmap(&tmAdd1);
+    if (p.has_raw) prefetch_tmap(&tmRaw);
+    if (p.has_act) prefetch_tmap(&tmAct);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1);
+      mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1);
+    }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    for (int s = 0; s < 4 * kMaxAddBufs; ++s) mbar_init(bar_base + 8u * (kBarAdd + s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -218,13 +419,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int n_kblocks = p.n_cchunks * p.ktaps;
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int sa = 0, sw = 0;
       uint32_t pa = 0, pw = 0;
+      if (p.w_resident) {   // n_ntiles == 1: the weights do not depend on the tile
+        mbar_expect_tx(w_full(0), (uint32_t)(p.n_cchunks * p.ktaps) * p.w_box_bytes);
+        for (int c = 0; c < p.n_cchunks; ++c)
+          for (int j = 0; j < p.ktaps; ++j)
+            tma_load_2d(w_base + (uint32_t)(c * p.ktaps + j) * p.w_stage_bytes, &tmW, w_full(0), c * p.KC, j * p.CoutT);
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_ntiles;
         const int mt = (tile / p.n_ntiles) % p.m_tiles_per_b;
@@ -236,6 +441,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(a_full(sa), p.a_box_bytes);
             tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), c * p.KC, row0, b);
             if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+            if (p.w_resident) continue;
           }
           for (int j = 0; j < p.ktaps; ++j) {
             if (!p.halo_mode) {
@@ -244,10 +450,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), c * p.KC, row0 + j * p.dil, b);
               if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
             }
-            mbar_wait(w_empty(sw), pw ^ 1, p.error_flag);
-            mbar_expect_tx(w_full(sw), p.w_box_bytes);
-            tma_load_2d(w_base + sw * p.w_stage_bytes, &tmW, w_full(sw), c * p.KC, j * p.CoutT + nt * p.n_tile);
-            if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
+            if (!p.w_resident) {
+              mbar_wait(w_empty(sw), pw ^ 1, p.error_flag);
+              mbar_expect_tx(w_full(sw), p.w_box_bytes);
+              tma_load_2d(w_base + sw * p.w_stage_bytes, &tmW, w_full(sw), c * p.KC, j * p.CoutT + nt * p.n_tile);
+              if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
+            }
           }
         }
       }
@@ -260,28 +468,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kk_n = p.KC / 16;
       int sa = 0, sw = 0, as = 0;
       uint32_t pa = 0, pw = 0, pacc = 0;
+      if (p.w_resident) mbar_wait(w_full(0), 0, p.error_flag);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(acc_empty(as), pacc ^ 1, p.error_flag);
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.n_tile);
         uint32_t accumulate = 0;
         for (int c = 0; c < p.n_cchunks; ++c) {
-          if (p.halo_mode) { mbar_wait(a_full(sa), pa, p.error_flag); }
+          if (p.halo_mode) { mbar_wait(a_full(sa), pa, p.error_flag); fence_after_sync(); }
           for (int j = 0; j < p.ktaps; ++j) {
             if (!p.halo_mode) { mbar_wait(a_full(sa), pa, p.error_flag); }
-            mbar_wait(w_full(sw), pw, p.error_flag);
+            if (!p.w_resident) { mbar_wait(w_full(sw), pw, p.error_flag); }
             fence_after_sync();
             const uint32_t a_addr = a_base + sa * p.a_stage_bytes + (p.halo_mode ? (uint32_t)(j * p.dil) * row_bytes : 0u);
-            const uint32_t w_addr = w_base + sw * p.w_stage_bytes;
+            const uint32_t w_addr = w_base + (p.w_resident ? (uint32_t)(c * p.ktaps + j) : (uint32_t)sw) * p.w_stage_bytes;
             for (int kk = 0; kk < kk_n; ++kk) {
-              const uint32_t aa = a_addr + kk * 32u, ww = w_addr + kk * 32u;
-              const uint32_t boff_a = p.desc_base_offset ? ((aa >> 7) & 7u) : 0u;
-              umma_bf16(d_tmem, make_desc(aa, p.sbo_bytes, p.swizzle_code, boff_a),
-                        make_desc(ww, p.sbo_bytes, p.swizzle_code, 0u), idesc, accumulate);
+              // HALO: the row-shifted start address keeps base_offset = 0 -- the UMMA unit applies the
+              // swizzle XOR to absolute shared-memory address bits (verified on B200, tools/tc_probe.py).
+              umma_bf16(d_tmem, make_desc(a_addr + kk * 32u, p.sbo_bytes, p.swizzle_code, 0u),
+                        make_desc(w_addr + kk * 32u, p.sbo_bytes, p.swizzle_code, 0u), idesc, accumulate);
               accumulate = 1;
             }
-            umma_commit(w_empty(sw));
-            if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
+            if (!p.w_resident) {
+              umma_commit(w_empty(sw));
+              if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
+            }
             if (!p.halo_mode) {
               umma_commit(a_empty(sa));
               if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
@@ -298,88 +509,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-    const int quarter = warp & 3;          // tcgen05.ld: warp w may only touch lanes 32*(w%4) .. +31
-    int as = 0;
-    uint32_t pacc = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_ntiles;
-      const int mt = (tile / p.n_ntiles) % p.m_tiles_per_b;
-      const int b = tile / (p.n_ntiles * p.m_tiles_per_b);
-      mbar_wait(acc_full(as), pacc, p.error_flag);
-      fence_after_sync();
-      const int q = mt * 128 + quarter * 32 + lane;
-      const int n = q * p.out_stride + p.out_phase;
-      const bool row_ok = (q < p.Lq) && (n < p.Lout);
-      const long long row_off = ((long long)b * p.Lout + n) * p.Cout;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.n_tile);
-      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);          // warp-collective: executed by every lane
-        const int ch = nt * p.n_tile + c0;
-        if (row_ok && ch < p.Cout) {
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch + i));
-              v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
-            }
-          }
-          if (p.bcond) {
-            const float* bc = p.bcond + (long long)b * p.bcond_bs + ch;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bc + i));
-              v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
-            }
-          }
-          if (p.add0) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.add0 + row_off + ch);
-            float f[8];
-            unpack_bf16x8(src[0], f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += f[i];
-            unpack_bf16x8(src[1], f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
-          }
-          if (p.add1) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.add1 + row_off + ch);
-            float f[8];
-            unpack_bf16x8(src[0], f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += f[i];
-            unpack_bf16x8(src[1], f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
-          }
-          if (p.scale != 1.0f) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= p.scale;
-          }
-          if (p.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + row_off + ch);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          if (p.out_raw) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out_raw + row_off + ch);
-            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-          }
-          if (p.out_act) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
-            uint4* dst = reinterpret_cast<uint4*>(p.out_act + row_off + ch);
-            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-          }
-        }
-      }
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(as));
-      if (++as == 2) { as = 0; pacc ^= 1; }
-    }
+    if (p.cw == 64) conv_tc_epilogue<64>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);
+    else if (p.cw == 32) conv_tc_epilogue<32>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);
+    else conv_tc_epilogue<16>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);
   }
 
   // ---- teardown: everyone done with TMEM before the allocating warp frees it ----

@@ -55,22 +55,22 @@ int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, u
   return VSG_OK;
 }
 
-int encode_3d(CUtensorMap* m, const void* base, uint64_t C, uint64_t L, uint64_t B, uint32_t box_c, uint32_t box_rows,
-              int kc) {
+// 3-D map over a channels-last bf16 tensor viewed as (C, rows, B) with explicit row / batch strides (elements).
+int encode_3d(CUtensorMap* m, const void* base, uint64_t C, uint64_t rows, uint64_t B, uint64_t row_stride,
+              uint64_t batch_stride, uint32_t box_c, uint32_t box_rows, int swz_elems) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(VSG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[3] = {C, L, B};
-  cuuint64_t strides[2] = {C * 2, C * L * 2};
+  cuuint64_t dims[3] = {C, rows, B};
+  cuuint64_t strides[2] = {row_stride * 2, batch_stride * 2};
   cuuint32_t box[3] = {box_c, box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(swz_elems), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VSG_ECUDA, "cuTensorMapEncodeTiled(3d) failed with %d", (int)r);
   return VSG_OK;
 }
 
-constexpr size_t kSmemBudget = 200 * 1024;
 constexpr size_t kSmemMax = 227 * 1024;
 
 struct EpiTC {
@@ -86,11 +86,13 @@ struct EpiTC {
 
 // HALO mode verified on B200 (tools/tc_probe.py): the UMMA unit applies the swizzle XOR to absolute
 // shared-memory address bits, so a row-shifted start address needs base_offset = 0.
-struct TCOptions { int halo_mode = 1; int desc_base_offset = 0; };
+struct TCOptions { int halo_mode = 1; int w_resident = 1; };
 
 TCOptions g_default_opts;
 
-// One convolution launch.  x: [B, Lin, Cin] bf16 channels-last; outputs: [B, Lout, Cout].
+constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic smem we plan within (1 KB alignment slack + barriers)
+
+// One convolution launch.  x: [B, Lin, Cin] bf16 channels-last; add/out tensors: [B, Lout, Cout].
 int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, int B, int Lin, int in_off0, int dil,
                    int Lq, int out_stride, int out_phase, int Lout, const EpiTC& e, const TCOptions& opt, int* error_flag,
                    cudaStream_t st) {
@@ -108,37 +110,78 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.total_tiles = p.m_tiles_per_b * p.n_ntiles * B;
   const int halo = (w.ktaps - 1) * dil;
   p.halo_mode = (opt.halo_mode && w.ktaps > 1 && 128 + halo <= 256) ? 1 : 0;
-  p.desc_base_offset = opt.desc_base_offset;
   p.a_rows = p.halo_mode ? 128 + halo : 128;
   p.a_box_bytes = (uint32_t)p.a_rows * KC * 2;
   p.w_box_bytes = (uint32_t)NT * KC * 2;
   p.a_stage_bytes = (p.a_box_bytes + 1023u) & ~1023u;
   p.w_stage_bytes = (p.w_box_bytes + 1023u) & ~1023u;
-  if (p.halo_mode) {
+  // epilogue staging
+  p.cw = NT >= 256 ? 32 : std::min(NT, 64);
+  p.n_echunks = NT / p.cw;
+  p.e_buf_bytes = (uint32_t)((32 * p.cw * 2 + 1023) & ~1023);
+  p.e_swz_mask = p.cw == 64 ? 7u : p.cw == 32 ? 3u : 1u;
+  p.has_add0 = e.add0 != nullptr; p.has_add1 = e.add1 != nullptr;
+  p.has_raw = e.out_raw != nullptr; p.has_act = e.out_act != nullptr;
+  p.n_add_bufs = p.cw == 64 ? 2 : p.cw == 32 ? 3 : 4;
+  p.e_warp_bytes = (uint32_t)((p.has_add0 + p.has_add1) * p.n_add_bufs + (p.has_raw + p.has_act) * 2) * p.e_buf_bytes;
+  const size_t e_bytes = 4 * (size_t)p.e_warp_bytes;
+  // operand rings
+  const size_t w_total = (size_t)p.n_cchunks * w.ktaps * p.w_stage_bytes;
+  const int a_per_tile = p.halo_mode ? p.n_cchunks : p.n_cchunks * w.ktaps;
+  p.w_resident = (opt.w_resident && p.n_ntiles == 1 && w_total <= 112 * 1024 &&
+                  w_total + e_bytes + 3 * (size_t)p.a_stage_bytes <= kSmemBudget) ? 1 : 0;
+  size_t w_bytes;
+  if (p.w_resident) {
+    w_bytes = w_total;
+    p.stages_w = 1;
+    p.stages_a = (int)std::min<size_t>(tc::kMaxStages, (kSmemBudget - w_bytes - e_bytes) / p.a_stage_bytes);
+    p.stages_a = std::min(p.stages_a, std::max(3, 3 * a_per_tile));
+  } else if (p.halo_mode) {
     p.stages_a = 2;
-    p.stages_w = (int)std::min<size_t>(tc::kMaxStages, (kSmemBudget - 2 * p.a_stage_bytes) / p.w_stage_bytes);
+    if (2 * (size_t)p.a_stage_bytes + e_bytes + 2 * (size_t)p.w_stage_bytes > kSmemBudget)
+      return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
+    p.stages_w = (int)std::min<size_t>(tc::kMaxStages, (kSmemBudget - e_bytes - 2 * p.a_stage_bytes) / p.w_stage_bytes);
+    w_bytes = (size_t)p.stages_w * p.w_stage_bytes;
   } else {
-    p.stages_a = p.stages_w = (int)std::min<size_t>(tc::kMaxStages, kSmemBudget / (p.a_stage_bytes + p.w_stage_bytes));
+    const size_t per = (size_t)p.a_stage_bytes + p.w_stage_bytes;
+    if (e_bytes + 2 * per > kSmemBudget) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
+    p.stages_a = p.stages_w = (int)std::min<size_t>(tc::kMaxStages, (kSmemBudget - e_bytes) / per);
+    w_bytes = (size_t)p.stages_w * p.w_stage_bytes;
   }
-  if (p.stages_a < 2 || p.stages_w < 2) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
+  if (p.stages_a < 2) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
+  p.w_off = (uint32_t)(p.stages_a * p.a_stage_bytes);
+  p.e_off = p.w_off + (uint32_t)w_bytes;
+  p.bar_off = p.e_off + (uint32_t)e_bytes;
+  const size_t smem = 1024 + (size_t)p.bar_off + 8 * tc::kNumBars + 64;
+  if (smem > kSmemMax) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory (%zu B)", smem);
   p.tmem_cols = (uint32_t)std::max(32, 2 * NT);
   p.swizzle_code = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
   p.sbo_bytes = 8u * KC * 2u;
   p.bias = e.bias; p.bcond = e.bcond; p.bcond_bs = e.bcond_bs;
-  p.add0 = e.add0; p.add1 = e.add1; p.scale = e.scale; p.slope = 0.1f;
-  p.out_raw = e.out_raw; p.out_act = e.out_act; p.out_f32 = e.out_f32;
+  p.scale = e.scale; p.slope = 0.1f;
+  p.out_f32 = e.out_f32;
   p.error_flag = error_flag;
 
-  CUtensorMap tmA;
-  VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.Cin, (uint64_t)Lin, (uint64_t)B, (uint32_t)KC, (uint32_t)p.a_rows, KC));
-  const size_t smem = 1024 + (size_t)p.stages_a * p.a_stage_bytes + (size_t)p.stages_w * p.w_stage_bytes + 512;
+  CUtensorMap tmA, tmAdd0, tmAdd1, tmRaw, tmAct;
+  VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.Cin, (uint64_t)Lin, (uint64_t)B, (uint64_t)w.Cin, (uint64_t)Lin * w.Cin,
+                    (uint32_t)KC, (uint32_t)p.a_rows, KC));
+  // epilogue tensors: rows are the q positions of this (poly)phase: row stride out_stride*Cout, base shifted by phase
+  auto emap = [&](CUtensorMap* m, const __nv_bfloat16* base) -> int {
+    return encode_3d(m, base + (size_t)out_phase * w.Cout, (uint64_t)w.Cout, (uint64_t)Lq, (uint64_t)B,
+                     (uint64_t)out_stride * w.Cout, (uint64_t)Lout * w.Cout, (uint32_t)p.cw, 32u, p.cw);
+  };
+  tmAdd0 = tmAdd1 = tmRaw = tmAct = tmA;
+  if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0));
+  if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1));
+  if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw));
+  if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act));
   static bool attr_set = false;
   if (!attr_set) {
     VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, P->sm_count);
-  conv_tc_kernel<<<grid, tc::kThreads, smem, st>>>(tmA, w.tmap, p);
+  conv_tc_kernel<<<grid, tc::kThreads, smem, st>>>(tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
   VSG_LAUNCH_CHECK("conv_tc_kernel");
   return VSG_OK;
 }
@@ -292,15 +335,14 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
 
 using namespace vsg;
 
-// Per-layer parity hook (tests only; allocates and synchronises): one bf16 tensor-core Conv1d.
-//   x: device bf16 [B, L, Cin] channels-last; w: host fp32 [Cout][Cin][k]; bias: host fp32 [Cout] or NULL;
-//   out: device fp32 [B, L, Cout] = conv1d(x, w, dilation, padding = (k-1)*dilation/2) + bias.
-//   flags bit 0: HALO mode (one A box per channel chunk), bit 1: fill the UMMA descriptor base_offset field.
-extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias, float* out, int32_t B,
-                                     int32_t L, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t flags,
-                                     int32_t device) {
+// Per-layer parity hook (tests only; allocates and synchronises): one bf16 tensor-core Conv1d with the full
+// fused epilogue.  See include/visinger_b200.h.
+extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias, const void* add0_bf16,
+                                     const void* add1_bf16, float scale, float* out_f32, void* out_raw_bf16,
+                                     void* out_act_bf16, int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t k,
+                                     int32_t dilation, int32_t flags, int32_t device) {
   g_launches = 0;
-  if (!x_bf16 || !w || !out) return fail(VSG_EINVAL, "null pointer");
+  if (!x_bf16 || !w) return fail(VSG_EINVAL, "null pointer");
   VSG_CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   VSG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -317,10 +359,15 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
     cudaMemset(err, 0, sizeof(int));
     EpiTC e;
     e.bias = wt.bias;
-    e.out_f32 = out;
+    e.add0 = (const __nv_bfloat16*)add0_bf16;
+    e.add1 = (const __nv_bfloat16*)add1_bf16;
+    e.scale = scale;
+    e.out_f32 = out_f32;
+    e.out_raw = (__nv_bfloat16*)out_raw_bf16;
+    e.out_act = (__nv_bfloat16*)out_act_bf16;
     TCOptions opt;
     opt.halo_mode = flags & 1;
-    opt.desc_base_offset = (flags >> 1) & 1;
+    opt.w_resident = (flags >> 1) & 1;
     rc = launch_conv_tc(&tmp, wt, (const __nv_bfloat16*)x_bf16, B, L, -((k - 1) * dilation / 2), dilation, L, 1, 0, L, e,
                         opt, err, 0);
     if (rc == VSG_OK) {
@@ -334,8 +381,8 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
 }
 
 // Select the default A-operand feeding mode of the tensor-core convolutions (process-wide; tests and tuning).
-extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t desc_base_offset) {
+extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident) {
   g_default_opts.halo_mode = halo_mode;
-  g_default_opts.desc_base_offset = desc_base_offset;
+  g_default_opts.w_resident = w_resident;
   return VSG_OK;
 }
