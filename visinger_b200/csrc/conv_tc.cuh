@@ -377,6 +377,76 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   if (lane == 0) bulk_wait_all();
 }
 
+// The MMA issuer runs on ONE thread, so its instruction count per tcgen05.mma is the issue-rate limit for
+// small-N convolutions (measured: ~80 cycles per MMA with a tight loop, ~490 with a naive one).  Everything
+// loop-invariant is hoisted into registers, descriptors are advanced by integer adds on their low word.
+template <bool HALO, bool RESIDENT, int KK>
+__device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_base, uint32_t w_base, uint32_t bar_base,
+                                                 uint32_t tmem_base) {
+  using namespace tc;
+  const int total_tiles = p.total_tiles, n_cchunks = p.n_cchunks, ktaps = p.ktaps, stages_a = p.stages_a,
+            stages_w = p.stages_w, n_tile = p.n_tile;
+  int* const error_flag = p.error_flag;
+  const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_tile);
+  // descriptor words: hi = SBO | version | layout (constant), lo = LBO(1) << 16 | (address >> 4)
+  const uint32_t desc_hi = ((p.sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((p.swizzle_code & 7u) << 29);
+  const uint32_t lo_const = 1u << 16;
+  const uint32_t a_lo0 = (a_base >> 4), w_lo0 = (w_base >> 4);
+  const uint32_t a_stage16 = p.a_stage_bytes >> 4, w_stage16 = p.w_stage_bytes >> 4;
+  const uint32_t tap_step16 = HALO ? (uint32_t)(p.dil * p.KC * 2) >> 4 : 0u;
+  const uint32_t bar_a_full = bar_base + 8u * kBarAFull, bar_a_empty = bar_base + 8u * kBarAEmpty;
+  const uint32_t bar_w_full = bar_base + 8u * kBarWFull, bar_w_empty = bar_base + 8u * kBarWEmpty;
+  const uint32_t bar_acc_full = bar_base + 8u * kBarAccFull, bar_acc_empty = bar_base + 8u * kBarAccEmpty;
+  auto mk = [&](uint32_t lo16) { return ((uint64_t)desc_hi << 32) | (uint64_t)(lo_const | (lo16 & 0x3FFFu)); };
+
+  int sa = 0, sw = 0, as = 0;
+  uint32_t pa = 0, pw = 0, pacc = 0;
+  if (RESIDENT) mbar_wait(bar_w_full, 0, error_flag);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    mbar_wait(bar_acc_empty + 8u * as, pacc ^ 1, error_flag);
+    fence_after_sync();
+    const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
+    uint32_t accumulate = 0;
+    uint32_t w_res16 = w_lo0;   // RESIDENT: walks the (chunk, tap) tiles in order
+    for (int c = 0; c < n_cchunks; ++c) {
+      if (HALO) { mbar_wait(bar_a_full + 8u * sa, pa, error_flag); fence_after_sync(); }
+      uint32_t a16 = a_lo0 + (uint32_t)sa * a_stage16;
+      for (int j = 0; j < ktaps; ++j) {
+        if (!HALO) {
+          mbar_wait(bar_a_full + 8u * sa, pa, error_flag);
+          a16 = a_lo0 + (uint32_t)sa * a_stage16;
+        }
+        uint32_t w16;
+        if (RESIDENT) { w16 = w_res16; w_res16 += w_stage16; }
+        else { mbar_wait(bar_w_full + 8u * sw, pw, error_flag); w16 = w_lo0 + (uint32_t)sw * w_stage16; }
+        if (!HALO || !RESIDENT) fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+          // HALO: the row-shifted start address keeps base_offset = 0 -- the UMMA unit applies the swizzle
+          // XOR to absolute shared-memory address bits (verified on B200, tools/tc_probe.py).
+          umma_bf16(d_tmem, mk(a16 + 2u * kk), mk(w16 + 2u * kk), idesc, accumulate);
+          accumulate = 1;
+        }
+        if (HALO) a16 += tap_step16;
+        if (!RESIDENT) {
+          umma_commit(bar_w_empty + 8u * sw);
+          if (++sw == stages_w) { sw = 0; pw ^= 1; }
+        }
+        if (!HALO) {
+          umma_commit(bar_a_empty + 8u * sa);
+          if (++sa == stages_a) { sa = 0; pa ^= 1; }
+        }
+      }
+      if (HALO) {
+        umma_commit(bar_a_empty + 8u * sa);
+        if (++sa == stages_a) { sa = 0; pa ^= 1; }
+      }
+    }
+    umma_commit(bar_acc_full + 8u * as);
+    if (++as == 2) { as = 0; pacc ^= 1; }
+  }
+}
+
 __global__ void __launch_bounds__(tc::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmAdd0, const __grid_constant__ CUtensorMap tmAdd1,
@@ -463,49 +533,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.n_tile);
-      const uint32_t row_bytes = (uint32_t)p.KC * 2u;
       const int kk_n = p.KC / 16;
-      int sa = 0, sw = 0, as = 0;
-      uint32_t pa = 0, pw = 0, pacc = 0;
-      if (p.w_resident) mbar_wait(w_full(0), 0, p.error_flag);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(acc_empty(as), pacc ^ 1, p.error_flag);
-        fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.n_tile);
-        uint32_t accumulate = 0;
-        for (int c = 0; c < p.n_cchunks; ++c) {
-          if (p.halo_mode) { mbar_wait(a_full(sa), pa, p.error_flag); fence_after_sync(); }
-          for (int j = 0; j < p.ktaps; ++j) {
-            if (!p.halo_mode) { mbar_wait(a_full(sa), pa, p.error_flag); }
-            if (!p.w_resident) { mbar_wait(w_full(sw), pw, p.error_flag); }
-            fence_after_sync();
-            const uint32_t a_addr = a_base + sa * p.a_stage_bytes + (p.halo_mode ? (uint32_t)(j * p.dil) * row_bytes : 0u);
-            const uint32_t w_addr = w_base + (p.w_resident ? (uint32_t)(c * p.ktaps + j) : (uint32_t)sw) * p.w_stage_bytes;
-            for (int kk = 0; kk < kk_n; ++kk) {
-              // HALO: the row-shifted start address keeps base_offset = 0 -- the UMMA unit applies the
-              // swizzle XOR to absolute shared-memory address bits (verified on B200, tools/tc_probe.py).
-              umma_bf16(d_tmem, make_desc(a_addr + kk * 32u, p.sbo_bytes, p.swizzle_code, 0u),
-                        make_desc(w_addr + kk * 32u, p.sbo_bytes, p.swizzle_code, 0u), idesc, accumulate);
-              accumulate = 1;
-            }
-            if (!p.w_resident) {
-              umma_commit(w_empty(sw));
-              if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
-            }
-            if (!p.halo_mode) {
-              umma_commit(a_empty(sa));
-              if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
-            }
-          }
-          if (p.halo_mode) {
-            umma_commit(a_empty(sa));
-            if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
-          }
-        }
-        umma_commit(acc_full(as));
-        if (++as == 2) { as = 0; pacc ^= 1; }
-      }
+#define VSG_MMA(H, R)                                                                                        \
+  do {                                                                                                       \
+    if (kk_n == 4) conv_tc_mma_loop<H, R, 4>(p, a_base, w_base, bar_base, tmem_base);                        \
+    else if (kk_n == 2) conv_tc_mma_loop<H, R, 2>(p, a_base, w_base, bar_base, tmem_base);                   \
+    else conv_tc_mma_loop<H, R, 1>(p, a_base, w_base, bar_base, tmem_base);                                  \
+  } while (0)
+      if (p.halo_mode && p.w_resident) VSG_MMA(true, true);
+      else if (p.halo_mode) VSG_MMA(true, false);
+      else if (p.w_resident) VSG_MMA(false, true);
+      else VSG_MMA(false, false);
+#undef VSG_MMA
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
