@@ -85,3 +85,54 @@ def test_generator_bf16_deterministic_and_batch_invariant(cuda_device):
     a, b = m(xd, g=gd), m(xd, g=gd)
     assert torch.equal(a, b)
     assert torch.equal(a[2:3], m(xd[2:3], g=gd[2:3]))
+
+
+@pytest.mark.parametrize("B,T,lengths", [(1, 1, None), (2, 300, [300, 211]), (3, 130, [130, 128, 5])])
+def test_flow_bf16_vs_oracle(cuda_device, B, T, lengths):
+    """bf16 tensor-core flow (gate / residual-skip / coupling epilogues) against the fp32 oracle.  bf16 storage of
+    the coupling state bounds the accuracy; BASELINE.json asks for it to be reported, the 1e-5 gate is fp32-mode."""
+    from helpers import flow_shapes, build_flow, FLOW_FULL
+    sd = O.synth_state_dict(flow_shapes(FLOW_FULL), 1234)
+    m = build_flow(FLOW_FULL, sd, cuda_device, precision="bf16")
+    x, mask, g = make_inputs(40 + T, B, 192, T, 256, lengths)
+    x = x * mask
+    with torch.no_grad():
+        ref_rev = O.flow(sd, x, mask, g, reverse=True)
+        ref_fwd = O.flow(sd, x, mask, g, reverse=False)
+    d = cuda_device
+    rev = m(x.to(d), mask.to(d), g=g.to(d), reverse=True).cpu()
+    fwd = m(x.to(d), mask.to(d), g=g.to(d), reverse=False).cpu()
+    rel = float((rev - ref_rev).norm() / ref_rev.norm())
+    print(f"bf16 flow B={B} T={T}: reverse rel-L2 {rel:.3e} max-abs {maxabs(rev, ref_rev):.3e}; "
+          f"forward max-abs {maxabs(fwd, ref_fwd):.3e}; |z|max {float(ref_rev.abs().max()):.2f}")
+    assert rel <= 2e-2 and maxabs(rev, ref_rev) <= 0.15 and maxabs(fwd, ref_fwd) <= 0.15
+    if lengths is not None:
+        for b, n in enumerate(lengths):
+            assert float(rev[b, :, n:].abs().max()) == 0.0 if n < T else True
+
+
+def test_hot_path_bf16_and_fp32(cuda_device):
+    """vsg_infer (models/visinger.py:107-111 in one call) in both modes against the oracle."""
+    from helpers import flow_shapes, FLOW_FULL
+    from visinger_b200.models.visinger import HotPath
+    fsd = O.synth_state_dict(flow_shapes(FLOW_FULL), 1234)
+    gsd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
+    sd = {"flow." + k: v for k, v in fsd.items()}
+    sd.update({"decoder." + k: v for k, v in gsd.items()})
+    B, T = 3, 90
+    mu, mask, g = make_inputs(77, B, 192, T, 256, [90, 64, 33])
+    gen = torch.Generator().manual_seed(5)
+    logs = 0.3 * torch.randn(B, 192, T, generator=gen) - 1.0
+    noise = torch.randn(B, 192, T, generator=gen)
+    with torch.no_grad():
+        wav_ref, z_ref = O.infer_hot_path(sd, mu, logs, noise, mask, g)
+    d = cuda_device
+    args = [t.to(d) for t in (mu, logs, noise, mask, g)]
+    hp32 = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, d, precision="fp32")
+    wav, z = hp32.infer(*args)
+    assert maxabs(z.cpu(), z_ref) <= 1e-5 and maxabs(wav.cpu().squeeze(1), wav_ref) <= 1e-4
+    hp16 = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, d, precision="bf16")
+    wav16, z16 = hp16.infer(*args)
+    rel = float((wav16.cpu().squeeze(1) - wav_ref).norm() / wav_ref.norm())
+    print(f"bf16 hot path: wav rel-L2 {rel:.3e}, z max-abs {maxabs(z16.cpu(), z_ref):.3e}")
+    assert rel <= 0.15

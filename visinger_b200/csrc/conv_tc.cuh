@@ -58,11 +58,23 @@ struct ConvTC {
   const float* bcond; int bcond_bs;   // [B][bcond_bs] or null
   float scale;                  // applied after the adds
   float slope;                  // leaky_relu slope for out_act
+  int mode;                     // EPI_TC_LINEAR / EPI_TC_GATE / EPI_TC_COUPLE
+  const float* mask;            // [B][Lout] row mask or null (LINEAR: v *= mask; COUPLE: see below)
+  int couple_sign;              // COUPLE: -1 reverse  x1 = (x1 - m) * mask,  +1 forward  x1 = m + x1 * mask
+  uint32_t e_out_swz_mask;      // swizzle of the output staging rows (GATE halves the row width)
   float* out_f32;               // optional fp32 copy of the raw value [B, Lout, Cout] (debug / parity hook)
   int* error_flag;              // set to 1 if a barrier wait times out
 };
 
+enum : int { EPI_TC_LINEAR = 0, EPI_TC_GATE = 1, EPI_TC_COUPLE = 2 };
+
 namespace tc {
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -217,64 +229,97 @@ constexpr int kNumBars = kBarAdd + 4 * kMaxAddBufs;
 
 }  // namespace tc
 
-template <int CW>
+// MODE: EPI_TC_LINEAR  v = (acc + bias + bcond + add0 + add1) * scale [* mask]
+//       EPI_TC_GATE    channel pairs (2c, 2c+1) hold the tanh / sigmoid halves (weights packed interleaved):
+//                      out[c] = tanh(a) * sigmoid(s)  -- fused_add_tanh_sigmoid_multiply, encoder.py:206-213;
+//                      the output tensor has Cout / 2 channels
+//       EPI_TC_COUPLE  m = (acc + bias) * mask; out = (add0 - m) * mask | m + add0 * mask  (flow.py:78,83)
+template <int CW, int MODE>
 __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, const CUtensorMap& tmAdd1,
                                                  const CUtensorMap& tmRaw, const CUtensorMap& tmAct, const ConvTC& p,
                                                  uint32_t smem_base, uint32_t bar_base, uint32_t tmem_base, int warp,
                                                  int lane) {
   using namespace tc;
+  constexpr int OW = (MODE == EPI_TC_GATE) ? CW / 2 : CW;   // output channels per chunk
   const int ew = warp - 2;               // staging-buffer owner index 0..3
   const int quarter = warp & 3;          // tcgen05.ld: warp w may only touch TMEM lanes 32*(w%4) .. +31
+  const int n_echunks = p.n_echunks, n_ntiles = p.n_ntiles, m_tiles_per_b = p.m_tiles_per_b, n_tile = p.n_tile;
+  const int n_add_bufs = p.n_add_bufs, total_tiles = p.total_tiles;
+  const uint32_t e_buf_bytes = p.e_buf_bytes, swz_in = p.e_swz_mask, swz_out = p.e_out_swz_mask;
+  const bool has_add0 = p.has_add0, has_add1 = p.has_add1 && MODE == EPI_TC_LINEAR, has_raw = p.has_raw,
+             has_act = p.has_act && MODE == EPI_TC_LINEAR;
+  const float scale = p.scale, slope = p.slope;
+  const float* const bias = p.bias;
+  const float* const bcond = p.bcond;
+  const float* const maskp = p.mask;
+  int* const error_flag = p.error_flag;
   const uint32_t e_base = smem_base + p.e_off + (uint32_t)ew * p.e_warp_bytes;
   const uint32_t add0_b = e_base;
-  const uint32_t add1_b = add0_b + (p.has_add0 ? (uint32_t)p.n_add_bufs * p.e_buf_bytes : 0u);
-  const uint32_t raw_b = add1_b + (p.has_add1 ? (uint32_t)p.n_add_bufs * p.e_buf_bytes : 0u);
-  const uint32_t act_b = raw_b + (p.has_raw ? 2u * p.e_buf_bytes : 0u);
-  const bool has_add = p.has_add0 || p.has_add1;
-  const bool has_out = p.has_raw || p.has_act;
-  const uint32_t add_bytes = (uint32_t)(p.has_add0 + p.has_add1) * 32u * CW * 2u;
-  auto add_bar = [&](int buf) { return bar_base + 8u * (kBarAdd + ew * kMaxAddBufs + buf); };
-  auto acc_full = [&](int s) { return bar_base + 8u * (kBarAccFull + s); };
-  auto acc_empty = [&](int s) { return bar_base + 8u * (kBarAccEmpty + s); };
+  const uint32_t add1_b = add0_b + (p.has_add0 ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
+  const uint32_t raw_b = add1_b + (p.has_add1 ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
+  const uint32_t act_b = raw_b + (p.has_raw ? 2u * e_buf_bytes : 0u);
+  const bool has_add = has_add0 || has_add1;
+  const bool has_out = has_raw || has_act;
+  const uint32_t add_bytes = (uint32_t)((has_add0 ? 1 : 0) + (has_add1 ? 1 : 0)) * 32u * CW * 2u;
+  const uint32_t add_bar0 = bar_base + 8u * (kBarAdd + ew * kMaxAddBufs);
+  const uint32_t acc_full0 = bar_base + 8u * kBarAccFull, acc_empty0 = bar_base + 8u * kBarAccEmpty;
 
-  const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int n_items = my_tiles * p.n_echunks;
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_items = my_tiles * n_echunks;
 
   // (tile, chunk) item -> TMA coordinates of this warp's 32-row slab
   auto issue_add = [&](int item) {   // lane 0 only
-    const int ti = item / p.n_echunks, cc = item % p.n_echunks;
+    const int ti = item / n_echunks, cc = item - ti * n_echunks;
     const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-    const int nt = tile % p.n_ntiles;
-    const int mt = (tile / p.n_ntiles) % p.m_tiles_per_b;
-    const int b = tile / (p.n_ntiles * p.m_tiles_per_b);
-    const int buf = item % p.n_add_bufs;
-    const int ch = nt * p.n_tile + cc * CW, row = mt * 128 + quarter * 32;
-    mbar_expect_tx(add_bar(buf), add_bytes);
-    if (p.has_add0) tma_load_3d(add0_b + buf * p.e_buf_bytes, &tmAdd0, add_bar(buf), ch, row, b);
-    if (p.has_add1) tma_load_3d(add1_b + buf * p.e_buf_bytes, &tmAdd1, add_bar(buf), ch, row, b);
+    const int nt = tile % n_ntiles;
+    const int mt = (tile / n_ntiles) % m_tiles_per_b;
+    const int b = tile / (n_ntiles * m_tiles_per_b);
+    const int buf = item % n_add_bufs;
+    const int ch = nt * n_tile + cc * CW, row = mt * 128 + quarter * 32;
+    mbar_expect_tx(add_bar0 + 8u * buf, add_bytes);
+    if (has_add0) tma_load_3d(add0_b + buf * e_buf_bytes, &tmAdd0, add_bar0 + 8u * buf, ch, row, b);
+    if (has_add1) tma_load_3d(add1_b + buf * e_buf_bytes, &tmAdd1, add_bar0 + 8u * buf, ch, row, b);
   };
   if (has_add && lane == 0) {
-    for (int i = 0; i < n_items && i < p.n_add_bufs - 1; ++i) issue_add(i);
+    for (int i = 0; i < n_items && i < n_add_bufs - 1; ++i) issue_add(i);
   }
 
-  int as = 0;
+  // bias is tile-invariant when the kernel has a single (n-tile, chunk): keep it in registers
+  const bool bias_hoisted = (n_ntiles * n_echunks == 1) && bias != nullptr;
+  float bias_r[CW];
+#pragma unroll
+  for (int i = 0; i < CW; ++i) bias_r[i] = 0.f;
+  if (bias_hoisted) {
+#pragma unroll
+    for (int i = 0; i < CW; i += 4) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + i));
+      bias_r[i] = bv.x; bias_r[i + 1] = bv.y; bias_r[i + 2] = bv.z; bias_r[i + 3] = bv.w;
+    }
+  }
+
+  int as = 0, item = 0, add_buf = 0;
   uint32_t pacc = 0, add_phase = 0, out_count = 0;
-  int item = 0;
-  const uint32_t row_off = (uint32_t)lane * (CW * 2);   // this lane's row inside a staging buffer
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const int nt = tile % p.n_ntiles;
-    const int mt = (tile / p.n_ntiles) % p.m_tiles_per_b;
-    const int b = tile / (p.n_ntiles * p.m_tiles_per_b);
-    mbar_wait(acc_full(as), pacc, p.error_flag);
+  const uint32_t row_off_in = (uint32_t)lane * (CW * 2);    // this lane's row inside an add staging buffer
+  const uint32_t row_off_out = (uint32_t)lane * (OW * 2);   // ... inside an output staging buffer
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int nt = tile % n_ntiles;
+    const int mt = (tile / n_ntiles) % m_tiles_per_b;
+    const int b = tile / (n_ntiles * m_tiles_per_b);
+    mbar_wait(acc_full0 + 8u * as, pacc, error_flag);
     fence_after_sync();
     const int row0 = mt * 128 + quarter * 32;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.n_tile);
-    for (int cc = 0; cc < p.n_echunks; ++cc, ++item) {
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * n_tile);
+    float mk = 1.0f;
+    if (maskp) {
+      const int q = row0 + lane;
+      mk = (q < p.Lq) ? __ldg(maskp + (long long)b * p.Lout + q) : 0.f;
+    }
+    for (int cc = 0; cc < n_echunks; ++cc, ++item) {
       if (has_add && lane == 0) {
-        const int nxt = item + p.n_add_bufs - 1;
+        const int nxt = item + n_add_bufs - 1;
         if (nxt < n_items) issue_add(nxt);   // its buffer was last read at item-1 (warp-synced below)
       }
-      const int ch = nt * p.n_tile + cc * CW;
+      const int ch = nt * n_tile + cc * CW;
       float v[CW];
       {
         uint32_t r[CW];
@@ -284,94 +329,122 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
 #pragma unroll
         for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
       }
-      if (p.bias) {
+      if (cc == n_echunks - 1) {   // accumulator drained: hand the TMEM stage back before doing the math
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty0 + 8u * as);
+      }
+      if (bias_hoisted) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) v[i] += bias_r[i];
+      } else if (bias) {
 #pragma unroll
         for (int i = 0; i < CW; i += 4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch + i));
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + ch + i));
           v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
         }
       }
-      if (p.bcond) {
-        const float* bc = p.bcond + (long long)b * p.bcond_bs + ch;
+      if (bcond) {
+        const float* bc = bcond + (long long)b * p.bcond_bs + ch;
 #pragma unroll
         for (int i = 0; i < CW; i += 4) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(bc + i));
           v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
         }
       }
+      if (MODE == EPI_TC_COUPLE) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) v[i] *= mk;     // m = post(h) * mask
+      }
       if (has_add) {
-        const int buf = item % p.n_add_bufs;
-        mbar_wait(add_bar(buf), (add_phase >> buf) & 1u, p.error_flag);
-        add_phase ^= 1u << buf;
-        if (p.has_add0) {
-          const uint32_t base = add0_b + buf * p.e_buf_bytes;
+        mbar_wait(add_bar0 + 8u * add_buf, (add_phase >> add_buf) & 1u, error_flag);
+        add_phase ^= 1u << add_buf;
+        if (has_add0) {
+          const uint32_t base = add0_b + add_buf * e_buf_bytes;
 #pragma unroll
           for (int c = 0; c < CW / 8; ++c) {
             float f[8];
-            unpack_bf16x8(lds128(base + swz(row_off + c * 16, p.e_swz_mask)), f);
+            unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (MODE == EPI_TC_COUPLE) v[8 * c + i] = p.couple_sign < 0 ? (f[i] - v[8 * c + i]) * mk : v[8 * c + i] + f[i] * mk;
+              else v[8 * c + i] += f[i];
+            }
+          }
+        }
+        if (has_add1) {
+          const uint32_t base = add1_b + add_buf * e_buf_bytes;
+#pragma unroll
+          for (int c = 0; c < CW / 8; ++c) {
+            float f[8];
+            unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[8 * c + i] += f[i];
           }
         }
-        if (p.has_add1) {
-          const uint32_t base = add1_b + buf * p.e_buf_bytes;
+        if (++add_buf == n_add_bufs) add_buf = 0;
+      }
+      if (MODE == EPI_TC_LINEAR) {
+        if (scale != 1.0f) {
 #pragma unroll
-          for (int c = 0; c < CW / 8; ++c) {
-            float f[8];
-            unpack_bf16x8(lds128(base + swz(row_off + c * 16, p.e_swz_mask)), f);
+          for (int i = 0; i < CW; ++i) v[i] *= scale;
+        }
+        if (maskp) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * c + i] += f[i];
-          }
+          for (int i = 0; i < CW; ++i) v[i] *= mk;
         }
       }
-      if (p.scale != 1.0f) {
+      if (MODE == EPI_TC_GATE) {
 #pragma unroll
-        for (int i = 0; i < CW; ++i) v[i] *= p.scale;
+        for (int c = 0; c < CW / 2; ++c) {
+          const float t = tanh_fast(v[2 * c]);
+          const float sg = 0.5f * tanh_fast(0.5f * v[2 * c + 1]) + 0.5f;   // sigmoid(x) = (1 + tanh(x/2)) / 2
+          v[c] = t * sg;
+        }
       }
+      const int och = (MODE == EPI_TC_GATE) ? ch / 2 : ch;
       if (p.out_f32) {   // debug / parity hook only: plain per-thread stores
         const int q = row0 + lane, n = q * p.out_stride + p.out_phase;
-        if (q < p.Lq && n < p.Lout && ch < p.Cout) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((long long)b * p.Lout + n) * p.Cout + ch);
+        const int oc_total = (MODE == EPI_TC_GATE) ? p.Cout / 2 : p.Cout;
+        if (q < p.Lq && n < p.Lout && och < oc_total) {
+          float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((long long)b * p.Lout + n) * oc_total + och);
 #pragma unroll
-          for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < OW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
       }
       if (has_out) {
-        const uint32_t ob = (out_count & 1u) * p.e_buf_bytes;
+        const uint32_t ob = (out_count & 1u) * e_buf_bytes;
         if (lane == 0) bulk_wait_read<1>();   // the store that last used this buffer (2 groups ago) has drained
         __syncwarp();
-        if (p.has_raw) {
+        if (has_raw) {
 #pragma unroll
-          for (int c = 0; c < CW / 8; ++c) {
+          for (int c = 0; c < OW / 8; ++c) {
             const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
                                        pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
-            sts128(raw_b + ob + swz(row_off + c * 16, p.e_swz_mask), u);
+            sts128(raw_b + ob + swz(row_off_out + c * 16, swz_out), u);
           }
         }
-        if (p.has_act) {
+        if (has_act) {
 #pragma unroll
-          for (int i = 0; i < CW; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+          for (int i = 0; i < OW; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
 #pragma unroll
-          for (int c = 0; c < CW / 8; ++c) {
+          for (int c = 0; c < OW / 8; ++c) {
             const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
                                        pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
-            sts128(act_b + ob + swz(row_off + c * 16, p.e_swz_mask), u);
+            sts128(act_b + ob + swz(row_off_out + c * 16, swz_out), u);
           }
         }
         fence_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) {
-          if (p.has_raw) tma_store_3d(&tmRaw, raw_b + ob, ch, row0, b);
-          if (p.has_act) tma_store_3d(&tmAct, act_b + ob, ch, row0, b);
+          if (has_raw) tma_store_3d(&tmRaw, raw_b + ob, och, row0, b);
+          if (has_act) tma_store_3d(&tmAct, act_b + ob, och, row0, b);
           bulk_commit();
         }
         ++out_count;
       }
       __syncwarp();   // every lane is done with this item's add buffer before lane 0 refills it
     }
-    fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(acc_empty(as));
     if (++as == 2) { as = 0; pacc ^= 1; }
   }
   if (lane == 0) bulk_wait_all();
@@ -548,9 +621,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-    if (p.cw == 64) conv_tc_epilogue<64>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);
-    else if (p.cw == 32) conv_tc_epilogue<32>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);
-    else conv_tc_epilogue<16>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);
+#define VSG_EPI(CWV)                                                                                              \
+  do {                                                                                                            \
+    if (p.mode == EPI_TC_LINEAR)                                                                                  \
+      conv_tc_epilogue<CWV, EPI_TC_LINEAR>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
+    else if (p.mode == EPI_TC_GATE)                                                                               \
+      conv_tc_epilogue<CWV, EPI_TC_GATE>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);   \
+    else                                                                                                          \
+      conv_tc_epilogue<CWV, EPI_TC_COUPLE>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
+  } while (0)
+    if (p.cw == 64) VSG_EPI(64);
+    else if (p.cw == 32) VSG_EPI(32);
+    else VSG_EPI(16);
+#undef VSG_EPI
   }
 
   // ---- teardown: everyone done with TMEM before the allocating warp frees it ----
@@ -577,6 +660,23 @@ __global__ void transpose_to_bf16_kernel(const float* __restrict__ x, __nv_bfloa
   for (int i = ty; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + tx;
     if (t < T && c < C) y[((long long)b * T + t) * C + c] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+// [B, T, C] bf16 -> [B, C, T] fp32; flip != 0 reverses the channel order (an odd number of Flips).
+__global__ void transpose_from_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int T,
+                                           int flip) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    tile[i][tx] = (c < C && t < T) ? __bfloat162float(x[((long long)b * T + t) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (c < C && t < T) y[((long long)b * C + (flip ? C - 1 - c : c)) * T + t] = tile[tx][i];
   }
 }
 

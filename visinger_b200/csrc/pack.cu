@@ -119,16 +119,19 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
     VSG_TRY(L.eff_weight(p + "pre", H, half, 1, W));
     VSG_TRY(L.bias(p + "pre", H, b, true));
     VSG_TRY(pack_conv_f32(L, W, b, H, half, 1, Identity{}, &fl.pre[0]));
+    VSG_TRY(pack_conv_tc(P, W, b, H, half, 1, &fl.pre_tc[0]));
     {
       std::vector<float> Wf(W.size());
       for (int co = 0; co < H; ++co)
         for (int ci = 0; ci < half; ++ci) Wf[(size_t)co * half + ci] = W[(size_t)co * half + (half - 1 - ci)];
       VSG_TRY(pack_conv_f32(L, Wf, b, H, half, 1, Identity{}, &fl.pre[1]));
+      VSG_TRY(pack_conv_tc(P, Wf, b, H, half, 1, &fl.pre_tc[1]));
     }
     // post: Conv1d(H -> half, 1)      flow.py:62 (mean_only)
     VSG_TRY(L.eff_weight(p + "post", half, H, 1, W));
     VSG_TRY(L.bias(p + "post", half, b, true));
     VSG_TRY(pack_conv_f32(L, W, b, half, H, 1, Identity{}, &fl.post[0]));
+    VSG_TRY(pack_conv_tc(P, W, b, half, H, 1, &fl.post_tc[0]));
     {
       std::vector<float> Wf(W.size()), bf(b.size());
       for (int co = 0; co < half; ++co) {
@@ -136,20 +139,41 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
         for (int ci = 0; ci < H; ++ci) Wf[(size_t)co * H + ci] = W[(size_t)(half - 1 - co) * H + ci];
       }
       VSG_TRY(pack_conv_f32(L, Wf, bf, half, H, 1, Identity{}, &fl.post[1]));
+      VSG_TRY(pack_conv_tc(P, Wf, bf, half, H, 1, &fl.post_tc[1]));
     }
     // WaveNet                        encoder.py:131-165
     fl.in_layers.resize(NL);
     fl.res_skip.resize(NL);
+    fl.in_tc.resize(NL);
+    fl.res_tc.resize(NL);
+    fl.skip_tc.resize(NL);
     for (int i = 0; i < NL; ++i) {
       const std::string pi = p + "enc.in_layers." + std::to_string(i);
       VSG_TRY(L.eff_weight(pi, 2 * H, H, K, W));
       VSG_TRY(L.bias(pi, 2 * H, b, true));
       VSG_TRY(pack_conv_f32(L, W, b, 2 * H, H, K, GateInterleave{H}, &fl.in_layers[i]));
+      {   // tensor-core pack: rows permuted so (tanh, sigmoid) halves of a channel sit in adjacent accumulator columns
+        GateInterleave gi{H};
+        std::vector<float> Wg(W.size()), bg(b.size());
+        for (int co = 0; co < 2 * H; ++co) {
+          bg[gi(co)] = b[co];
+          memcpy(&Wg[(size_t)gi(co) * H * K], &W[(size_t)co * H * K], (size_t)H * K * sizeof(float));
+        }
+        VSG_TRY(pack_conv_tc(P, Wg, bg, 2 * H, H, K, &fl.in_tc[i]));
+      }
       const int rs = (i < NL - 1) ? 2 * H : H;
       const std::string pr = p + "enc.res_skip_layers." + std::to_string(i);
       VSG_TRY(L.eff_weight(pr, rs, H, 1, W));
       VSG_TRY(L.bias(pr, rs, b, true));
       VSG_TRY(pack_conv_f32(L, W, b, rs, H, 1, Identity{}, &fl.res_skip[i]));
+      if (i < NL - 1) {
+        std::vector<float> Wr(W.begin(), W.begin() + (size_t)H * H), br(b.begin(), b.begin() + H);
+        std::vector<float> Ws(W.begin() + (size_t)H * H, W.end()), bs(b.begin() + H, b.end());
+        VSG_TRY(pack_conv_tc(P, Wr, br, H, H, 1, &fl.res_tc[i]));
+        VSG_TRY(pack_conv_tc(P, Ws, bs, H, H, 1, &fl.skip_tc[i]));
+      } else {
+        VSG_TRY(pack_conv_tc(P, W, b, H, H, 1, &fl.skip_tc[i]));
+      }
     }
     if (c.flow_gin > 0) {
       const int O = 2 * H * NL, I = c.flow_gin;

@@ -30,14 +30,23 @@ EncodeTiledFn encode_fn() {
 }
 
 CUtensorMapSwizzle swizzle_for(int kc) {
-  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  return kc >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kc >= 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+         : kc >= 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
 }
 
 int pick_kc(int cin) { return cin % 64 == 0 ? 64 : cin % 32 == 0 ? 32 : cin % 16 == 0 ? 16 : 0; }
+// Largest UMMA N (multiple of 16, <= 256) that divides Cout and is itself a multiple of its epilogue chunk.
 int pick_ntile(int cout) {
-  for (int n : {256, 128, 64, 32, 16})
+  if (cout % 16) return 0;
+  for (int n = 256; n >= 16; n -= 16)
     if (cout % n == 0) return n;
   return 0;
+}
+int pick_cw(int nt) {
+  if (nt >= 256) return 32;
+  for (int c : {64, 32, 16})
+    if (nt % c == 0) return c;
+  return 16;
 }
 
 int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows,
@@ -74,6 +83,10 @@ int encode_3d(CUtensorMap* m, const void* base, uint64_t C, uint64_t rows, uint6
 constexpr size_t kSmemMax = 227 * 1024;
 
 struct EpiTC {
+  int mode = EPI_TC_LINEAR;
+  const float* mask = nullptr;      // [B][Lout]
+  int couple_sign = -1;
+  int ld = 0;                       // leading dimension (channels per row) of the add / out tensors; 0 = their own width
   const float* bias = nullptr;
   const float* bcond = nullptr; int bcond_bs = 0;
   const __nv_bfloat16* add0 = nullptr;
@@ -95,7 +108,8 @@ constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic smem we plan with
 // One convolution launch.  x: [B, Lin, Cin] bf16 channels-last; add/out tensors: [B, Lout, Cout].
 int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, int B, int Lin, int in_off0, int dil,
                    int Lq, int out_stride, int out_phase, int Lout, const EpiTC& e, const TCOptions& opt, int* error_flag,
-                   cudaStream_t st) {
+                   cudaStream_t st, int x_ld = 0) {
+  if (x_ld == 0) x_ld = w.Cin;
   if (!w.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 16 "
                                                  "(conv %d -> %d)", w.Cin, w.Cout);
   if (Lq <= 0 || B <= 0) return VSG_OK;
@@ -116,8 +130,13 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.a_stage_bytes = (p.a_box_bytes + 1023u) & ~1023u;
   p.w_stage_bytes = (p.w_box_bytes + 1023u) & ~1023u;
   // epilogue staging
-  p.cw = NT >= 256 ? 32 : std::min(NT, 64);
+  p.cw = pick_cw(NT);
   p.n_echunks = NT / p.cw;
+  p.mode = e.mode; p.mask = e.mask; p.couple_sign = e.couple_sign;
+  const int ow = e.mode == EPI_TC_GATE ? p.cw / 2 : p.cw;            // output channels per chunk
+  const int cout_eff = e.mode == EPI_TC_GATE ? w.Cout / 2 : w.Cout;  // channels of the add / out tensors
+  const int ld = e.ld ? e.ld : cout_eff;
+  p.e_out_swz_mask = ow >= 64 ? 7u : ow >= 32 ? 3u : ow >= 16 ? 1u : 0u;
   p.e_buf_bytes = (uint32_t)((32 * p.cw * 2 + 1023) & ~1023);
   p.e_swz_mask = p.cw == 64 ? 7u : p.cw == 32 ? 3u : 1u;
   p.has_add0 = e.add0 != nullptr; p.has_add1 = e.add1 != nullptr;
@@ -154,7 +173,8 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.bar_off = p.e_off + (uint32_t)e_bytes;
   const size_t smem = 1024 + (size_t)p.bar_off + 8 * tc::kNumBars + 64;
   if (smem > kSmemMax) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory (%zu B)", smem);
-  p.tmem_cols = (uint32_t)std::max(32, 2 * NT);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < (uint32_t)(2 * NT)) p.tmem_cols <<= 1;
   p.swizzle_code = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
   p.sbo_bytes = 8u * KC * 2u;
   p.bias = e.bias; p.bcond = e.bcond; p.bcond_bs = e.bcond_bs;
@@ -163,18 +183,18 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.error_flag = error_flag;
 
   CUtensorMap tmA, tmAdd0, tmAdd1, tmRaw, tmAct;
-  VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.Cin, (uint64_t)Lin, (uint64_t)B, (uint64_t)w.Cin, (uint64_t)Lin * w.Cin,
+  VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.Cin, (uint64_t)Lin, (uint64_t)B, (uint64_t)x_ld, (uint64_t)Lin * x_ld,
                     (uint32_t)KC, (uint32_t)p.a_rows, KC));
-  // epilogue tensors: rows are the q positions of this (poly)phase: row stride out_stride*Cout, base shifted by phase
-  auto emap = [&](CUtensorMap* m, const __nv_bfloat16* base) -> int {
-    return encode_3d(m, base + (size_t)out_phase * w.Cout, (uint64_t)w.Cout, (uint64_t)Lq, (uint64_t)B,
-                     (uint64_t)out_stride * w.Cout, (uint64_t)Lout * w.Cout, (uint32_t)p.cw, 32u, p.cw);
+  // epilogue tensors: rows are the q positions of this (poly)phase: row stride out_stride*ld, base shifted by phase
+  auto emap = [&](CUtensorMap* m, const __nv_bfloat16* base, int width, int box_c) -> int {
+    return encode_3d(m, base + (size_t)out_phase * ld, (uint64_t)width, (uint64_t)Lq, (uint64_t)B,
+                     (uint64_t)out_stride * ld, (uint64_t)Lout * ld, (uint32_t)box_c, 32u, box_c);
   };
   tmAdd0 = tmAdd1 = tmRaw = tmAct = tmA;
-  if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0));
-  if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1));
-  if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw));
-  if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act));
+  if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0, w.Cout, p.cw));
+  if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1, w.Cout, p.cw));
+  if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw, cout_eff, ow));
+  if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act, cout_eff, ow));
   static bool attr_set = false;
   if (!attr_set) {
     VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
@@ -225,12 +245,92 @@ int pack_conv_tc(VsgPack* P, const std::vector<float>& W, const std::vector<floa
   return VSG_OK;
 }
 
-size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T) { return flow_ws_bytes_f32(P, B, T); }
+size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T) {
+  const VsgConfig& c = P->cfg;
+  size_t n = 0;
+  n += align256((size_t)B * c.flow_n_flows * 2 * c.flow_hidden * c.flow_n_layers * sizeof(float));   // cond
+  n += align256((size_t)B * T * c.flow_channels * 2);                                               // state, channels-last
+  n += 3 * align256((size_t)B * T * c.flow_hidden * 2);                                             // h, acts, out
+  return n + 512;
+}
 
+// ResidualCouplingBlock.forward (modules/visinger/flow.py:33-40) on the tensor-core kernels.  The coupling state,
+// WaveNet state, gate output and skip sum all live channels-last in bf16; every elementwise op of the reference
+// (mask multiplies, gate, residual / skip routing, coupling) is an epilogue of the convolution that produces it.
 int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, float* y, int B, int T,
                     int reverse, Workspace& ws, cudaStream_t st) {
-  // The flow is 4 % of the path's FLOPs; until its tensor-core kernels land it runs the fp32 kernels in both modes.
-  return flow_forward_f32(P, x, mask, g, y, B, T, reverse, ws, st);
+  const VsgConfig& c = P->cfg;
+  const int C = c.flow_channels, H = c.flow_hidden, NL = c.flow_n_layers, NF = c.flow_n_flows, half = C / 2;
+  const int K = c.flow_kernel_size;
+  if (!P->flow_layers.empty() && !P->flow_layers[0].pre_tc[0].has_tmap)
+    return fail(VSG_EUNSUPPORTED, "bf16 flow needs channels/2 and hidden_channels to be multiples of 16");
+  const int condO = 2 * H * NL;
+  typedef __nv_bfloat16 bf;
+  float* cond = ws.take<float>((size_t)B * NF * condO);
+  bf* u = ws.take<bf>((size_t)B * T * C);
+  bf* h = ws.take<bf>((size_t)B * T * H);
+  bf* acts = ws.take<bf>((size_t)B * T * H);
+  bf* out = ws.take<bf>((size_t)B * T * H);
+  int* err = ws.take<int>(1);
+  if (ws.overflow) return fail(VSG_ENOMEM, "flow workspace too small: need %zu bytes", ws.off);
+  VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+  const TCOptions opt = g_default_opts;
+  if (c.flow_gin > 0) {
+    if (!g) return fail(VSG_EINVAL, "flow was built with gin_channels=%d but g is NULL", c.flow_gin);
+    for (int f = 0; f < NF; ++f)
+      VSG_TRY(launch_cond(P->flow_layers[f].cond_w, P->flow_layers[f].cond_b, g, cond + (size_t)f * condO * B, condO,
+                          c.flow_gin, B, st));
+  }
+  {
+    dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(x, u, C, T);
+    VSG_LAUNCH_CHECK("transpose_to_bf16_kernel");
+  }
+  for (int step = 0; step < NF; ++step) {
+    const int f = reverse ? NF - 1 - step : step;
+    const int flipped = reverse ? (NF - f) & 1 : f & 1;
+    const FlowLayer& fl = P->flow_layers[f];
+    const bf* x0 = u + (flipped ? half : 0);
+    bf* x1 = u + (flipped ? 0 : half);
+    {  // h = pre(x0) * mask
+      EpiTC e;
+      e.bias = fl.pre_tc[flipped].bias; e.mask = mask; e.out_raw = h;
+      VSG_TRY(launch_conv_tc(P, fl.pre_tc[flipped], x0, B, T, 0, 1, T, 1, 0, T, e, opt, err, st, C));
+    }
+    int dil = 1;
+    for (int i = 0; i < NL; ++i) {
+      const bool last = (i == NL - 1);
+      {  // acts = tanh(.) * sigmoid(.) of in_layer(h) + cond
+        EpiTC e;
+        e.mode = EPI_TC_GATE; e.bias = fl.in_tc[i].bias; e.out_raw = acts;
+        if (c.flow_gin > 0) { e.bcond = cond + (size_t)f * condO * B + (size_t)i * 2 * H; e.bcond_bs = condO; }
+        VSG_TRY(launch_conv_tc(P, fl.in_tc[i], h, B, T, -((K * dil - dil) / 2), dil, T, 1, 0, T, e, opt, err, st));
+      }
+      if (!last) {  // h = (h + res(acts)) * mask
+        EpiTC e;
+        e.bias = fl.res_tc[i].bias; e.add0 = h; e.mask = mask; e.out_raw = h;
+        VSG_TRY(launch_conv_tc(P, fl.res_tc[i], acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+      }
+      {  // out (+)= skip(acts); masked after the last layer
+        EpiTC e;
+        e.bias = fl.skip_tc[i].bias; e.add0 = (i > 0) ? out : nullptr; e.mask = last ? mask : nullptr; e.out_raw = out;
+        VSG_TRY(launch_conv_tc(P, fl.skip_tc[i], acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+      }
+      dil *= c.flow_dilation_rate;
+    }
+    {  // m = post(out) * mask ; x1 = (x1 - m) * mask | m + x1 * mask
+      EpiTC e;
+      e.mode = EPI_TC_COUPLE; e.couple_sign = reverse ? -1 : 1;
+      e.bias = fl.post_tc[flipped].bias; e.mask = mask; e.add0 = x1; e.out_raw = x1; e.ld = C;
+      VSG_TRY(launch_conv_tc(P, fl.post_tc[flipped], out, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+    }
+  }
+  {
+    dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(u, y, C, T, (NF & 1) ? 1 : 0);
+    VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
+  }
+  return VSG_OK;
 }
 
 size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T) {

@@ -77,6 +77,11 @@ struct FlowLayer {
   std::vector<ConvW32> res_skip;
   float* cond_w = nullptr;          // [2H*n_layers][gin], rows gate-interleaved per layer
   float* cond_b = nullptr;
+  // bf16 tensor-core packs
+  ConvWTC pre_tc[2], post_tc[2];
+  std::vector<ConvWTC> in_tc;       // gate-interleaved
+  std::vector<ConvWTC> res_tc;      // res_skip rows [0, H): the residual half (absent for the last layer)
+  std::vector<ConvWTC> skip_tc;     // res_skip rows [H, 2H) (all H rows for the last layer)
 };
 
 struct ResBlockPack {
