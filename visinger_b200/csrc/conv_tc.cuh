@@ -218,6 +218,26 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Walks this CTA's tiles (tile = blockIdx.x + i * gridDim.x) as (n-tile, m-tile, utterance) coordinates without
+// per-tile integer divisions: the stride is decomposed once, then advanced with carries.
+struct TileIter {
+  int nt, mt, b, s_nt, s_mt, s_b, n_ntiles, m_tiles;
+  __device__ __forceinline__ void init(int tile0, int step, int n_ntiles_, int m_tiles_) {
+    n_ntiles = n_ntiles_; m_tiles = m_tiles_;
+    nt = tile0 % n_ntiles; mt = (tile0 / n_ntiles) % m_tiles; b = tile0 / (n_ntiles * m_tiles);
+    s_nt = step % n_ntiles; s_mt = (step / n_ntiles) % m_tiles; s_b = step / (n_ntiles * m_tiles);
+  }
+  __device__ __forceinline__ void next() {
+    nt += s_nt;
+    int c = nt >= n_ntiles ? 1 : 0;
+    nt -= c ? n_ntiles : 0;
+    mt += s_mt + c;
+    c = mt >= m_tiles ? 1 : 0;
+    mt -= c ? m_tiles : 0;
+    b += s_b + c;
+  }
+};
+
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kMaxAddBufs = 4;
@@ -267,21 +287,23 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_items = my_tiles * n_echunks;
 
-  // (tile, chunk) item -> TMA coordinates of this warp's 32-row slab
-  auto issue_add = [&](int item) {   // lane 0 only
-    const int ti = item / n_echunks, cc = item - ti * n_echunks;
-    const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-    const int nt = tile % n_ntiles;
-    const int mt = (tile / n_ntiles) % m_tiles_per_b;
-    const int b = tile / (n_ntiles * m_tiles_per_b);
-    const int buf = item % n_add_bufs;
-    const int ch = nt * n_tile + cc * CW, row = mt * 128 + quarter * 32;
-    mbar_expect_tx(add_bar0 + 8u * buf, add_bytes);
-    if (has_add0) tma_load_3d(add0_b + buf * e_buf_bytes, &tmAdd0, add_bar0 + 8u * buf, ch, row, b);
-    if (has_add1) tma_load_3d(add1_b + buf * e_buf_bytes, &tmAdd1, add_bar0 + 8u * buf, ch, row, b);
+  // add-operand prefetch cursor: walks (tile, chunk) items n_add_bufs-1 ahead of the consumer
+  TileIter pf;
+  pf.init((int)blockIdx.x, (int)gridDim.x, n_ntiles, m_tiles_per_b);
+  int pf_cc = 0, pf_buf = 0, pf_left = n_items;
+  auto issue_next_add = [&]() {   // lane 0 only
+    if (pf_left <= 0) return;
+    const int ch = pf.nt * n_tile + pf_cc * CW, row = pf.mt * 128 + quarter * 32;
+    const uint32_t bar = add_bar0 + 8u * pf_buf;
+    mbar_expect_tx(bar, add_bytes);
+    if (has_add0) tma_load_3d(add0_b + pf_buf * e_buf_bytes, &tmAdd0, bar, ch, row, pf.b);
+    if (has_add1) tma_load_3d(add1_b + pf_buf * e_buf_bytes, &tmAdd1, bar, ch, row, pf.b);
+    --pf_left;
+    if (++pf_buf == n_add_bufs) pf_buf = 0;
+    if (++pf_cc == n_echunks) { pf_cc = 0; pf.next(); }
   };
   if (has_add && lane == 0) {
-    for (int i = 0; i < n_items && i < n_add_bufs - 1; ++i) issue_add(i);
+    for (int i = 0; i < n_add_bufs - 1; ++i) issue_next_add();
   }
 
   // bias is tile-invariant when the kernel has a single (n-tile, chunk): keep it in registers
@@ -301,10 +323,10 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   uint32_t pacc = 0, add_phase = 0, out_count = 0;
   const uint32_t row_off_in = (uint32_t)lane * (CW * 2);    // this lane's row inside an add staging buffer
   const uint32_t row_off_out = (uint32_t)lane * (OW * 2);   // ... inside an output staging buffer
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int nt = tile % n_ntiles;
-    const int mt = (tile / n_ntiles) % m_tiles_per_b;
-    const int b = tile / (n_ntiles * m_tiles_per_b);
+  TileIter it;
+  it.init((int)blockIdx.x, (int)gridDim.x, n_ntiles, m_tiles_per_b);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next()) {
+    const int nt = it.nt, mt = it.mt, b = it.b;
     mbar_wait(acc_full0 + 8u * as, pacc, error_flag);
     fence_after_sync();
     const int row0 = mt * 128 + quarter * 32;
@@ -315,10 +337,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
       mk = (q < p.Lq) ? __ldg(maskp + (long long)b * p.Lout + q) : 0.f;
     }
     for (int cc = 0; cc < n_echunks; ++cc, ++item) {
-      if (has_add && lane == 0) {
-        const int nxt = item + n_add_bufs - 1;
-        if (nxt < n_items) issue_add(nxt);   // its buffer was last read at item-1 (warp-synced below)
-      }
+      if (has_add && lane == 0) issue_next_add();   // refills the buffer read at item-1 (warp-synced below)
       const int ch = nt * n_tile + cc * CW;
       float v[CW];
       {
@@ -520,7 +539,10 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
   }
 }
 
-__global__ void __launch_bounds__(tc::kThreads, 1)
+// SMALL = true: the low-channel instantiation (epilogue chunks of <= 32 channels): register budget for TWO
+// resident CTAs per SM, which doubles the single-thread MMA issue rate and the epilogue warps in flight.
+template <bool SMALL>
+__global__ void __launch_bounds__(tc::kThreads, SMALL ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmAdd0, const __grid_constant__ CUtensorMap tmAdd1,
                const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmAct, const ConvTC p) {
@@ -573,10 +595,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < p.ktaps; ++j)
             tma_load_2d(w_base + (uint32_t)(c * p.ktaps + j) * p.w_stage_bytes, &tmW, w_full(0), c * p.KC, j * p.CoutT);
       }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_ntiles;
-        const int mt = (tile / p.n_ntiles) % p.m_tiles_per_b;
-        const int b = tile / (p.n_ntiles * p.m_tiles_per_b);
+      TileIter it;
+      it.init((int)blockIdx.x, (int)gridDim.x, p.n_ntiles, p.m_tiles_per_b);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it.next()) {
+        const int nt = it.nt, mt = it.mt, b = it.b;
         const int row0 = mt * 128 + p.in_off0;
         for (int c = 0; c < p.n_cchunks; ++c) {
           if (p.halo_mode) {
@@ -630,7 +652,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else                                                                                                          \
       conv_tc_epilogue<CWV, EPI_TC_COUPLE>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
   } while (0)
-    if (p.cw == 64) VSG_EPI(64);
+    if (!SMALL && p.cw == 64) VSG_EPI(64);
     else if (p.cw == 32) VSG_EPI(32);
     else VSG_EPI(16);
 #undef VSG_EPI

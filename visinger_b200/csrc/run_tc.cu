@@ -130,7 +130,9 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.a_stage_bytes = (p.a_box_bytes + 1023u) & ~1023u;
   p.w_stage_bytes = (p.w_box_bytes + 1023u) & ~1023u;
   // epilogue staging
-  p.cw = pick_cw(NT);
+  // low-channel convolutions run the SMALL kernel instantiation (<= 32-channel epilogue chunks, 2 CTAs / SM)
+  const bool small = NT <= 64 && NT % 16 == 0 && (NT <= 32 || NT % 32 == 0);
+  p.cw = small ? std::min(NT, 32) : pick_cw(NT);
   p.n_echunks = NT / p.cw;
   p.mode = e.mode; p.mask = e.mask; p.couple_sign = e.couple_sign;
   const int ow = e.mode == EPI_TC_GATE ? p.cw / 2 : p.cw;            // output channels per chunk
@@ -153,8 +155,11 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (p.w_resident) {
     w_bytes = w_total;
     p.stages_w = 1;
-    p.stages_a = (int)std::min<size_t>(tc::kMaxStages, (kSmemBudget - w_bytes - e_bytes) / p.a_stage_bytes);
-    p.stages_a = std::min(p.stages_a, std::max(3, 3 * a_per_tile));
+    // SMALL kernels: stay within half an SM's shared memory when >= 3 A stages still fit, so two CTAs co-reside
+    const size_t half_budget = 110 * 1024;
+    const size_t budget = (small && w_bytes + e_bytes + 3 * (size_t)p.a_stage_bytes <= half_budget) ? half_budget : kSmemBudget;
+    p.stages_a = (int)std::min<size_t>(tc::kMaxStages, (budget - w_bytes - e_bytes) / p.a_stage_bytes);
+    p.stages_a = std::min(p.stages_a, std::max(4, 3 * a_per_tile));
   } else if (p.halo_mode) {
     p.stages_a = 2;
     if (2 * (size_t)p.a_stage_bytes + e_bytes + 2 * (size_t)p.w_stage_bytes > kSmemBudget)
@@ -197,11 +202,19 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act, cout_eff, ow));
   static bool attr_set = false;
   if (!attr_set) {
-    VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
-  const int grid = std::min(p.total_tiles, P->sm_count);
-  conv_tc_kernel<<<grid, tc::kThreads, smem, st>>>(tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
+  if (small) {
+    // two CTAs per SM when two copies of the shared-memory carve-up (+1 KB reserved each) and of the TMEM fit
+    const bool two = 2 * (smem + 1024) <= 228 * 1024 && 2 * p.tmem_cols <= 512;
+    const int grid = std::min(p.total_tiles, (two ? 2 : 1) * P->sm_count);
+    conv_tc_kernel<true><<<grid, tc::kThreads, smem, st>>>(tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
+  } else {
+    const int grid = std::min(p.total_tiles, P->sm_count);
+    conv_tc_kernel<false><<<grid, tc::kThreads, smem, st>>>(tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
+  }
   VSG_LAUNCH_CHECK("conv_tc_kernel");
   return VSG_OK;
 }
