@@ -179,8 +179,10 @@ int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias,
                           int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t flags,
                           int32_t device);
 
-/* Process-wide defaults of the tensor-core convolutions: activation-operand feeding mode, resident weights. */
-int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident);
+/* Process-wide tuning defaults of the tensor-core path: activation-operand feeding mode, resident weights, and the
+ * L2-resident batch tiling of the decoder (target MB of one intermediate tensor per sub-batch, 0 = no tiling, <0 =
+ * keep; minimum tiles per launch, <=0 = keep). */
+int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t l2_tensor_mb, int32_t min_tiles);
 
 #ifdef __cplusplus
 }

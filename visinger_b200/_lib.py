@@ -153,7 +153,7 @@ def lib() -> ctypes.CDLL:
         L.vsg_debug_conv1d_bf16.argtypes = [vp, vp, vp, vp, vp, ctypes.c_float, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
                                             i32]
         L.vsg_set_tc_options.restype = ctypes.c_int
-        L.vsg_set_tc_options.argtypes = [i32, i32]
+        L.vsg_set_tc_options.argtypes = [i32, i32, i32, i32]
         if L.vsg_abi_version() != 1:
             raise RuntimeError("visinger_b200: ABI version mismatch between _lib.py and the shared library")
         _lib = L
@@ -279,8 +279,9 @@ def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int,
     return (out, raw, act) if want_bf16 else out
 
 
-def set_tc_options(halo_mode: int, w_resident: int = 1) -> None:
-    check(lib().vsg_set_tc_options(int(halo_mode), int(w_resident)), "vsg_set_tc_options")
+def set_tc_options(halo_mode: int = 1, w_resident: int = 1, l2_tensor_mb: int = -1, min_tiles: int = -1) -> None:
+    check(lib().vsg_set_tc_options(int(halo_mode), int(w_resident), int(l2_tensor_mb), int(min_tiles)),
+          "vsg_set_tc_options")
 
 
 def stream_ptr(device: torch.device) -> int:

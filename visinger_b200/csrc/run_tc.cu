@@ -346,10 +346,40 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
   return VSG_OK;
 }
 
+// ---- L2-resident batch tiling --------------------------------------------------------------------------------
+// Un-fused, one stage of the decoder streams 54 tensor passes through memory.  The stage tensors of
+// ONE utterance are small (<= 9.6 MB in bf16), so each upsampling stage is run over sub-batches whose intermediates
+// (x, leaky_relu(x), conv1 output, running resblock sum) stay in the 126 MB L2 between producer and consumer conv;
+// they are overwritten by the next conv pair before they are ever evicted, so they never reach HBM.
+struct SubBatchPlan { int sub[VSG_MAX_UPS]; size_t inter_elems; size_t io_elems; };
+
+int g_l2_tensor_mb = 13;      // target size of one intermediate tensor of a sub-batch
+int g_min_tiles = 592;        // keep >= 4 waves of 148 CTAs per launch when sub-batching
+
+SubBatchPlan plan_sub_batches(const VsgPack* P, int B, int T) {
+  SubBatchPlan pl;
+  pl.inter_elems = 0;
+  pl.io_elems = (size_t)B * P->cfg.dec_upsample_initial_channel * T;
+  long long L = T;
+  for (size_t i = 0; i < P->ups.size(); ++i) {
+    const UpStage& us = P->ups[i];
+    L *= us.rate;
+    const size_t per_utt = (size_t)us.Cout * (size_t)L;            // elements of one stage tensor of one utterance
+    const long long tiles_per_utt = (L + 127) / 128;
+    long long sub = std::max<long long>(1, ((long long)g_l2_tensor_mb << 20) / (long long)(per_utt * 2));
+    if (sub * tiles_per_utt < g_min_tiles) sub = (g_min_tiles + tiles_per_utt - 1) / tiles_per_utt;
+    if (g_l2_tensor_mb <= 0 || sub * 2 > B) sub = B;               // not worth splitting
+    pl.sub[i] = (int)std::min<long long>(sub, B);
+    pl.inter_elems = std::max(pl.inter_elems, per_utt * (size_t)pl.sub[i]);
+    pl.io_elems = std::max(pl.io_elems, per_utt * (size_t)B);
+  }
+  return pl;
+}
+
 size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T) {
-  const size_t E = dec_max_elems(P, B, T);
+  const SubBatchPlan pl = plan_sub_batches(P, B, T);
   return align256((size_t)B * T * P->cfg.dec_initial_channel * 2) + align256((size_t)B * P->cfg.dec_upsample_initial_channel * 4) +
-         8 * align256(E * 2) + 256;
+         2 * align256(pl.io_elems * 2) + 7 * align256(pl.inter_elems * 2) + 512;
 }
 
 // Generator.forward (modules/visinger/decoder.py:40-59) on the tensor-core kernels.
@@ -357,18 +387,19 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
                          cudaStream_t st) {
   const VsgConfig& c = P->cfg;
   const int C0 = c.dec_initial_channel, UIC = c.dec_upsample_initial_channel, NK = c.dec_n_kernels;
-  const size_t E = dec_max_elems(P, B, T);
+  if (!P->conv_pre_tc.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 decoder needs channel counts that are multiples of 16");
+  const SubBatchPlan pl = plan_sub_batches(P, B, T);
   typedef __nv_bfloat16 bf;
   bf* zt = ws.take<bf>((size_t)B * T * C0);
   float* cond = ws.take<float>((size_t)B * UIC);
-  bf* bIn = ws.take<bf>(E);   // leaky_relu'd stage input (what ups / conv_post consume)
-  bf* bU = ws.take<bf>(E);    // upsampled x (residual for the first pair of every resblock)
-  bf* bUA = ws.take<bf>(E);   // leaky_relu(x)
-  bf* bR = ws.take<bf>(E);    // resblock running x
-  bf* bRA = ws.take<bf>(E);   // leaky_relu of it
-  bf* bT = ws.take<bf>(E);    // leaky_relu(conv1 output)  (ResBlock2: ping-pong partner of bR)
-  bf* bTA = ws.take<bf>(E);   // (ResBlock2 only)
-  bf* bS = ws.take<bf>(E);    // running sum over the NK resblocks
+  bf* io[2] = {ws.take<bf>(pl.io_elems), ws.take<bf>(pl.io_elems)};   // leaky_relu'd stage input / output, whole batch
+  bf* bU = ws.take<bf>(pl.inter_elems);    // upsampled x (residual for the first pair of every resblock)
+  bf* bUA = ws.take<bf>(pl.inter_elems);   // leaky_relu(x)
+  bf* bR = ws.take<bf>(pl.inter_elems);    // resblock running x
+  bf* bRA = ws.take<bf>(pl.inter_elems);   // leaky_relu of it
+  bf* bT = ws.take<bf>(pl.inter_elems);    // leaky_relu(conv1 output)  (ResBlock2: ping-pong partner of bR)
+  bf* bTA = ws.take<bf>(pl.inter_elems);   // (ResBlock2 only)
+  bf* bS = ws.take<bf>(pl.inter_elems);    // running sum over the NK resblocks
   int* err = ws.take<int>(1);
   if (ws.overflow) return fail(VSG_ENOMEM, "generator workspace too small: need %zu bytes", ws.off);
   VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
@@ -383,62 +414,71 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
     transpose_to_bf16_kernel<<<grid, block, 0, st>>>(z, zt, C0, T);
     VSG_LAUNCH_CHECK("transpose_to_bf16_kernel");
   }
+  int cur_io = 0;
   {  // x = conv_pre(z) + cond(g); only leaky_relu(x) is ever consumed (decoder.py:41-45)
     EpiTC e;
     e.bias = P->conv_pre_tc.bias;
     if (c.dec_gin > 0) { e.bcond = cond; e.bcond_bs = UIC; }
-    e.out_act = bIn;
+    e.out_act = io[cur_io];
     VSG_TRY(launch_conv_tc(P, P->conv_pre_tc, zt, B, T, -3, 1, T, 1, 0, T, e, opt, err, st));
   }
   int L = T, ch = UIC;
   for (int i = 0; i < c.dec_n_ups; ++i) {
     const UpStage& us = P->ups[i];
-    const int Lout = L * us.rate;
-    for (int r = 0; r < us.rate; ++r) {   // ConvTranspose1d as polyphase convolutions (decoder.py:46)
-      EpiTC e;
-      e.bias = us.phases[r].tc.bias;
-      e.out_raw = bU; e.out_act = bUA;
-      const int Lq = (Lout - r + us.rate - 1) / us.rate;
-      VSG_TRY(launch_conv_tc(P, us.phases[r].tc, bIn, B, L, us.phases[r].in_off0, 1, Lq, us.rate, r, Lout, e, opt, err, st));
-    }
+    const int Lin = L, Cin = ch, Lout = L * us.rate;
     ch = us.Cout; L = Lout;
-    for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
-      const ResBlockPack& rb = us.blocks[j];
-      const int nd = (int)rb.dilations.size(), k = rb.kernel;
-      const bf* cur = bU; const bf* curA = bUA;
-      for (int q = 0; q < nd; ++q) {
-        const bool last = (q == nd - 1);
-        const int d = rb.dilations[q];
-        EpiTC e2;
-        e2.add0 = cur;
-        if (last) {
-          e2.add1 = (j > 0) ? bS : nullptr;
-          if (j == NK - 1) { e2.scale = 1.0f / (float)NK; e2.out_act = bIn; }
-          else e2.out_raw = bS;
-        }
-        if (c.dec_resblock == 1) {        // ResBlock1 (decoder.py:91-104)
-          EpiTC e1;
-          e1.bias = rb.c1_tc[q].bias; e1.out_act = bT;
-          VSG_TRY(launch_conv_tc(P, rb.c1_tc[q], curA, B, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
-          e2.bias = rb.c2_tc[q].bias;
-          if (!last) { e2.out_raw = bR; e2.out_act = bRA; }
-          VSG_TRY(launch_conv_tc(P, rb.c2_tc[q], bT, B, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
-          cur = bR; curA = bRA;
-        } else {                           // ResBlock2 (decoder.py:124-133)
-          e2.bias = rb.c1_tc[q].bias;
-          bf* nr = (cur == bR) ? bT : bR;
-          bf* nra = (cur == bR) ? bTA : bRA;
-          if (!last) { e2.out_raw = nr; e2.out_act = nra; }
-          VSG_TRY(launch_conv_tc(P, rb.c1_tc[q], curA, B, L, -((k * d - d) / 2), d, L, 1, 0, L, e2, opt, err, st));
-          cur = nr; curA = nra;
+    const bf* stage_in = io[cur_io];
+    bf* stage_out = io[cur_io ^ 1];
+    for (int b0 = 0; b0 < B; b0 += pl.sub[i]) {
+      const int nb = std::min(pl.sub[i], B - b0);
+      const bf* xin = stage_in + (size_t)b0 * Lin * Cin;
+      bf* xout = stage_out + (size_t)b0 * L * ch;
+      for (int r = 0; r < us.rate; ++r) {   // ConvTranspose1d as polyphase convolutions (decoder.py:46)
+        EpiTC e;
+        e.bias = us.phases[r].tc.bias;
+        e.out_raw = bU; e.out_act = bUA;
+        const int Lq = (Lout - r + us.rate - 1) / us.rate;
+        VSG_TRY(launch_conv_tc(P, us.phases[r].tc, xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r, Lout, e, opt, err, st));
+      }
+      for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
+        const ResBlockPack& rb = us.blocks[j];
+        const int nd = (int)rb.dilations.size(), k = rb.kernel;
+        const bf* cur = bU; const bf* curA = bUA;
+        for (int q = 0; q < nd; ++q) {
+          const bool last = (q == nd - 1);
+          const int d = rb.dilations[q];
+          EpiTC e2;
+          e2.add0 = cur;
+          if (last) {
+            e2.add1 = (j > 0) ? bS : nullptr;
+            if (j == NK - 1) { e2.scale = 1.0f / (float)NK; e2.out_act = xout; }
+            else e2.out_raw = bS;
+          }
+          if (c.dec_resblock == 1) {        // ResBlock1 (decoder.py:91-104)
+            EpiTC e1;
+            e1.bias = rb.c1_tc[q].bias; e1.out_act = bT;
+            VSG_TRY(launch_conv_tc(P, rb.c1_tc[q], curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
+            e2.bias = rb.c2_tc[q].bias;
+            if (!last) { e2.out_raw = bR; e2.out_act = bRA; }
+            VSG_TRY(launch_conv_tc(P, rb.c2_tc[q], bT, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
+            cur = bR; curA = bRA;
+          } else {                           // ResBlock2 (decoder.py:124-133)
+            e2.bias = rb.c1_tc[q].bias;
+            bf* nr = (cur == bR) ? bT : bR;
+            bf* nra = (cur == bR) ? bTA : bRA;
+            if (!last) { e2.out_raw = nr; e2.out_act = nra; }
+            VSG_TRY(launch_conv_tc(P, rb.c1_tc[q], curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e2, opt, err, st));
+            cur = nr; curA = nra;
+          }
         }
       }
     }
+    cur_io ^= 1;
   }
-  {  // wav = tanh(conv_post(leaky_relu(x)))   (decoder.py:55-57); bIn already holds leaky_relu(x)
+  {  // wav = tanh(conv_post(leaky_relu(x)))   (decoder.py:55-57); the stage output already holds leaky_relu(x)
     dim3 grid((L + 255) / 256, B);
-    conv_post_bf16_kernel<<<grid, 256, (size_t)ch * P->conv_post_k * sizeof(float), st>>>(bIn, P->conv_post_w, wav, ch, L,
-                                                                                           P->conv_post_k);
+    conv_post_bf16_kernel<<<grid, 256, (size_t)ch * P->conv_post_k * sizeof(float), st>>>(io[cur_io], P->conv_post_w, wav,
+                                                                                           ch, L, P->conv_post_k);
     VSG_LAUNCH_CHECK("conv_post_bf16_kernel");
   }
   return VSG_OK;
@@ -494,8 +534,10 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
 }
 
 // Select the default A-operand feeding mode of the tensor-core convolutions (process-wide; tests and tuning).
-extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident) {
+extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t l2_tensor_mb, int32_t min_tiles) {
   g_default_opts.halo_mode = halo_mode;
   g_default_opts.w_resident = w_resident;
+  if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
+  if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;
 }

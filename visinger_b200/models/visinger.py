@@ -85,6 +85,21 @@ class HotPath(PackedModuleMixin, nn.Module):
         self.last_launches = _lib.last_launch_count()
         return wav, z_q
 
+    # -- CUDA-graph replay of the whole path -----------------------------------------------------
+    @torch.no_grad()
+    def graph(self, B: int, T: int, device=None) -> "HotPathGraph":
+        """Capture prior sampling -> flow reverse -> decoder for a fixed (B, T) into one CUDA graph.
+
+        The run calls of the C ABI neither allocate nor synchronise, so the ~300-1200 kernel launches of one
+        pass (more with L2-resident batch tiling) replay from a single cudaGraphLaunch.  Inputs are written into
+        the graph's static buffers (`.mu_p, .logs_p, .noise, .mask, .g`), outputs read from `.wav, .z_q`."""
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        key = (B, T, _lib.precision_code(self.precision), str(dev))
+        cache = self.__dict__.setdefault("_graphs", {})
+        if key not in cache:
+            cache[key] = HotPathGraph(self, B, T, dev)
+        return cache[key]
+
     @torch.no_grad()
     def decode(self, z, g):
         """Generator only, through the shared pack (used by bench.py for the decoder roofline)."""
@@ -104,3 +119,55 @@ class HotPath(PackedModuleMixin, nn.Module):
         _lib.check(rc, "vsg_generator_forward")
         self.last_launches = _lib.last_launch_count()
         return wav
+
+
+class HotPathGraph:
+    """A captured (B, T)-shaped pass of `HotPath`: static input/output/workspace buffers + one torch.cuda.CUDAGraph."""
+
+    def __init__(self, hp: HotPath, B: int, T: int, device: torch.device):
+        C, gin = hp.flow.channels, hp.flow.gin_channels
+        f32 = dict(dtype=torch.float32, device=device)
+        self.mu_p = torch.zeros(B, C, T, **f32)
+        self.logs_p = torch.zeros(B, C, T, **f32)
+        self.noise = torch.zeros(B, C, T, **f32)
+        self.mask = torch.ones(B, 1, T, **f32)
+        self.g = torch.zeros(B, max(gin, 1), 1, **f32)
+        self.wav = torch.empty(B, 1, T * hp.decoder.hop_size, **f32)
+        self.z_q = torch.empty(B, C, T, **f32)
+        pack = hp._pack()
+        prec = _lib.precision_code(hp.precision)
+        self._ws = torch.empty(pack.workspace_bytes(B, T, prec), dtype=torch.uint8, device=device)  # private: pointers are baked
+        self._pack = pack
+        L = _lib.lib()
+
+        def run():
+            rc = L.vsg_infer(pack.handle, self.mu_p.data_ptr(), self.logs_p.data_ptr(), self.noise.data_ptr(),
+                             self.mask.data_ptr(), self.g.data_ptr() if gin else None, self.wav.data_ptr(),
+                             self.z_q.data_ptr(), B, T, prec, self._ws.data_ptr(), self._ws.numel(),
+                             _lib.stream_ptr(device))
+            _lib.check(rc, "vsg_infer")
+
+        with torch.cuda.device(device):
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):      # warm-up outside capture (one-time function attributes, lazy module load)
+                run()
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
+            self.launches = _lib.last_launch_count()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                run()
+
+    def replay(self):
+        self._graph.replay()
+        return self.wav, self.z_q
+
+    def __call__(self, mu_p, logs_p, noise, mask, g=None):
+        self.mu_p.copy_(mu_p, non_blocking=True)
+        self.logs_p.copy_(logs_p, non_blocking=True)
+        self.noise.copy_(noise, non_blocking=True)
+        self.mask.copy_(mask, non_blocking=True)
+        if g is not None:
+            self.g.copy_(g, non_blocking=True)
+        return self.replay()
