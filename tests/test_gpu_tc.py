@@ -31,19 +31,23 @@ def _case(cin, cout, k, dil, B, L):
     return x, w, b, ref, gen
 
 
-@pytest.mark.parametrize("flags", [0, 1, 3], ids=["reload", "halo", "halo+resident"])
+@pytest.mark.parametrize("flags", [0, 1, 3 | (1 << 4), 3 | (2 << 4), 3],
+                         ids=["reload", "halo", "halo+resident,mb1", "halo+resident,mb<=2", "halo+resident,mb<=4"])
 @pytest.mark.parametrize("cin,cout,k,dil,B,L", CASES)
 def test_tc_conv1d_matches_fconv1d(cuda_device, cin, cout, k, dil, B, L, flags):
-    """A-operand feeding modes: per-tap reload, halo (row-shifted UMMA descriptors), halo + resident weights."""
+    """A-operand feeding modes: per-tap reload, halo (row-shifted UMMA descriptors), halo + resident weights, and
+    1 / 2 / 4 blocks of 128 rows per tile (flags bits 4..: cap on blocks per tile)."""
     from visinger_b200 import _lib
     x, w, b, ref, _ = _case(cin, cout, k, dil, B, L)
     got = _lib.debug_conv1d_bf16(x.to(cuda_device).contiguous(), w, b, dil, flags=flags).cpu()
     assert maxabs(got, ref) <= CONV_TOL
 
 
+@pytest.mark.parametrize("mbcap", [1, 2, 4])
 @pytest.mark.parametrize("cin,cout,k,dil,B,L", [(256, 256, 3, 1, 2, 300), (128, 128, 7, 3, 1, 333), (64, 64, 11, 5, 2, 257),
-                                                (32, 32, 7, 1, 2, 1000), (16, 16, 3, 1, 3, 4100), (16, 16, 11, 5, 1, 70)])
-def test_tc_conv1d_fused_epilogue(cuda_device, cin, cout, k, dil, B, L):
+                                                (32, 32, 7, 1, 2, 1000), (16, 16, 3, 1, 3, 4100), (16, 16, 11, 5, 1, 70),
+                                                (64, 64, 3, 1, 2, 513), (32, 32, 11, 5, 1, 511)])
+def test_tc_conv1d_fused_epilogue(cuda_device, cin, cout, k, dil, B, L, mbcap):
     """Residual + running-sum adds (TMA-loaded), scale, and the two bf16 outputs (TMA-stored): what the
     reference does as `x = xt + x`, `xs += ...`, `x = xs / 3`, `F.leaky_relu` (decoder.py:48-54,93-102)."""
     from visinger_b200 import _lib
@@ -52,7 +56,7 @@ def test_tc_conv1d_fused_epilogue(cuda_device, cin, cout, k, dil, B, L):
     add1 = torch.randn(B, L, cout, generator=gen).to(torch.bfloat16)
     want = (ref + add0.double() + add1.double()) / 3.0
     d = cuda_device
-    out, raw, act = _lib.debug_conv1d_bf16(x.to(d).contiguous(), w, b, dil, flags=3, add0=add0.to(d).contiguous(),
+    out, raw, act = _lib.debug_conv1d_bf16(x.to(d).contiguous(), w, b, dil, flags=3 | (mbcap << 4), add0=add0.to(d).contiguous(),
                                            add1=add1.to(d).contiguous(), scale=1.0 / 3.0, want_bf16=True)
     assert maxabs(out.cpu(), want) <= CONV_TOL
     assert maxabs(raw.cpu().double(), want) <= 2e-2          # bf16 rounding of O(1) values

@@ -18,13 +18,16 @@
 // ConvTranspose1d runs as `stride` polyphase launches of the same kernel (out_stride / out_phase).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
-// lane), warps 2..5 = epilogue.  The accumulator is double-buffered in TMEM (2 x N_TILE columns) so the
-// epilogue of tile i overlaps the main loop of tile i+1.
-// Epilogue: each warp owns 32 rows (its TMEM lane quarter) and walks the tile in chunks of `cw` channels:
-// tcgen05.ld -> + bias (+ speaker condition) -> + residual / running resblock sum (TMA-loaded into swizzled
-// shared memory, prefetched n_add_bufs-1 chunks ahead, across tiles) -> x scale -> write the raw value and
-// leaky_relu(value) as bf16 into swizzled staging buffers -> TMA store.  All global traffic of the kernel
-// is bulk TMA: no per-thread global loads or stores on the hot path.
+// lane), warps 2..5 = epilogue.  A CTA tile is `mb` blocks of 128 time steps (mb = 1, 2 or 4) x N_TILE channels:
+// every weight tile feeds mb MMAs (weight traffic / mb) and all per-tile costs (barrier waits, index math,
+// TMA issue, staging synchronisation) are amortised over mb*128 rows -- the low-channel stages are bound by that
+// overhead, not by HBM or tensor throughput.  The accumulator is double-buffered in TMEM (2 x mb x N_TILE
+// columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+// Epilogue, per chunk of `cw` channels: each warp owns the rows of its TMEM lane quarter in every block:
+// tcgen05.ld -> + bias (+ speaker condition) -> + residual / running resblock sum (one CTA-wide TMA load per
+// chunk into swizzled shared memory, prefetched n_add_bufs-1 chunks ahead, across tiles) -> x scale / mask /
+// gate / coupling -> raw value and leaky_relu(value) as bf16 into a CTA-wide swizzled staging tile
+// [mb*128 rows x cw] -> ONE bulk TMA store per output.  All global traffic of the kernel is bulk TMA.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -38,9 +41,10 @@ struct ConvTC {
   int n_cchunks, KC, ktaps, dil, in_off0;
   int Cout, n_tile, n_ntiles, CoutT;   // CoutT: rows per tap in the packed weight matrix
   int out_stride, out_phase;
+  int mb;                       // 128-row blocks per tile
   int m_tiles_per_b, total_tiles;
-  int halo_mode;                // 1: one A box per channel chunk, taps via row-shifted descriptors
-  int a_rows;                   // rows per A box
+  int halo_mode;                // 1: one A tile per channel chunk, taps via row-shifted descriptors
+  int a_box_rows, a_n_boxes;    // the A tile is fetched as a_n_boxes TMA boxes of a_box_rows rows (<= 256 each)
   int w_resident;               // 1: all (chunk, tap) weight tiles are loaded once and stay in shared memory
   int stages_a, stages_w;
   uint32_t a_stage_bytes, w_stage_bytes, a_box_bytes, w_box_bytes;
@@ -48,9 +52,10 @@ struct ConvTC {
   uint32_t tmem_cols;
   uint32_t swizzle_code;        // UMMA layout type: 2 = 128B, 4 = 64B, 6 = 32B
   uint32_t sbo_bytes;           // 8 rows * row bytes
-  // epilogue: per warp, 32 rows x cw channels per chunk, staged in swizzled shared memory, moved by TMA
+  // epilogue: CTA-wide staging tiles of mb*128 rows x cw channels, moved by TMA in boxes of e_box_rows rows
   int cw, n_echunks;
-  uint32_t e_buf_bytes, e_warp_bytes, e_swz_mask;
+  int e_box_rows, e_n_boxes;
+  uint32_t e_buf_bytes, e_swz_mask;
   int n_add_bufs;
   int has_add0, has_add1;       // residual / running resblock sum: same geometry as the output, TMA-loaded
   int has_raw, has_act;         // outputs: value as is / leaky_relu(value), TMA-stored
@@ -245,7 +250,9 @@ constexpr int kMaxCW = 64;
 // barrier slots
 constexpr int kBarAFull = 0, kBarAEmpty = kMaxStages, kBarWFull = 2 * kMaxStages, kBarWEmpty = 3 * kMaxStages;
 constexpr int kBarAccFull = 4 * kMaxStages, kBarAccEmpty = kBarAccFull + 2, kBarAdd = kBarAccEmpty + 2;
-constexpr int kNumBars = kBarAdd + 4 * kMaxAddBufs;
+constexpr int kNumBars = kBarAdd + kMaxAddBufs;
+// named barriers of the 4 epilogue warps (id 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 }  // namespace tc
 
@@ -261,10 +268,11 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
                                                  int lane) {
   using namespace tc;
   constexpr int OW = (MODE == EPI_TC_GATE) ? CW / 2 : CW;   // output channels per chunk
-  const int ew = warp - 2;               // staging-buffer owner index 0..3
+  const bool leader = (warp == 2 && lane == 0);             // issues every epilogue TMA operation of the CTA
   const int quarter = warp & 3;          // tcgen05.ld: warp w may only touch TMEM lanes 32*(w%4) .. +31
   const int n_echunks = p.n_echunks, n_ntiles = p.n_ntiles, m_tiles_per_b = p.m_tiles_per_b, n_tile = p.n_tile;
-  const int n_add_bufs = p.n_add_bufs, total_tiles = p.total_tiles;
+  const int n_add_bufs = p.n_add_bufs, total_tiles = p.total_tiles, mb = p.mb;
+  const int e_box_rows = p.e_box_rows, e_n_boxes = p.e_n_boxes;
   const uint32_t e_buf_bytes = p.e_buf_bytes, swz_in = p.e_swz_mask, swz_out = p.e_out_swz_mask;
   const bool has_add0 = p.has_add0, has_add1 = p.has_add1 && MODE == EPI_TC_LINEAR, has_raw = p.has_raw,
              has_act = p.has_act && MODE == EPI_TC_LINEAR;
@@ -273,36 +281,38 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const float* const bcond = p.bcond;
   const float* const maskp = p.mask;
   int* const error_flag = p.error_flag;
-  const uint32_t e_base = smem_base + p.e_off + (uint32_t)ew * p.e_warp_bytes;
-  const uint32_t add0_b = e_base;
+  // staging carve-up: [add0 x n_add_bufs][add1 x n_add_bufs][raw x 2][act x 2], each e_buf_bytes
+  const uint32_t add0_b = smem_base + p.e_off;
   const uint32_t add1_b = add0_b + (p.has_add0 ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
   const uint32_t raw_b = add1_b + (p.has_add1 ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
   const uint32_t act_b = raw_b + (p.has_raw ? 2u * e_buf_bytes : 0u);
   const bool has_add = has_add0 || has_add1;
   const bool has_out = has_raw || has_act;
-  const uint32_t add_bytes = (uint32_t)((has_add0 ? 1 : 0) + (has_add1 ? 1 : 0)) * 32u * CW * 2u;
-  const uint32_t add_bar0 = bar_base + 8u * (kBarAdd + ew * kMaxAddBufs);
+  const uint32_t add_box_bytes = (uint32_t)e_box_rows * CW * 2u, out_box_bytes = (uint32_t)e_box_rows * OW * 2u;
+  const uint32_t add_bytes = (uint32_t)((has_add0 ? 1 : 0) + (has_add1 ? 1 : 0)) * (uint32_t)e_n_boxes * add_box_bytes;
+  const uint32_t add_bar0 = bar_base + 8u * kBarAdd;
   const uint32_t acc_full0 = bar_base + 8u * kBarAccFull, acc_empty0 = bar_base + 8u * kBarAccEmpty;
 
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int n_items = my_tiles * n_echunks;
 
-  // add-operand prefetch cursor: walks (tile, chunk) items n_add_bufs-1 ahead of the consumer
+  // add-operand prefetch cursor (leader only): walks (tile, chunk) units n_add_bufs-1 ahead of the consumers
   TileIter pf;
   pf.init((int)blockIdx.x, (int)gridDim.x, n_ntiles, m_tiles_per_b);
-  int pf_cc = 0, pf_buf = 0, pf_left = n_items;
-  auto issue_next_add = [&]() {   // lane 0 only
+  int pf_cc = 0, pf_buf = 0, pf_left = my_tiles * n_echunks;
+  auto issue_next_add = [&]() {
     if (pf_left <= 0) return;
-    const int ch = pf.nt * n_tile + pf_cc * CW, row = pf.mt * 128 + quarter * 32;
+    const int ch = pf.nt * n_tile + pf_cc * CW, row = pf.mt * (128 * mb);
     const uint32_t bar = add_bar0 + 8u * pf_buf;
     mbar_expect_tx(bar, add_bytes);
-    if (has_add0) tma_load_3d(add0_b + pf_buf * e_buf_bytes, &tmAdd0, bar, ch, row, pf.b);
-    if (has_add1) tma_load_3d(add1_b + pf_buf * e_buf_bytes, &tmAdd1, bar, ch, row, pf.b);
+    for (int bx = 0; bx < e_n_boxes; ++bx) {
+      if (has_add0) tma_load_3d(add0_b + pf_buf * e_buf_bytes + bx * add_box_bytes, &tmAdd0, bar, ch, row + bx * e_box_rows, pf.b);
+      if (has_add1) tma_load_3d(add1_b + pf_buf * e_buf_bytes + bx * add_box_bytes, &tmAdd1, bar, ch, row + bx * e_box_rows, pf.b);
+    }
     --pf_left;
     if (++pf_buf == n_add_bufs) pf_buf = 0;
     if (++pf_cc == n_echunks) { pf_cc = 0; pf.next(); }
   };
-  if (has_add && lane == 0) {
+  if (has_add && leader) {
     for (int i = 0; i < n_add_bufs - 1; ++i) issue_next_add();
   }
 
@@ -319,154 +329,163 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
     }
   }
 
-  int as = 0, item = 0, add_buf = 0;
+  int as = 0, add_buf = 0;
   uint32_t pacc = 0, add_phase = 0, out_count = 0;
-  const uint32_t row_off_in = (uint32_t)lane * (CW * 2);    // this lane's row inside an add staging buffer
-  const uint32_t row_off_out = (uint32_t)lane * (OW * 2);   // ... inside an output staging buffer
   TileIter it;
   it.init((int)blockIdx.x, (int)gridDim.x, n_ntiles, m_tiles_per_b);
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next()) {
-    const int nt = it.nt, mt = it.mt, b = it.b;
+    const int nt = it.nt, b = it.b;
+    const int tile_row0 = it.mt * (128 * mb);
     mbar_wait(acc_full0 + 8u * as, pacc, error_flag);
     fence_after_sync();
-    const int row0 = mt * 128 + quarter * 32;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * n_tile);
-    float mk = 1.0f;
-    if (maskp) {
-      const int q = row0 + lane;
-      mk = (q < p.Lq) ? __ldg(maskp + (long long)b * p.Lout + q) : 0.f;
-    }
-    for (int cc = 0; cc < n_echunks; ++cc, ++item) {
-      if (has_add && lane == 0) issue_next_add();   // refills the buffer read at item-1 (warp-synced below)
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * mb * n_tile);
+    for (int cc = 0; cc < n_echunks; ++cc) {
+      if (has_add && leader) issue_next_add();   // refills the buffer drained by the previous unit (barrier B below)
       const int ch = nt * n_tile + cc * CW;
-      float v[CW];
-      {
-        uint32_t r[CW];
-#pragma unroll
-        for (int i = 0; i < CW / 16; ++i) tmem_ld16_nowait(taddr + (uint32_t)(cc * CW + i * 16), r + 16 * i);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
-      }
-      if (cc == n_echunks - 1) {   // accumulator drained: hand the TMEM stage back before doing the math
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty0 + 8u * as);
-      }
-      if (bias_hoisted) {
-#pragma unroll
-        for (int i = 0; i < CW; ++i) v[i] += bias_r[i];
-      } else if (bias) {
-#pragma unroll
-        for (int i = 0; i < CW; i += 4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + ch + i));
-          v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
-        }
-      }
-      if (bcond) {
-        const float* bc = bcond + (long long)b * p.bcond_bs + ch;
-#pragma unroll
-        for (int i = 0; i < CW; i += 4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(bc + i));
-          v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
-        }
-      }
-      if (MODE == EPI_TC_COUPLE) {
-#pragma unroll
-        for (int i = 0; i < CW; ++i) v[i] *= mk;     // m = post(h) * mask
-      }
+      const int och = (MODE == EPI_TC_GATE) ? ch / 2 : ch;
       if (has_add) {
         mbar_wait(add_bar0 + 8u * add_buf, (add_phase >> add_buf) & 1u, error_flag);
         add_phase ^= 1u << add_buf;
-        if (has_add0) {
-          const uint32_t base = add0_b + add_buf * e_buf_bytes;
+      }
+      const uint32_t ob = (out_count & 1u) * e_buf_bytes;
+      if (has_out) {
+        if (leader) bulk_wait_read<1>();   // the store that last used this staging buffer (2 units ago) has drained
+        epi_bar_sync(1);                   // barrier A: staging buffer free
+      }
+      for (int bi = 0; bi < mb; ++bi) {
+        const int srow = bi * 128 + quarter * 32 + lane;      // row inside the staging tile
+        const int q = tile_row0 + srow;
+        float v[CW];
+        {
+          uint32_t r[CW];
+          const uint32_t taddr = taddr0 + (uint32_t)(bi * n_tile + cc * CW);
 #pragma unroll
-          for (int c = 0; c < CW / 8; ++c) {
-            float f[8];
-            unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
+          for (int i = 0; i < CW / 16; ++i) tmem_ld16_nowait(taddr + (uint32_t)(i * 16), r + 16 * i);
+          tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (MODE == EPI_TC_COUPLE) v[8 * c + i] = p.couple_sign < 0 ? (f[i] - v[8 * c + i]) * mk : v[8 * c + i] + f[i] * mk;
-              else v[8 * c + i] += f[i];
+          for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        if (cc == n_echunks - 1 && bi == mb - 1) {   // accumulator drained: hand the TMEM stage back first
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty0 + 8u * as);
+        }
+        float mk = 1.0f;
+        if (maskp) mk = (q < p.Lq) ? __ldg(maskp + (long long)b * p.Lout + q) : 0.f;
+        if (bias_hoisted) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] += bias_r[i];
+        } else if (bias) {
+#pragma unroll
+          for (int i = 0; i < CW; i += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + ch + i));
+            v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+          }
+        }
+        if (bcond) {
+          const float* bc = bcond + (long long)b * p.bcond_bs + ch;
+#pragma unroll
+          for (int i = 0; i < CW; i += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bc + i));
+            v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+          }
+        }
+        if (MODE == EPI_TC_COUPLE) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] *= mk;     // m = post(h) * mask
+        }
+        if (has_add) {
+          const uint32_t row_off_in = (uint32_t)srow * (CW * 2);
+          if (has_add0) {
+            const uint32_t base = add0_b + add_buf * e_buf_bytes;
+#pragma unroll
+            for (int c = 0; c < CW / 8; ++c) {
+              float f[8];
+              unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (MODE == EPI_TC_COUPLE) v[8 * c + i] = p.couple_sign < 0 ? (f[i] - v[8 * c + i]) * mk : v[8 * c + i] + f[i] * mk;
+                else v[8 * c + i] += f[i];
+              }
+            }
+          }
+          if (has_add1) {
+            const uint32_t base = add1_b + add_buf * e_buf_bytes;
+#pragma unroll
+            for (int c = 0; c < CW / 8; ++c) {
+              float f[8];
+              unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 * c + i] += f[i];
             }
           }
         }
-        if (has_add1) {
-          const uint32_t base = add1_b + add_buf * e_buf_bytes;
+        if (MODE == EPI_TC_LINEAR) {
+          if (scale != 1.0f) {
 #pragma unroll
-          for (int c = 0; c < CW / 8; ++c) {
-            float f[8];
-            unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
+            for (int i = 0; i < CW; ++i) v[i] *= scale;
+          }
+          if (maskp) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * c + i] += f[i];
+            for (int i = 0; i < CW; ++i) v[i] *= mk;
           }
         }
-        if (++add_buf == n_add_bufs) add_buf = 0;
-      }
-      if (MODE == EPI_TC_LINEAR) {
-        if (scale != 1.0f) {
+        if (MODE == EPI_TC_GATE) {
 #pragma unroll
-          for (int i = 0; i < CW; ++i) v[i] *= scale;
+          for (int c = 0; c < CW / 2; ++c) {
+            const float t = tanh_fast(v[2 * c]);
+            const float sg = 0.5f * tanh_fast(0.5f * v[2 * c + 1]) + 0.5f;   // sigmoid(x) = (1 + tanh(x/2)) / 2
+            v[c] = t * sg;
+          }
         }
-        if (maskp) {
+        if (p.out_f32) {   // debug / parity hook only: plain per-thread stores
+          const int n = q * p.out_stride + p.out_phase;
+          const int oc_total = (MODE == EPI_TC_GATE) ? p.Cout / 2 : p.Cout;
+          if (q < p.Lq && n < p.Lout && och < oc_total) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((long long)b * p.Lout + n) * oc_total + och);
 #pragma unroll
-          for (int i = 0; i < CW; ++i) v[i] *= mk;
+            for (int i = 0; i < OW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+        if (has_out) {
+          const uint32_t row_off_out = (uint32_t)srow * (OW * 2);
+          if (has_raw) {
+#pragma unroll
+            for (int c = 0; c < OW / 8; ++c) {
+              const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                                         pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+              sts128(raw_b + ob + swz(row_off_out + c * 16, swz_out), u);
+            }
+          }
+          if (has_act) {
+#pragma unroll
+            for (int i = 0; i < OW; ++i) v[i] = fmaxf(v[i], v[i] * slope);   // leaky_relu, 0 < slope < 1
+#pragma unroll
+            for (int c = 0; c < OW / 8; ++c) {
+              const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                                         pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+              sts128(act_b + ob + swz(row_off_out + c * 16, swz_out), u);
+            }
+          }
         }
       }
-      if (MODE == EPI_TC_GATE) {
-#pragma unroll
-        for (int c = 0; c < CW / 2; ++c) {
-          const float t = tanh_fast(v[2 * c]);
-          const float sg = 0.5f * tanh_fast(0.5f * v[2 * c + 1]) + 0.5f;   // sigmoid(x) = (1 + tanh(x/2)) / 2
-          v[c] = t * sg;
-        }
-      }
-      const int och = (MODE == EPI_TC_GATE) ? ch / 2 : ch;
-      if (p.out_f32) {   // debug / parity hook only: plain per-thread stores
-        const int q = row0 + lane, n = q * p.out_stride + p.out_phase;
-        const int oc_total = (MODE == EPI_TC_GATE) ? p.Cout / 2 : p.Cout;
-        if (q < p.Lq && n < p.Lout && och < oc_total) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((long long)b * p.Lout + n) * oc_total + och);
-#pragma unroll
-          for (int i = 0; i < OW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-      }
+      if (has_out) fence_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
+      epi_bar_sync(2);                     // barrier B: staging tile complete; add buffer fully consumed
+      if (has_add) { if (++add_buf == n_add_bufs) add_buf = 0; }
       if (has_out) {
-        const uint32_t ob = (out_count & 1u) * e_buf_bytes;
-        if (lane == 0) bulk_wait_read<1>();   // the store that last used this buffer (2 groups ago) has drained
-        __syncwarp();
-        if (has_raw) {
-#pragma unroll
-          for (int c = 0; c < OW / 8; ++c) {
-            const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
-                                       pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
-            sts128(raw_b + ob + swz(row_off_out + c * 16, swz_out), u);
+        if (leader) {
+          for (int bx = 0; bx < e_n_boxes; ++bx) {
+            if (has_raw) tma_store_3d(&tmRaw, raw_b + ob + bx * out_box_bytes, och, tile_row0 + bx * e_box_rows, b);
+            if (has_act) tma_store_3d(&tmAct, act_b + ob + bx * out_box_bytes, och, tile_row0 + bx * e_box_rows, b);
           }
-        }
-        if (has_act) {
-#pragma unroll
-          for (int i = 0; i < OW; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
-#pragma unroll
-          for (int c = 0; c < OW / 8; ++c) {
-            const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
-                                       pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
-            sts128(act_b + ob + swz(row_off_out + c * 16, swz_out), u);
-          }
-        }
-        fence_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
-        __syncwarp();
-        if (lane == 0) {
-          if (has_raw) tma_store_3d(&tmRaw, raw_b + ob, och, row0, b);
-          if (has_act) tma_store_3d(&tmAct, act_b + ob, och, row0, b);
           bulk_commit();
         }
         ++out_count;
       }
-      __syncwarp();   // every lane is done with this item's add buffer before lane 0 refills it
     }
     if (++as == 2) { as = 0; pacc ^= 1; }
   }
-  if (lane == 0) bulk_wait_all();
+  if (leader) bulk_wait_all();
 }
 
 // The MMA issuer runs on ONE thread, so its instruction count per tcgen05.mma is the issue-rate limit for
@@ -477,7 +496,7 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
                                                  uint32_t tmem_base) {
   using namespace tc;
   const int total_tiles = p.total_tiles, n_cchunks = p.n_cchunks, ktaps = p.ktaps, stages_a = p.stages_a,
-            stages_w = p.stages_w, n_tile = p.n_tile;
+            stages_w = p.stages_w, n_tile = p.n_tile, mb = p.mb;
   int* const error_flag = p.error_flag;
   const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_tile);
   // descriptor words: hi = SBO | version | layout (constant), lo = LBO(1) << 16 | (address >> 4)
@@ -486,6 +505,7 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
   const uint32_t a_lo0 = (a_base >> 4), w_lo0 = (w_base >> 4);
   const uint32_t a_stage16 = p.a_stage_bytes >> 4, w_stage16 = p.w_stage_bytes >> 4;
   const uint32_t tap_step16 = HALO ? (uint32_t)(p.dil * p.KC * 2) >> 4 : 0u;
+  const uint32_t blk_step16 = (uint32_t)(128 * p.KC * 2) >> 4;     // one 128-row block further down the A tile
   const uint32_t bar_a_full = bar_base + 8u * kBarAFull, bar_a_empty = bar_base + 8u * kBarAEmpty;
   const uint32_t bar_w_full = bar_base + 8u * kBarWFull, bar_w_empty = bar_base + 8u * kBarWEmpty;
   const uint32_t bar_acc_full = bar_base + 8u * kBarAccFull, bar_acc_empty = bar_base + 8u * kBarAccEmpty;
@@ -497,8 +517,7 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     mbar_wait(bar_acc_empty + 8u * as, pacc ^ 1, error_flag);
     fence_after_sync();
-    const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
-    uint32_t accumulate = 0;
+    const uint32_t d_tmem0 = tmem_base + (uint32_t)(as * mb * n_tile);
     uint32_t w_res16 = w_lo0;   // RESIDENT: walks the (chunk, tap) tiles in order
     for (int c = 0; c < n_cchunks; ++c) {
       if (HALO) { mbar_wait(bar_a_full + 8u * sa, pa, error_flag); fence_after_sync(); }
@@ -512,12 +531,17 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
         if (RESIDENT) { w16 = w_res16; w_res16 += w_stage16; }
         else { mbar_wait(bar_w_full + 8u * sw, pw, error_flag); w16 = w_lo0 + (uint32_t)sw * w_stage16; }
         if (!HALO || !RESIDENT) fence_after_sync();
+        const uint32_t accumulate = (c | j) ? 1u : 0u;
+        uint32_t ab16 = a16, d_tmem = d_tmem0;
+        for (int bi = 0; bi < mb; ++bi) {        // every weight tile feeds mb MMAs
 #pragma unroll
-        for (int kk = 0; kk < KK; ++kk) {
-          // HALO: the row-shifted start address keeps base_offset = 0 -- the UMMA unit applies the swizzle
-          // XOR to absolute shared-memory address bits (verified on B200, tools/tc_probe.py).
-          umma_bf16(d_tmem, mk(a16 + 2u * kk), mk(w16 + 2u * kk), idesc, accumulate);
-          accumulate = 1;
+          for (int kk = 0; kk < KK; ++kk) {
+            // HALO: the row-shifted start address keeps base_offset = 0 -- the UMMA unit applies the swizzle
+            // XOR to absolute shared-memory address bits (verified on B200, tools/tc_probe.py).
+            umma_bf16(d_tmem, mk(ab16 + 2u * kk), mk(w16 + 2u * kk), idesc, (kk > 0) ? 1u : accumulate);
+          }
+          ab16 += blk_step16;
+          d_tmem += (uint32_t)n_tile;
         }
         if (HALO) a16 += tap_step16;
         if (!RESIDENT) {
@@ -575,7 +599,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
-    for (int s = 0; s < 4 * kMaxAddBufs; ++s) mbar_init(bar_base + 8u * (kBarAdd + s), 1);
+    for (int s = 0; s < kMaxAddBufs; ++s) mbar_init(bar_base + 8u * (kBarAdd + s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -599,17 +623,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       it.init((int)blockIdx.x, (int)gridDim.x, p.n_ntiles, p.m_tiles_per_b);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it.next()) {
         const int nt = it.nt, mt = it.mt, b = it.b;
-        const int row0 = mt * 128 + p.in_off0;
+        const int row0 = mt * (128 * p.mb) + p.in_off0;
         for (int c = 0; c < p.n_cchunks; ++c) {
           if (p.halo_mode) {
             mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);
-            mbar_expect_tx(a_full(sa), p.a_box_bytes);
-            tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), c * p.KC, row0, b);
+            mbar_expect_tx(a_full(sa), (uint32_t)p.a_n_boxes * p.a_box_bytes);
+            for (int bx = 0; bx < p.a_n_boxes; ++bx)
+              tma_load_3d(a_base + sa * p.a_stage_bytes + bx * p.a_box_bytes, &tmA, a_full(sa), c * p.KC,
+                          row0 + bx * p.a_box_rows, b);
             if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
             if (p.w_resident) continue;
           }
           for (int j = 0; j < p.ktaps; ++j) {
-            if (!p.halo_mode) {
+            if (!p.halo_mode) {   // RELOAD mode: mb == 1, one 128-row box per (chunk, tap)
               mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);
               mbar_expect_tx(a_full(sa), p.a_box_bytes);
               tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), c * p.KC, row0 + j * p.dil, b);

@@ -99,7 +99,7 @@ struct EpiTC {
 
 // HALO mode verified on B200 (tools/tc_probe.py): the UMMA unit applies the swizzle XOR to absolute
 // shared-memory address bits, so a row-shifted start address needs base_offset = 0.
-struct TCOptions { int halo_mode = 1; int w_resident = 1; };
+struct TCOptions { int halo_mode = 1; int w_resident = 1; int max_mb = 4; };
 
 TCOptions g_default_opts;
 
@@ -114,72 +114,91 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
                                                  "(conv %d -> %d)", w.Cin, w.Cout);
   if (Lq <= 0 || B <= 0) return VSG_OK;
   const int KC = pick_kc(w.Cin), NT = pick_ntile(w.Cout);
-  ConvTC p;
-  memset(&p, 0, sizeof(p));
-  p.B = B; p.Lq = Lq; p.Lout = Lout;
-  p.KC = KC; p.n_cchunks = w.Cin / KC; p.ktaps = w.ktaps; p.dil = dil; p.in_off0 = in_off0;
-  p.Cout = w.Cout; p.n_tile = NT; p.n_ntiles = w.Cout / NT; p.CoutT = w.CoutT;
-  p.out_stride = out_stride; p.out_phase = out_phase;
-  p.m_tiles_per_b = (Lq + 127) / 128;
-  p.total_tiles = p.m_tiles_per_b * p.n_ntiles * B;
   const int halo = (w.ktaps - 1) * dil;
-  p.halo_mode = (opt.halo_mode && w.ktaps > 1 && 128 + halo <= 256) ? 1 : 0;
-  p.a_rows = p.halo_mode ? 128 + halo : 128;
-  p.a_box_bytes = (uint32_t)p.a_rows * KC * 2;
-  p.w_box_bytes = (uint32_t)NT * KC * 2;
-  p.a_stage_bytes = (p.a_box_bytes + 1023u) & ~1023u;
-  p.w_stage_bytes = (p.w_box_bytes + 1023u) & ~1023u;
-  // epilogue staging
+  const bool halo_ok = opt.halo_mode && 128 + halo <= 256;
   // low-channel convolutions run the SMALL kernel instantiation (<= 32-channel epilogue chunks, 2 CTAs / SM)
-  const bool small = NT <= 64 && NT % 16 == 0 && (NT <= 32 || NT % 32 == 0);
-  p.cw = small ? std::min(NT, 32) : pick_cw(NT);
-  p.n_echunks = NT / p.cw;
-  p.mode = e.mode; p.mask = e.mask; p.couple_sign = e.couple_sign;
-  const int ow = e.mode == EPI_TC_GATE ? p.cw / 2 : p.cw;            // output channels per chunk
+  const bool small = NT <= 64 && (NT <= 32 || NT % 32 == 0);
+  const int cw = small ? std::min(NT, 32) : pick_cw(NT);
+  const int ow = e.mode == EPI_TC_GATE ? cw / 2 : cw;                // output channels per chunk
   const int cout_eff = e.mode == EPI_TC_GATE ? w.Cout / 2 : w.Cout;  // channels of the add / out tensors
   const int ld = e.ld ? e.ld : cout_eff;
+  const int n_adds = (e.add0 ? 1 : 0) + (e.add1 ? 1 : 0), n_outs = (e.out_raw ? 1 : 0) + (e.out_act ? 1 : 0);
+  const size_t half_budget = 110 * 1024;
+
+  // Plan the tile: try mb = 4, 2, 1 blocks of 128 rows; prefer the largest that lets two CTAs share an SM (small
+  // kernels), else the largest that fits at all.
+  ConvTC p;
+  auto plan = [&](int mb, size_t budget, ConvTC* out) -> bool {
+    ConvTC q;
+    memset(&q, 0, sizeof(q));
+    if (mb > 1 && !halo_ok) return false;
+    if (2 * mb * NT > 512) return false;
+    if (mb > 1 && Lq < 128 * mb) return false;
+    q.mb = mb;
+    q.KC = KC; q.n_cchunks = w.Cin / KC; q.ktaps = w.ktaps; q.dil = dil; q.in_off0 = in_off0;
+    q.Cout = w.Cout; q.n_tile = NT; q.n_ntiles = w.Cout / NT; q.CoutT = w.CoutT;
+    q.halo_mode = (halo_ok && (w.ktaps > 1 || mb > 1)) ? 1 : 0;
+    const int rows = q.halo_mode ? 128 * mb + halo : 128;
+    q.a_n_boxes = (rows + 255) / 256;
+    q.a_box_rows = (((rows + q.a_n_boxes - 1) / q.a_n_boxes) + 7) & ~7;
+    q.a_box_bytes = (uint32_t)q.a_box_rows * KC * 2;
+    q.a_stage_bytes = ((uint32_t)q.a_n_boxes * q.a_box_bytes + 1023u) & ~1023u;
+    q.w_box_bytes = (uint32_t)NT * KC * 2;
+    q.w_stage_bytes = (q.w_box_bytes + 1023u) & ~1023u;
+    q.cw = cw; q.n_echunks = NT / cw;
+    q.e_box_rows = std::min(128 * mb, 256);
+    q.e_n_boxes = 128 * mb / q.e_box_rows;
+    q.e_buf_bytes = (uint32_t)((128 * mb * cw * 2 + 1023) & ~1023);
+    q.n_add_bufs = 2 + (cw <= 32 && mb <= 2 ? 1 : 0);
+    const size_t e_bytes = ((size_t)n_adds * q.n_add_bufs + (size_t)n_outs * 2) * q.e_buf_bytes;
+    const size_t w_total = (size_t)q.n_cchunks * w.ktaps * q.w_stage_bytes;
+    const int a_per_tile = q.halo_mode ? q.n_cchunks : q.n_cchunks * w.ktaps;
+    size_t w_bytes;
+    q.w_resident = (opt.w_resident && q.n_ntiles == 1 && w_total <= 112 * 1024 &&
+                    w_total + e_bytes + 2 * (size_t)q.a_stage_bytes <= budget) ? 1 : 0;
+    if (q.w_resident) {
+      w_bytes = w_total;
+      q.stages_w = 1;
+      q.stages_a = (int)std::min<size_t>(tc::kMaxStages, (budget - w_bytes - e_bytes) / q.a_stage_bytes);
+      q.stages_a = std::min(q.stages_a, std::max(mb >= 2 ? 3 : 4, 3 * a_per_tile));
+    } else if (q.halo_mode) {
+      q.stages_a = 2;
+      if (2 * (size_t)q.a_stage_bytes + e_bytes + 2 * (size_t)q.w_stage_bytes > budget) return false;
+      q.stages_w = (int)std::min<size_t>(tc::kMaxStages, (budget - e_bytes - 2 * q.a_stage_bytes) / q.w_stage_bytes);
+      w_bytes = (size_t)q.stages_w * q.w_stage_bytes;
+    } else {
+      const size_t per = (size_t)q.a_stage_bytes + q.w_stage_bytes;
+      if (e_bytes + 2 * per > budget) return false;
+      q.stages_a = q.stages_w = (int)std::min<size_t>(tc::kMaxStages, (budget - e_bytes) / per);
+      w_bytes = (size_t)q.stages_w * q.w_stage_bytes;
+    }
+    if (q.stages_a < 2) return false;
+    q.w_off = (uint32_t)(q.stages_a * q.a_stage_bytes);
+    q.e_off = q.w_off + (uint32_t)w_bytes;
+    q.bar_off = q.e_off + (uint32_t)e_bytes;
+    *out = q;
+    return true;
+  };
+  bool planned = false;
+  const int mb_max = opt.max_mb;
+  if (small)
+    for (int mb = std::min(4, mb_max); mb >= 1 && !planned; mb >>= 1)
+      if (2 * mb * NT <= 256) planned = plan(mb, half_budget, &p);      // two CTAs per SM: half the smem and TMEM each
+  for (int mb = std::min(NT <= 128 ? (small ? 4 : 2) : 1, mb_max); mb >= 1 && !planned; mb >>= 1) planned = plan(mb, kSmemBudget, &p);
+  if (!planned) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
+  p.B = B; p.Lq = Lq; p.Lout = Lout;
+  p.out_stride = out_stride; p.out_phase = out_phase;
+  p.m_tiles_per_b = (Lq + 128 * p.mb - 1) / (128 * p.mb);
+  p.total_tiles = p.m_tiles_per_b * p.n_ntiles * B;
+  p.e_swz_mask = cw >= 64 ? 7u : cw >= 32 ? 3u : 1u;
   p.e_out_swz_mask = ow >= 64 ? 7u : ow >= 32 ? 3u : ow >= 16 ? 1u : 0u;
-  p.e_buf_bytes = (uint32_t)((32 * p.cw * 2 + 1023) & ~1023);
-  p.e_swz_mask = p.cw == 64 ? 7u : p.cw == 32 ? 3u : 1u;
+  p.mode = e.mode; p.mask = e.mask; p.couple_sign = e.couple_sign;
   p.has_add0 = e.add0 != nullptr; p.has_add1 = e.add1 != nullptr;
   p.has_raw = e.out_raw != nullptr; p.has_act = e.out_act != nullptr;
-  p.n_add_bufs = p.cw == 64 ? 2 : p.cw == 32 ? 3 : 4;
-  p.e_warp_bytes = (uint32_t)((p.has_add0 + p.has_add1) * p.n_add_bufs + (p.has_raw + p.has_act) * 2) * p.e_buf_bytes;
-  const size_t e_bytes = 4 * (size_t)p.e_warp_bytes;
-  // operand rings
-  const size_t w_total = (size_t)p.n_cchunks * w.ktaps * p.w_stage_bytes;
-  const int a_per_tile = p.halo_mode ? p.n_cchunks : p.n_cchunks * w.ktaps;
-  p.w_resident = (opt.w_resident && p.n_ntiles == 1 && w_total <= 112 * 1024 &&
-                  w_total + e_bytes + 3 * (size_t)p.a_stage_bytes <= kSmemBudget) ? 1 : 0;
-  size_t w_bytes;
-  if (p.w_resident) {
-    w_bytes = w_total;
-    p.stages_w = 1;
-    // SMALL kernels: stay within half an SM's shared memory when >= 3 A stages still fit, so two CTAs co-reside
-    const size_t half_budget = 110 * 1024;
-    const size_t budget = (small && w_bytes + e_bytes + 3 * (size_t)p.a_stage_bytes <= half_budget) ? half_budget : kSmemBudget;
-    p.stages_a = (int)std::min<size_t>(tc::kMaxStages, (budget - w_bytes - e_bytes) / p.a_stage_bytes);
-    p.stages_a = std::min(p.stages_a, std::max(4, 3 * a_per_tile));
-  } else if (p.halo_mode) {
-    p.stages_a = 2;
-    if (2 * (size_t)p.a_stage_bytes + e_bytes + 2 * (size_t)p.w_stage_bytes > kSmemBudget)
-      return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
-    p.stages_w = (int)std::min<size_t>(tc::kMaxStages, (kSmemBudget - e_bytes - 2 * p.a_stage_bytes) / p.w_stage_bytes);
-    w_bytes = (size_t)p.stages_w * p.w_stage_bytes;
-  } else {
-    const size_t per = (size_t)p.a_stage_bytes + p.w_stage_bytes;
-    if (e_bytes + 2 * per > kSmemBudget) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
-    p.stages_a = p.stages_w = (int)std::min<size_t>(tc::kMaxStages, (kSmemBudget - e_bytes) / per);
-    w_bytes = (size_t)p.stages_w * p.w_stage_bytes;
-  }
-  if (p.stages_a < 2) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
-  p.w_off = (uint32_t)(p.stages_a * p.a_stage_bytes);
-  p.e_off = p.w_off + (uint32_t)w_bytes;
-  p.bar_off = p.e_off + (uint32_t)e_bytes;
   const size_t smem = 1024 + (size_t)p.bar_off + 8 * tc::kNumBars + 64;
   if (smem > kSmemMax) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory (%zu B)", smem);
   p.tmem_cols = 32;
-  while (p.tmem_cols < (uint32_t)(2 * NT)) p.tmem_cols <<= 1;
+  while (p.tmem_cols < (uint32_t)(2 * p.mb * NT)) p.tmem_cols <<= 1;
   p.swizzle_code = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
   p.sbo_bytes = 8u * KC * 2u;
   p.bias = e.bias; p.bcond = e.bcond; p.bcond_bs = e.bcond_bs;
@@ -189,11 +208,11 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
 
   CUtensorMap tmA, tmAdd0, tmAdd1, tmRaw, tmAct;
   VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.Cin, (uint64_t)Lin, (uint64_t)B, (uint64_t)x_ld, (uint64_t)Lin * x_ld,
-                    (uint32_t)KC, (uint32_t)p.a_rows, KC));
+                    (uint32_t)KC, (uint32_t)p.a_box_rows, KC));
   // epilogue tensors: rows are the q positions of this (poly)phase: row stride out_stride*ld, base shifted by phase
   auto emap = [&](CUtensorMap* m, const __nv_bfloat16* base, int width, int box_c) -> int {
     return encode_3d(m, base + (size_t)out_phase * ld, (uint64_t)width, (uint64_t)Lq, (uint64_t)B,
-                     (uint64_t)out_stride * ld, (uint64_t)Lout * ld, (uint32_t)box_c, 32u, box_c);
+                     (uint64_t)out_stride * ld, (uint64_t)Lout * ld, (uint32_t)box_c, (uint32_t)p.e_box_rows, box_c);
   };
   tmAdd0 = tmAdd1 = tmRaw = tmAct = tmA;
   if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0, w.Cout, p.cw));
@@ -353,7 +372,9 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
 // they are overwritten by the next conv pair before they are ever evicted, so they never reach HBM.
 struct SubBatchPlan { int sub[VSG_MAX_UPS]; size_t inter_elems; size_t io_elems; };
 
-int g_l2_tensor_mb = 13;      // target size of one intermediate tensor of a sub-batch
+int g_l2_tensor_mb = 0;       // target size of one intermediate tensor of a sub-batch; 0 = off.  Measured on B200
+                              // (round 1): with one kernel per conv the extra launches cost more than the L2 hits save
+                              // (11.4 ms -> 16.0 ms per B16xT1000 step at 13 MB), so it is off until the fused kernels land.
 int g_min_tiles = 592;        // keep >= 4 waves of 148 CTAs per launch when sub-batching
 
 SubBatchPlan plan_sub_batches(const VsgPack* P, int B, int T) {
@@ -521,6 +542,7 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
     TCOptions opt;
     opt.halo_mode = flags & 1;
     opt.w_resident = (flags >> 1) & 1;
+    opt.max_mb = (flags >> 4) ? (flags >> 4) : 4;
     rc = launch_conv_tc(&tmp, wt, (const __nv_bfloat16*)x_bf16, B, L, -((k - 1) * dilation / 2), dilation, L, 1, 0, L, e,
                         opt, err, 0);
     if (rc == VSG_OK) {
@@ -535,8 +557,9 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
 
 // Select the default A-operand feeding mode of the tensor-core convolutions (process-wide; tests and tuning).
 extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t l2_tensor_mb, int32_t min_tiles) {
-  g_default_opts.halo_mode = halo_mode;
+  g_default_opts.halo_mode = halo_mode & 1;
   g_default_opts.w_resident = w_resident;
+  g_default_opts.max_mb = (halo_mode >> 4) ? (halo_mode >> 4) : 4;      // bits 4.. of halo_mode: cap on blocks per tile
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;
