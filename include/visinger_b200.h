@@ -50,8 +50,12 @@ enum {
 enum {
   VSG_PRECISION_FP32 = 0, /* fp32 storage, fp32 FFMA accumulate: the parity mode
                              (waveform max-abs <= 1e-4, flow z <= 1e-5 vs the reference) */
-  VSG_PRECISION_BF16 = 1  /* bf16 operands + storage, fp32 accumulate on tcgen05 tensor
+  VSG_PRECISION_BF16 = 1, /* bf16 operands + storage, fp32 accumulate on tcgen05 tensor
                              cores (TMEM accumulators, TMA-fed): the throughput mode     */
+  VSG_PRECISION_BF16X3 = 2 /* split-bf16 on the same tensor-core kernels: every activation and weight is a
+                             (hi, lo) bf16 pair (~16 mantissa bits), every product three MMAs
+                             (hi*hi + hi*lo + lo*hi), fp32 accumulate.  Decoder within the fp32-mode
+                             waveform tolerance; the flow (z <= 1e-5) keeps the fp32 FFMA kernels    */
 };
 
 #define VSG_MAX_UPS 8
@@ -172,7 +176,8 @@ int32_t vsg_last_launch_count(void);
  *   v = (conv1d(x, w, dilation, padding = (k-1)*dilation/2) + bias + add0 + add1) * scale
  *   out_f32 (device fp32 [B, L, Cout] or NULL) = v; out_raw_bf16 = bf16(v); out_act_bf16 = bf16(leaky_relu(v, 0.1)).
  *   flags bit 0: HALO mode (one activation box per channel chunk, taps through row-shifted UMMA descriptors);
- *   bit 1: keep the weights resident in shared memory.
+ *   bit 1: keep the weights resident in shared memory; bit 2: split-bf16 (x, add0, add1, out_raw, out_act then
+ *   carry two bf16 planes per row: [B, L, 2*C] = [hi | lo]); bits 4..: cap on 128-row blocks per tile (0 = 4).
  */
 int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias, const void* add0_bf16,
                           const void* add1_bf16, float scale, float* out_f32, void* out_raw_bf16, void* out_act_bf16,

@@ -140,3 +140,38 @@ def test_hot_path_bf16_and_fp32(cuda_device):
     rel = float((wav16.cpu().squeeze(1) - wav_ref).norm() / wav_ref.norm())
     print(f"bf16 hot path: wav rel-L2 {rel:.3e}, z max-abs {maxabs(z16.cpu(), z_ref):.3e}")
     assert rel <= 0.15
+
+
+@pytest.mark.parametrize("cin,cout,k,dil,B,L", [(256, 256, 3, 1, 2, 300), (128, 128, 11, 5, 1, 700), (64, 64, 7, 3, 2, 513),
+                                                (32, 32, 11, 1, 1, 1000), (16, 16, 3, 5, 2, 4100), (192, 512, 7, 1, 1, 100)])
+def test_tc_conv1d_split_bf16(cuda_device, cin, cout, k, dil, B, L):
+    """Split-bf16 (bf16x3) mode: fp32 operands carried as (hi, lo) bf16 pairs, three MMAs per product.  Against an
+    fp64 convolution of the UN-rounded fp32 operands the error must be ~1e-5, not the ~4e-3 of plain bf16."""
+    from visinger_b200 import _lib
+    gen = torch.Generator().manual_seed(cin * 3 + cout + k + dil)
+    x = torch.randn(B, L, cin, generator=gen)
+    w = torch.randn(cout, cin, k, generator=gen) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=gen) * 0.1
+    add0 = torch.randn(B, L, cout, generator=gen)
+    ref = F.conv1d(x.transpose(1, 2).double(), w.double(), b.double(), dilation=dil, padding=(k - 1) * dil // 2).transpose(1, 2)
+    want = (ref + add0.double()) * 0.5
+    d = cuda_device
+    out, raw, act = _lib.debug_conv1d_bf16(_lib.split_bf16(x).to(d), w, b, dil, flags=3 | 4,
+                                           add0=_lib.split_bf16(add0).to(d), scale=0.5, want_bf16=True)
+    assert maxabs(out.cpu(), want) <= 5e-5
+    assert maxabs(_lib.merge_bf16(raw.cpu()), want) <= 1e-4
+    assert maxabs(_lib.merge_bf16(act.cpu()), F.leaky_relu(want, 0.1)) <= 1e-4
+
+
+@pytest.mark.parametrize("B,T", [(1, 7), (2, 64)])
+def test_generator_bf16x3_meets_fp32_tolerance(cuda_device, B, T):
+    """The split-bf16 tensor-core decoder must stay inside the fp32-mode waveform tolerance (max-abs <= 1e-4)."""
+    sd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
+    m = build_gen(GEN_FULL, sd, cuda_device, precision="bf16x3")
+    x, _, g = make_inputs(500 + T, B, 192, T, 256)
+    with torch.no_grad():
+        ref = O.generator(sd, x, g)
+    got = m(x.to(cuda_device), g=g.to(cuda_device)).cpu()
+    err = maxabs(got, ref)
+    print(f"bf16x3 generator B={B} T={T}: max-abs {err:.3e}, rel-L2 {float((got - ref).norm() / ref.norm()):.3e}")
+    assert err <= 1e-4

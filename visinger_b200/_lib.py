@@ -30,7 +30,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
-_PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16}
+PRECISION_BF16X3 = 2
+_PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16,
+               "bf16x3": PRECISION_BF16X3}
 
 VSG_MAX_UPS = 8
 VSG_MAX_RESBLOCK_KERNELS = 4
@@ -43,7 +45,7 @@ def precision_code(p) -> int:
     try:
         return _PRECISIONS[str(p).lower()]
     except KeyError:
-        raise ValueError(f"unknown precision {p!r}; use 'fp32' or 'bf16'") from None
+        raise ValueError(f"unknown precision {p!r}; use 'fp32', 'bf16' or 'bf16x3'") from None
 
 
 class VsgConfig(ctypes.Structure):
@@ -260,13 +262,15 @@ def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int,
     require_cuda(x_bld, "x")
     assert x_bld.dtype == torch.bfloat16 and x_bld.is_contiguous()
     B, Lx, Cin = x_bld.shape
+    planes = 2 if (flags & 4) else 1           # split-bf16: [hi | lo] planes per row
+    Cin //= planes
     Cout, _, k = w.shape
     wh = w.detach().to("cpu", torch.float32).contiguous()
     bh = bias.detach().to("cpu", torch.float32).contiguous() if bias is not None else None
     dev = x_bld.device
     out = torch.empty(B, Lx, Cout, dtype=torch.float32, device=dev)
-    raw = torch.zeros(B, Lx, Cout, dtype=torch.bfloat16, device=dev) if want_bf16 else None
-    act = torch.zeros(B, Lx, Cout, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    raw = torch.zeros(B, Lx, planes * Cout, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    act = torch.zeros(B, Lx, planes * Cout, dtype=torch.bfloat16, device=dev) if want_bf16 else None
     for t in (add0, add1):
         assert t is None or (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous())
     torch.cuda.synchronize(dev)
@@ -277,6 +281,19 @@ def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int,
                                      B, Lx, Cin, Cout, k, dilation, flags, dev.index or 0)
     check(rc, "vsg_debug_conv1d_bf16")
     return (out, raw, act) if want_bf16 else out
+
+
+def split_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[..., C] fp32 -> [..., 2C] bf16 planes [hi | lo] with hi = bf16(x), lo = bf16(x - hi)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def merge_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Inverse view of split_bf16: [..., 2C] bf16 planes -> [..., C] fp32 = hi + lo."""
+    C = x.shape[-1] // 2
+    return x[..., :C].float() + x[..., C:].float()
 
 
 def set_tc_options(halo_mode: int = 1, w_resident: int = 1, l2_tensor_mb: int = -1, min_tiles: int = -1) -> None:

@@ -10,7 +10,7 @@ int check_common(const VsgPack* pack, int B, int T, int precision) {
   if (!pack) return fail(VSG_EINVAL, "pack is NULL");
   if (B < 0 || T < 0) return fail(VSG_EINVAL, "negative batch (%d) or length (%d)", B, T);
   if (B > 65535) return fail(VSG_EUNSUPPORTED, "batch %d exceeds 65535", B);
-  if (precision != VSG_PRECISION_FP32 && precision != VSG_PRECISION_BF16)
+  if (precision != VSG_PRECISION_FP32 && precision != VSG_PRECISION_BF16 && precision != VSG_PRECISION_BF16X3)
     return fail(VSG_EINVAL, "unknown precision %d", precision);
   return VSG_OK;
 }
@@ -27,11 +27,11 @@ struct DeviceGuard {
 
 size_t flow_ws(const VsgPack* p, int B, int T, int prec) {
   if (!p->has_flow) return 0;
-  return prec == VSG_PRECISION_FP32 ? flow_ws_bytes_f32(p, B, T) : flow_ws_bytes_tc(p, B, T);
+  return prec == VSG_PRECISION_BF16 ? flow_ws_bytes_tc(p, B, T) : flow_ws_bytes_f32(p, B, T);
 }
 size_t dec_ws(const VsgPack* p, int B, int T, int prec) {
   if (!p->has_dec) return 0;
-  return prec == VSG_PRECISION_FP32 ? dec_ws_bytes_f32(p, B, T) : dec_ws_bytes_tc(p, B, T);
+  return prec == VSG_PRECISION_FP32 ? dec_ws_bytes_f32(p, B, T) : dec_ws_bytes_tc(p, B, T, prec == VSG_PRECISION_BF16X3);
 }
 
 }  // namespace
@@ -64,7 +64,8 @@ extern "C" int vsg_flow_forward(const VsgPack* pack, const float* x, const float
   DeviceGuard dg(pack->device);
   if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
   Workspace ws(workspace, workspace_bytes);
-  if (precision == VSG_PRECISION_FP32)
+  // the flow's 1e-5 tolerance needs full fp32 state: only the plain bf16 mode runs it on the tensor cores
+  if (precision != VSG_PRECISION_BF16)
     return flow_forward_f32(pack, x, mask, g, y, B, T, reverse, ws, (cudaStream_t)stream);
   return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, (cudaStream_t)stream);
 }
@@ -84,7 +85,7 @@ extern "C" int vsg_generator_forward(const VsgPack* pack, const float* z, const 
   Workspace ws(workspace, workspace_bytes);
   if (precision == VSG_PRECISION_FP32)
     return generator_forward_f32(pack, z, g, wav, B, T, ws, (cudaStream_t)stream);
-  return generator_forward_tc(pack, z, g, wav, B, T, ws, (cudaStream_t)stream);
+  return generator_forward_tc(pack, z, g, wav, B, T, ws, (cudaStream_t)stream, precision == VSG_PRECISION_BF16X3);
 }
 
 extern "C" int vsg_infer(const VsgPack* pack, const float* mu_p, const float* logs_p, const float* noise,
@@ -111,7 +112,7 @@ extern "C" int vsg_infer(const VsgPack* pack, const float* mu_p, const float* lo
   // z_p = (mu_p + noise * exp(logs_p)) * mask                       models/visinger.py:107
   VSG_TRY(prior_sample(mu_p, logs_p, noise, mask, z, B, C, T, st));
   // z_q = flow(z_p, mask, g, reverse=True) * mask                    models/visinger.py:109
-  if (precision == VSG_PRECISION_FP32) VSG_TRY(flow_forward_f32(pack, z, mask, g, z, B, T, 1, ws, st));
+  if (precision != VSG_PRECISION_BF16) VSG_TRY(flow_forward_f32(pack, z, mask, g, z, B, T, 1, ws, st));
   else VSG_TRY(flow_forward_tc(pack, z, mask, g, z, B, T, 1, ws, st));
   VSG_TRY(mask_mul(z, mask, z, B, C, T, st));
   if (z_q_out)
@@ -119,7 +120,7 @@ extern "C" int vsg_infer(const VsgPack* pack, const float* mu_p, const float* lo
   // wav = decoder(z_q * mask, g)                                      models/visinger.py:111
   ws.off = mark;   // the flow scratch is dead; the decoder reuses it
   if (precision == VSG_PRECISION_FP32) VSG_TRY(generator_forward_f32(pack, z, g, wav, B, T, ws, st));
-  else VSG_TRY(generator_forward_tc(pack, z, g, wav, B, T, ws, st));
+  else VSG_TRY(generator_forward_tc(pack, z, g, wav, B, T, ws, st, precision == VSG_PRECISION_BF16X3));
   (void)launches;
   return VSG_OK;
 }

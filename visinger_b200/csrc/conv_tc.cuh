@@ -36,10 +36,21 @@
 
 namespace vsg {
 
+constexpr int kMaxAChunks = 16;
+
 struct ConvTC {
   int B, Lq, Lout;              // q positions per utterance, output length
-  int n_cchunks, KC, ktaps, dil, in_off0;
+  int KC, ktaps, dil, in_off0;
+  // K loop: n_achunks activation chunks of KC channels at channel offset a_coff[c]; chunk c is multiplied with
+  // n_wpass[c] weight column blocks at offsets w_coff[c][.] (plain bf16: one pass per chunk; split-bf16 "x3":
+  // the hi chunk meets W_hi and W_lo, the lo chunk meets W_hi -- 3 MMAs per product, ~16 mantissa bits)
+  int n_achunks;
+  int a_coff[kMaxAChunks];
+  int n_wpass[kMaxAChunks];
+  int w_coff[kMaxAChunks][2];
+  int n_wtiles;                 // sum of n_wpass * ktaps: weight tiles per n-tile
   int Cout, n_tile, n_ntiles, CoutT;   // CoutT: rows per tap in the packed weight matrix
+  int n_parts, part_coff;       // epilogue tensors hold n_parts bf16 planes (hi[, lo]) part_coff channels apart
   int out_stride, out_phase;
   int mb;                       // 128-row blocks per tile
   int m_tiles_per_b, total_tiles;
@@ -55,7 +66,7 @@ struct ConvTC {
   // epilogue: CTA-wide staging tiles of mb*128 rows x cw channels, moved by TMA in boxes of e_box_rows rows
   int cw, n_echunks;
   int e_box_rows, e_n_boxes;
-  uint32_t e_buf_bytes, e_swz_mask;
+  uint32_t e_buf_bytes, e_part_bytes, e_swz_mask;
   int n_add_bufs;
   int has_add0, has_add1;       // residual / running resblock sum: same geometry as the output, TMA-loaded
   int has_raw, has_act;         // outputs: value as is / leaky_relu(value), TMA-stored
@@ -256,6 +267,32 @@ __device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0
 
 }  // namespace tc
 
+// Write one row chunk of OW fp32 values into a swizzled bf16 staging tile: one plane (plain bf16) or two planes
+// hi = bf16(v), lo = bf16(v - hi) (split-bf16: the pair carries ~16 mantissa bits).
+template <int OW>
+__device__ __forceinline__ void stage_out(const float* v, uint32_t base, uint32_t row_off, uint32_t swz_mask, int n_parts,
+                                          uint32_t part_bytes) {
+  using namespace tc;
+#pragma unroll
+  for (int c = 0; c < OW / 8; ++c) {
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+    const uint32_t addr = base + swz(row_off + c * 16, swz_mask);
+    sts128(addr, make_uint4(h[0], h[1], h[2], h[3]));
+    if (n_parts == 2) {
+      uint32_t l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float r0 = v[8 * c + 2 * i] - __uint_as_float(h[i] << 16);
+        const float r1 = v[8 * c + 2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
+        l[i] = pack_bf16x2(r0, r1);
+      }
+      sts128(addr + part_bytes, make_uint4(l[0], l[1], l[2], l[3]));
+    }
+  }
+}
+
 // MODE: EPI_TC_LINEAR  v = (acc + bias + bcond + add0 + add1) * scale [* mask]
 //       EPI_TC_GATE    channel pairs (2c, 2c+1) hold the tanh / sigmoid halves (weights packed interleaved):
 //                      out[c] = tanh(a) * sigmoid(s)  -- fused_add_tanh_sigmoid_multiply, encoder.py:206-213;
@@ -273,7 +310,9 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const int n_echunks = p.n_echunks, n_ntiles = p.n_ntiles, m_tiles_per_b = p.m_tiles_per_b, n_tile = p.n_tile;
   const int n_add_bufs = p.n_add_bufs, total_tiles = p.total_tiles, mb = p.mb;
   const int e_box_rows = p.e_box_rows, e_n_boxes = p.e_n_boxes;
+  const int n_parts = p.n_parts, part_coff = p.part_coff;
   const uint32_t e_buf_bytes = p.e_buf_bytes, swz_in = p.e_swz_mask, swz_out = p.e_out_swz_mask;
+  const uint32_t part_bytes = p.e_part_bytes;     // one bf16 plane (hi or lo) of a staging buffer
   const bool has_add0 = p.has_add0, has_add1 = p.has_add1 && MODE == EPI_TC_LINEAR, has_raw = p.has_raw,
              has_act = p.has_act && MODE == EPI_TC_LINEAR;
   const float scale = p.scale, slope = p.slope;
@@ -289,7 +328,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const bool has_add = has_add0 || has_add1;
   const bool has_out = has_raw || has_act;
   const uint32_t add_box_bytes = (uint32_t)e_box_rows * CW * 2u, out_box_bytes = (uint32_t)e_box_rows * OW * 2u;
-  const uint32_t add_bytes = (uint32_t)((has_add0 ? 1 : 0) + (has_add1 ? 1 : 0)) * (uint32_t)e_n_boxes * add_box_bytes;
+  const uint32_t add_bytes = (uint32_t)((has_add0 ? 1 : 0) + (has_add1 ? 1 : 0)) * (uint32_t)(e_n_boxes * n_parts) * add_box_bytes;
   const uint32_t add_bar0 = bar_base + 8u * kBarAdd;
   const uint32_t acc_full0 = bar_base + 8u * kBarAccFull, acc_empty0 = bar_base + 8u * kBarAccEmpty;
 
@@ -304,10 +343,12 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
     const int ch = pf.nt * n_tile + pf_cc * CW, row = pf.mt * (128 * mb);
     const uint32_t bar = add_bar0 + 8u * pf_buf;
     mbar_expect_tx(bar, add_bytes);
-    for (int bx = 0; bx < e_n_boxes; ++bx) {
-      if (has_add0) tma_load_3d(add0_b + pf_buf * e_buf_bytes + bx * add_box_bytes, &tmAdd0, bar, ch, row + bx * e_box_rows, pf.b);
-      if (has_add1) tma_load_3d(add1_b + pf_buf * e_buf_bytes + bx * add_box_bytes, &tmAdd1, bar, ch, row + bx * e_box_rows, pf.b);
-    }
+    for (int pt = 0; pt < n_parts; ++pt)
+      for (int bx = 0; bx < e_n_boxes; ++bx) {
+        const uint32_t off = pf_buf * e_buf_bytes + pt * part_bytes + bx * add_box_bytes;
+        if (has_add0) tma_load_3d(add0_b + off, &tmAdd0, bar, ch + pt * part_coff, row + bx * e_box_rows, pf.b);
+        if (has_add1) tma_load_3d(add1_b + off, &tmAdd1, bar, ch + pt * part_coff, row + bx * e_box_rows, pf.b);
+      }
     --pf_left;
     if (++pf_buf == n_add_bufs) pf_buf = 0;
     if (++pf_cc == n_echunks) { pf_cc = 0; pf.next(); }
@@ -402,6 +443,12 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
             for (int c = 0; c < CW / 8; ++c) {
               float f[8];
               unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
+              if (n_parts == 2) {
+                float g2[8];
+                unpack_bf16x8(lds128(base + part_bytes + swz(row_off_in + c * 16, swz_in)), g2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += g2[i];
+              }
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 if (MODE == EPI_TC_COUPLE) v[8 * c + i] = p.couple_sign < 0 ? (f[i] - v[8 * c + i]) * mk : v[8 * c + i] + f[i] * mk;
@@ -415,6 +462,12 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
             for (int c = 0; c < CW / 8; ++c) {
               float f[8];
               unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
+              if (n_parts == 2) {
+                float g2[8];
+                unpack_bf16x8(lds128(base + part_bytes + swz(row_off_in + c * 16, swz_in)), g2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += g2[i];
+              }
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[8 * c + i] += f[i];
             }
@@ -449,23 +502,11 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
         }
         if (has_out) {
           const uint32_t row_off_out = (uint32_t)srow * (OW * 2);
-          if (has_raw) {
-#pragma unroll
-            for (int c = 0; c < OW / 8; ++c) {
-              const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
-                                         pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
-              sts128(raw_b + ob + swz(row_off_out + c * 16, swz_out), u);
-            }
-          }
+          if (has_raw) stage_out<OW>(v, raw_b + ob, row_off_out, swz_out, n_parts, part_bytes);
           if (has_act) {
 #pragma unroll
             for (int i = 0; i < OW; ++i) v[i] = fmaxf(v[i], v[i] * slope);   // leaky_relu, 0 < slope < 1
-#pragma unroll
-            for (int c = 0; c < OW / 8; ++c) {
-              const uint4 u = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
-                                         pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
-              sts128(act_b + ob + swz(row_off_out + c * 16, swz_out), u);
-            }
+            stage_out<OW>(v, act_b + ob, row_off_out, swz_out, n_parts, part_bytes);
           }
         }
       }
@@ -474,10 +515,12 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
       if (has_add) { if (++add_buf == n_add_bufs) add_buf = 0; }
       if (has_out) {
         if (leader) {
-          for (int bx = 0; bx < e_n_boxes; ++bx) {
-            if (has_raw) tma_store_3d(&tmRaw, raw_b + ob + bx * out_box_bytes, och, tile_row0 + bx * e_box_rows, b);
-            if (has_act) tma_store_3d(&tmAct, act_b + ob + bx * out_box_bytes, och, tile_row0 + bx * e_box_rows, b);
-          }
+          for (int pt = 0; pt < n_parts; ++pt)
+            for (int bx = 0; bx < e_n_boxes; ++bx) {
+              const uint32_t off = ob + pt * part_bytes + bx * out_box_bytes;
+              if (has_raw) tma_store_3d(&tmRaw, raw_b + off, och + pt * part_coff, tile_row0 + bx * e_box_rows, b);
+              if (has_act) tma_store_3d(&tmAct, act_b + off, och + pt * part_coff, tile_row0 + bx * e_box_rows, b);
+            }
           bulk_commit();
         }
         ++out_count;
@@ -495,7 +538,7 @@ template <bool HALO, bool RESIDENT, int KK>
 __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_base, uint32_t w_base, uint32_t bar_base,
                                                  uint32_t tmem_base) {
   using namespace tc;
-  const int total_tiles = p.total_tiles, n_cchunks = p.n_cchunks, ktaps = p.ktaps, stages_a = p.stages_a,
+  const int total_tiles = p.total_tiles, n_achunks = p.n_achunks, ktaps = p.ktaps, stages_a = p.stages_a,
             stages_w = p.stages_w, n_tile = p.n_tile, mb = p.mb;
   int* const error_flag = p.error_flag;
   const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_tile);
@@ -518,39 +561,44 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
     mbar_wait(bar_acc_empty + 8u * as, pacc ^ 1, error_flag);
     fence_after_sync();
     const uint32_t d_tmem0 = tmem_base + (uint32_t)(as * mb * n_tile);
-    uint32_t w_res16 = w_lo0;   // RESIDENT: walks the (chunk, tap) tiles in order
-    for (int c = 0; c < n_cchunks; ++c) {
+    uint32_t w_res16 = w_lo0;   // RESIDENT: walks the (chunk, pass, tap) tiles in order
+    uint32_t first = 1;
+    for (int c = 0; c < n_achunks; ++c) {
       if (HALO) { mbar_wait(bar_a_full + 8u * sa, pa, error_flag); fence_after_sync(); }
-      uint32_t a16 = a_lo0 + (uint32_t)sa * a_stage16;
-      for (int j = 0; j < ktaps; ++j) {
-        if (!HALO) {
-          mbar_wait(bar_a_full + 8u * sa, pa, error_flag);
-          a16 = a_lo0 + (uint32_t)sa * a_stage16;
-        }
-        uint32_t w16;
-        if (RESIDENT) { w16 = w_res16; w_res16 += w_stage16; }
-        else { mbar_wait(bar_w_full + 8u * sw, pw, error_flag); w16 = w_lo0 + (uint32_t)sw * w_stage16; }
-        if (!HALO || !RESIDENT) fence_after_sync();
-        const uint32_t accumulate = (c | j) ? 1u : 0u;
-        uint32_t ab16 = a16, d_tmem = d_tmem0;
-        for (int bi = 0; bi < mb; ++bi) {        // every weight tile feeds mb MMAs
-#pragma unroll
-          for (int kk = 0; kk < KK; ++kk) {
-            // HALO: the row-shifted start address keeps base_offset = 0 -- the UMMA unit applies the swizzle
-            // XOR to absolute shared-memory address bits (verified on B200, tools/tc_probe.py).
-            umma_bf16(d_tmem, mk(ab16 + 2u * kk), mk(w16 + 2u * kk), idesc, (kk > 0) ? 1u : accumulate);
+      const int n_wp = p.n_wpass[c];
+      for (int wp = 0; wp < n_wp; ++wp) {
+        uint32_t a16 = a_lo0 + (uint32_t)sa * a_stage16;
+        for (int j = 0; j < ktaps; ++j) {
+          if (!HALO) {
+            mbar_wait(bar_a_full + 8u * sa, pa, error_flag);
+            a16 = a_lo0 + (uint32_t)sa * a_stage16;
           }
-          ab16 += blk_step16;
-          d_tmem += (uint32_t)n_tile;
-        }
-        if (HALO) a16 += tap_step16;
-        if (!RESIDENT) {
-          umma_commit(bar_w_empty + 8u * sw);
-          if (++sw == stages_w) { sw = 0; pw ^= 1; }
-        }
-        if (!HALO) {
-          umma_commit(bar_a_empty + 8u * sa);
-          if (++sa == stages_a) { sa = 0; pa ^= 1; }
+          uint32_t w16;
+          if (RESIDENT) { w16 = w_res16; w_res16 += w_stage16; }
+          else { mbar_wait(bar_w_full + 8u * sw, pw, error_flag); w16 = w_lo0 + (uint32_t)sw * w_stage16; }
+          if (!HALO || !RESIDENT) fence_after_sync();
+          const uint32_t accumulate = first ? 0u : 1u;
+          first = 0;
+          uint32_t ab16 = a16, d_tmem = d_tmem0;
+          for (int bi = 0; bi < mb; ++bi) {        // every weight tile feeds mb MMAs
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) {
+              // HALO: the row-shifted start address keeps base_offset = 0 -- the UMMA unit applies the swizzle
+              // XOR to absolute shared-memory address bits (verified on B200, tools/tc_probe.py).
+              umma_bf16(d_tmem, mk(ab16 + 2u * kk), mk(w16 + 2u * kk), idesc, (kk > 0) ? 1u : accumulate);
+            }
+            ab16 += blk_step16;
+            d_tmem += (uint32_t)n_tile;
+          }
+          if (HALO) a16 += tap_step16;
+          if (!RESIDENT) {
+            umma_commit(bar_w_empty + 8u * sw);
+            if (++sw == stages_w) { sw = 0; pw ^= 1; }
+          }
+          if (!HALO) {
+            umma_commit(bar_a_empty + 8u * sa);
+            if (++sa == stages_a) { sa = 0; pa ^= 1; }
+          }
         }
       }
       if (HALO) {
@@ -614,38 +662,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int sa = 0, sw = 0;
       uint32_t pa = 0, pw = 0;
       if (p.w_resident) {   // n_ntiles == 1: the weights do not depend on the tile
-        mbar_expect_tx(w_full(0), (uint32_t)(p.n_cchunks * p.ktaps) * p.w_box_bytes);
-        for (int c = 0; c < p.n_cchunks; ++c)
-          for (int j = 0; j < p.ktaps; ++j)
-            tma_load_2d(w_base + (uint32_t)(c * p.ktaps + j) * p.w_stage_bytes, &tmW, w_full(0), c * p.KC, j * p.CoutT);
+        mbar_expect_tx(w_full(0), (uint32_t)p.n_wtiles * p.w_box_bytes);
+        int wt = 0;
+        for (int c = 0; c < p.n_achunks; ++c)
+          for (int wp = 0; wp < p.n_wpass[c]; ++wp)
+            for (int j = 0; j < p.ktaps; ++j, ++wt)
+              tma_load_2d(w_base + (uint32_t)wt * p.w_stage_bytes, &tmW, w_full(0), p.w_coff[c][wp], j * p.CoutT);
       }
       TileIter it;
       it.init((int)blockIdx.x, (int)gridDim.x, p.n_ntiles, p.m_tiles_per_b);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it.next()) {
         const int nt = it.nt, mt = it.mt, b = it.b;
         const int row0 = mt * (128 * p.mb) + p.in_off0;
-        for (int c = 0; c < p.n_cchunks; ++c) {
+        for (int c = 0; c < p.n_achunks; ++c) {
           if (p.halo_mode) {
             mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);
             mbar_expect_tx(a_full(sa), (uint32_t)p.a_n_boxes * p.a_box_bytes);
             for (int bx = 0; bx < p.a_n_boxes; ++bx)
-              tma_load_3d(a_base + sa * p.a_stage_bytes + bx * p.a_box_bytes, &tmA, a_full(sa), c * p.KC,
+              tma_load_3d(a_base + sa * p.a_stage_bytes + bx * p.a_box_bytes, &tmA, a_full(sa), p.a_coff[c],
                           row0 + bx * p.a_box_rows, b);
             if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
             if (p.w_resident) continue;
           }
-          for (int j = 0; j < p.ktaps; ++j) {
-            if (!p.halo_mode) {   // RELOAD mode: mb == 1, one 128-row box per (chunk, tap)
-              mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);
-              mbar_expect_tx(a_full(sa), p.a_box_bytes);
-              tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), c * p.KC, row0 + j * p.dil, b);
-              if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
-            }
-            if (!p.w_resident) {
-              mbar_wait(w_empty(sw), pw ^ 1, p.error_flag);
-              mbar_expect_tx(w_full(sw), p.w_box_bytes);
-              tma_load_2d(w_base + sw * p.w_stage_bytes, &tmW, w_full(sw), c * p.KC, j * p.CoutT + nt * p.n_tile);
-              if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
+          for (int wp = 0; wp < p.n_wpass[c]; ++wp) {
+            for (int j = 0; j < p.ktaps; ++j) {
+              if (!p.halo_mode) {   // RELOAD mode: mb == 1, one 128-row box per (chunk, pass, tap)
+                mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);
+                mbar_expect_tx(a_full(sa), p.a_box_bytes);
+                tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), p.a_coff[c], row0 + j * p.dil, b);
+                if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+              }
+              if (!p.w_resident) {
+                mbar_wait(w_empty(sw), pw ^ 1, p.error_flag);
+                mbar_expect_tx(w_full(sw), p.w_box_bytes);
+                tma_load_2d(w_base + sw * p.w_stage_bytes, &tmW, w_full(sw), p.w_coff[c][wp], j * p.CoutT + nt * p.n_tile);
+                if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
+              }
             }
           }
         }
@@ -695,8 +747,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ---- glue kernels of the bf16 path --------------------------------------------------------------
 
-// [B, C, T] fp32 (reference layout) -> [B, T, C] bf16 (channels-last), optional leaky_relu.  32x32 smem tile.
-__global__ void transpose_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int T) {
+// [B, C, T] fp32 (reference layout) -> [B, T, C] bf16 (channels-last).  32x32 smem tile.
+// split != 0: rows are [hi (C) | lo (C)] with hi = bf16(x), lo = bf16(x - hi)  (split-bf16 mode).
+__global__ void transpose_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int T,
+                                         int split) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
@@ -705,9 +759,15 @@ __global__ void transpose_to_bf16_kernel(const float* __restrict__ x, __nv_bfloa
     tile[i][tx] = (c < C && t < T) ? x[((long long)b * C + c) * T + t] : 0.f;
   }
   __syncthreads();
+  const int W = split ? 2 * C : C;
   for (int i = ty; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + tx;
-    if (t < T && c < C) y[((long long)b * T + t) * C + c] = __float2bfloat16(tile[tx][i]);
+    if (t < T && c < C) {
+      const float v = tile[tx][i];
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      y[((long long)b * T + t) * W + c] = hi;
+      if (split) y[((long long)b * T + t) * W + C + c] = __float2bfloat16(v - __bfloat162float(hi));
+    }
   }
 }
 
@@ -730,8 +790,9 @@ __global__ void transpose_from_bf16_kernel(const __nv_bfloat16* __restrict__ x, 
 
 // conv_post on the channels-last bf16 stream: input is already leaky_relu'd (out_act of the last stage).
 // wav[b, n] = tanh(sum_{j, c} w[c][j] * x[b, n + j - pad, c]).  One thread per sample.
+// split != 0: rows are [hi (C) | lo (C)] and x = hi + lo.
 __global__ void conv_post_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[C][k]*/,
-                                      float* __restrict__ wav, int C, int L, int k) {
+                                      float* __restrict__ wav, int C, int L, int k, int split) {
   extern __shared__ float wsm[];   // [k][C]
   for (int i = threadIdx.x; i < C * k; i += blockDim.x) {
     const int c = i / k, j = i - c * k;
@@ -740,15 +801,21 @@ __global__ void conv_post_bf16_kernel(const __nv_bfloat16* __restrict__ x, const
   __syncthreads();
   const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (n >= L) return;
-  const int pad = (k - 1) / 2;
+  const int pad = (k - 1) / 2, W = split ? 2 * C : C;
   float s = 0.f;
   for (int j = 0; j < k; ++j) {
     const int pos = n + j - pad;
     if (pos < 0 || pos >= L) continue;
-    const uint4* row = reinterpret_cast<const uint4*>(x + ((long long)b * L + pos) * C);
+    const uint4* row = reinterpret_cast<const uint4*>(x + ((long long)b * L + pos) * W);
     for (int c8 = 0; c8 < C / 8; ++c8) {
       float f[8];
       tc::unpack_bf16x8(__ldg(row + c8), f);
+      if (split) {
+        float g2[8];
+        tc::unpack_bf16x8(__ldg(row + C / 8 + c8), g2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += g2[i];
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) s = fmaf(wsm[j * C + c8 * 8 + i], f[i], s);
     }

@@ -207,6 +207,7 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
   VSG_TRY(L.bias(pre + "conv_pre", UIC, b, true));
   VSG_TRY(pack_conv_f32(L, W, b, UIC, C0, 7, Identity{}, &P->conv_pre));
   VSG_TRY(pack_conv_tc(P, W, b, UIC, C0, 7, &P->conv_pre_tc));
+  VSG_TRY(pack_conv_tc(P, W, b, UIC, C0, 7, &P->conv_pre_x3, true));
   if (c.dec_gin > 0) {   // cond: Conv1d(gin -> UIC, 1)            decoder.py:37-38
     VSG_TRY(L.eff_weight(pre + "cond", UIC, c.dec_gin, 1, W));
     VSG_TRY(L.bias(pre + "cond", UIC, b, true));
@@ -248,6 +249,7 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
             Wc[((size_t)co * st.Cin + ci) * nr + jj] = W[((size_t)ci * st.Cout + co) * k + j0 + s * (nr - 1 - jj)];
       VSG_TRY(pack_conv_f32(L, Wc, b, st.Cout, st.Cin, nr, Identity{}, &ph.f32));
       VSG_TRY(pack_conv_tc(P, Wc, b, st.Cout, st.Cin, nr, &ph.tc));
+      VSG_TRY(pack_conv_tc(P, Wc, b, st.Cout, st.Cin, nr, &ph.x3, true));
     }
     // resblocks                                                            decoder.py:28-32
     st.blocks.resize(c.dec_n_kernels);
@@ -259,20 +261,22 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
       if (nd <= 0 || nd > VSG_MAX_RESBLOCK_DILATIONS) return fail(VSG_EINVAL, "bad dilation count");
       rb.dilations.assign(c.dec_resblock_dilations[j], c.dec_resblock_dilations[j] + nd);
       const std::string pb = pre + "resblocks." + std::to_string(i * c.dec_n_kernels + j) + ".";
-      rb.c1.resize(nd); rb.c1_tc.resize(nd);
-      if (c.dec_resblock == 1) { rb.c2.resize(nd); rb.c2_tc.resize(nd); }
+      rb.c1.resize(nd); rb.c1_tc.resize(nd); rb.c1_x3.resize(nd);
+      if (c.dec_resblock == 1) { rb.c2.resize(nd); rb.c2_tc.resize(nd); rb.c2_x3.resize(nd); }
       for (int q = 0; q < nd; ++q) {
         const std::string n1 = pb + (c.dec_resblock == 1 ? "convs1." : "convs.") + std::to_string(q);
         VSG_TRY(L.eff_weight(n1, ch, ch, rb.kernel, W));
         VSG_TRY(L.bias(n1, ch, b, true));
         VSG_TRY(pack_conv_f32(L, W, b, ch, ch, rb.kernel, Identity{}, &rb.c1[q]));
         VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_tc[q]));
+        VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_x3[q], true));
         if (c.dec_resblock == 1) {
           const std::string n2 = pb + "convs2." + std::to_string(q);
           VSG_TRY(L.eff_weight(n2, ch, ch, rb.kernel, W));
           VSG_TRY(L.bias(n2, ch, b, true));
           VSG_TRY(pack_conv_f32(L, W, b, ch, ch, rb.kernel, Identity{}, &rb.c2[q]));
           VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_tc[q]));
+          VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_x3[q], true));
         }
       }
     }

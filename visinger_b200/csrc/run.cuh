@@ -19,10 +19,10 @@ int generator_forward_f32(const VsgPack* P, const float* z, const float* g, floa
 
 // bf16 tensor-core mode (run_tc.cu)
 size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T);
-size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T);
+size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T, bool x3);
 int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, float* y, int B, int T,
                     int reverse, Workspace& ws, cudaStream_t st);
 int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float* wav, int B, int T, Workspace& ws,
-                         cudaStream_t st);
+                         cudaStream_t st, bool x3);
 
 }  // namespace vsg

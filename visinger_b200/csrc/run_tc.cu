@@ -109,7 +109,8 @@ constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic smem we plan with
 int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, int B, int Lin, int in_off0, int dil,
                    int Lq, int out_stride, int out_phase, int Lout, const EpiTC& e, const TCOptions& opt, int* error_flag,
                    cudaStream_t st, int x_ld = 0) {
-  if (x_ld == 0) x_ld = w.Cin;
+  if (x_ld == 0) x_ld = w.CinT;
+  if (w.x3 && e.mode != EPI_TC_LINEAR) return fail(VSG_EUNSUPPORTED, "split-bf16 supports the linear epilogue only");
   if (!w.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 16 "
                                                  "(conv %d -> %d)", w.Cin, w.Cout);
   if (Lq <= 0 || B <= 0) return VSG_OK;
@@ -121,7 +122,8 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   const int cw = small ? std::min(NT, 32) : pick_cw(NT);
   const int ow = e.mode == EPI_TC_GATE ? cw / 2 : cw;                // output channels per chunk
   const int cout_eff = e.mode == EPI_TC_GATE ? w.Cout / 2 : w.Cout;  // channels of the add / out tensors
-  const int ld = e.ld ? e.ld : cout_eff;
+  const int n_parts = w.x3 ? 2 : 1;                                    // bf16 planes of every epilogue tensor
+  const int ld = e.ld ? e.ld : n_parts * cout_eff;
   const int n_adds = (e.add0 ? 1 : 0) + (e.add1 ? 1 : 0), n_outs = (e.out_raw ? 1 : 0) + (e.out_act ? 1 : 0);
   const size_t half_budget = 110 * 1024;
 
@@ -135,7 +137,20 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     if (2 * mb * NT > 512) return false;
     if (mb > 1 && Lq < 128 * mb) return false;
     q.mb = mb;
-    q.KC = KC; q.n_cchunks = w.Cin / KC; q.ktaps = w.ktaps; q.dil = dil; q.in_off0 = in_off0;
+    q.KC = KC; q.ktaps = w.ktaps; q.dil = dil; q.in_off0 = in_off0;
+    const int nc = w.Cin / KC;
+    if ((w.x3 ? 2 : 1) * nc > kMaxAChunks) return false;
+    q.n_achunks = 0; q.n_wtiles = 0;
+    for (int part = 0; part < (w.x3 ? 2 : 1); ++part)       // x3: hi chunks meet W_hi and W_lo, lo chunks meet W_hi
+      for (int c = 0; c < nc; ++c) {
+        const int i = q.n_achunks++;
+        q.a_coff[i] = part * w.Cin + c * KC;
+        q.n_wpass[i] = (w.x3 && part == 0) ? 2 : 1;
+        q.w_coff[i][0] = c * KC;
+        q.w_coff[i][1] = w.Cin + c * KC;
+        q.n_wtiles += q.n_wpass[i] * w.ktaps;
+      }
+    q.n_parts = n_parts; q.part_coff = cout_eff;
     q.Cout = w.Cout; q.n_tile = NT; q.n_ntiles = w.Cout / NT; q.CoutT = w.CoutT;
     q.halo_mode = (halo_ok && (w.ktaps > 1 || mb > 1)) ? 1 : 0;
     const int rows = q.halo_mode ? 128 * mb + halo : 128;
@@ -148,11 +163,12 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     q.cw = cw; q.n_echunks = NT / cw;
     q.e_box_rows = std::min(128 * mb, 256);
     q.e_n_boxes = 128 * mb / q.e_box_rows;
-    q.e_buf_bytes = (uint32_t)((128 * mb * cw * 2 + 1023) & ~1023);
+    q.e_part_bytes = (uint32_t)((128 * mb * cw * 2 + 1023) & ~1023);
+    q.e_buf_bytes = (uint32_t)n_parts * q.e_part_bytes;
     q.n_add_bufs = 2 + (cw <= 32 && mb <= 2 ? 1 : 0);
     const size_t e_bytes = ((size_t)n_adds * q.n_add_bufs + (size_t)n_outs * 2) * q.e_buf_bytes;
-    const size_t w_total = (size_t)q.n_cchunks * w.ktaps * q.w_stage_bytes;
-    const int a_per_tile = q.halo_mode ? q.n_cchunks : q.n_cchunks * w.ktaps;
+    const size_t w_total = (size_t)q.n_wtiles * q.w_stage_bytes;
+    const int a_per_tile = q.halo_mode ? q.n_achunks : q.n_wtiles;
     size_t w_bytes;
     q.w_resident = (opt.w_resident && q.n_ntiles == 1 && w_total <= 112 * 1024 &&
                     w_total + e_bytes + 2 * (size_t)q.a_stage_bytes <= budget) ? 1 : 0;
@@ -207,7 +223,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.error_flag = error_flag;
 
   CUtensorMap tmA, tmAdd0, tmAdd1, tmRaw, tmAct;
-  VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.Cin, (uint64_t)Lin, (uint64_t)B, (uint64_t)x_ld, (uint64_t)Lin * x_ld,
+  VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.CinT, (uint64_t)Lin, (uint64_t)B, (uint64_t)x_ld, (uint64_t)Lin * x_ld,
                     (uint32_t)KC, (uint32_t)p.a_box_rows, KC));
   // epilogue tensors: rows are the q positions of this (poly)phase: row stride out_stride*ld, base shifted by phase
   auto emap = [&](CUtensorMap* m, const __nv_bfloat16* base, int width, int box_c) -> int {
@@ -215,10 +231,10 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
                      (uint64_t)out_stride * ld, (uint64_t)Lout * ld, (uint32_t)box_c, (uint32_t)p.e_box_rows, box_c);
   };
   tmAdd0 = tmAdd1 = tmRaw = tmAct = tmA;
-  if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0, w.Cout, p.cw));
-  if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1, w.Cout, p.cw));
-  if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw, cout_eff, ow));
-  if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act, cout_eff, ow));
+  if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0, n_parts * w.Cout, p.cw));
+  if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1, n_parts * w.Cout, p.cw));
+  if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw, n_parts * cout_eff, ow));
+  if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act, n_parts * cout_eff, ow));
   static bool attr_set = false;
   if (!attr_set) {
     VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
@@ -251,17 +267,23 @@ size_t dec_max_elems(const VsgPack* P, int B, int T) {
 }  // namespace
 
 // Conv1d-style weight W[co][ci][j] -> bf16 [j][co][ci] (K-major rows) + its 2-D TMA map.
+// x3: every row is [W_hi (Cin) | W_lo (Cin)] with W_hi = bf16(W), W_lo = bf16(W - W_hi).
 int pack_conv_tc(VsgPack* P, const std::vector<float>& W, const std::vector<float>& b, int Cout, int Cin, int k,
-                 ConvWTC* out) {
-  out->Cin = Cin; out->Cout = Cout; out->CinT = Cin; out->CoutT = Cout; out->ktaps = k;
-  out->has_tmap = false;
+                 ConvWTC* out, bool x3) {
+  const int CinT = x3 ? 2 * Cin : Cin;
+  out->Cin = Cin; out->Cout = Cout; out->CinT = CinT; out->CoutT = Cout; out->ktaps = k;
+  out->has_tmap = false; out->x3 = x3;
   const int KC = pick_kc(Cin), NT = pick_ntile(Cout);
   if (KC == 0 || NT == 0 || k < 1) return VSG_OK;   // not representable on the tensor-core path; fp32 mode still works
-  std::vector<__nv_bfloat16> wp((size_t)k * Cout * Cin);
+  std::vector<__nv_bfloat16> wp((size_t)k * Cout * CinT);
   for (int j = 0; j < k; ++j)
     for (int co = 0; co < Cout; ++co)
-      for (int ci = 0; ci < Cin; ++ci)
-        wp[((size_t)j * Cout + co) * Cin + ci] = __float2bfloat16(W[((size_t)co * Cin + ci) * k + j]);
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float v = W[((size_t)co * Cin + ci) * k + j];
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        wp[((size_t)j * Cout + co) * CinT + ci] = hi;
+        if (x3) wp[((size_t)j * Cout + co) * CinT + Cin + ci] = __float2bfloat16(v - __bfloat162float(hi));
+      }
   void* dw = nullptr;
   VSG_CUDA_TRY(cudaMalloc(&dw, wp.size() * sizeof(__nv_bfloat16) + 256));
   P->allocs.push_back(dw);
@@ -272,7 +294,7 @@ int pack_conv_tc(VsgPack* P, const std::vector<float>& W, const std::vector<floa
   P->allocs.push_back(db);
   VSG_CUDA_TRY(cudaMemcpy(db, b.data(), (size_t)Cout * sizeof(float), cudaMemcpyHostToDevice));
   out->bias = (float*)db;
-  VSG_TRY(encode_2d(&out->tmap, dw, (uint64_t)Cin, (uint64_t)k * Cout, (uint32_t)KC, (uint32_t)NT, KC));
+  VSG_TRY(encode_2d(&out->tmap, dw, (uint64_t)CinT, (uint64_t)k * Cout, (uint32_t)KC, (uint32_t)NT, KC));
   out->has_tmap = true;
   return VSG_OK;
 }
@@ -315,7 +337,7 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
   }
   {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(x, u, C, T);
+    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(x, u, C, T, 0);
     VSG_LAUNCH_CHECK("transpose_to_bf16_kernel");
   }
   for (int step = 0; step < NF; ++step) {
@@ -397,30 +419,35 @@ SubBatchPlan plan_sub_batches(const VsgPack* P, int B, int T) {
   return pl;
 }
 
-size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T) {
+size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T, bool x3) {
   const SubBatchPlan pl = plan_sub_batches(P, B, T);
-  return align256((size_t)B * T * P->cfg.dec_initial_channel * 2) + align256((size_t)B * P->cfg.dec_upsample_initial_channel * 4) +
-         2 * align256(pl.io_elems * 2) + 7 * align256(pl.inter_elems * 2) + 512;
+  const size_t np = x3 ? 2 : 1;
+  return align256((size_t)B * T * P->cfg.dec_initial_channel * 2 * np) + align256((size_t)B * P->cfg.dec_upsample_initial_channel * 4) +
+         2 * align256(pl.io_elems * 2 * np) + 7 * align256(pl.inter_elems * 2 * np) + 512;
 }
 
 // Generator.forward (modules/visinger/decoder.py:40-59) on the tensor-core kernels.
+// x3: split-bf16 mode -- every activation tensor carries two bf16 planes [hi | lo] per row and every product is
+// three MMAs (hi*W_hi + hi*W_lo + lo*W_hi): fp32-tolerance results on the tensor cores.
 int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float* wav, int B, int T, Workspace& ws,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool x3) {
   const VsgConfig& c = P->cfg;
   const int C0 = c.dec_initial_channel, UIC = c.dec_upsample_initial_channel, NK = c.dec_n_kernels;
   if (!P->conv_pre_tc.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 decoder needs channel counts that are multiples of 16");
   const SubBatchPlan pl = plan_sub_batches(P, B, T);
   typedef __nv_bfloat16 bf;
-  bf* zt = ws.take<bf>((size_t)B * T * C0);
+  const size_t np = x3 ? 2 : 1;             // bf16 planes per activation tensor
+  auto W = [&](const ConvWTC& plain, const ConvWTC& split) -> const ConvWTC& { return x3 ? split : plain; };
+  bf* zt = ws.take<bf>((size_t)B * T * C0 * np);
   float* cond = ws.take<float>((size_t)B * UIC);
-  bf* io[2] = {ws.take<bf>(pl.io_elems), ws.take<bf>(pl.io_elems)};   // leaky_relu'd stage input / output, whole batch
-  bf* bU = ws.take<bf>(pl.inter_elems);    // upsampled x (residual for the first pair of every resblock)
-  bf* bUA = ws.take<bf>(pl.inter_elems);   // leaky_relu(x)
-  bf* bR = ws.take<bf>(pl.inter_elems);    // resblock running x
-  bf* bRA = ws.take<bf>(pl.inter_elems);   // leaky_relu of it
-  bf* bT = ws.take<bf>(pl.inter_elems);    // leaky_relu(conv1 output)  (ResBlock2: ping-pong partner of bR)
-  bf* bTA = ws.take<bf>(pl.inter_elems);   // (ResBlock2 only)
-  bf* bS = ws.take<bf>(pl.inter_elems);    // running sum over the NK resblocks
+  bf* io[2] = {ws.take<bf>(pl.io_elems * np), ws.take<bf>(pl.io_elems * np)};   // leaky_relu'd stage input / output
+  bf* bU = ws.take<bf>(pl.inter_elems * np);    // upsampled x (residual for the first pair of every resblock)
+  bf* bUA = ws.take<bf>(pl.inter_elems * np);   // leaky_relu(x)
+  bf* bR = ws.take<bf>(pl.inter_elems * np);    // resblock running x
+  bf* bRA = ws.take<bf>(pl.inter_elems * np);   // leaky_relu of it
+  bf* bT = ws.take<bf>(pl.inter_elems * np);    // leaky_relu(conv1 output)  (ResBlock2: ping-pong partner of bR)
+  bf* bTA = ws.take<bf>(pl.inter_elems * np);   // (ResBlock2 only)
+  bf* bS = ws.take<bf>(pl.inter_elems * np);    // running sum over the NK resblocks
   int* err = ws.take<int>(1);
   if (ws.overflow) return fail(VSG_ENOMEM, "generator workspace too small: need %zu bytes", ws.off);
   VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
@@ -432,7 +459,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
   }
   {  // boundary: [B, C, T] fp32 -> [B, T, C] bf16, once
     dim3 grid((T + 31) / 32, (C0 + 31) / 32, B), block(32, 8);
-    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(z, zt, C0, T);
+    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(z, zt, C0, T, x3 ? 1 : 0);
     VSG_LAUNCH_CHECK("transpose_to_bf16_kernel");
   }
   int cur_io = 0;
@@ -441,7 +468,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
     e.bias = P->conv_pre_tc.bias;
     if (c.dec_gin > 0) { e.bcond = cond; e.bcond_bs = UIC; }
     e.out_act = io[cur_io];
-    VSG_TRY(launch_conv_tc(P, P->conv_pre_tc, zt, B, T, -3, 1, T, 1, 0, T, e, opt, err, st));
+    VSG_TRY(launch_conv_tc(P, W(P->conv_pre_tc, P->conv_pre_x3), zt, B, T, -3, 1, T, 1, 0, T, e, opt, err, st));
   }
   int L = T, ch = UIC;
   for (int i = 0; i < c.dec_n_ups; ++i) {
@@ -452,14 +479,15 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
     bf* stage_out = io[cur_io ^ 1];
     for (int b0 = 0; b0 < B; b0 += pl.sub[i]) {
       const int nb = std::min(pl.sub[i], B - b0);
-      const bf* xin = stage_in + (size_t)b0 * Lin * Cin;
-      bf* xout = stage_out + (size_t)b0 * L * ch;
+      const bf* xin = stage_in + (size_t)b0 * Lin * Cin * np;
+      bf* xout = stage_out + (size_t)b0 * L * ch * np;
       for (int r = 0; r < us.rate; ++r) {   // ConvTranspose1d as polyphase convolutions (decoder.py:46)
         EpiTC e;
         e.bias = us.phases[r].tc.bias;
         e.out_raw = bU; e.out_act = bUA;
         const int Lq = (Lout - r + us.rate - 1) / us.rate;
-        VSG_TRY(launch_conv_tc(P, us.phases[r].tc, xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r, Lout, e, opt, err, st));
+        VSG_TRY(launch_conv_tc(P, W(us.phases[r].tc, us.phases[r].x3), xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r,
+                               Lout, e, opt, err, st));
       }
       for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
         const ResBlockPack& rb = us.blocks[j];
@@ -478,17 +506,17 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
           if (c.dec_resblock == 1) {        // ResBlock1 (decoder.py:91-104)
             EpiTC e1;
             e1.bias = rb.c1_tc[q].bias; e1.out_act = bT;
-            VSG_TRY(launch_conv_tc(P, rb.c1_tc[q], curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
+            VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
             e2.bias = rb.c2_tc[q].bias;
             if (!last) { e2.out_raw = bR; e2.out_act = bRA; }
-            VSG_TRY(launch_conv_tc(P, rb.c2_tc[q], bT, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
+            VSG_TRY(launch_conv_tc(P, W(rb.c2_tc[q], rb.c2_x3[q]), bT, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
             cur = bR; curA = bRA;
           } else {                           // ResBlock2 (decoder.py:124-133)
             e2.bias = rb.c1_tc[q].bias;
             bf* nr = (cur == bR) ? bT : bR;
             bf* nra = (cur == bR) ? bTA : bRA;
             if (!last) { e2.out_raw = nr; e2.out_act = nra; }
-            VSG_TRY(launch_conv_tc(P, rb.c1_tc[q], curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e2, opt, err, st));
+            VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e2, opt, err, st));
             cur = nr; curA = nra;
           }
         }
@@ -499,7 +527,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
   {  // wav = tanh(conv_post(leaky_relu(x)))   (decoder.py:55-57); the stage output already holds leaky_relu(x)
     dim3 grid((L + 255) / 256, B);
     conv_post_bf16_kernel<<<grid, 256, (size_t)ch * P->conv_post_k * sizeof(float), st>>>(io[cur_io], P->conv_post_w, wav,
-                                                                                           ch, L, P->conv_post_k);
+                                                                                           ch, L, P->conv_post_k, x3 ? 1 : 0);
     VSG_LAUNCH_CHECK("conv_post_bf16_kernel");
   }
   return VSG_OK;
@@ -526,7 +554,7 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
   std::vector<float> W(w, w + (size_t)Cout * Cin * k), bz(Cout, 0.f);
   if (bias) bz.assign(bias, bias + Cout);
   ConvWTC wt;
-  int rc = pack_conv_tc(&tmp, W, bz, Cout, Cin, k, &wt);
+  int rc = pack_conv_tc(&tmp, W, bz, Cout, Cin, k, &wt, (flags & 4) != 0);
   int* err = nullptr;
   if (rc == VSG_OK && cudaMalloc(&err, sizeof(int)) != cudaSuccess) rc = fail(VSG_ECUDA, "cudaMalloc failed");
   if (rc == VSG_OK) {

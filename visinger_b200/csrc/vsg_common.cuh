@@ -63,11 +63,12 @@ struct ConvWTC {
   int Cin = 0, Cout = 0, CinT = 0, CoutT = 0, ktaps = 0;
   CUtensorMap tmap;     // 2-D map over [ktaps*CoutT rows][CinT]
   bool has_tmap = false;
+  bool x3 = false;      // split-bf16 pack: rows are [W_hi (Cin) | W_lo (Cin)], CinT = 2*Cin
 };
 
 struct UpsPhase {
   ConvW32 f32;
-  ConvWTC tc;
+  ConvWTC tc, x3;
   int in_off0 = 0;
 };
 
@@ -89,6 +90,7 @@ struct ResBlockPack {
   std::vector<int> dilations;
   std::vector<ConvW32> c1, c2;      // ResBlock2 uses c1 only
   std::vector<ConvWTC> c1_tc, c2_tc;
+  std::vector<ConvWTC> c1_x3, c2_x3;   // split-bf16 packs
 };
 
 struct UpStage {
@@ -110,7 +112,7 @@ struct VsgPack {
   std::vector<vsg::FlowLayer> flow_layers;
   // decoder
   vsg::ConvW32 conv_pre;
-  vsg::ConvWTC conv_pre_tc;
+  vsg::ConvWTC conv_pre_tc, conv_pre_x3;
   float* dec_cond_w = nullptr;   // [uic][gin]
   float* dec_cond_b = nullptr;
   std::vector<vsg::UpStage> ups;
