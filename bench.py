@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("VSG_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("VSG_BENCH_PRECISION", "bf16"), choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -256,7 +256,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (split-bf16 pairs, fp32 accumulate)", "fp32": "f32"}[args.precision],
+            "data": "synthetic",
             "config": {"workload": f"hot path: prior sample -> ResidualCouplingBlock.reverse -> HiFi-GAN Generator; "
                                    f"B={B} utterances x T={T} latent frames ({audio_per_step:.0f} s audio) per GPU per step; "
                                    "config/models/visinger.yaml shapes, random weights",

@@ -119,8 +119,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   const bool halo_ok = opt.halo_mode && 128 + halo <= 256;
   // low-channel convolutions run the SMALL kernel instantiation (<= 32-channel epilogue chunks, 2 CTAs / SM)
   const bool small = NT <= 64 && (NT <= 32 || NT % 32 == 0);
-  const int cw = small ? std::min(NT, 32) : pick_cw(NT);
-  const int ow = e.mode == EPI_TC_GATE ? cw / 2 : cw;                // output channels per chunk
+  const int cw_max = small ? std::min(NT, 32) : pick_cw(NT);
   const int cout_eff = e.mode == EPI_TC_GATE ? w.Cout / 2 : w.Cout;  // channels of the add / out tensors
   const int n_parts = w.x3 ? 2 : 1;                                    // bf16 planes of every epilogue tensor
   const int ld = e.ld ? e.ld : n_parts * cout_eff;
@@ -130,9 +129,10 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   // Plan the tile: try mb = 4, 2, 1 blocks of 128 rows; prefer the largest that lets two CTAs share an SM (small
   // kernels), else the largest that fits at all.
   ConvTC p;
-  auto plan = [&](int mb, size_t budget, ConvTC* out) -> bool {
+  auto plan = [&](int mb, int cw, size_t budget, ConvTC* out) -> bool {
     ConvTC q;
     memset(&q, 0, sizeof(q));
+    if (NT % cw) return false;
     if (mb > 1 && !halo_ok) return false;
     if (2 * mb * NT > 512) return false;
     if (mb > 1 && Lq < 128 * mb) return false;
@@ -199,9 +199,12 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   const int mb_max = opt.max_mb;
   if (small)
     for (int mb = std::min(4, mb_max); mb >= 1 && !planned; mb >>= 1)
-      if (2 * mb * NT <= 256) planned = plan(mb, half_budget, &p);      // two CTAs per SM: half the smem and TMEM each
-  for (int mb = std::min(NT <= 128 ? (small ? 4 : 2) : 1, mb_max); mb >= 1 && !planned; mb >>= 1) planned = plan(mb, kSmemBudget, &p);
+      if (2 * mb * NT <= 256) planned = plan(mb, cw_max, half_budget, &p);   // two CTAs per SM: half the smem and TMEM each
+  for (int mb = std::min(NT <= 128 ? (small ? 4 : 2) : 1, mb_max); mb >= 1 && !planned; mb >>= 1)
+    for (int cw = cw_max; cw >= 16 && !planned; cw >>= 1) planned = plan(mb, cw, kSmemBudget, &p);
   if (!planned) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
+  const int cw = p.cw;
+  const int ow = e.mode == EPI_TC_GATE ? cw / 2 : cw;                // output channels per chunk
   p.B = B; p.Lq = Lq; p.Lout = Lout;
   p.out_stride = out_stride; p.out_phase = out_phase;
   p.m_tiles_per_b = (Lq + 128 * p.mb - 1) / (128 * p.mb);

@@ -10,10 +10,16 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from copy import deepcopy
+
 from .. import _lib
+from ..modules.rel_transformer import SinusoidalPositionalEmbedding
 from ..modules.visinger._packing import PackedModuleMixin
 from ..modules.visinger.flow import ResidualCouplingBlock
 from ..modules.visinger.decoder import Generator
+from ..modules.visinger.encoder import (DEFAULT_MAX_TARGET_POSITIONS, Embedding, FramePriorNetwork, PosteriorEncoder,
+                                        TextEncoder)
+from ..modules.visinger.predictor import PhonemePredictor, PitchPredictor
 
 
 class HotPath(PackedModuleMixin, nn.Module):
@@ -171,3 +177,112 @@ class HotPathGraph:
         if g is not None:
             self.g.copy_(g, non_blocking=True)
         return self.replay()
+
+
+class VISinger(nn.Module):
+    """Drop-in for the reference `VISinger` (models/visinger.py:18-135) on the inference branch.
+
+    Same constructor `VISinger(ph_dict_size, pitch_size, dur_size, hparams, out_dims=None)`, same child names and
+    state-dict keys (reference checkpoints load with `load_state_dict`), same
+    `forward(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed=None, spk_id=None, f0=None, uv=None, mel=None,
+    infer=False, **kwargs) -> dict` with keys `wav_out` [B, T*hop] and `f0_pred`.
+
+    The prior network (text encoder, pitch predictor, frame prior) runs in PyTorch on the GPU; from `z_p` on --
+    prior sampling, flow reverse, HiFi-GAN decoder (models/visinger.py:107-111) -- one `vsg_infer` call runs the
+    hand-written CUDA path.  `infer=False` (training) is out of scope and raises.
+
+    Extra keyword arguments (not in the reference): `noise` injects the prior noise instead of
+    `torch.randn_like(mu_p)` (CPU and CUDA generators differ, so parity tests need it); `precision` selects
+    "fp32" | "bf16" | "bf16x3" for the native path.
+    """
+
+    def __init__(self, ph_dict_size, pitch_size, dur_size, hparams, out_dims=None, precision="fp32"):
+        super().__init__()
+        self.hparams = deepcopy(hparams)
+        hp = hparams
+        self.enc_layers = hp["enc_layers"]
+        self.dec_blocks = hp["dec_blocks"]
+        self.hidden_size = H = hp["hidden_size"]
+        self.use_pos_embed = hp["use_pos_embed"]
+        self.segment_size = hp["segment_size"]
+        self.out_dims = hp["num_mel_bins"] if out_dims is None else out_dims
+        self.precision = precision
+        if hp["use_spk_id"]:
+            self.spk_id_proj = Embedding(hp["num_spk"], hp["gin_channels"])
+        if hp["use_spk_embed"]:
+            self.spk_embed_proj = nn.Linear(256, hp["gin_channels"], bias=True)
+        self.text_encoder = TextEncoder(ph_dict_size, pitch_size, dur_size, H, hp["ffn_filter_channels"], hp["num_heads"],
+                                        self.enc_layers, hp["ffn_kernel_size"], hp["p_dropout"], True)
+        self.embed_positions = SinusoidalPositionalEmbedding(H, 0, init_size=DEFAULT_MAX_TARGET_POSITIONS)
+        if hp["use_pitch_embed"]:
+            self.pitch_predictor = PitchPredictor(H, hp["ffn_filter_channels"], hp["num_heads"],
+                                                  n_layers=hp["pitch_predictor_layers"], kernel_size=hp["ffn_kernel_size"],
+                                                  p_dropout=hp["p_dropout"], gin_channels=hp["gin_channels"], out_dim=2)
+        if hp["use_phoneme_pred"]:
+            self.phoneme_predictor = PhonemePredictor(ph_dict_size, H, hp["ffn_filter_channels"], hp["num_heads"],
+                                                      n_layers=hp["phoneme_predictor_layers"],
+                                                      kernel_size=hp["ffn_kernel_size"], p_dropout=hp["p_dropout"])
+        self.frame_prior = FramePriorNetwork(H, hp["ffn_filter_channels"], hp["num_heads"], hp["frame_prior_layers"],
+                                             hp["ffn_kernel_size"], p_dropout=hp["p_dropout"], gin_channels=1)
+        self.posterior_encoder = PosteriorEncoder(hp["num_linear_bins"], H, H, 5, 1, 16, gin_channels=hp["gin_channels"])
+        self.flow = ResidualCouplingBlock(H, H, 5, 1, 4, gin_channels=hp["gin_channels"])
+        self.decoder = Generator(H, hp["dec_blocks"], hp["dec_kernel_size"], hp["dec_dilation_sizes"], hp["upsample_rates"],
+                                 hp["initial_upsample_channels"], hp["upsample_kernel_sizes"],
+                                 gin_channels=hp["gin_channels"])
+        # the fused native path shares the flow / decoder modules (and hence their parameters) without re-registering them
+        object.__setattr__(self, "_hot", HotPath(self.flow, self.decoder, precision))
+
+    def forward(self, text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed=None, spk_id=None, f0=None, uv=None,
+                mel=None, infer=False, noise=None, **kwargs):
+        if not infer:
+            raise NotImplementedError("visinger_b200.VISinger implements forward(infer=True); training stays with the reference")
+        with torch.no_grad():
+            ret = {}
+            mu_p, logs_p, mask, spk_emb = self.prior(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id,
+                                                     f0, uv, ret)
+            if noise is None:
+                noise = torch.randn_like(mu_p)
+            self._hot.precision = self.precision
+            wav, z_q = self._hot.infer(mu_p, logs_p, noise, mask, spk_emb)              # models/visinger.py:107-111
+            ret["wav_out"] = wav.squeeze(1)
+            ret["z_q"] = z_q
+            return ret
+
+    def prior(self, text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed=None, spk_id=None, f0=None, uv=None,
+              ret=None):
+        """models/visinger.py:75-90: everything upstream of z_p (plain PyTorch, any device).
+        Returns (mu_p, logs_p, tgt_nonpadding [B, 1, T], spk_emb [B, gin, 1]); fills ret["f0_pred"]."""
+        ret = {} if ret is None else ret
+        mask = (mel2ph > 0).float().unsqueeze(1)
+        prior_inp = self.text_encoder(text_tokens, pitch_tokens, dur_tokens, mel2ph) * mask
+        if self.use_pos_embed:                                                      # models/visinger.py:79-82
+            pos = self.embed_positions(prior_inp.shape[0], prior_inp.shape[2], prior_inp.transpose(1, 2)[..., 0])
+            prior_inp = prior_inp + pos.transpose(1, 2)
+        spk_emb = self.speaker_embedding(spk_embed, spk_id).transpose(1, 2)         # [B, gin, 1]
+        cond_pitch = None
+        if self.hparams["use_pitch_embed"]:
+            cond_pitch = self.forward_pitch(prior_inp, f0, uv, spk_emb, mask, ret)
+        mu_p, logs_p = self.frame_prior(prior_inp, mask, cond_pitch)
+        return mu_p, logs_p, mask, spk_emb
+
+    def infer(self, *args, **kwargs):
+        """Alias of forward(..., infer=True) (BASELINE.json calls the path `VISinger.infer`)."""
+        kwargs["infer"] = True
+        return self.forward(*args, **kwargs)
+
+    def speaker_embedding(self, spk_embed=None, spk_id=None):
+        out = 0
+        if self.hparams["use_spk_embed"]:
+            out = out + self.spk_embed_proj(spk_embed)[:, None, :]
+        if self.hparams["use_spk_id"]:
+            out = out + self.spk_id_proj(spk_id)[:, None, :]
+        return out
+
+    def forward_pitch(self, pitch_inp, f0, uv, spk_emb, mask, ret):
+        ret["f0_pred"] = pred = self.pitch_predictor(pitch_inp, mask, spk_emb)          # [B, T, 2]
+        if f0 is None:
+            f0 = pred[:, :, 0]
+            voiced = pred[:, :, 1] <= 0
+        else:
+            voiced = uv == 0
+        return (f0 * voiced).unsqueeze(1) * mask                                        # log-f0 on voiced frames

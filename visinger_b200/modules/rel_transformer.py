@@ -1,0 +1,189 @@
+"""Windowed relative-position self-attention encoder -- PyTorch mirror of the reference's
+`modules/rel_transformer.py` (RelativeEncoder :257-320, MultiHeadAttention :103-254, FFN :323-345,
+LayerNorm :24-42, SinusoidalPositionalEmbedding :45-100).
+
+This is NOT on the B200 hot path: it is the prior network that runs before `z_p`,
+kept in PyTorch so that `visinger_b200.models.visinger.VISinger` is a complete drop-in for
+`VISinger.forward(infer=True)`.  It is written from the reference's behaviour, with the reference's parameter
+names and shapes (so checkpoints load), but in its own formulation: the relative-position logits/values are
+moved between "relative" and "absolute" indexing with diagonal views instead of the pad-and-reshape trick.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class LayerNorm(nn.Module):
+    """Channel layer-norm over dim 1 of [B, C, T], eps 1e-4, parameters `gamma` / `beta` (reference :24-42)."""
+
+    def __init__(self, channels, eps=1e-4):
+        super().__init__()
+        self.channels, self.eps = channels, eps
+        self.gamma = nn.Parameter(torch.ones(channels))
+        self.beta = nn.Parameter(torch.zeros(channels))
+
+    def forward(self, x):
+        return F.layer_norm(x.transpose(1, -1), (self.channels,), self.gamma, self.beta, self.eps).transpose(1, -1)
+
+
+class SinusoidalPositionalEmbedding(nn.Module):
+    """tensor2tensor-style sinusoidal table indexed by the running count of non-padding entries (reference :45-100).
+    Keeps the reference's `_float_tensor` buffer so state-dicts match."""
+
+    def __init__(self, embedding_dim, padding_idx, init_size=1024):
+        super().__init__()
+        self.embedding_dim, self.padding_idx = embedding_dim, padding_idx
+        self.weights = self.get_embedding(init_size, embedding_dim, padding_idx)
+        self.register_buffer("_float_tensor", torch.FloatTensor(1))
+
+    @staticmethod
+    def get_embedding(num_embeddings, embedding_dim, padding_idx=None):
+        half = embedding_dim // 2
+        freq = torch.exp(torch.arange(half, dtype=torch.float) * -(math.log(10000) / (half - 1)))
+        ang = torch.arange(num_embeddings, dtype=torch.float)[:, None] * freq[None, :]
+        table = torch.cat([ang.sin(), ang.cos()], dim=1)
+        if embedding_dim % 2 == 1:
+            table = torch.cat([table, torch.zeros(num_embeddings, 1)], dim=1)
+        if padding_idx is not None:
+            table[padding_idx] = 0
+        return table
+
+    def forward(self, bsz, seq_len, input):
+        """`input` [B, T]: entries equal to padding_idx are padding.  Returns [bsz, seq_len, -1] exactly as the reference
+        does (a `.view`, which only equals [B, T, dim] when seq_len == T -- reference encoder.py:51 relies on that)."""
+        need = self.padding_idx + 1 + seq_len
+        if self.weights is None or need > self.weights.size(0) or input.shape[1] + self.padding_idx + 1 > self.weights.size(0):
+            self.weights = self.get_embedding(max(need, input.shape[1] + self.padding_idx + 1), self.embedding_dim,
+                                              self.padding_idx)
+        self.weights = self.weights.to(self._float_tensor)
+        keep = input.ne(self.padding_idx).int()
+        positions = (torch.cumsum(keep, dim=1).type_as(keep) * keep).long() + self.padding_idx
+        return self.weights.index_select(0, positions.reshape(-1)).view(bsz, seq_len, -1).detach()
+
+
+class MultiHeadAttention(nn.Module):
+    """Self-attention with learned relative-position key/value embeddings inside a +-window (reference :103-254).
+    Outside the window the relative logit is 0 (not -inf): attention stays global."""
+
+    def __init__(self, channels, out_channels, n_heads, window_size=None, heads_share=True, p_dropout=0.0,
+                 block_length=None, proximal_bias=False, proximal_init=False):
+        super().__init__()
+        assert channels % n_heads == 0
+        if block_length is not None or proximal_bias:
+            raise NotImplementedError("block_length / proximal_bias are never used by VISinger")
+        self.channels, self.out_channels, self.n_heads = channels, out_channels, n_heads
+        self.window_size, self.heads_share = window_size, heads_share
+        self.k_channels = channels // n_heads
+        self.conv_q = nn.Conv1d(channels, channels, 1)
+        self.conv_k = nn.Conv1d(channels, channels, 1)
+        self.conv_v = nn.Conv1d(channels, channels, 1)
+        if window_size is not None:
+            n_rel = 1 if heads_share else n_heads
+            std = self.k_channels ** -0.5
+            self.emb_rel_k = nn.Parameter(torch.randn(n_rel, window_size * 2 + 1, self.k_channels) * std)
+            self.emb_rel_v = nn.Parameter(torch.randn(n_rel, window_size * 2 + 1, self.k_channels) * std)
+        self.conv_o = nn.Conv1d(channels, out_channels, 1)
+        nn.init.xavier_uniform_(self.conv_q.weight)
+        nn.init.xavier_uniform_(self.conv_k.weight)
+        if proximal_init:
+            self.conv_k.weight.data.copy_(self.conv_q.weight.data)
+            self.conv_k.bias.data.copy_(self.conv_q.bias.data)
+        nn.init.xavier_uniform_(self.conv_v.weight)
+
+    def forward(self, x, c, attn_mask=None):
+        B, _, T = x.shape
+        h, d = self.n_heads, self.k_channels
+        q = self.conv_q(x).view(B, h, d, T).transpose(2, 3)            # [B, h, T, d]
+        k = self.conv_k(c).view(B, h, d, -1).transpose(2, 3)
+        v = self.conv_v(c).view(B, h, d, -1).transpose(2, 3)
+        scale = 1.0 / math.sqrt(d)
+        scores = torch.matmul(q, k.transpose(-2, -1)) * scale           # [B, h, T, T]
+        w = self.window_size
+        if w is not None:
+            assert k.shape[2] == T, "Relative attention is only available for self-attention."
+            rel = torch.matmul(q, self.emb_rel_k.unsqueeze(0).transpose(-2, -1)) * scale   # [B, h, T, 2w+1]
+            for r in range(2 * w + 1):                                   # relative offset o = r - w on diagonal o
+                o = r - w
+                n = T - abs(o)
+                if n <= 0:
+                    continue
+                i0 = max(0, -o)
+                scores.diagonal(offset=o, dim1=-2, dim2=-1).add_(rel[:, :, i0:i0 + n, r])
+        if attn_mask is not None:
+            scores = scores.masked_fill(attn_mask == 0, -1e4)
+        p = F.softmax(scores, dim=-1)
+        out = torch.matmul(p, v)                                         # [B, h, T, d]
+        if w is not None:
+            p_rel = p.new_zeros(B, h, T, 2 * w + 1)
+            for r in range(2 * w + 1):
+                o = r - w
+                n = T - abs(o)
+                if n <= 0:
+                    continue
+                i0 = max(0, -o)
+                p_rel[:, :, i0:i0 + n, r] = p.diagonal(offset=o, dim1=-2, dim2=-1)
+            out = out + torch.matmul(p_rel, self.emb_rel_v.unsqueeze(0))
+        out = out.transpose(2, 3).contiguous().view(B, h * d, T)
+        return self.conv_o(out)
+
+
+class FFN(nn.Module):
+    """conv(k) -> ReLU -> conv(1), both on masked input (reference :323-345; `activation` is never passed => ReLU)."""
+
+    def __init__(self, in_channels, out_channels, filter_channels, kernel_size, p_dropout=0.0, activation=None):
+        super().__init__()
+        self.activation = activation
+        self.conv_1 = nn.Conv1d(in_channels, filter_channels, kernel_size, padding=kernel_size // 2)
+        self.conv_2 = nn.Conv1d(filter_channels, out_channels, 1)
+
+    def forward(self, x, x_mask):
+        x = self.conv_1(x * x_mask)
+        x = x * torch.sigmoid(1.702 * x) if self.activation == "gelu" else torch.relu(x)
+        return self.conv_2(x * x_mask)
+
+
+class RelativeEncoder(nn.Module):
+    """Post-LN transformer encoder over [B, C, T] with an optional broadcast condition `g` (reference :257-320)."""
+
+    def __init__(self, hidden_channels, filter_channels, n_heads, n_layers, kernel_size=1, p_dropout=0.0, window_size=4,
+                 block_length=None, pre_ln=False, gin_channels=None, **kwargs):
+        super().__init__()
+        self.hidden_channels, self.n_layers, self.pre_ln = hidden_channels, n_layers, pre_ln
+        self.attn_layers = nn.ModuleList()
+        self.norm_layers_1 = nn.ModuleList()
+        self.ffn_layers = nn.ModuleList()
+        self.norm_layers_2 = nn.ModuleList()
+        for _ in range(n_layers):
+            self.attn_layers.append(MultiHeadAttention(hidden_channels, hidden_channels, n_heads, window_size=window_size,
+                                                       p_dropout=p_dropout, block_length=block_length))
+            self.norm_layers_1.append(LayerNorm(hidden_channels))
+            self.ffn_layers.append(FFN(hidden_channels, hidden_channels, filter_channels, kernel_size, p_dropout=p_dropout))
+            self.norm_layers_2.append(LayerNorm(hidden_channels))
+        if pre_ln:
+            self.last_ln = LayerNorm(hidden_channels)
+        if gin_channels is not None:
+            self.pre_net = nn.Conv1d(gin_channels, hidden_channels, 1)
+
+    def forward(self, x, x_mask, g=None):
+        attn_mask = x_mask.unsqueeze(2) * x_mask.unsqueeze(-1)
+        if g is not None:
+            g = self.pre_net(g)
+        for i in range(self.n_layers):
+            if g is not None:
+                x = x + g
+            x = x * x_mask
+            h = self.norm_layers_1[i](x) if self.pre_ln else x
+            x = x + self.attn_layers[i](h, h, attn_mask)
+            if not self.pre_ln:
+                x = self.norm_layers_1[i](x)
+            h = self.norm_layers_2[i](x) if self.pre_ln else x
+            x = x + self.ffn_layers[i](h, x_mask)
+            if not self.pre_ln:
+                x = self.norm_layers_2[i](x)
+        if self.pre_ln:
+            x = self.last_ln(x)
+        return x * x_mask
