@@ -6,7 +6,7 @@ import torch
 SMALL_HPARAMS = dict(
     hidden_size=32, p_dropout=0.1, enc_layers=2, ffn_kernel_size=9, ffn_filter_channels=64, num_heads=2,
     use_pos_embed=True, dec_blocks="1", dec_kernel_size=[3, 7, 11], dec_dilation_sizes=[[1, 3, 5]] * 3,
-    upsample_rates=[5, 3, 2], initial_upsample_channels=64, upsample_kernel_sizes=[11, 7, 4], gin_channels=16,
+    upsample_rates=[5, 3], initial_upsample_channels=64, upsample_kernel_sizes=[11, 7], gin_channels=16,
     frame_prior_layers=2, use_pitch_embed=True, pitch_predictor_layers=2, use_phoneme_pred=True,
     phoneme_predictor_layers=1, predictor_grad=0.1, segment_size=32, num_mel_bins=16, num_linear_bins=33,
     use_spk_id=True, use_spk_embed=False, num_spk=2)

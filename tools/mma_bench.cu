@@ -20,13 +20,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint
 // mode bits: 0 = fence between MMAs, 1 = alternate between two accumulators, 2 = shift A start by (i%11) rows
 __global__ void __launch_bounds__(128, 1) bench(int N, int M, int n_mma, int kc, int mode, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tslot;
   const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < 58 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -38,7 +39,57 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int M, int n_mma, int kc,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tslot;
-  if (threadIdx.x == 0) {
+  if (warp == 1 && (mode & 8)) {
+    // whole-warp issue: uniform control flow, elect.sync guards the instruction (CUTLASS style)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)N >> 3) << 17) | (((uint32_t)M >> 4) << 24);
+    const uint32_t row_bytes = kc * 2, sbo = 8 * row_bytes, layout = kc == 64 ? 2u : kc == 32 ? 4u : 6u;
+    const uint32_t a0 = base, b0 = base + 24 * 1024;
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      const uint32_t aa = a0 + ((mode & 4) ? (uint32_t)(i % 11) * row_bytes : 0u);
+      const uint64_t ad = make_desc(aa, sbo, layout), bd = make_desc(b0, sbo, layout);
+      uint32_t elected;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+      if (elected)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(i > 1 ? 1u : 0u) : "memory");
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (lane == 0) {
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+        if (clock64() - t0 > 2000000000LL) break;
+      }
+      const long long t2 = clock64();
+      if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+  } else if ((mode & 16) && (threadIdx.x == 0 || threadIdx.x == 64)) {
+    const int who = threadIdx.x == 0 ? 0 : 1;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)N >> 3) << 17) | (((uint32_t)M >> 4) << 24);
+    const uint32_t row_bytes = kc * 2, sbo = 8 * row_bytes, layout = kc == 64 ? 2u : kc == 32 ? 4u : 6u;
+    const uint32_t a0 = base, b0 = base + 24 * 1024;
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma / 2; ++i) {
+      const uint32_t aa = a0 + (uint32_t)(i % 11) * row_bytes;
+      const uint64_t ad = make_desc(aa, sbo, layout), bd = make_desc(b0, sbo, layout);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(tmem + who * 256), "l"(ad), "l"(bd), "r"(idesc), "r"(i > 1 ? 1u : 0u) : "memory");
+    }
+    const long long t1 = clock64();
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(who ? &bar2 : &bar)) : "memory");
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(smem_u32(who ? &bar2 : &bar)) : "memory");
+      if (clock64() - t0 > 2000000000LL) break;
+    }
+    const long long t2 = clock64();
+    if (blockIdx.x == 0 && who == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  } else if (threadIdx.x == 0 && !(mode & 8) && !(mode & 16)) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)N >> 3) << 17) | (((uint32_t)M >> 4) << 24);
     const uint32_t row_bytes = kc * 2, sbo = 8 * row_bytes, layout = kc == 64 ? 2u : kc == 32 ? 4u : 6u;
     const uint32_t a0 = base, b0 = base + 24 * 1024;
@@ -73,11 +124,11 @@ int main() {
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int n_mma = 2000;
   printf("%4s %4s %3s %5s %10s %10s\n", "M", "N", "kc", "mode", "issue/mma", "total/mma");
-  for (int M : {128, 64})
-    for (int kc : {64, 16})
-      for (int N : {16, 32, 64, 128, 256})
-        for (int mode : {0, 1, 2, 4}) {
-          for (int rep = 0; rep < 2; ++rep) bench<<<148, 128, 50 * 1024>>>(N, M, n_mma, kc, mode, d);
+  for (int M : {128})
+    for (int kc : {64})
+      for (int N : {16, 64, 128, 256})
+        for (int mode : {4, 16}) {
+          for (int rep = 0; rep < 2; ++rep) bench<<<148, 128, 60 * 1024>>>(N, M, n_mma, kc, mode, d);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
           long long h[2];

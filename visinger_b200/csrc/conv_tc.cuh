@@ -17,8 +17,11 @@
 //     memory for the whole persistent kernel: one TMA burst at start, no per-tap barrier round trips.
 // ConvTranspose1d runs as `stride` polyphase launches of the same kernel (out_stride / out_phase).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
-// lane), warps 2..5 = epilogue.  A CTA tile is `mb` blocks of 128 time steps (mb = 1, 2 or 4) x N_TILE channels:
+// Warp roles (224 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer 0, warps 2..5 = epilogue,
+// warp 6 = MMA issuer 1.  tcgen05.mma is issued by ONE thread and costs ~80 cycles of that thread per instruction
+// (tools/mma_bench.cu), more than the tensor time of an N <= 128 MMA; with mb >= 2 the two issuers take alternate
+// 128-row blocks of the tile (different accumulators), which doubles the issue rate (measured 40 / 48 / 64 cycles per
+// MMA at N = 16 / 64 / 128).  A CTA tile is `mb` blocks of 128 time steps (mb = 1, 2 or 4) x N_TILE channels:
 // every weight tile feeds mb MMAs (weight traffic / mb) and all per-tile costs (barrier waits, index math,
 // TMA issue, staging synchronisation) are amortised over mb*128 rows -- the low-channel stages are bound by that
 // overhead, not by HBM or tensor throughput.  The accumulator is double-buffered in TMEM (2 x mb x N_TILE
@@ -254,7 +257,7 @@ struct TileIter {
   }
 };
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;   // 7 warps: TMA producer, MMA issuer 0, 4 epilogue warps, MMA issuer 1
 constexpr int kMaxStages = 8;
 constexpr int kMaxAddBufs = 4;
 constexpr int kMaxCW = 64;
@@ -298,7 +301,7 @@ __device__ __forceinline__ void stage_out(const float* v, uint32_t base, uint32_
 //                      out[c] = tanh(a) * sigmoid(s)  -- fused_add_tanh_sigmoid_multiply, encoder.py:206-213;
 //                      the output tensor has Cout / 2 channels
 //       EPI_TC_COUPLE  m = (acc + bias) * mask; out = (add0 - m) * mask | m + add0 * mask  (flow.py:78,83)
-template <int CW, int MODE>
+template <int CW, int MODE, int NP>
 __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, const CUtensorMap& tmAdd1,
                                                  const CUtensorMap& tmRaw, const CUtensorMap& tmAct, const ConvTC& p,
                                                  uint32_t smem_base, uint32_t bar_base, uint32_t tmem_base, int warp,
@@ -310,7 +313,8 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const int n_echunks = p.n_echunks, n_ntiles = p.n_ntiles, m_tiles_per_b = p.m_tiles_per_b, n_tile = p.n_tile;
   const int n_add_bufs = p.n_add_bufs, total_tiles = p.total_tiles, mb = p.mb;
   const int e_box_rows = p.e_box_rows, e_n_boxes = p.e_n_boxes;
-  const int n_parts = p.n_parts, part_coff = p.part_coff;
+  constexpr int n_parts = NP;            // bf16 planes per tensor: 1 = plain bf16, 2 = split-bf16 (hi, lo)
+  const int part_coff = p.part_coff;
   const uint32_t e_buf_bytes = p.e_buf_bytes, swz_in = p.e_swz_mask, swz_out = p.e_out_swz_mask;
   const uint32_t part_bytes = p.e_part_bytes;     // one bf16 plane (hi or lo) of a staging buffer
   const bool has_add0 = p.has_add0, has_add1 = p.has_add1 && MODE == EPI_TC_LINEAR, has_raw = p.has_raw,
@@ -536,7 +540,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
 // loop-invariant is hoisted into registers, descriptors are advanced by integer adds on their low word.
 template <bool HALO, bool RESIDENT, int KK>
 __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_base, uint32_t w_base, uint32_t bar_base,
-                                                 uint32_t tmem_base) {
+                                                 uint32_t tmem_base, int issuer, int n_issuers) {
   using namespace tc;
   const int total_tiles = p.total_tiles, n_achunks = p.n_achunks, ktaps = p.ktaps, stages_a = p.stages_a,
             stages_w = p.stages_w, n_tile = p.n_tile, mb = p.mb;
@@ -579,16 +583,16 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
           if (!HALO || !RESIDENT) fence_after_sync();
           const uint32_t accumulate = first ? 0u : 1u;
           first = 0;
-          uint32_t ab16 = a16, d_tmem = d_tmem0;
-          for (int bi = 0; bi < mb; ++bi) {        // every weight tile feeds mb MMAs
+          uint32_t ab16 = a16 + (uint32_t)issuer * blk_step16, d_tmem = d_tmem0 + (uint32_t)(issuer * n_tile);
+          for (int bi = issuer; bi < mb; bi += n_issuers) {   // every weight tile feeds mb MMAs, split over the issuers
 #pragma unroll
             for (int kk = 0; kk < KK; ++kk) {
               // HALO: the row-shifted start address keeps base_offset = 0 -- the UMMA unit applies the swizzle
               // XOR to absolute shared-memory address bits (verified on B200, tools/tc_probe.py).
               umma_bf16(d_tmem, mk(ab16 + 2u * kk), mk(w16 + 2u * kk), idesc, (kk > 0) ? 1u : accumulate);
             }
-            ab16 += blk_step16;
-            d_tmem += (uint32_t)n_tile;
+            ab16 += blk_step16 * (uint32_t)n_issuers;
+            d_tmem += (uint32_t)(n_tile * n_issuers);
           }
           if (HALO) a16 += tap_step16;
           if (!RESIDENT) {
@@ -642,11 +646,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.has_add1) prefetch_tmap(&tmAdd1);
     if (p.has_raw) prefetch_tmap(&tmRaw);
     if (p.has_act) prefetch_tmap(&tmAct);
+    const uint32_t n_iss = p.mb >= 2 ? 2u : 1u;      // every issuer commits to the stage / accumulator barriers
     for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1);
-      mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1);
+      mbar_init(a_full(s), 1); mbar_init(a_empty(s), n_iss);
+      mbar_init(w_full(s), 1); mbar_init(w_empty(s), n_iss);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), n_iss); mbar_init(acc_empty(s), 4); }
     for (int s = 0; s < kMaxAddBufs; ++s) mbar_init(bar_base + 8u * (kBarAdd + s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -703,15 +708,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 6) {
+    // ===================== MMA issuers =====================
+    const int n_issuers = p.mb >= 2 ? 2 : 1;
+    const int issuer = warp == 1 ? 0 : 1;
+    if (lane == 0 && issuer < n_issuers) {
       const int kk_n = p.KC / 16;
 #define VSG_MMA(H, R)                                                                                        \
   do {                                                                                                       \
-    if (kk_n == 4) conv_tc_mma_loop<H, R, 4>(p, a_base, w_base, bar_base, tmem_base);                        \
-    else if (kk_n == 2) conv_tc_mma_loop<H, R, 2>(p, a_base, w_base, bar_base, tmem_base);                   \
-    else conv_tc_mma_loop<H, R, 1>(p, a_base, w_base, bar_base, tmem_base);                                  \
+    if (kk_n == 4) conv_tc_mma_loop<H, R, 4>(p, a_base, w_base, bar_base, tmem_base, issuer, n_issuers);     \
+    else if (kk_n == 2) conv_tc_mma_loop<H, R, 2>(p, a_base, w_base, bar_base, tmem_base, issuer, n_issuers); \
+    else conv_tc_mma_loop<H, R, 1>(p, a_base, w_base, bar_base, tmem_base, issuer, n_issuers);               \
   } while (0)
       if (p.halo_mode && p.w_resident) VSG_MMA(true, true);
       else if (p.halo_mode) VSG_MMA(true, false);
@@ -723,12 +730,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
 #define VSG_EPI(CWV)                                                                                              \
   do {                                                                                                            \
-    if (p.mode == EPI_TC_LINEAR)                                                                                  \
-      conv_tc_epilogue<CWV, EPI_TC_LINEAR>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
+    if (p.mode == EPI_TC_LINEAR && p.n_parts == 2)                                                                \
+      conv_tc_epilogue<CWV, EPI_TC_LINEAR, 2>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
+    else if (p.mode == EPI_TC_LINEAR)                                                                             \
+      conv_tc_epilogue<CWV, EPI_TC_LINEAR, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
     else if (p.mode == EPI_TC_GATE)                                                                               \
-      conv_tc_epilogue<CWV, EPI_TC_GATE>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);   \
+      conv_tc_epilogue<CWV, EPI_TC_GATE, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);   \
     else                                                                                                          \
-      conv_tc_epilogue<CWV, EPI_TC_COUPLE>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
+      conv_tc_epilogue<CWV, EPI_TC_COUPLE, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
   } while (0)
     if (!SMALL && p.cw == 64) VSG_EPI(64);
     else if (p.cw == 32) VSG_EPI(32);

@@ -253,6 +253,12 @@ class VISinger(nn.Module):
         """models/visinger.py:75-90: everything upstream of z_p (plain PyTorch, any device).
         Returns (mu_p, logs_p, tgt_nonpadding [B, 1, T], spk_emb [B, gin, 1]); fills ret["f0_pred"]."""
         ret = {} if ret is None else ret
+        # cuDNN convolutions default to TF32 on the GPU, which alone costs ~1e-4 on mu_p (SURVEY.md 8c); the prior runs in
+        # true fp32 so that the whole forward stays inside the reference's fp32 tolerance.
+        with torch.backends.cudnn.flags(enabled=torch.backends.cudnn.enabled, allow_tf32=False):
+            return self._prior(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret)
+
+    def _prior(self, text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret):
         mask = (mel2ph > 0).float().unsqueeze(1)
         prior_inp = self.text_encoder(text_tokens, pitch_tokens, dur_tokens, mel2ph) * mask
         if self.use_pos_embed:                                                      # models/visinger.py:79-82
