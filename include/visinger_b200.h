@@ -184,6 +184,15 @@ int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias,
                           int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t flags,
                           int32_t device);
 
+/* Tuning aids for tools/tune_plans.py: force the tile plan (0 / -1 = automatic) and the number of timed repetitions of
+ * the following vsg_debug_conv1d_bf16 calls; average kernel milliseconds of the last such call. */
+int vsg_debug_set_plan(int32_t mb, int32_t cw, int32_t two_ctas, int32_t resident, int32_t reps);
+float vsg_debug_last_ms(void);
+
+/* Host-only tuning aid: print (stderr) the tile plan the launcher would choose for one convolution. */
+int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t B, int32_t L, int32_t n_adds,
+                   int32_t n_outs, int32_t x3);
+
 /* Process-wide tuning defaults of the tensor-core path: activation-operand feeding mode, resident weights, and the
  * L2-resident batch tiling of the decoder (target MB of one intermediate tensor per sub-batch, 0 = no tiling, <0 =
  * keep; minimum tiles per launch, <=0 = keep). */

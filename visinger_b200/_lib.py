@@ -70,7 +70,7 @@ class VsgTensor(ctypes.Structure):
 
 
 def _source_files():
-    files = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    files = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh", ".h", ".inc"))]
     return files + [_HEADER]
 
 

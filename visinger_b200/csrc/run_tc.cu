@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 
 namespace vsg {
 
@@ -99,11 +100,19 @@ struct EpiTC {
 
 // HALO mode verified on B200 (tools/tc_probe.py): the UMMA unit applies the swizzle XOR to absolute
 // shared-memory address bits, so a row-shifted start address needs base_offset = 0.
-struct TCOptions { int halo_mode = 1; int w_resident = 1; int max_mb = 4; };
+struct TCOptions {
+  int halo_mode = 1; int w_resident = 1; int max_mb = 4; int plan_only = 0;
+  int force_mb = 0, force_cw = 0, force_two = -1, force_resident = -1;   // tuning overrides (0 / -1 = automatic)
+};
 
 TCOptions g_default_opts;
 
 constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic smem we plan within (1 KB alignment slack + barriers)
+
+struct TunedPlan { int cin, cout, k, n_adds, n_outs, x3, mb, cw, two, resident; };
+static const TunedPlan kTunedPlans[] = {
+#include "tc_plan_table.inc"
+    {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
 
 // One convolution launch.  x: [B, Lin, Cin] bf16 channels-last; add/out tensors: [B, Lout, Cout].
 int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, int B, int Lin, int in_off0, int dil,
@@ -129,7 +138,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   // Plan the tile: try mb = 4, 2, 1 blocks of 128 rows; prefer the largest that lets two CTAs share an SM (small
   // kernels), else the largest that fits at all.
   ConvTC p;
-  auto plan = [&](int mb, int cw, size_t budget, ConvTC* out) -> bool {
+  auto plan = [&](int mb, int cw, size_t budget, int force_resident, ConvTC* out) -> bool {
     ConvTC q;
     memset(&q, 0, sizeof(q));
     if (NT % cw) return false;
@@ -165,12 +174,12 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     q.e_n_boxes = 128 * mb / q.e_box_rows;
     q.e_part_bytes = (uint32_t)((128 * mb * cw * 2 + 1023) & ~1023);
     q.e_buf_bytes = (uint32_t)n_parts * q.e_part_bytes;
-    q.n_add_bufs = 2 + (cw <= 32 && mb <= 2 ? 1 : 0);
+    q.n_add_bufs = 2 + (small && cw <= 32 && mb <= 2 ? 1 : 0);
     const size_t e_bytes = ((size_t)n_adds * q.n_add_bufs + (size_t)n_outs * 2) * q.e_buf_bytes;
     const size_t w_total = (size_t)q.n_wtiles * q.w_stage_bytes;
     const int a_per_tile = q.halo_mode ? q.n_achunks : q.n_wtiles;
     size_t w_bytes;
-    q.w_resident = (opt.w_resident && q.n_ntiles == 1 && w_total <= 112 * 1024 &&
+    q.w_resident = (opt.w_resident && force_resident != 0 && q.n_ntiles == 1 && w_total <= 112 * 1024 &&
                     w_total + e_bytes + 2 * (size_t)q.a_stage_bytes <= budget) ? 1 : 0;
     if (q.w_resident) {
       w_bytes = w_total;
@@ -195,13 +204,59 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     *out = q;
     return true;
   };
+  // Candidate plans: (blocks per tile) x (one or two CTAs per SM) x (epilogue chunk width), ranked by a small cycle
+  // model of one 128-row block (constants measured on B200, tools/mma_bench.cu and the ncu source pages):
+  //   MMA issue   ~80 cycles per tcgen05.mma from one thread, ~40 with the second issuer (mb >= 2), never below the
+  //               tensor time N/2 of an M=128 x N MMA;
+  //   epilogue    per chunk: ~400 cycles of CTA-wide synchronisation + TMA issue (shared by the mb blocks of the tile)
+  //               plus ~150 + 4*cw cycles per block, scaled by the number of TMA-loaded / TMA-stored tensors;
+  //   weights     streamed weight tiles cost their bytes / ~32 B per cycle per tile (shared by mb blocks) and want >= 3
+  //               stages in flight; resident weights are free after the prologue.
+  // Two CTAs per SM overlap all of it ~1.9x.
   bool planned = false;
+  double best_cost = 1e30;
+  TCOptions topt = opt;
+  if (!opt.force_mb && !opt.force_cw && opt.force_two < 0 && opt.force_resident < 0) {
+    // measured best plans (tools/tune_plans.py on a B200) take precedence over the model
+    for (const TunedPlan& t : kTunedPlans)
+      if (t.cin == w.Cin && t.cout == w.Cout && t.k == w.ktaps && t.n_adds == n_adds && t.n_outs == n_outs &&
+          t.x3 == (w.x3 ? 1 : 0) && (Lq >= 128 * t.mb)) {
+        topt.force_mb = t.mb; topt.force_cw = t.cw; topt.force_two = t.two; topt.force_resident = t.resident;
+        break;
+      }
+  }
   const int mb_max = opt.max_mb;
-  if (small)
-    for (int mb = std::min(4, mb_max); mb >= 1 && !planned; mb >>= 1)
-      if (2 * mb * NT <= 256) planned = plan(mb, cw_max, half_budget, &p);   // two CTAs per SM: half the smem and TMEM each
-  for (int mb = std::min(NT <= 128 ? (small ? 4 : 2) : 1, mb_max); mb >= 1 && !planned; mb >>= 1)
-    for (int cw = cw_max; cw >= 16 && !planned; cw >>= 1) planned = plan(mb, cw, kSmemBudget, &p);
+  const double n_mma = (double)(w.x3 ? 3 : 1) * (w.Cin / 16) * w.ktaps;
+  for (int two = small ? 1 : 0; two >= 0; --two)
+    for (int mb = std::min(NT <= 128 ? (small ? 4 : 2) : 1, mb_max); mb >= 1; mb >>= 1)
+      for (int cw = cw_max; cw >= 16; cw >>= 1) {
+        if (two && 2 * mb * NT > 256) continue;   // two CTAs per SM: half the TMEM (and half the smem) each
+        if ((topt.force_mb && mb != topt.force_mb) || (topt.force_cw && cw != topt.force_cw) ||
+            (topt.force_two >= 0 && two != topt.force_two)) continue;
+        ConvTC q;
+        if (!plan(mb, cw, two ? half_budget : kSmemBudget, topt.force_resident, &q)) continue;
+        if (topt.force_resident >= 0 && q.w_resident != topt.force_resident) continue;
+        const double mma = n_mma * std::max(mb >= 2 ? 40.0 : 80.0, NT / 2.0);
+        const double epi = (double)(NT / cw) * (400.0 / mb + 150.0 + 4.0 * cw) * (1.0 + 0.5 * n_adds + 0.5 * (n_outs - 1));
+        double wcy = 0.0;
+        if (!q.w_resident) {
+          wcy = (double)q.n_wtiles * q.w_box_bytes / mb / 32.0;
+          if (q.stages_w < 3) wcy *= 1.5;
+        }
+        const double stage_pen = q.stages_a < 3 && q.w_resident ? 1.1 : 1.0;   // shallow A ring exposes TMA latency
+        const double cost = std::max(std::max(mma, epi), wcy) * stage_pen / (two ? 1.9 : 1.0);
+        if (cost < best_cost) { best_cost = cost; p = q; planned = true; }
+      }
+  if (!planned && (topt.force_mb || topt.force_cw)) {   // a tuned entry that does not fit this launch: use the model
+    topt = TCOptions();
+    topt.halo_mode = opt.halo_mode; topt.w_resident = opt.w_resident; topt.max_mb = opt.max_mb;
+    for (int two = small ? 1 : 0; two >= 0 && !planned; --two)
+      for (int mb = std::min(NT <= 128 ? (small ? 4 : 2) : 1, mb_max); mb >= 1 && !planned; mb >>= 1)
+        for (int cw = cw_max; cw >= 16 && !planned; cw >>= 1) {
+          if (two && 2 * mb * NT > 256) continue;
+          planned = plan(mb, cw, two ? half_budget : kSmemBudget, -1, &p);
+        }
+  }
   if (!planned) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory");
   const int cw = p.cw;
   const int ow = e.mode == EPI_TC_GATE ? cw / 2 : cw;                // output channels per chunk
@@ -224,6 +279,16 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.scale = e.scale; p.slope = 0.1f;
   p.out_f32 = e.out_f32;
   p.error_flag = error_flag;
+
+  static const bool debug_plan = getenv("VSG_DEBUG_PLAN") != nullptr;
+  if (debug_plan || opt.plan_only) {
+    const bool two_ctas = small && 2 * (smem + 1024) <= 228 * 1024 && 2 * p.tmem_cols <= 512;
+    fprintf(stderr, "[vsg plan] conv %d->%d k%d d%d%s B%d Lq%d adds%d outs%d | %s%s mb%d cw%d halo%d resident%d stagesA%d "
+                    "stagesW%d addbufs%d smem %zu KB tmem %u tiles %d\n", w.Cin, w.Cout, w.ktaps, dil, w.x3 ? " x3" : "", B, Lq,
+            n_adds, n_outs, small ? "small" : "large", two_ctas ? " 2cta" : "", p.mb, p.cw, p.halo_mode, p.w_resident,
+            p.stages_a, p.stages_w, p.n_add_bufs, smem / 1024, p.tmem_cols, p.total_tiles);
+  }
+  if (opt.plan_only) return VSG_OK;
 
   CUtensorMap tmA, tmAdd0, tmAdd1, tmRaw, tmAct;
   VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.CinT, (uint64_t)Lin, (uint64_t)B, (uint64_t)x_ld, (uint64_t)Lin * x_ld,
@@ -542,6 +607,18 @@ using namespace vsg;
 
 // Per-layer parity hook (tests only; allocates and synchronises): one bf16 tensor-core Conv1d with the full
 // fused epilogue.  See include/visinger_b200.h.
+static TCOptions g_debug_force;      // plan override + repetitions for the next vsg_debug_conv1d_bf16 calls
+static int g_debug_reps = 1;
+static float g_debug_ms = 0.f;
+
+extern "C" int vsg_debug_set_plan(int32_t mb, int32_t cw, int32_t two, int32_t resident, int32_t reps) {
+  g_debug_force.force_mb = mb; g_debug_force.force_cw = cw; g_debug_force.force_two = two;
+  g_debug_force.force_resident = resident;
+  g_debug_reps = reps > 0 ? reps : 1;
+  return VSG_OK;
+}
+extern "C" float vsg_debug_last_ms(void) { return g_debug_ms; }
+
 extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias, const void* add0_bf16,
                                      const void* add1_bf16, float scale, float* out_f32, void* out_raw_bf16,
                                      void* out_act_bf16, int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t k,
@@ -574,16 +651,46 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
     opt.halo_mode = flags & 1;
     opt.w_resident = (flags >> 1) & 1;
     opt.max_mb = (flags >> 4) ? (flags >> 4) : 4;
+    opt.force_mb = g_debug_force.force_mb; opt.force_cw = g_debug_force.force_cw;
+    opt.force_two = g_debug_force.force_two; opt.force_resident = g_debug_force.force_resident;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
     rc = launch_conv_tc(&tmp, wt, (const __nv_bfloat16*)x_bf16, B, L, -((k - 1) * dilation / 2), dilation, L, 1, 0, L, e,
-                        opt, err, 0);
+                        opt, err, 0);                                  // warm-up + correctness run
+    if (rc == VSG_OK && g_debug_reps > 1) {
+      cudaEventRecord(e0, 0);
+      for (int r = 0; r < g_debug_reps && rc == VSG_OK; ++r)
+        rc = launch_conv_tc(&tmp, wt, (const __nv_bfloat16*)x_bf16, B, L, -((k - 1) * dilation / 2), dilation, L, 1, 0, L,
+                            e, opt, err, 0);
+      cudaEventRecord(e1, 0);
+    }
     if (rc == VSG_OK) {
       cudaError_t ce = cudaDeviceSynchronize();
       if (ce != cudaSuccess) rc = fail(VSG_ECUDA, "conv_tc_kernel execution failed: %s", cudaGetErrorString(ce));
+      else if (g_debug_reps > 1) { cudaEventElapsedTime(&g_debug_ms, e0, e1); g_debug_ms /= g_debug_reps; }
     }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
   if (err) cudaFree(err);
   for (void* q : tmp.allocs) cudaFree(q);
   return rc;
+}
+
+// Host-only: print the tile plan the launcher would choose for one convolution (tuning aid; no GPU needed).
+extern "C" int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t B, int32_t L, int32_t n_adds,
+                              int32_t n_outs, int32_t x3) {
+  VsgPack tmp;
+  ConvWTC wt;
+  wt.Cin = Cin; wt.Cout = Cout; wt.CinT = x3 ? 2 * Cin : Cin; wt.CoutT = Cout; wt.ktaps = k; wt.has_tmap = true; wt.x3 = x3 != 0;
+  static __nv_bfloat16 dummy;
+  EpiTC e;
+  if (n_adds > 0) e.add0 = &dummy;
+  if (n_adds > 1) e.add1 = &dummy;
+  if (n_outs > 0) e.out_act = &dummy;
+  if (n_outs > 1) e.out_raw = &dummy;
+  TCOptions opt = g_default_opts;
+  opt.plan_only = 1;
+  return launch_conv_tc(&tmp, wt, &dummy, B, L, -((k - 1) * dilation / 2), dilation, L, 1, 0, L, e, opt, nullptr, 0);
 }
 
 // Select the default A-operand feeding mode of the tensor-core convolutions (process-wide; tests and tuning).
