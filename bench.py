@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--l2-mb", type=int, default=-1, help="L2-resident batch tiling target (MB per tensor; 0 = off)")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch of the conv kernels")
     return ap.parse_args()
 
 
@@ -175,9 +176,9 @@ def main():
     fsd = O.synth_state_dict(flow_shapes(FLOW_FULL), 1234)
     gsd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
     hp = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, dev, precision=args.precision)
-    if args.l2_mb >= 0:
+    if args.l2_mb >= 0 or args.no_pdl:
         from visinger_b200 import _lib
-        _lib.set_tc_options(l2_tensor_mb=args.l2_mb)
+        _lib.set_tc_options(halo_mode=1 | (256 if args.no_pdl else 0), l2_tensor_mb=args.l2_mb)
 
     x, mask, g = make_inputs(rank, B, 192, T, 256)
     logs = torch.full_like(x, -1.0)
@@ -251,6 +252,10 @@ def main():
         value = world * audio_per_step * args.steps / (ms * 1e-3)
         e2e_value = world * audio_per_step * args.steps / (ms_e2e * 1e-3)
         dec_tflops = DEC_FLOP_PER_FRAME * B * T * args.steps / (ms_dec * 1e-3) / 1e12
+        traffic = None          # DRAM bytes of the decoder's conv kernels per pass, from the committed ncu capture
+        tp = os.path.join(ROOT, "profiles", "r1_decoder_traffic.json")
+        if os.path.exists(tp) and args.precision == "bf16" and (B, T) == (16, 1000):
+            traffic = json.load(open(tp))["traffic_bytes"]
         peak = pk["bf16_sustained"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -269,7 +274,9 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": dec_tflops / peak, "traffic": None,
+                         "frac": dec_tflops / peak, "traffic": traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the 108 conv_tc_kernel launches of "
+                                         "one decoder pass (profiles/r1_decoder_traffic.json)",
                          "kernel": "decoder convolutions (vsg_generator_forward region)",
                          "algorithmic": f"{DEC_FLOP_PER_FRAME} FLOP/frame x {B * T} frames",
                          "ms": ms_dec / args.steps, "peak_source": pk["src"] + ", sustained bf16"},

@@ -660,20 +660,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue while this one runs, and do
+  // not touch anything the previous kernel produced (activations, residuals, output buffers) before it has completed.
+  // Only the resident-weight fetch below is independent of the previous kernel and is issued ahead of the wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp == 0 && lane == 0 && p.w_resident) {   // n_ntiles == 1: the weights do not depend on the tile
+    mbar_expect_tx(w_full(0), (uint32_t)p.n_wtiles * p.w_box_bytes);
+    int wt = 0;
+    for (int c = 0; c < p.n_achunks; ++c)
+      for (int wp = 0; wp < p.n_wpass[c]; ++wp)
+        for (int j = 0; j < p.ktaps; ++j, ++wt)
+          tma_load_2d(w_base + (uint32_t)wt * p.w_stage_bytes, &tmW, w_full(0), p.w_coff[c][wp], j * p.CoutT);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int sa = 0, sw = 0;
       uint32_t pa = 0, pw = 0;
-      if (p.w_resident) {   // n_ntiles == 1: the weights do not depend on the tile
-        mbar_expect_tx(w_full(0), (uint32_t)p.n_wtiles * p.w_box_bytes);
-        int wt = 0;
-        for (int c = 0; c < p.n_achunks; ++c)
-          for (int wp = 0; wp < p.n_wpass[c]; ++wp)
-            for (int j = 0; j < p.ktaps; ++j, ++wt)
-              tma_load_2d(w_base + (uint32_t)wt * p.w_stage_bytes, &tmW, w_full(0), p.w_coff[c][wp], j * p.CoutT);
-      }
       TileIter it;
       it.init((int)blockIdx.x, (int)gridDim.x, p.n_ntiles, p.m_tiles_per_b);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it.next()) {

@@ -103,6 +103,7 @@ struct EpiTC {
 struct TCOptions {
   int halo_mode = 1; int w_resident = 1; int max_mb = 4; int plan_only = 0;
   int force_mb = 0, force_cw = 0, force_two = -1, force_resident = -1;   // tuning overrides (0 / -1 = automatic)
+  int use_pdl = 1;
 };
 
 TCOptions g_default_opts;
@@ -309,15 +310,29 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
+  // Programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, resident-weight fetch) may
+  // overlap the tail of the previous kernel in the stream; it executes griddepcontrol.wait before touching activations.
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = opt.use_pdl ? 1 : 0;
+  cudaError_t le;
   if (small) {
     // two CTAs per SM when two copies of the shared-memory carve-up (+1 KB reserved each) and of the TMEM fit
     const bool two = 2 * (smem + 1024) <= 228 * 1024 && 2 * p.tmem_cols <= 512;
-    const int grid = std::min(p.total_tiles, (two ? 2 : 1) * P->sm_count);
-    conv_tc_kernel<true><<<grid, tc::kThreads, smem, st>>>(tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
+    cfg.gridDim = dim3(std::min(p.total_tiles, (two ? 2 : 1) * P->sm_count));
+    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
   } else {
-    const int grid = std::min(p.total_tiles, P->sm_count);
-    conv_tc_kernel<false><<<grid, tc::kThreads, smem, st>>>(tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
+    cfg.gridDim = dim3(std::min(p.total_tiles, P->sm_count));
+    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
   }
+  if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of conv_tc_kernel failed: %s", cudaGetErrorString(le));
   VSG_LAUNCH_CHECK("conv_tc_kernel");
   return VSG_OK;
 }
@@ -697,7 +712,8 @@ extern "C" int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dila
 extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t l2_tensor_mb, int32_t min_tiles) {
   g_default_opts.halo_mode = halo_mode & 1;
   g_default_opts.w_resident = w_resident;
-  g_default_opts.max_mb = (halo_mode >> 4) ? (halo_mode >> 4) : 4;      // bits 4.. of halo_mode: cap on blocks per tile
+  g_default_opts.max_mb = ((halo_mode >> 4) & 15) ? ((halo_mode >> 4) & 15) : 4;   // bits 4..7: cap on blocks per tile
+  g_default_opts.use_pdl = (halo_mode & 256) ? 0 : 1;                               // bit 8: disable dependent launch
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;
