@@ -184,6 +184,17 @@ int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias,
                           int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t flags,
                           int32_t device);
 
+/*
+ * Per-layer parity hook for the fused ResBlock1 pair kernel (tests and tuning only; allocates and synchronises):
+ *   v = (conv1d(leaky_relu(conv1d(xa, w1, dilation d1) + b1, 0.1), w2) + b2 + add0 + add1) * scale
+ * -- one (c1, c2) step of ResBlock1.forward (modules/visinger/decoder.py:91-104) with xa = leaky_relu(x) and add0 = x.
+ *   xa_bf16, add0, add1, out_raw, out_act: device bf16 [B, L, C] channels-last; w1, w2: HOST fp32 [C][C][k];
+ *   b1, b2: HOST fp32 [C]; out_f32: device fp32 [B, L, C] or NULL.  C in {16, 32}.
+ */
+int vsg_debug_pair_bf16(const void* xa_bf16, const float* w1, const float* b1, const float* w2, const float* b2,
+                        const void* add0_bf16, const void* add1_bf16, float scale, float* out_f32, void* out_raw_bf16,
+                        void* out_act_bf16, int32_t B, int32_t L, int32_t C, int32_t k, int32_t d1, int32_t device);
+
 /* Tuning aids for tools/tune_plans.py: force the tile plan (0 / -1 = automatic) and the number of timed repetitions of
  * the following vsg_debug_conv1d_bf16 calls; average kernel milliseconds of the last such call. */
 int vsg_debug_set_plan(int32_t mb, int32_t cw, int32_t two_ctas, int32_t resident, int32_t reps);

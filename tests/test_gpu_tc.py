@@ -175,3 +175,32 @@ def test_generator_bf16x3_meets_fp32_tolerance(cuda_device, B, T):
     err = maxabs(got, ref)
     print(f"bf16x3 generator B={B} T={T}: max-abs {err:.3e}, rel-L2 {float((got - ref).norm() / ref.norm()):.3e}")
     assert err <= 1e-4
+
+
+@pytest.mark.parametrize("C,k,d1,B,L", [(16, 3, 1, 2, 1000), (16, 3, 5, 1, 777), (16, 7, 3, 2, 512), (16, 11, 5, 1, 2049),
+                                        (32, 3, 3, 2, 640), (32, 7, 1, 1, 1500), (32, 11, 5, 2, 256), (32, 11, 1, 1, 4100)])
+def test_fused_resblock_pair_kernel(cuda_device, C, k, d1, B, L):
+    """One (c1, c2) step of ResBlock1 (decoder.py:93-102) in a single kernel: conv1 -> +b1 -> leaky_relu -> (bf16, in
+    shared memory) -> conv2 -> +b2 + residual + running sum -> x scale.  The reference below rounds the intermediate
+    to bf16 exactly where the kernel does."""
+    from visinger_b200 import _lib
+    gen = torch.Generator().manual_seed(C * 7 + k * 3 + d1)
+    x = torch.randn(B, L, C, generator=gen).to(torch.bfloat16)
+    xa = F.leaky_relu(x.float(), 0.1).to(torch.bfloat16)
+    w1 = (torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5).to(torch.bfloat16).float()
+    w2 = (torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5).to(torch.bfloat16).float()
+    b1, b2 = torch.randn(C, generator=gen) * 0.1, torch.randn(C, generator=gen) * 0.1
+    add1 = torch.randn(B, L, C, generator=gen).to(torch.bfloat16)
+    t = F.conv1d(xa.float().transpose(1, 2).double(), w1.double(), b1.double(), dilation=d1, padding=(k - 1) * d1 // 2)
+    t = F.leaky_relu(t, 0.1).float().to(torch.bfloat16)
+    y = F.conv1d(t.double(), w2.double(), b2.double(), padding=(k - 1) // 2).transpose(1, 2)
+    want = (y + x.double() + add1.double()) / 3.0
+    d = cuda_device
+    out, raw, act = _lib.debug_pair_bf16(xa.to(d).contiguous(), w1, b1, w2, b2, d1, add0=x.to(d).contiguous(),
+                                         add1=add1.to(d).contiguous(), scale=1.0 / 3.0)
+    err = (out.cpu().double() - want).abs()
+    # an intermediate element that sits on a bf16 rounding boundary may round the other way (fp32 vs fp64 accumulation):
+    # bound the worst case loosely and the typical case tightly
+    assert float(err.max()) <= 1e-2 and float(err.mean()) <= 2e-4
+    assert torch.equal(raw.cpu(), out.cpu().to(torch.bfloat16))
+    assert maxabs(act.cpu().double(), F.leaky_relu(out.cpu().double(), 0.1)) <= 2e-2

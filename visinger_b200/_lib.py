@@ -156,6 +156,8 @@ def lib() -> ctypes.CDLL:
                                             i32]
         L.vsg_set_tc_options.restype = ctypes.c_int
         L.vsg_set_tc_options.argtypes = [i32, i32, i32, i32]
+        L.vsg_debug_pair_bf16.restype = ctypes.c_int
+        L.vsg_debug_pair_bf16.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_float, vp, vp, vp, i32, i32, i32, i32, i32, i32]
         if L.vsg_abi_version() != 1:
             raise RuntimeError("visinger_b200: ABI version mismatch between _lib.py and the shared library")
         _lib = L
@@ -281,6 +283,27 @@ def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int,
                                      B, Lx, Cin, Cout, k, dilation, flags, dev.index or 0)
     check(rc, "vsg_debug_conv1d_bf16")
     return (out, raw, act) if want_bf16 else out
+
+
+def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, add1=None, scale: float = 1.0):
+    """Per-layer parity hook of the fused ResBlock1 pair kernel.  xa_bld / add0 / add1: CUDA bf16 [B, L, C];
+    returns (out_f32, out_raw_bf16, out_act_bf16)."""
+    require_cuda(xa_bld, "xa")
+    assert xa_bld.dtype == torch.bfloat16 and xa_bld.is_contiguous()
+    B, Lx, C = xa_bld.shape
+    k = w1.shape[2]
+    h = [t.detach().to("cpu", torch.float32).contiguous() for t in (w1, b1, w2, b2)]
+    dev = xa_bld.device
+    out = torch.zeros(B, Lx, C, dtype=torch.float32, device=dev)
+    raw = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev)
+    act = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev)
+    torch.cuda.synchronize(dev)
+    rc = lib().vsg_debug_pair_bf16(xa_bld.data_ptr(), h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), h[3].data_ptr(),
+                                   add0.data_ptr() if add0 is not None else None,
+                                   add1.data_ptr() if add1 is not None else None, float(scale), out.data_ptr(),
+                                   raw.data_ptr(), act.data_ptr(), B, Lx, C, k, d1, dev.index or 0)
+    check(rc, "vsg_debug_pair_bf16")
+    return out, raw, act
 
 
 def split_bf16(x: torch.Tensor) -> torch.Tensor:

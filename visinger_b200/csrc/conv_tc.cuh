@@ -56,7 +56,11 @@ struct ConvTC {
   int n_parts, part_coff;       // epilogue tensors hold n_parts bf16 planes (hi[, lo]) part_coff channels apart
   int out_stride, out_phase;
   int mb;                       // 128-row blocks per tile
+  int tile_stride;              // rows between consecutive tiles (128*mb, or less when a fused pair discards its halo rows)
   int m_tiles_per_b, total_tiles;
+  int bar_slot0, tmem_col0;     // barrier bank / TMEM column offset of this half (fused pair: second conv uses bank 1)
+  uint32_t a_off;               // start of the A ring inside shared memory (0 for the plain kernel)
+  int t_row_off;                // fused pair: time of row 0 of the intermediate tile relative to the tile's first output row
   int halo_mode;                // 1: one A tile per channel chunk, taps via row-shifted descriptors
   int a_box_rows, a_n_boxes;    // the A tile is fetched as a_n_boxes TMA boxes of a_box_rows rows (<= 256 each)
   int w_resident;               // 1: all (chunk, tap) weight tiles are loaded once and stay in shared memory
@@ -307,7 +311,10 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
                                                  uint32_t smem_base, uint32_t bar_base, uint32_t tmem_base, int warp,
                                                  int lane) {
   using namespace tc;
+  bar_base += 8u * (uint32_t)p.bar_slot0;
+  tmem_base += (uint32_t)p.tmem_col0;
   constexpr int OW = (MODE == EPI_TC_GATE) ? CW / 2 : CW;   // output channels per chunk
+  const int tile_stride = p.tile_stride;
   const bool leader = (warp == 2 && lane == 0);             // issues every epilogue TMA operation of the CTA
   const int quarter = warp & 3;          // tcgen05.ld: warp w may only touch TMEM lanes 32*(w%4) .. +31
   const int n_echunks = p.n_echunks, n_ntiles = p.n_ntiles, m_tiles_per_b = p.m_tiles_per_b, n_tile = p.n_tile;
@@ -344,7 +351,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   int pf_cc = 0, pf_buf = 0, pf_left = my_tiles * n_echunks;
   auto issue_next_add = [&]() {
     if (pf_left <= 0) return;
-    const int ch = pf.nt * n_tile + pf_cc * CW, row = pf.mt * (128 * mb);
+    const int ch = pf.nt * n_tile + pf_cc * CW, row = pf.mt * tile_stride;
     const uint32_t bar = add_bar0 + 8u * pf_buf;
     mbar_expect_tx(bar, add_bytes);
     for (int pt = 0; pt < n_parts; ++pt)
@@ -380,7 +387,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   it.init((int)blockIdx.x, (int)gridDim.x, n_ntiles, m_tiles_per_b);
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next()) {
     const int nt = it.nt, b = it.b;
-    const int tile_row0 = it.mt * (128 * mb);
+    const int tile_row0 = it.mt * tile_stride;
     mbar_wait(acc_full0 + 8u * as, pacc, error_flag);
     fence_after_sync();
     const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * mb * n_tile);
@@ -498,7 +505,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
         if (p.out_f32) {   // debug / parity hook only: plain per-thread stores
           const int n = q * p.out_stride + p.out_phase;
           const int oc_total = (MODE == EPI_TC_GATE) ? p.Cout / 2 : p.Cout;
-          if (q < p.Lq && n < p.Lout && och < oc_total) {
+          if (srow < tile_stride && q < p.Lq && n < p.Lout && och < oc_total) {
             float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((long long)b * p.Lout + n) * oc_total + och);
 #pragma unroll
             for (int i = 0; i < OW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -553,6 +560,8 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
   const uint32_t a_stage16 = p.a_stage_bytes >> 4, w_stage16 = p.w_stage_bytes >> 4;
   const uint32_t tap_step16 = HALO ? (uint32_t)(p.dil * p.KC * 2) >> 4 : 0u;
   const uint32_t blk_step16 = (uint32_t)(128 * p.KC * 2) >> 4;     // one 128-row block further down the A tile
+  bar_base += 8u * (uint32_t)p.bar_slot0;
+  tmem_base += (uint32_t)p.tmem_col0;
   const uint32_t bar_a_full = bar_base + 8u * kBarAFull, bar_a_empty = bar_base + 8u * kBarAEmpty;
   const uint32_t bar_w_full = bar_base + 8u * kBarWFull, bar_w_empty = bar_base + 8u * kBarWEmpty;
   const uint32_t bar_acc_full = bar_base + 8u * kBarAccFull, bar_acc_empty = bar_base + 8u * kBarAccEmpty;
@@ -625,7 +634,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_base = smem_base;
+  const uint32_t a_base = smem_base + p.a_off;
   const uint32_t w_base = smem_base + p.w_off;
   const uint32_t bar_base = smem_base + p.bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * (kBarAFull + s); };
@@ -683,7 +692,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       it.init((int)blockIdx.x, (int)gridDim.x, p.n_ntiles, p.m_tiles_per_b);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it.next()) {
         const int nt = it.nt, mt = it.mt, b = it.b;
-        const int row0 = mt * (128 * p.mb) + p.in_off0;
+        const int row0 = mt * p.tile_stride + p.in_off0;
         for (int c = 0; c < p.n_achunks; ++c) {
           if (p.halo_mode) {
             mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);

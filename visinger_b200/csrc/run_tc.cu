@@ -3,6 +3,7 @@
 #include "run.cuh"
 #include "pack_tc.cuh"
 #include "conv_tc.cuh"
+#include "pair_tc.cuh"
 
 #include <algorithm>
 #include <mutex>
@@ -104,6 +105,7 @@ struct TCOptions {
   int halo_mode = 1; int w_resident = 1; int max_mb = 4; int plan_only = 0;
   int force_mb = 0, force_cw = 0, force_two = -1, force_resident = -1;   // tuning overrides (0 / -1 = automatic)
   int use_pdl = 1;
+  int fuse_pairs = 1;
 };
 
 TCOptions g_default_opts;
@@ -263,7 +265,8 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   const int ow = e.mode == EPI_TC_GATE ? cw / 2 : cw;                // output channels per chunk
   p.B = B; p.Lq = Lq; p.Lout = Lout;
   p.out_stride = out_stride; p.out_phase = out_phase;
-  p.m_tiles_per_b = (Lq + 128 * p.mb - 1) / (128 * p.mb);
+  p.tile_stride = 128 * p.mb;
+  p.m_tiles_per_b = (Lq + p.tile_stride - 1) / p.tile_stride;
   p.total_tiles = p.m_tiles_per_b * p.n_ntiles * B;
   p.e_swz_mask = cw >= 64 ? 7u : cw >= 32 ? 3u : 1u;
   p.e_out_swz_mask = ow >= 64 ? 7u : ow >= 32 ? 3u : ow >= 16 ? 1u : 0u;
@@ -334,6 +337,114 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   }
   if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of conv_tc_kernel failed: %s", cudaGetErrorString(le));
   VSG_LAUNCH_CHECK("conv_tc_kernel");
+  return VSG_OK;
+}
+
+// ---- fused ResBlock1 pair (pair_tc.cuh) ---------------------------------------------------------------------------
+bool pair_supported(const ConvWTC& w1, const ConvWTC& w2, int d1, int L) {
+  const int C = w1.Cin, k = w1.ktaps;
+  if (!w1.has_tmap || !w2.has_tmap || w1.x3 || w2.x3) return false;
+  if (w1.Cout != C || w2.Cin != C || w2.Cout != C || w2.ktaps != k || (C != 16 && C != 32) || k % 2 == 0) return false;
+  if (256 + (k - 1) * d1 > 512 || L < 256) return false;
+  return true;
+}
+
+// x_new = conv2(leaky_relu(conv1(xa) + b1)) + b2 [+ add0 + add1] [* scale]; xa = leaky_relu(x) [B, L, C] bf16.
+int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const __nv_bfloat16* xa, int B, int L, int d1,
+                   const EpiTC& e, const TCOptions& opt, int* error_flag, cudaStream_t st) {
+  const int C = w1.Cin, k = w1.ktaps, mb = 2;
+  const int h2 = (k - 1) / 2, pad1 = (k - 1) * d1 / 2, halo1 = (k - 1) * d1;
+  const int V = 128 * mb - (k - 1);
+  const int n_adds = (e.add0 ? 1 : 0) + (e.add1 ? 1 : 0), n_outs = (e.out_raw ? 1 : 0) + (e.out_act ? 1 : 0);
+  ConvTC p1, p2;
+  memset(&p1, 0, sizeof(p1));
+  memset(&p2, 0, sizeof(p2));
+  for (ConvTC* q : {&p1, &p2}) {
+    q->B = B; q->Lq = L; q->Lout = L; q->KC = C; q->ktaps = k; q->n_achunks = 1; q->a_coff[0] = 0; q->n_wpass[0] = 1;
+    q->w_coff[0][0] = 0; q->n_wtiles = k; q->Cout = C; q->n_tile = C; q->n_ntiles = 1; q->CoutT = C; q->out_stride = 1;
+    q->mb = mb; q->tile_stride = V; q->m_tiles_per_b = (L + V - 1) / V; q->total_tiles = q->m_tiles_per_b * B;
+    q->halo_mode = 1; q->w_resident = 1; q->stages_w = 1; q->n_parts = 1; q->part_coff = C;
+    q->w_box_bytes = (uint32_t)C * C * 2; q->w_stage_bytes = (q->w_box_bytes + 1023u) & ~1023u;
+    q->swizzle_code = C == 32 ? 4u : 6u; q->sbo_bytes = 8u * C * 2u; q->slope = 0.1f; q->scale = 1.f;
+    q->error_flag = error_flag; q->cw = C; q->n_echunks = 1;
+  }
+  // front half: conv1 (dilated) over the activated input
+  p1.dil = d1; p1.in_off0 = -h2 - pad1; p1.t_row_off = -h2; p1.bias = w1.bias;
+  const int rows1 = 128 * mb + halo1;
+  p1.a_n_boxes = (rows1 + 255) / 256;
+  p1.a_box_rows = (((rows1 + p1.a_n_boxes - 1) / p1.a_n_boxes) + 7) & ~7;
+  p1.a_box_bytes = (uint32_t)p1.a_box_rows * C * 2;
+  p1.a_stage_bytes = ((uint32_t)p1.a_n_boxes * p1.a_box_bytes + 1023u) & ~1023u;
+  p1.bar_slot0 = 0; p1.tmem_col0 = 0;
+  // back half: conv2 (dilation 1) over the intermediate tile + the ordinary fused epilogue
+  p2.dil = 1; p2.bias = w2.bias;
+  const int rows2 = (128 * mb + k - 1 + 7) & ~7;
+  p2.a_stage_bytes = ((uint32_t)rows2 * C * 2 + 1023u) & ~1023u;
+  p2.stages_a = 2;
+  p2.bar_slot0 = tc::kNumBars; p2.tmem_col0 = 2 * mb * C;
+  p2.e_box_rows = V; p2.e_n_boxes = 1;
+  p2.e_part_bytes = (uint32_t)((128 * mb * C * 2 + 1023) & ~1023); p2.e_buf_bytes = p2.e_part_bytes;
+  p2.n_add_bufs = 2;
+  p2.e_swz_mask = p2.e_out_swz_mask = C >= 32 ? 3u : 1u;
+  p2.mode = EPI_TC_LINEAR; p2.scale = e.scale;
+  p2.has_add0 = e.add0 != nullptr; p2.has_add1 = e.add1 != nullptr;
+  p2.has_raw = e.out_raw != nullptr; p2.has_act = e.out_act != nullptr;
+  p2.out_f32 = e.out_f32;
+  const size_t w_bytes = (size_t)k * p1.w_stage_bytes;
+  const size_t e_bytes = ((size_t)n_adds * p2.n_add_bufs + (size_t)n_outs * 2) * p2.e_buf_bytes;
+  const size_t fixed = 2 * w_bytes + 2 * (size_t)p2.a_stage_bytes + e_bytes;
+  if (fixed + 2 * (size_t)p1.a_stage_bytes > kSmemBudget) return fail(VSG_EUNSUPPORTED, "fused pair does not fit in shared memory");
+  p1.stages_a = (int)std::min<size_t>(4, (kSmemBudget - fixed) / p1.a_stage_bytes);
+  p1.a_off = 0;
+  p1.w_off = (uint32_t)(p1.stages_a * p1.a_stage_bytes);
+  p2.a_off = p1.w_off + (uint32_t)w_bytes;
+  p2.w_off = p2.a_off + 2 * p2.a_stage_bytes;
+  p2.e_off = p2.w_off + (uint32_t)w_bytes;
+  p2.bar_off = p2.e_off + (uint32_t)e_bytes;
+  p1.bar_off = p2.bar_off;
+  const size_t smem = 1024 + (size_t)p2.bar_off + 8 * (2 * tc::kNumBars) + 64;
+  if (smem > kSmemMax) return fail(VSG_EUNSUPPORTED, "fused pair does not fit in shared memory (%zu B)", smem);
+  p2.tmem_cols = 32;
+  while (p2.tmem_cols < (uint32_t)(4 * mb * C)) p2.tmem_cols <<= 1;
+  p1.tmem_cols = p2.tmem_cols;
+  static const bool debug_plan = getenv("VSG_DEBUG_PLAN") != nullptr;
+  if (debug_plan || opt.plan_only)
+    fprintf(stderr, "[vsg plan] PAIR %d k%d d%d B%d L%d adds%d outs%d | V%d stagesA1 %d smem %zu KB tmem %u tiles %d\n", C, k,
+            d1, B, L, n_adds, n_outs, V, p1.stages_a, smem / 1024, p2.tmem_cols, p1.total_tiles);
+  if (opt.plan_only) return VSG_OK;
+
+  CUtensorMap tmA, tmAdd0, tmAdd1, tmRaw, tmAct;
+  VSG_TRY(encode_3d(&tmA, xa, (uint64_t)C, (uint64_t)L, (uint64_t)B, (uint64_t)C, (uint64_t)L * C, (uint32_t)C,
+                    (uint32_t)p1.a_box_rows, C));
+  auto emap = [&](CUtensorMap* m, const __nv_bfloat16* base) -> int {
+    return encode_3d(m, base, (uint64_t)C, (uint64_t)L, (uint64_t)B, (uint64_t)C, (uint64_t)L * C, (uint32_t)C, (uint32_t)V, C);
+  };
+  tmAdd0 = tmAdd1 = tmRaw = tmAct = tmA;
+  if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0));
+  if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1));
+  if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw));
+  if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act));
+  static bool attr_set = false;
+  if (!attr_set) {
+    VSG_CUDA_TRY(cudaFuncSetAttribute(pair_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    VSG_CUDA_TRY(cudaFuncSetAttribute(pair_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = dim3(std::min(p1.total_tiles, P->sm_count));
+  cfg.blockDim = dim3(tc::kPairThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = opt.use_pdl ? 1 : 0;
+  cudaError_t le = C == 16 ? cudaLaunchKernelEx(&cfg, pair_tc_kernel<16>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2)
+                           : cudaLaunchKernelEx(&cfg, pair_tc_kernel<32>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2);
+  if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of pair_tc_kernel failed: %s", cudaGetErrorString(le));
+  VSG_LAUNCH_CHECK("pair_tc_kernel");
   return VSG_OK;
 }
 
@@ -586,7 +697,13 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
             if (j == NK - 1) { e2.scale = 1.0f / (float)NK; e2.out_act = xout; }
             else e2.out_raw = bS;
           }
-          if (c.dec_resblock == 1) {        // ResBlock1 (decoder.py:91-104)
+          if (c.dec_resblock == 1 && !x3 && opt.fuse_pairs && pair_supported(rb.c1_tc[q], rb.c2_tc[q], d, L)) {
+            // low-channel stages: both convs of the pair in ONE kernel, the intermediate never leaves the SM
+            e2.bias = rb.c2_tc[q].bias;
+            if (!last) { e2.out_raw = bR; e2.out_act = bRA; }
+            VSG_TRY(launch_pair_tc(P, rb.c1_tc[q], rb.c2_tc[q], curA, nb, L, d, e2, opt, err, st));
+            cur = bR; curA = bRA;
+          } else if (c.dec_resblock == 1) {        // ResBlock1 (decoder.py:91-104)
             EpiTC e1;
             e1.bias = rb.c1_tc[q].bias; e1.out_act = bT;
             VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
@@ -691,6 +808,57 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
   return rc;
 }
 
+// Per-layer parity hook for the fused ResBlock1 pair (tests only; allocates and synchronises).
+//   xa: device bf16 [B, L, C] = leaky_relu(x); w1/w2: HOST fp32 [C][C][k]; b1/b2: HOST fp32 [C]; add0/add1 as above;
+//   v = (conv1d(leaky_relu(conv1d(xa, w1, dilation d1) + b1), w2) + b2 + add0 + add1) * scale.
+extern "C" int vsg_debug_pair_bf16(const void* xa_bf16, const float* w1, const float* b1, const float* w2, const float* b2,
+                                   const void* add0_bf16, const void* add1_bf16, float scale, float* out_f32,
+                                   void* out_raw_bf16, void* out_act_bf16, int32_t B, int32_t L, int32_t C, int32_t k,
+                                   int32_t d1, int32_t device) {
+  g_launches = 0;
+  if (!xa_bf16 || !w1 || !w2 || !b1 || !b2) return fail(VSG_EINVAL, "null pointer");
+  VSG_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VSG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  VsgPack tmp;
+  tmp.device = device;
+  tmp.sm_count = prop.multiProcessorCount;
+  std::vector<float> W1(w1, w1 + (size_t)C * C * k), W2(w2, w2 + (size_t)C * C * k), B1(b1, b1 + C), B2(b2, b2 + C);
+  ConvWTC wt1, wt2;
+  int rc = pack_conv_tc(&tmp, W1, B1, C, C, k, &wt1);
+  if (rc == VSG_OK) rc = pack_conv_tc(&tmp, W2, B2, C, C, k, &wt2);
+  int* err = nullptr;
+  if (rc == VSG_OK && cudaMalloc(&err, sizeof(int)) != cudaSuccess) rc = fail(VSG_ECUDA, "cudaMalloc failed");
+  if (rc == VSG_OK && !pair_supported(wt1, wt2, d1, L)) rc = fail(VSG_EUNSUPPORTED, "shape not supported by the fused pair");
+  if (rc == VSG_OK) {
+    cudaMemset(err, 0, sizeof(int));
+    EpiTC e;
+    e.bias = wt2.bias;
+    e.add0 = (const __nv_bfloat16*)add0_bf16; e.add1 = (const __nv_bfloat16*)add1_bf16;
+    e.scale = scale; e.out_f32 = out_f32;
+    e.out_raw = (__nv_bfloat16*)out_raw_bf16; e.out_act = (__nv_bfloat16*)out_act_bf16;
+    TCOptions opt;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    rc = launch_pair_tc(&tmp, wt1, wt2, (const __nv_bfloat16*)xa_bf16, B, L, d1, e, opt, err, 0);
+    if (rc == VSG_OK && g_debug_reps > 1) {
+      cudaEventRecord(e0, 0);
+      for (int r = 0; r < g_debug_reps && rc == VSG_OK; ++r)
+        rc = launch_pair_tc(&tmp, wt1, wt2, (const __nv_bfloat16*)xa_bf16, B, L, d1, e, opt, err, 0);
+      cudaEventRecord(e1, 0);
+    }
+    if (rc == VSG_OK) {
+      cudaError_t ce = cudaDeviceSynchronize();
+      if (ce != cudaSuccess) rc = fail(VSG_ECUDA, "pair_tc_kernel execution failed: %s", cudaGetErrorString(ce));
+      else if (g_debug_reps > 1) { cudaEventElapsedTime(&g_debug_ms, e0, e1); g_debug_ms /= g_debug_reps; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  if (err) cudaFree(err);
+  for (void* q : tmp.allocs) cudaFree(q);
+  return rc;
+}
+
 // Host-only: print the tile plan the launcher would choose for one convolution (tuning aid; no GPU needed).
 extern "C" int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t B, int32_t L, int32_t n_adds,
                               int32_t n_outs, int32_t x3) {
@@ -714,6 +882,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.w_resident = w_resident;
   g_default_opts.max_mb = ((halo_mode >> 4) & 15) ? ((halo_mode >> 4) & 15) : 4;   // bits 4..7: cap on blocks per tile
   g_default_opts.use_pdl = (halo_mode & 256) ? 0 : 1;                               // bit 8: disable dependent launch
+  g_default_opts.fuse_pairs = (halo_mode & 512) ? 0 : 1;                            // bit 9: disable fused resblock pairs
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;
