@@ -257,7 +257,7 @@ def release_workspaces() -> None:
 
 
 def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int, flags: int = 0, add0=None,
-                      add1=None, scale: float = 1.0, want_bf16: bool = False):
+                      add1=None, scale: float = 1.0, want_bf16: bool = False, want_f32: bool = True, want_raw: bool = True):
     """Per-layer parity hook: one Conv1d (+ fused epilogue) on the tcgen05 kernel.
     x_bld / add0 / add1: CUDA bf16 [B, L, C] channels-last; w: [Cout, Cin, k] fp32 (any device).
     Returns out_f32 [B, L, Cout], or (out_f32, out_raw_bf16, out_act_bf16) when want_bf16."""
@@ -271,21 +271,23 @@ def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int,
     bh = bias.detach().to("cpu", torch.float32).contiguous() if bias is not None else None
     dev = x_bld.device
     out = torch.empty(B, Lx, Cout, dtype=torch.float32, device=dev)
-    raw = torch.zeros(B, Lx, planes * Cout, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    raw = torch.zeros(B, Lx, planes * Cout, dtype=torch.bfloat16, device=dev) if (want_bf16 and want_raw) else None
     act = torch.zeros(B, Lx, planes * Cout, dtype=torch.bfloat16, device=dev) if want_bf16 else None
     for t in (add0, add1):
         assert t is None or (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous())
     torch.cuda.synchronize(dev)
     rc = lib().vsg_debug_conv1d_bf16(x_bld.data_ptr(), wh.data_ptr(), bh.data_ptr() if bh is not None else None,
                                      add0.data_ptr() if add0 is not None else None,
-                                     add1.data_ptr() if add1 is not None else None, float(scale), out.data_ptr(),
-                                     raw.data_ptr() if want_bf16 else None, act.data_ptr() if want_bf16 else None,
+                                     add1.data_ptr() if add1 is not None else None, float(scale),
+                                     out.data_ptr() if want_f32 else None,
+                                     raw.data_ptr() if raw is not None else None, act.data_ptr() if want_bf16 else None,
                                      B, Lx, Cin, Cout, k, dilation, flags, dev.index or 0)
     check(rc, "vsg_debug_conv1d_bf16")
     return (out, raw, act) if want_bf16 else out
 
 
-def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, add1=None, scale: float = 1.0):
+def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, add1=None, scale: float = 1.0,
+                    want_f32: bool = True):
     """Per-layer parity hook of the fused ResBlock1 pair kernel.  xa_bld / add0 / add1: CUDA bf16 [B, L, C];
     returns (out_f32, out_raw_bf16, out_act_bf16)."""
     require_cuda(xa_bld, "xa")
@@ -300,7 +302,8 @@ def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, ad
     torch.cuda.synchronize(dev)
     rc = lib().vsg_debug_pair_bf16(xa_bld.data_ptr(), h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), h[3].data_ptr(),
                                    add0.data_ptr() if add0 is not None else None,
-                                   add1.data_ptr() if add1 is not None else None, float(scale), out.data_ptr(),
+                                   add1.data_ptr() if add1 is not None else None, float(scale),
+                                   out.data_ptr() if want_f32 else None,
                                    raw.data_ptr(), act.data_ptr(), B, Lx, C, k, d1, dev.index or 0)
     check(rc, "vsg_debug_pair_bf16")
     return out, raw, act

@@ -341,12 +341,17 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
 }
 
 // ---- fused ResBlock1 pair (pair_tc.cuh) ---------------------------------------------------------------------------
-bool pair_supported(const ConvWTC& w1, const ConvWTC& w2, int d1, int L) {
+bool pair_supported(const ConvWTC& w1, const ConvWTC& w2, int d1, int L, int n_adds, int n_outs) {
   const int C = w1.Cin, k = w1.ktaps;
   if (!w1.has_tmap || !w2.has_tmap || w1.x3 || w2.x3) return false;
   if (w1.Cout != C || w2.Cin != C || w2.Cout != C || w2.ktaps != k || (C != 16 && C != 32) || k % 2 == 0) return false;
   if (256 + (k - 1) * d1 > 512 || L < 256) return false;
-  return true;
+  // shared-memory footprint (mirrors launch_pair_tc): 2 input stages + both weight sets + 2 intermediate tiles + staging
+  auto r1k = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
+  const int rows1 = 256 + (k - 1) * d1, nb = (rows1 + 255) / 256, box = (((rows1 + nb - 1) / nb) + 7) & ~7;
+  const size_t a1 = r1k((size_t)nb * box * C * 2), wb = (size_t)k * r1k((size_t)C * C * 2);
+  const size_t tb = r1k((size_t)((256 + k - 1 + 7) & ~7) * C * 2), eb = (size_t)(n_adds * 2 + n_outs * 2) * r1k(256 * C * 2);
+  return 2 * a1 + 2 * wb + 2 * tb + eb <= kSmemBudget;
 }
 
 // x_new = conv2(leaky_relu(conv1(xa) + b1)) + b2 [+ add0 + add1] [* scale]; xa = leaky_relu(x) [B, L, C] bf16.
@@ -384,16 +389,22 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   p2.bar_slot0 = tc::kNumBars; p2.tmem_col0 = 2 * mb * C;
   p2.e_box_rows = V; p2.e_n_boxes = 1;
   p2.e_part_bytes = (uint32_t)((128 * mb * C * 2 + 1023) & ~1023); p2.e_buf_bytes = p2.e_part_bytes;
-  p2.n_add_bufs = 2;
+  p2.n_add_bufs = 2;          // raised below to as many as fit (residual loads come from HBM: ~1.5 us of latency to cover)
   p2.e_swz_mask = p2.e_out_swz_mask = C >= 32 ? 3u : 1u;
   p2.mode = EPI_TC_LINEAR; p2.scale = e.scale;
   p2.has_add0 = e.add0 != nullptr; p2.has_add1 = e.add1 != nullptr;
   p2.has_raw = e.out_raw != nullptr; p2.has_act = e.out_act != nullptr;
   p2.out_f32 = e.out_f32;
   const size_t w_bytes = (size_t)k * p1.w_stage_bytes;
-  const size_t e_bytes = ((size_t)n_adds * p2.n_add_bufs + (size_t)n_outs * 2) * p2.e_buf_bytes;
-  const size_t fixed = 2 * w_bytes + 2 * (size_t)p2.a_stage_bytes + e_bytes;
+  size_t e_bytes = ((size_t)n_adds * p2.n_add_bufs + (size_t)n_outs * 2) * p2.e_buf_bytes;
+  size_t fixed = 2 * w_bytes + 2 * (size_t)p2.a_stage_bytes + e_bytes;
   if (fixed + 2 * (size_t)p1.a_stage_bytes > kSmemBudget) return fail(VSG_EUNSUPPORTED, "fused pair does not fit in shared memory");
+  while (n_adds > 0 && p2.n_add_bufs < tc::kMaxAddBufs &&
+         fixed + (size_t)n_adds * p2.e_buf_bytes + 3 * (size_t)p1.a_stage_bytes <= kSmemBudget) {
+    ++p2.n_add_bufs;
+    e_bytes += (size_t)n_adds * p2.e_buf_bytes;
+    fixed += (size_t)n_adds * p2.e_buf_bytes;
+  }
   p1.stages_a = (int)std::min<size_t>(4, (kSmemBudget - fixed) / p1.a_stage_bytes);
   p1.a_off = 0;
   p1.w_off = (uint32_t)(p1.stages_a * p1.a_stage_bytes);
@@ -409,8 +420,8 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   p1.tmem_cols = p2.tmem_cols;
   static const bool debug_plan = getenv("VSG_DEBUG_PLAN") != nullptr;
   if (debug_plan || opt.plan_only)
-    fprintf(stderr, "[vsg plan] PAIR %d k%d d%d B%d L%d adds%d outs%d | V%d stagesA1 %d smem %zu KB tmem %u tiles %d\n", C, k,
-            d1, B, L, n_adds, n_outs, V, p1.stages_a, smem / 1024, p2.tmem_cols, p1.total_tiles);
+    fprintf(stderr, "[vsg plan] PAIR %d k%d d%d B%d L%d adds%d outs%d | V%d stagesA1 %d addbufs%d smem %zu KB tmem %u tiles %d\n",
+            C, k, d1, B, L, n_adds, n_outs, V, p1.stages_a, p2.n_add_bufs, smem / 1024, p2.tmem_cols, p1.total_tiles);
   if (opt.plan_only) return VSG_OK;
 
   CUtensorMap tmA, tmAdd0, tmAdd1, tmRaw, tmAct;
@@ -697,7 +708,12 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
             if (j == NK - 1) { e2.scale = 1.0f / (float)NK; e2.out_act = xout; }
             else e2.out_raw = bS;
           }
-          if (c.dec_resblock == 1 && !x3 && opt.fuse_pairs && pair_supported(rb.c1_tc[q], rb.c2_tc[q], d, L)) {
+          // measured on B200 (tools/time_pair.py, B=16): C=32 pair 156-204 us vs 188-241 us un-fused; at C=16 the single
+          // epilogue warp set of the one-CTA-per-SM pair kernel is slower (239-275 us) than two co-resident un-fused CTAs
+          // (210-235 us), so only C=32 is fused by default (fuse_pairs == 2 forces both).
+          const bool fuse = c.dec_resblock == 1 && !x3 && opt.fuse_pairs && (ch == 32 || opt.fuse_pairs == 2) &&
+                            pair_supported(rb.c1_tc[q], rb.c2_tc[q], d, L, 1 + (e2.add1 ? 1 : 0), last ? 1 : 2);
+          if (fuse) {
             // low-channel stages: both convs of the pair in ONE kernel, the intermediate never leaves the SM
             e2.bias = rb.c2_tc[q].bias;
             if (!last) { e2.out_raw = bR; e2.out_act = bRA; }
@@ -829,7 +845,7 @@ extern "C" int vsg_debug_pair_bf16(const void* xa_bf16, const float* w1, const f
   if (rc == VSG_OK) rc = pack_conv_tc(&tmp, W2, B2, C, C, k, &wt2);
   int* err = nullptr;
   if (rc == VSG_OK && cudaMalloc(&err, sizeof(int)) != cudaSuccess) rc = fail(VSG_ECUDA, "cudaMalloc failed");
-  if (rc == VSG_OK && !pair_supported(wt1, wt2, d1, L)) rc = fail(VSG_EUNSUPPORTED, "shape not supported by the fused pair");
+  if (rc == VSG_OK && !pair_supported(wt1, wt2, d1, L, (add0_bf16 ? 1 : 0) + (add1_bf16 ? 1 : 0), (out_raw_bf16 ? 1 : 0) + (out_act_bf16 ? 1 : 0))) rc = fail(VSG_EUNSUPPORTED, "shape not supported by the fused pair");
   if (rc == VSG_OK) {
     cudaMemset(err, 0, sizeof(int));
     EpiTC e;
