@@ -12,6 +12,7 @@
 #include "pack_tc.cuh"
 
 #include <math.h>
+#include <algorithm>
 
 namespace vsg {
 
@@ -250,6 +251,31 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
       VSG_TRY(pack_conv_f32(L, Wc, b, st.Cout, st.Cin, nr, Identity{}, &ph.f32));
       VSG_TRY(pack_conv_tc(P, Wc, b, st.Cout, st.Cin, nr, &ph.tc));
       VSG_TRY(pack_conv_tc(P, Wc, b, st.Cout, st.Cin, nr, &ph.x3, true));
+    }
+    {   // merged polyphase convolution for the tensor-core path (one launch, contiguous stores)
+      int off_min = 1 << 30, off_max = -(1 << 30);
+      for (int r = 0; r < st.rate; ++r) {
+        const int nr = st.phases[r].f32.ktaps;
+        off_min = std::min(off_min, st.phases[r].in_off0);
+        off_max = std::max(off_max, st.phases[r].in_off0 + nr - 1);
+      }
+      const int kt = off_max - off_min + 1, s = st.rate, k = st.kernel, p = st.pad;
+      std::vector<float> Wm((size_t)s * st.Cout * st.Cin * kt, 0.f), bm((size_t)s * st.Cout);
+      for (int r = 0; r < s; ++r) {
+        const int j0 = (r + p) % s, nr = (k - 1 - j0) / s + 1, off_r = st.phases[r].in_off0;
+        for (int co = 0; co < st.Cout; ++co) {
+          bm[(size_t)r * st.Cout + co] = b[co];
+          for (int ci = 0; ci < st.Cin; ++ci)
+            for (int t = 0; t < kt; ++t) {
+              const int tp = off_min + t - off_r;            // tap index inside phase r
+              if (tp < 0 || tp >= nr) continue;
+              Wm[(((size_t)r * st.Cout + co) * st.Cin + ci) * kt + t] = W[((size_t)ci * st.Cout + co) * k + j0 + s * (nr - 1 - tp)];
+            }
+        }
+      }
+      st.merged_in_off0 = off_min;
+      VSG_TRY(pack_conv_tc(P, Wm, bm, s * st.Cout, st.Cin, kt, &st.merged_tc));
+      VSG_TRY(pack_conv_tc(P, Wm, bm, s * st.Cout, st.Cin, kt, &st.merged_x3, true));
     }
     // resblocks                                                            decoder.py:28-32
     st.blocks.resize(c.dec_n_kernels);

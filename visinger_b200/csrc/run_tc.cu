@@ -106,6 +106,7 @@ struct TCOptions {
   int force_mb = 0, force_cw = 0, force_two = -1, force_resident = -1;   // tuning overrides (0 / -1 = automatic)
   int use_pdl = 1;
   int fuse_pairs = 1;
+  int merge_ups = 1;
 };
 
 TCOptions g_default_opts;
@@ -686,13 +687,23 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       const int nb = std::min(pl.sub[i], B - b0);
       const bf* xin = stage_in + (size_t)b0 * Lin * Cin * np;
       bf* xout = stage_out + (size_t)b0 * L * ch * np;
-      for (int r = 0; r < us.rate; ++r) {   // ConvTranspose1d as polyphase convolutions (decoder.py:46)
+      if (opt.merge_ups && us.merged_tc.has_tmap && Lout == Lin * us.rate) {
+        // ConvTranspose1d (decoder.py:46) as ONE convolution Cin -> rate*Cout over the input rate: its channels-last
+        // output [nb, Lin, rate*Cout] is, byte for byte, the upsampled [nb, Lin*rate, Cout] tensor
         EpiTC e;
-        e.bias = us.phases[r].tc.bias;
+        e.bias = us.merged_tc.bias;
         e.out_raw = bU; e.out_act = bUA;
-        const int Lq = (Lout - r + us.rate - 1) / us.rate;
-        VSG_TRY(launch_conv_tc(P, W(us.phases[r].tc, us.phases[r].x3), xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r,
-                               Lout, e, opt, err, st));
+        VSG_TRY(launch_conv_tc(P, W(us.merged_tc, us.merged_x3), xin, nb, Lin, us.merged_in_off0, 1, Lin, 1, 0, Lin, e, opt,
+                               err, st));
+      } else {
+        for (int r = 0; r < us.rate; ++r) {   // one strided launch per polyphase
+          EpiTC e;
+          e.bias = us.phases[r].tc.bias;
+          e.out_raw = bU; e.out_act = bUA;
+          const int Lq = (Lout - r + us.rate - 1) / us.rate;
+          VSG_TRY(launch_conv_tc(P, W(us.phases[r].tc, us.phases[r].x3), xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r,
+                                 Lout, e, opt, err, st));
+        }
       }
       for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
         const ResBlockPack& rb = us.blocks[j];
@@ -899,6 +910,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.max_mb = ((halo_mode >> 4) & 15) ? ((halo_mode >> 4) & 15) : 4;   // bits 4..7: cap on blocks per tile
   g_default_opts.use_pdl = (halo_mode & 256) ? 0 : 1;                               // bit 8: disable dependent launch
   g_default_opts.fuse_pairs = (halo_mode & 512) ? 0 : 1;                            // bit 9: disable fused resblock pairs
+  g_default_opts.merge_ups = (halo_mode & 1024) ? 0 : 1;                            // bit 10: one launch per polyphase
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;

@@ -96,6 +96,10 @@ struct ResBlockPack {
 struct UpStage {
   int rate = 0, kernel = 0, Cin = 0, Cout = 0, pad = 0;
   std::vector<UpsPhase> phases;
+  // all `rate` polyphase sub-convolutions as ONE Conv1d(Cin -> rate*Cout): phase r owns output channels
+  // [r*Cout, (r+1)*Cout), taps zero-padded to a common window; its [B, L, rate*Cout] output IS [B, L*rate, Cout]
+  ConvWTC merged_tc, merged_x3;
+  int merged_in_off0 = 0;
   std::vector<ResBlockPack> blocks;
 };
 
