@@ -191,9 +191,17 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
       q.stages_a = (int)std::min<size_t>(tc::kMaxStages, (budget - w_bytes - e_bytes) / q.a_stage_bytes);
       q.stages_a = std::min(q.stages_a, std::max(mb >= 2 ? 3 : 4, 3 * a_per_tile));
     } else if (q.halo_mode) {
-      q.stages_a = 2;
+      // One A stage feeds (passes x taps x mb x KC/16) MMAs; a TMA round trip is ~3000 cycles, so a short-kernel conv
+      // (k = 3: ~1500 cycles of MMA per stage at C = 256) needs 3-4 stages in flight where k = 11 is fine with 2.
+      const double mma_cyc = std::max(mb >= 2 ? 40.0 : 80.0, NT / 2.0);
+      const double stage_cyc = (double)(w.x3 ? 1.5 : 1.0) * w.ktaps * mb * (KC / 16) * mma_cyc;
+      int want_a = std::min(4, std::max(2, (int)(3000.0 / stage_cyc) + 2));
       if (2 * (size_t)q.a_stage_bytes + e_bytes + 2 * (size_t)q.w_stage_bytes > budget) return false;
-      q.stages_w = (int)std::min<size_t>(tc::kMaxStages, (budget - e_bytes - 2 * q.a_stage_bytes) / q.w_stage_bytes);
+      while (want_a > 2 && (size_t)want_a * q.a_stage_bytes + e_bytes + 3 * (size_t)q.w_stage_bytes > budget) --want_a;
+      q.stages_a = want_a;
+      q.stages_w = (int)std::min<size_t>(tc::kMaxStages, (budget - e_bytes - (size_t)want_a * q.a_stage_bytes) / q.w_stage_bytes);
+      if (q.stages_w < 2) { q.stages_a = 2; q.stages_w = (int)((budget - e_bytes - 2 * (size_t)q.a_stage_bytes) / q.w_stage_bytes); }
+      q.stages_w = std::min(q.stages_w, tc::kMaxStages);
       w_bytes = (size_t)q.stages_w * q.w_stage_bytes;
     } else {
       const size_t per = (size_t)q.a_stage_bytes + q.w_stage_bytes;
@@ -687,7 +695,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       const int nb = std::min(pl.sub[i], B - b0);
       const bf* xin = stage_in + (size_t)b0 * Lin * Cin * np;
       bf* xout = stage_out + (size_t)b0 * L * ch * np;
-      if (opt.merge_ups && us.merged_tc.has_tmap && Lout == Lin * us.rate) {
+      if (opt.merge_ups && !x3 && us.merged_tc.has_tmap && Lout == Lin * us.rate) {   // (split-bf16 planes would interleave wrongly)
         // ConvTranspose1d (decoder.py:46) as ONE convolution Cin -> rate*Cout over the input rate: its channels-last
         // output [nb, Lin, rate*Cout] is, byte for byte, the upsampled [nb, Lin*rate, Cout] tensor
         EpiTC e;
