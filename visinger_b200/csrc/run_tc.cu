@@ -107,6 +107,7 @@ struct TCOptions {
   int use_pdl = 1;
   int fuse_pairs = 1;
   int merge_ups = 1;
+  int split_n = 1;
 };
 
 TCOptions g_default_opts;
@@ -127,12 +128,13 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (!w.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 16 "
                                                  "(conv %d -> %d)", w.Cin, w.Cout);
   if (Lq <= 0 || B <= 0) return VSG_OK;
-  const int KC = pick_kc(w.Cin), NT = pick_ntile(w.Cout);
+  const int KC = pick_kc(w.Cin);
+  int NT = pick_ntile(w.Cout);                 // output-channel tile; N = 256 convs may also run as 2 x 128 (see below)
   const int halo = (w.ktaps - 1) * dil;
   const bool halo_ok = opt.halo_mode && 128 + halo <= 256;
   // low-channel convolutions run the SMALL kernel instantiation (<= 32-channel epilogue chunks, 2 CTAs / SM)
-  const bool small = NT <= 64 && (NT <= 32 || NT % 32 == 0);
-  const int cw_max = small ? std::min(NT, 32) : pick_cw(NT);
+  bool small = NT <= 64 && (NT <= 32 || NT % 32 == 0);
+  int cw_max = small ? std::min(NT, 32) : pick_cw(NT);
   const int cout_eff = e.mode == EPI_TC_GATE ? w.Cout / 2 : w.Cout;  // channels of the add / out tensors
   const int n_parts = w.x3 ? 2 : 1;                                    // bf16 planes of every epilogue tensor
   const int ld = e.ld ? e.ld : n_parts * cout_eff;
@@ -239,6 +241,17 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   }
   const int mb_max = opt.max_mb;
   const double n_mma = (double)(w.x3 ? 3 : 1) * (w.Cin / 16) * w.ktaps;
+  // N = 256 streams 32 KB of weights per (chunk, tap) for only 4 MMAs: with short kernels (k = 3) the L2 -> SM weight
+  // traffic, not the tensor pipe, is the limit (ncu: 4.8 TB/s of L2 reads at C = 256, k = 3).  Splitting N into
+  // 2 x 128 lets a tile take two 128-row blocks (TMEM: 2 x 2 x 128 columns), which quarters the weight bytes per row.
+  int nt_cand[2] = {NT, 0};
+  if (NT == 256 && opt.max_mb >= 2 && opt.split_n) nt_cand[1] = 128;
+  const int nt_final_default = NT;
+  for (int ci = 0; ci < 2; ++ci) {
+    if (!nt_cand[ci]) continue;
+    NT = nt_cand[ci];
+    small = NT <= 64 && (NT <= 32 || NT % 32 == 0);
+    cw_max = small ? std::min(NT, 32) : pick_cw(NT);
   for (int two = small ? 1 : 0; two >= 0; --two)
     for (int mb = std::min(NT <= 128 ? (small ? 4 : 2) : 1, mb_max); mb >= 1; mb >>= 1)
       for (int cw = cw_max; cw >= 16; cw >>= 1) {
@@ -252,13 +265,18 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
         const double epi = (double)(NT / cw) * (400.0 / mb + 150.0 + 4.0 * cw) * (1.0 + 0.5 * n_adds + 0.5 * (n_outs - 1));
         double wcy = 0.0;
         if (!q.w_resident) {
-          wcy = (double)q.n_wtiles * q.w_box_bytes / mb / 32.0;
+          wcy = (double)q.n_wtiles * q.w_box_bytes / mb / 20.0;    // ~20 B / cycle / SM of streamed weights (measured)
           if (q.stages_w < 3) wcy *= 1.5;
         }
         const double stage_pen = q.stages_a < 3 && q.w_resident ? 1.1 : 1.0;   // shallow A ring exposes TMA latency
-        const double cost = std::max(std::max(mma, epi), wcy) * stage_pen / (two ? 1.9 : 1.0);
+        // cost per output column so that different N tiles compare; every n-tile re-reads the activations
+        const double cost = std::max(std::max(mma, epi), wcy) * stage_pen / (two ? 1.9 : 1.0) / NT * (1.0 + 0.03 * (w.Cout / NT - 1));
         if (cost < best_cost) { best_cost = cost; p = q; planned = true; }
       }
+  }
+  NT = planned ? p.n_tile : nt_final_default;
+  small = NT <= 64 && (NT <= 32 || NT % 32 == 0);
+  cw_max = small ? std::min(NT, 32) : pick_cw(NT);
   if (!planned && (topt.force_mb || topt.force_cw)) {   // a tuned entry that does not fit this launch: use the model
     topt = TCOptions();
     topt.halo_mode = opt.halo_mode; topt.w_resident = opt.w_resident; topt.max_mb = opt.max_mb;
@@ -311,6 +329,9 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     return encode_3d(m, base + (size_t)out_phase * ld, (uint64_t)width, (uint64_t)Lq, (uint64_t)B,
                      (uint64_t)out_stride * ld, (uint64_t)Lout * ld, (uint32_t)box_c, (uint32_t)p.e_box_rows, box_c);
   };
+  CUtensorMap tmW = w.tmap;
+  if (p.n_tile != pick_ntile(w.Cout))    // the packed map's box is pick_ntile rows: rebuild it for the chosen N tile
+    VSG_TRY(encode_2d(&tmW, w.w, (uint64_t)w.CinT, (uint64_t)w.ktaps * w.Cout, (uint32_t)KC, (uint32_t)p.n_tile, KC));
   tmAdd0 = tmAdd1 = tmRaw = tmAct = tmA;
   if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0, n_parts * w.Cout, p.cw));
   if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1, n_parts * w.Cout, p.cw));
@@ -339,10 +360,10 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     // two CTAs per SM when two copies of the shared-memory carve-up (+1 KB reserved each) and of the TMEM fit
     const bool two = 2 * (smem + 1024) <= 228 * 1024 && 2 * p.tmem_cols <= 512;
     cfg.gridDim = dim3(std::min(p.total_tiles, (two ? 2 : 1) * P->sm_count));
-    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
+    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, tmA, tmW, tmAdd0, tmAdd1, tmRaw, tmAct, p);
   } else {
     cfg.gridDim = dim3(std::min(p.total_tiles, P->sm_count));
-    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, tmA, w.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p);
+    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, tmA, tmW, tmAdd0, tmAdd1, tmRaw, tmAct, p);
   }
   if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of conv_tc_kernel failed: %s", cudaGetErrorString(le));
   VSG_LAUNCH_CHECK("conv_tc_kernel");
@@ -919,6 +940,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.use_pdl = (halo_mode & 256) ? 0 : 1;                               // bit 8: disable dependent launch
   g_default_opts.fuse_pairs = (halo_mode & 512) ? 0 : 1;                            // bit 9: disable fused resblock pairs
   g_default_opts.merge_ups = (halo_mode & 1024) ? 0 : 1;                            // bit 10: one launch per polyphase
+  g_default_opts.split_n = (halo_mode & 2048) ? 0 : 1;                              // bit 11: never split N = 256 tiles
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;
