@@ -177,7 +177,8 @@ int32_t vsg_last_launch_count(void);
  *   out_f32 (device fp32 [B, L, Cout] or NULL) = v; out_raw_bf16 = bf16(v); out_act_bf16 = bf16(leaky_relu(v, 0.1)).
  *   flags bit 0: HALO mode (one activation box per channel chunk, taps through row-shifted UMMA descriptors);
  *   bit 1: keep the weights resident in shared memory; bit 2: split-bf16 (x, add0, add1, out_raw, out_act then
- *   carry two bf16 planes per row: [B, L, 2*C] = [hi | lo]); bits 4..: cap on 128-row blocks per tile (0 = 4).
+ *   carry two bf16 planes per row: [B, L, 2*C] = [hi | lo]); bit 3: add0 holds leaky_relu(r, 0.1) of the residual r and
+ *   is inverted in the epilogue (r = a > 0 ? a : 10 a); bits 4..: cap on 128-row blocks per tile (0 = 4).
  */
 int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const float* bias, const void* add0_bf16,
                           const void* add1_bf16, float scale, float* out_f32, void* out_raw_bf16, void* out_act_bf16,

@@ -65,6 +65,21 @@ def test_tc_conv1d_fused_epilogue(cuda_device, cin, cout, k, dil, B, L, mbcap):
     assert torch.equal(raw.cpu(), out.cpu().to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("cin,cout,k,dil,B,L", [(256, 256, 3, 1, 2, 300), (32, 32, 7, 3, 2, 1000), (16, 16, 11, 5, 1, 700)])
+def test_tc_conv1d_residual_from_activated_stream(cuda_device, cin, cout, k, dil, B, L):
+    """Plain-bf16 decoder keeps ONE copy of the resblock stream, a = leaky_relu(x); `x = xt + x` (decoder.py:102)
+    recovers x from it in the epilogue.  bf16(0.1 x) * 10 carries the same relative rounding as bf16(x)."""
+    from visinger_b200 import _lib
+    x, w, b, ref, gen = _case(cin, cout, k, dil, B, L)
+    res = torch.randn(B, L, cout, generator=gen)
+    a = F.leaky_relu(res, 0.1).to(torch.bfloat16)
+    resid = torch.where(a.float() > 0, a.float(), a.float() * 10.0)      # what the kernel must reconstruct
+    assert maxabs(resid, res) <= 2e-2
+    d = cuda_device
+    out = _lib.debug_conv1d_bf16(x.to(d).contiguous(), w, b, dil, flags=3 | 8, add0=a.to(d).contiguous())
+    assert maxabs(out.cpu(), ref + resid.double()) <= CONV_TOL
+
+
 @pytest.mark.parametrize("B,T", [(1, 7), (2, 64), (3, 150)])
 def test_generator_bf16_vs_oracle(cuda_device, B, T):
     sd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)

@@ -128,7 +128,8 @@ def lib() -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = build()
+        # VSG_LIB_OVERRIDE: load another build of the same library (A/B timing of two kernel versions on one GPU box)
+        path = os.environ.get("VSG_LIB_OVERRIDE") or build()
         L = ctypes.CDLL(path)
         vp, i32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t
         L.vsg_abi_version.restype = ctypes.c_int
@@ -287,7 +288,7 @@ def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int,
 
 
 def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, add1=None, scale: float = 1.0,
-                    want_f32: bool = True):
+                    want_f32: bool = True, want_raw: bool = True):
     """Per-layer parity hook of the fused ResBlock1 pair kernel.  xa_bld / add0 / add1: CUDA bf16 [B, L, C];
     returns (out_f32, out_raw_bf16, out_act_bf16)."""
     require_cuda(xa_bld, "xa")
@@ -297,14 +298,15 @@ def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, ad
     h = [t.detach().to("cpu", torch.float32).contiguous() for t in (w1, b1, w2, b2)]
     dev = xa_bld.device
     out = torch.zeros(B, Lx, C, dtype=torch.float32, device=dev)
-    raw = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev)
+    raw = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev) if want_raw else None
     act = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev)
     torch.cuda.synchronize(dev)
     rc = lib().vsg_debug_pair_bf16(xa_bld.data_ptr(), h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), h[3].data_ptr(),
                                    add0.data_ptr() if add0 is not None else None,
                                    add1.data_ptr() if add1 is not None else None, float(scale),
                                    out.data_ptr() if want_f32 else None,
-                                   raw.data_ptr(), act.data_ptr(), B, Lx, C, k, d1, dev.index or 0)
+                                   raw.data_ptr() if raw is not None else None, act.data_ptr(), B, Lx, C, k, d1,
+                                   dev.index or 0)
     check(rc, "vsg_debug_pair_bf16")
     return out, raw, act
 

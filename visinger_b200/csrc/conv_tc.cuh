@@ -75,7 +75,14 @@ struct ConvTC {
   int e_box_rows, e_n_boxes;
   uint32_t e_buf_bytes, e_part_bytes, e_swz_mask;
   int n_add_bufs;
+  // The epilogue runs on epi_sets (1 or 2) sets of 4 warps; with two sets (mb >= 2) set s takes the 128-row blocks
+  // s, s + 2, ... of every tile.  A single set is one warp per SM sub-partition: latency-bound code with nothing to
+  // overlap it with (ncu: the 4 warps busy ~80 % of the time, everything upstream waiting on them).  The sets share the
+  // staging tiles, the add prefetch and the bulk stores (set 0's leader issues them); the named barriers span both.
+  int epi_sets;
   int has_add0, has_add1;       // residual / running resblock sum: same geometry as the output, TMA-loaded
+  int add0_is_act;              // add0 holds leaky_relu(x); the residual x is recovered as a > 0 ? a : a / slope.  In bf16
+                                // that is as exact as storing x itself, and the producer then writes ONE tensor, not two
   int has_raw, has_act;         // outputs: value as is / leaky_relu(value), TMA-stored
   const float* bias;            // [Cout] or null
   const float* bcond; int bcond_bs;   // [B][bcond_bs] or null
@@ -162,6 +169,15 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // tcgen05.commit: arrive on `bar` once every MMA issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// One lane of a CONVERGED warp.  `if (elect_one()) <tcgen05 instruction>` in warp-uniform control flow is the form the
+// compiler turns into a bare uniform-datapath instruction; the same instruction inside an `if (lane == 0)` region is
+// wrapped in a per-instruction ELECT / BRA.U.ANY loop with R2UR moves (~80 cycles per tcgen05.mma, measured).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred;
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M = 128.
@@ -262,6 +278,7 @@ struct TileIter {
 };
 
 constexpr int kThreads = 224;   // 7 warps: TMA producer, MMA issuer 0, 4 epilogue warps, MMA issuer 1
+constexpr int kThreads2 = 352;  // + 4 warps: second epilogue set
 constexpr int kMaxStages = 8;
 constexpr int kMaxAddBufs = 4;
 constexpr int kMaxCW = 64;
@@ -270,7 +287,9 @@ constexpr int kBarAFull = 0, kBarAEmpty = kMaxStages, kBarWFull = 2 * kMaxStages
 constexpr int kBarAccFull = 4 * kMaxStages, kBarAccEmpty = kBarAccFull + 2, kBarAdd = kBarAccEmpty + 2;
 constexpr int kNumBars = kBarAdd + kMaxAddBufs;
 // named barriers of the 4 epilogue warps (id 0 is __syncthreads)
-__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
 
 }  // namespace tc
 
@@ -309,13 +328,15 @@ template <int CW, int MODE, int NP>
 __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, const CUtensorMap& tmAdd1,
                                                  const CUtensorMap& tmRaw, const CUtensorMap& tmAct, const ConvTC& p,
                                                  uint32_t smem_base, uint32_t bar_base, uint32_t tmem_base, int warp,
-                                                 int lane) {
+                                                 int lane, int set = 0, int lead_warp = 2) {
   using namespace tc;
   bar_base += 8u * (uint32_t)p.bar_slot0;
   tmem_base += (uint32_t)p.tmem_col0;
   constexpr int OW = (MODE == EPI_TC_GATE) ? CW / 2 : CW;   // output channels per chunk
   const int tile_stride = p.tile_stride;
-  const bool leader = (warp == 2 && lane == 0);             // issues every epilogue TMA operation of the CTA
+  const bool leader = (warp == lead_warp && lane == 0);     // issues every epilogue TMA operation of the CTA
+  const int n_sets = p.epi_sets > 1 ? 2 : 1;
+  const int epi_threads = 128 * n_sets;
   const int quarter = warp & 3;          // tcgen05.ld: warp w may only touch TMEM lanes 32*(w%4) .. +31
   const int n_echunks = p.n_echunks, n_ntiles = p.n_ntiles, m_tiles_per_b = p.m_tiles_per_b, n_tile = p.n_tile;
   const int n_add_bufs = p.n_add_bufs, total_tiles = p.total_tiles, mb = p.mb;
@@ -327,6 +348,8 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const bool has_add0 = p.has_add0, has_add1 = p.has_add1 && MODE == EPI_TC_LINEAR, has_raw = p.has_raw,
              has_act = p.has_act && MODE == EPI_TC_LINEAR;
   const float scale = p.scale, slope = p.slope;
+  const bool add0_is_act = p.add0_is_act != 0;
+  const float inv_slope = 1.0f / p.slope;
   const float* const bias = p.bias;
   const float* const bcond = p.bcond;
   const float* const maskp = p.mask;
@@ -402,9 +425,9 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
       const uint32_t ob = (out_count & 1u) * e_buf_bytes;
       if (has_out) {
         if (leader) bulk_wait_read<1>();   // the store that last used this staging buffer (2 units ago) has drained
-        epi_bar_sync(1);                   // barrier A: staging buffer free
+        epi_bar_sync(1, epi_threads);      // barrier A: staging buffer free
       }
-      for (int bi = 0; bi < mb; ++bi) {
+      for (int bi = set; bi < mb; bi += n_sets) {
         const int srow = bi * 128 + quarter * 32 + lane;      // row inside the staging tile
         const int q = tile_row0 + srow;
         float v[CW];
@@ -417,7 +440,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
         }
-        if (cc == n_echunks - 1 && bi == mb - 1) {   // accumulator drained: hand the TMEM stage back first
+        if (cc == n_echunks - 1 && bi + n_sets >= mb) {   // accumulator drained: hand the TMEM stage back first
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty0 + 8u * as);
@@ -459,6 +482,10 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
                 unpack_bf16x8(lds128(base + part_bytes + swz(row_off_in + c * 16, swz_in)), g2);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += g2[i];
+              }
+              if (add0_is_act) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * inv_slope;
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -522,7 +549,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
         }
       }
       if (has_out) fence_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
-      epi_bar_sync(2);                     // barrier B: staging tile complete; add buffer fully consumed
+      epi_bar_sync(2, epi_threads);        // barrier B: staging tile complete; add buffer fully consumed
       if (has_add) { if (++add_buf == n_add_bufs) add_buf = 0; }
       if (has_out) {
         if (leader) {
@@ -542,9 +569,10 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   if (leader) bulk_wait_all();
 }
 
-// The MMA issuer runs on ONE thread, so its instruction count per tcgen05.mma is the issue-rate limit for
-// small-N convolutions (measured: ~80 cycles per MMA with a tight loop, ~490 with a naive one).  Everything
-// loop-invariant is hoisted into registers, descriptors are advanced by integer adds on their low word.
+// The MMA issue loop is executed by a whole, converged warp: every operand is warp-uniform (kernel parameters, loop
+// counters, the shuffled warp index / TMEM base), so the loop compiles to uniform-datapath code with back-to-back
+// UTCHMMA instructions and the tensor pipe, not the issuing thread, sets the pace (tools/mma_bench2.cu: 40 / 48 / 64
+// cycles per M=128 MMA at N <= 32 / 64 / 128).  Issued from a single-lane region the same loop cost ~80 cycles per MMA.
 template <bool HALO, bool RESIDENT, int KK>
 __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_base, uint32_t w_base, uint32_t bar_base,
                                                  uint32_t tmem_base, int issuer, int n_issuers) {
@@ -598,28 +626,28 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
             for (int kk = 0; kk < KK; ++kk) {
               // HALO: the row-shifted start address keeps base_offset = 0 -- the UMMA unit applies the swizzle
               // XOR to absolute shared-memory address bits (verified on B200, tools/tc_probe.py).
-              umma_bf16(d_tmem, mk(ab16 + 2u * kk), mk(w16 + 2u * kk), idesc, (kk > 0) ? 1u : accumulate);
+              if (elect_one()) umma_bf16(d_tmem, mk(ab16 + 2u * kk), mk(w16 + 2u * kk), idesc, (kk > 0) ? 1u : accumulate);
             }
             ab16 += blk_step16 * (uint32_t)n_issuers;
             d_tmem += (uint32_t)(n_tile * n_issuers);
           }
           if (HALO) a16 += tap_step16;
           if (!RESIDENT) {
-            umma_commit(bar_w_empty + 8u * sw);
+            if (elect_one()) umma_commit(bar_w_empty + 8u * sw);
             if (++sw == stages_w) { sw = 0; pw ^= 1; }
           }
           if (!HALO) {
-            umma_commit(bar_a_empty + 8u * sa);
+            if (elect_one()) umma_commit(bar_a_empty + 8u * sa);
             if (++sa == stages_a) { sa = 0; pa ^= 1; }
           }
         }
       }
       if (HALO) {
-        umma_commit(bar_a_empty + 8u * sa);
+        if (elect_one()) umma_commit(bar_a_empty + 8u * sa);
         if (++sa == stages_a) { sa = 0; pa ^= 1; }
       }
     }
-    umma_commit(bar_acc_full + 8u * as);
+    if (elect_one()) umma_commit(bar_acc_full + 8u * as);
     if (++as == 2) { as = 0; pacc ^= 1; }
   }
 }
@@ -646,7 +674,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = bar_base + 8u * kNumBars;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -660,7 +688,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(a_full(s), 1); mbar_init(a_empty(s), n_iss);
       mbar_init(w_full(s), 1); mbar_init(w_empty(s), n_iss);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), n_iss); mbar_init(acc_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), n_iss); mbar_init(acc_empty(s), p.epi_sets > 1 ? 8 : 4); }
     for (int s = 0; s < kMaxAddBufs; ++s) mbar_init(bar_base + 8u * (kBarAdd + s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -668,7 +696,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
   // Programmatic dependent launch: let the next kernel of the stream start its prologue while this one runs, and do
   // not touch anything the previous kernel produced (activations, residuals, output buffers) before it has completed.
   // Only the resident-weight fetch below is independent of the previous kernel and is issued ahead of the wait.
@@ -726,7 +754,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuers =====================
     const int n_issuers = p.mb >= 2 ? 2 : 1;
     const int issuer = warp == 1 ? 0 : 1;
-    if (lane == 0 && issuer < n_issuers) {
+    if (issuer < n_issuers) {   // the whole warp runs the issue loop (see conv_tc_mma_loop)
       const int kk_n = p.KC / 16;
 #define VSG_MMA(H, R)                                                                                        \
   do {                                                                                                       \
@@ -741,17 +769,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #undef VSG_MMA
     }
   } else {
-    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    // ===================== epilogue (1 or 2 sets of 4 warps, one TMEM lane quarter per warp) =====================
+    const int set = warp >= 7 ? 1 : 0, lead_warp = 2;
 #define VSG_EPI(CWV)                                                                                              \
   do {                                                                                                            \
     if (p.mode == EPI_TC_LINEAR && p.n_parts == 2)                                                                \
-      conv_tc_epilogue<CWV, EPI_TC_LINEAR, 2>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
+      conv_tc_epilogue<CWV, EPI_TC_LINEAR, 2>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp); \
     else if (p.mode == EPI_TC_LINEAR)                                                                             \
-      conv_tc_epilogue<CWV, EPI_TC_LINEAR, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
+      conv_tc_epilogue<CWV, EPI_TC_LINEAR, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp); \
     else if (p.mode == EPI_TC_GATE)                                                                               \
-      conv_tc_epilogue<CWV, EPI_TC_GATE, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane);   \
+      conv_tc_epilogue<CWV, EPI_TC_GATE, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);   \
     else                                                                                                          \
-      conv_tc_epilogue<CWV, EPI_TC_COUPLE, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane); \
+      conv_tc_epilogue<CWV, EPI_TC_COUPLE, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp); \
   } while (0)
     if (!SMALL && p.cw == 64) VSG_EPI(64);
     else if (p.cw == 32) VSG_EPI(32);

@@ -12,8 +12,10 @@
 //   mid warps (7..10)      TMEM -> + b1 -> leaky_relu -> zero rows outside [0, L) (conv2's zero padding) -> bf16 ->
 //                          swizzled K-major tile in shared memory = conv2's A operand (never written to HBM)
 //   MMA back (warp 6)      conv2 from that tile through row-shifted descriptors -> accumulator bank 1
-//   epilogue (warps 2..5)  the ordinary conv_tc epilogue: + b2 + residual (+ running resblock sum, x 1/3) -> raw and
-//                          leaky_relu'd bf16 -> one bulk TMA store each, V rows per tile
+//   epilogue (warps 2..5   the ordinary conv_tc epilogue: + b2 + residual (+ running resblock sum, x 1/3) -> raw and
+//             and 11..14)  leaky_relu'd bf16 -> one bulk TMA store each, V rows per tile.  Two sets of 4 warps, one
+//                          128-row block of the tile each: ncu showed one set (one warp per SM sub-partition) busy
+//                          ~80 % of the time with everything upstream waiting on it.
 // All five stages run concurrently on different tiles (two-deep rings between them).
 #pragma once
 #include "conv_tc.cuh"
@@ -21,7 +23,7 @@
 namespace vsg {
 
 namespace tc {
-constexpr int kPairThreads = 352;   // 11 warps
+constexpr int kPairThreads = 480;   // 15 warps
 __device__ __forceinline__ void mid_bar_sync() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
 }  // namespace tc
 
@@ -102,7 +104,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_base = smem_base + p2.bar_off;
   const uint32_t tmem_slot = bar_base + 8u * (2 * kNumBars);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t bar1 = bar_base + 8u * (uint32_t)p1.bar_slot0, bar2 = bar_base + 8u * (uint32_t)p2.bar_slot0;
 
   if (warp == 0 && lane == 0) {
@@ -118,7 +120,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(bb + 8u * (kBarWFull + s), 1); mbar_init(bb + 8u * (kBarWEmpty + s), 1);
       }
       // bank 0 accumulators are drained by the 4 mid warps, bank 1 by the 4 epilogue warps
-      for (int s = 0; s < 2; ++s) { mbar_init(bb + 8u * (kBarAccFull + s), 1); mbar_init(bb + 8u * (kBarAccEmpty + s), 4); }
+      for (int s = 0; s < 2; ++s) { mbar_init(bb + 8u * (kBarAccFull + s), 1); mbar_init(bb + 8u * (kBarAccEmpty + s), (bank && p2.epi_sets > 1) ? 8 : 4); }
       for (int s = 0; s < kMaxAddBufs; ++s) mbar_init(bb + 8u * (kBarAdd + s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -127,7 +129,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0 && lane == 0) {   // both convs keep their weights resident: one TMA burst, independent of the previous kernel
     mbar_expect_tx(bar1 + 8u * kBarWFull, (uint32_t)p1.n_wtiles * p1.w_box_bytes);
@@ -158,13 +160,15 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) conv_tc_mma_loop<true, true, C / 16>(p1, smem_base + p1.a_off, smem_base + p1.w_off, bar_base, tmem_base, 0, 1);
+    conv_tc_mma_loop<true, true, C / 16>(p1, smem_base + p1.a_off, smem_base + p1.w_off, bar_base, tmem_base, 0, 1);
   } else if (warp == 6) {
-    if (lane == 0) conv_tc_mma_loop<true, true, C / 16>(p2, smem_base + p2.a_off, smem_base + p2.w_off, bar_base, tmem_base, 0, 1);
-  } else if (warp >= 7) {
+    conv_tc_mma_loop<true, true, C / 16>(p2, smem_base + p2.a_off, smem_base + p2.w_off, bar_base, tmem_base, 0, 1);
+  } else if (warp >= 7 && warp <= 10) {
     pair_mid_epilogue<C>(p1, p2, smem_base, bar_base, tmem_base, warp, lane);
   } else {
-    conv_tc_epilogue<C, EPI_TC_LINEAR, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p2, smem_base, bar_base, tmem_base, warp, lane);
+    const int set = warp >= 11 ? 1 : 0;
+    if (set < p2.epi_sets)
+      conv_tc_epilogue<C, EPI_TC_LINEAR, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p2, smem_base, bar_base, tmem_base, warp, lane, set, 2);
   }
 
   fence_before_sync();

@@ -89,6 +89,7 @@ struct EpiTC {
   const float* mask = nullptr;      // [B][Lout]
   int couple_sign = -1;
   int ld = 0;                       // leading dimension (channels per row) of the add / out tensors; 0 = their own width
+  int add0_is_act = 0;              // add0 holds leaky_relu(residual): invert it in the epilogue
   const float* bias = nullptr;
   const float* bcond = nullptr; int bcond_bs = 0;
   const __nv_bfloat16* add0 = nullptr;
@@ -108,6 +109,8 @@ struct TCOptions {
   int fuse_pairs = 1;
   int merge_ups = 1;
   int split_n = 1;
+  int single_stream = 1;
+  int epi_sets = 2;
 };
 
 TCOptions g_default_opts;
@@ -181,6 +184,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     q.e_part_bytes = (uint32_t)((128 * mb * cw * 2 + 1023) & ~1023);
     q.e_buf_bytes = (uint32_t)n_parts * q.e_part_bytes;
     q.n_add_bufs = 2 + (small && cw <= 32 && mb <= 2 ? 1 : 0);
+    q.epi_sets = 1;
     const size_t e_bytes = ((size_t)n_adds * q.n_add_bufs + (size_t)n_outs * 2) * q.e_buf_bytes;
     const size_t w_total = (size_t)q.n_wtiles * q.w_stage_bytes;
     const int a_per_tile = q.halo_mode ? q.n_achunks : q.n_wtiles;
@@ -300,6 +304,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.mode = e.mode; p.mask = e.mask; p.couple_sign = e.couple_sign;
   p.has_add0 = e.add0 != nullptr; p.has_add1 = e.add1 != nullptr;
   p.has_raw = e.out_raw != nullptr; p.has_act = e.out_act != nullptr;
+  p.add0_is_act = e.add0_is_act;
   const size_t smem = 1024 + (size_t)p.bar_off + 8 * tc::kNumBars + 64;
   if (smem > kSmemMax) return fail(VSG_EUNSUPPORTED, "conv tile does not fit in shared memory (%zu B)", smem);
   p.tmem_cols = 32;
@@ -420,10 +425,12 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   p2.e_box_rows = V; p2.e_n_boxes = 1;
   p2.e_part_bytes = (uint32_t)((128 * mb * C * 2 + 1023) & ~1023); p2.e_buf_bytes = p2.e_part_bytes;
   p2.n_add_bufs = 2;          // raised below to as many as fit (residual loads come from HBM: ~1.5 us of latency to cover)
+  p2.epi_sets = opt.epi_sets; p1.epi_sets = 1;
   p2.e_swz_mask = p2.e_out_swz_mask = C >= 32 ? 3u : 1u;
   p2.mode = EPI_TC_LINEAR; p2.scale = e.scale;
   p2.has_add0 = e.add0 != nullptr; p2.has_add1 = e.add1 != nullptr;
   p2.has_raw = e.out_raw != nullptr; p2.has_act = e.out_act != nullptr;
+  p2.add0_is_act = e.add0_is_act;
   p2.out_f32 = e.out_f32;
   const size_t w_bytes = (size_t)k * p1.w_stage_bytes;
   size_t e_bytes = ((size_t)n_adds * p2.n_add_bufs + (size_t)n_outs * 2) * p2.e_buf_bytes;
@@ -721,28 +728,35 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
         // output [nb, Lin, rate*Cout] is, byte for byte, the upsampled [nb, Lin*rate, Cout] tensor
         EpiTC e;
         e.bias = us.merged_tc.bias;
-        e.out_raw = bU; e.out_act = bUA;
+        e.out_act = bUA;
+        if (x3 || !opt.single_stream) e.out_raw = bU;
         VSG_TRY(launch_conv_tc(P, W(us.merged_tc, us.merged_x3), xin, nb, Lin, us.merged_in_off0, 1, Lin, 1, 0, Lin, e, opt,
                                err, st));
       } else {
         for (int r = 0; r < us.rate; ++r) {   // one strided launch per polyphase
           EpiTC e;
           e.bias = us.phases[r].tc.bias;
-          e.out_raw = bU; e.out_act = bUA;
+          e.out_act = bUA;
+          if (x3 || !opt.single_stream) e.out_raw = bU;
           const int Lq = (Lout - r + us.rate - 1) / us.rate;
           VSG_TRY(launch_conv_tc(P, W(us.phases[r].tc, us.phases[r].x3), xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r,
                                  Lout, e, opt, err, st));
         }
       }
+      // Plain bf16: only leaky_relu(x) is stored for the running stream; the residual x is recovered from it in the
+      // consumer's epilogue (a > 0 ? a : a / slope -- as exact in bf16 as a second, raw copy), so the upsampler and every
+      // non-final conv2 write one tensor instead of two.  Split-bf16 keeps the raw copy (exactness of the lo plane).
+      const bool one_stream = !x3 && opt.single_stream;
       for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
         const ResBlockPack& rb = us.blocks[j];
         const int nd = (int)rb.dilations.size(), k = rb.kernel;
-        const bf* cur = bU; const bf* curA = bUA;
+        const bf* cur = one_stream ? bUA : bU; const bf* curA = bUA;
         for (int q = 0; q < nd; ++q) {
           const bool last = (q == nd - 1);
           const int d = rb.dilations[q];
           EpiTC e2;
           e2.add0 = cur;
+          e2.add0_is_act = one_stream ? 1 : 0;
           if (last) {
             e2.add1 = (j > 0) ? bS : nullptr;
             if (j == NK - 1) { e2.scale = 1.0f / (float)NK; e2.out_act = xout; }
@@ -751,29 +765,30 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
           // measured on B200 (tools/time_pair.py, B=16): C=32 pair 156-204 us vs 188-241 us un-fused; at C=16 the single
           // epilogue warp set of the one-CTA-per-SM pair kernel is slower (239-275 us) than two co-resident un-fused CTAs
           // (210-235 us), so only C=32 is fused by default (fuse_pairs == 2 forces both).
+          const int n_outs_pair = last ? 1 : (one_stream ? 1 : 2);
           const bool fuse = c.dec_resblock == 1 && !x3 && opt.fuse_pairs && (ch == 32 || opt.fuse_pairs == 2) &&
-                            pair_supported(rb.c1_tc[q], rb.c2_tc[q], d, L, 1 + (e2.add1 ? 1 : 0), last ? 1 : 2);
+                            pair_supported(rb.c1_tc[q], rb.c2_tc[q], d, L, 1 + (e2.add1 ? 1 : 0), n_outs_pair);
           if (fuse) {
             // low-channel stages: both convs of the pair in ONE kernel, the intermediate never leaves the SM
             e2.bias = rb.c2_tc[q].bias;
-            if (!last) { e2.out_raw = bR; e2.out_act = bRA; }
+            if (!last) { e2.out_act = bRA; if (!one_stream) e2.out_raw = bR; }
             VSG_TRY(launch_pair_tc(P, rb.c1_tc[q], rb.c2_tc[q], curA, nb, L, d, e2, opt, err, st));
-            cur = bR; curA = bRA;
+            cur = one_stream ? bRA : bR; curA = bRA;
           } else if (c.dec_resblock == 1) {        // ResBlock1 (decoder.py:91-104)
             EpiTC e1;
             e1.bias = rb.c1_tc[q].bias; e1.out_act = bT;
             VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
             e2.bias = rb.c2_tc[q].bias;
-            if (!last) { e2.out_raw = bR; e2.out_act = bRA; }
+            if (!last) { e2.out_act = bRA; if (!one_stream) e2.out_raw = bR; }
             VSG_TRY(launch_conv_tc(P, W(rb.c2_tc[q], rb.c2_x3[q]), bT, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
-            cur = bR; curA = bRA;
+            cur = one_stream ? bRA : bR; curA = bRA;
           } else {                           // ResBlock2 (decoder.py:124-133)
             e2.bias = rb.c1_tc[q].bias;
-            bf* nr = (cur == bR) ? bT : bR;
-            bf* nra = (cur == bR) ? bTA : bRA;
-            if (!last) { e2.out_raw = nr; e2.out_act = nra; }
+            bf* nr = (cur == bR || cur == bRA) ? bT : bR;
+            bf* nra = (cur == bR || cur == bRA) ? bTA : bRA;
+            if (!last) { e2.out_act = nra; if (!one_stream) e2.out_raw = nr; }
             VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e2, opt, err, st));
-            cur = nr; curA = nra;
+            cur = one_stream ? nra : nr; curA = nra;
           }
         }
       }
@@ -831,6 +846,7 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
     e.bias = wt.bias;
     e.add0 = (const __nv_bfloat16*)add0_bf16;
     e.add1 = (const __nv_bfloat16*)add1_bf16;
+    e.add0_is_act = (flags >> 3) & 1;
     e.scale = scale;
     e.out_f32 = out_f32;
     e.out_raw = (__nv_bfloat16*)out_raw_bf16;
@@ -941,6 +957,8 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.fuse_pairs = (halo_mode & 512) ? 0 : 1;                            // bit 9: disable fused resblock pairs
   g_default_opts.merge_ups = (halo_mode & 1024) ? 0 : 1;                            // bit 10: one launch per polyphase
   g_default_opts.split_n = (halo_mode & 2048) ? 0 : 1;                              // bit 11: never split N = 256 tiles
+  g_default_opts.single_stream = (halo_mode & 4096) ? 0 : 1;                        // bit 12: store raw + activated copies
+  g_default_opts.epi_sets = (halo_mode & 8192) ? 1 : 2;                             // bit 13: one set of epilogue warps
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;
