@@ -18,10 +18,11 @@
 // ConvTranspose1d runs as `stride` polyphase launches of the same kernel (out_stride / out_phase).
 //
 // Warp roles (224 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer 0, warps 2..5 = epilogue,
-// warp 6 = MMA issuer 1.  tcgen05.mma is issued by ONE thread and costs ~80 cycles of that thread per instruction
-// (tools/mma_bench.cu), more than the tensor time of an N <= 128 MMA; with mb >= 2 the two issuers take alternate
-// 128-row blocks of the tile (different accumulators), which doubles the issue rate (measured 40 / 48 / 64 cycles per
-// MMA at N = 16 / 64 / 128).  A CTA tile is `mb` blocks of 128 time steps (mb = 1, 2 or 4) x N_TILE channels:
+// warp 6 = MMA issuer 1 (with mb >= 2 the two issuers take alternate 128-row blocks of the tile).  The producer and
+// issuer warps run CONVERGED with `elect_one` around each TMA / tcgen05 instruction: that compiles to bare
+// uniform-datapath instructions (UTCHMMA back to back), so the tensor pipe sets the pace -- 40 / 48 / 64 cycles per
+// M=128 MMA at N <= 32 / 64 / 128 (tools/mma_bench2.cu) -- where a single-lane region cost ~80 cycles per instruction.
+// A CTA tile is `mb` blocks of 128 time steps (mb = 1, 2 or 4) x N_TILE channels:
 // every weight tile feeds mb MMAs (weight traffic / mb) and all per-tile costs (barrier waits, index math,
 // TMA issue, staging synchronisation) are amortised over mb*128 rows -- the low-channel stages are bound by that
 // overhead, not by HBM or tensor throughput.  The accumulator is double-buffered in TMEM (2 x mb x N_TILE
@@ -334,7 +335,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   tmem_base += (uint32_t)p.tmem_col0;
   constexpr int OW = (MODE == EPI_TC_GATE) ? CW / 2 : CW;   // output channels per chunk
   const int tile_stride = p.tile_stride;
-  const bool leader = (warp == lead_warp && lane == 0);     // issues every epilogue TMA operation of the CTA
+  const bool lead = (warp == lead_warp);   // this (converged) warp issues every epilogue TMA operation of the CTA
   const int n_sets = p.epi_sets > 1 ? 2 : 1;
   const int epi_threads = 128 * n_sets;
   const int quarter = warp & 3;          // tcgen05.ld: warp w may only touch TMEM lanes 32*(w%4) .. +31
@@ -376,18 +377,20 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
     if (pf_left <= 0) return;
     const int ch = pf.nt * n_tile + pf_cc * CW, row = pf.mt * tile_stride;
     const uint32_t bar = add_bar0 + 8u * pf_buf;
-    mbar_expect_tx(bar, add_bytes);
-    for (int pt = 0; pt < n_parts; ++pt)
-      for (int bx = 0; bx < e_n_boxes; ++bx) {
-        const uint32_t off = pf_buf * e_buf_bytes + pt * part_bytes + bx * add_box_bytes;
-        if (has_add0) tma_load_3d(add0_b + off, &tmAdd0, bar, ch + pt * part_coff, row + bx * e_box_rows, pf.b);
-        if (has_add1) tma_load_3d(add1_b + off, &tmAdd1, bar, ch + pt * part_coff, row + bx * e_box_rows, pf.b);
-      }
+    if (elect_one()) {
+      mbar_expect_tx(bar, add_bytes);
+      for (int pt = 0; pt < n_parts; ++pt)
+        for (int bx = 0; bx < e_n_boxes; ++bx) {
+          const uint32_t off = pf_buf * e_buf_bytes + pt * part_bytes + bx * add_box_bytes;
+          if (has_add0) tma_load_3d(add0_b + off, &tmAdd0, bar, ch + pt * part_coff, row + bx * e_box_rows, pf.b);
+          if (has_add1) tma_load_3d(add1_b + off, &tmAdd1, bar, ch + pt * part_coff, row + bx * e_box_rows, pf.b);
+        }
+    }
     --pf_left;
     if (++pf_buf == n_add_bufs) pf_buf = 0;
     if (++pf_cc == n_echunks) { pf_cc = 0; pf.next(); }
   };
-  if (has_add && leader) {
+  if (has_add && lead) {
     for (int i = 0; i < n_add_bufs - 1; ++i) issue_next_add();
   }
 
@@ -415,7 +418,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
     fence_after_sync();
     const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * mb * n_tile);
     for (int cc = 0; cc < n_echunks; ++cc) {
-      if (has_add && leader) issue_next_add();   // refills the buffer drained by the previous unit (barrier B below)
+      if (has_add && lead) issue_next_add();     // refills the buffer drained by the previous unit (barrier B below)
       const int ch = nt * n_tile + cc * CW;
       const int och = (MODE == EPI_TC_GATE) ? ch / 2 : ch;
       if (has_add) {
@@ -424,7 +427,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
       }
       const uint32_t ob = (out_count & 1u) * e_buf_bytes;
       if (has_out) {
-        if (leader) bulk_wait_read<1>();   // the store that last used this staging buffer (2 units ago) has drained
+        if (lead && elect_one()) bulk_wait_read<1>();   // the store that last used this staging buffer (2 units ago) has drained
         epi_bar_sync(1, epi_threads);      // barrier A: staging buffer free
       }
       for (int bi = set; bi < mb; bi += n_sets) {
@@ -552,7 +555,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
       epi_bar_sync(2, epi_threads);        // barrier B: staging tile complete; add buffer fully consumed
       if (has_add) { if (++add_buf == n_add_bufs) add_buf = 0; }
       if (has_out) {
-        if (leader) {
+        if (lead && elect_one()) {     // elect.sync is deterministic: the same lane owns every bulk group
           for (int pt = 0; pt < n_parts; ++pt)
             for (int bx = 0; bx < e_n_boxes; ++bx) {
               const uint32_t off = ob + pt * part_bytes + bx * out_box_bytes;
@@ -566,7 +569,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
     }
     if (++as == 2) { as = 0; pacc ^= 1; }
   }
-  if (leader) bulk_wait_all();
+  if (lead && elect_one()) bulk_wait_all();
 }
 
 // The MMA issue loop is executed by a whole, converged warp: every operand is warp-uniform (kernel parameters, loop
@@ -712,8 +715,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, one elected lane per instruction) =====================
+    {
       int sa = 0, sw = 0;
       uint32_t pa = 0, pw = 0;
       TileIter it;
@@ -724,10 +727,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < p.n_achunks; ++c) {
           if (p.halo_mode) {
             mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);
-            mbar_expect_tx(a_full(sa), (uint32_t)p.a_n_boxes * p.a_box_bytes);
-            for (int bx = 0; bx < p.a_n_boxes; ++bx)
-              tma_load_3d(a_base + sa * p.a_stage_bytes + bx * p.a_box_bytes, &tmA, a_full(sa), p.a_coff[c],
-                          row0 + bx * p.a_box_rows, b);
+            if (elect_one()) {
+              mbar_expect_tx(a_full(sa), (uint32_t)p.a_n_boxes * p.a_box_bytes);
+              for (int bx = 0; bx < p.a_n_boxes; ++bx)
+                tma_load_3d(a_base + sa * p.a_stage_bytes + bx * p.a_box_bytes, &tmA, a_full(sa), p.a_coff[c],
+                            row0 + bx * p.a_box_rows, b);
+            }
             if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
             if (p.w_resident) continue;
           }
@@ -735,14 +740,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < p.ktaps; ++j) {
               if (!p.halo_mode) {   // RELOAD mode: mb == 1, one 128-row box per (chunk, pass, tap)
                 mbar_wait(a_empty(sa), pa ^ 1, p.error_flag);
-                mbar_expect_tx(a_full(sa), p.a_box_bytes);
-                tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), p.a_coff[c], row0 + j * p.dil, b);
+                if (elect_one()) {
+                  mbar_expect_tx(a_full(sa), p.a_box_bytes);
+                  tma_load_3d(a_base + sa * p.a_stage_bytes, &tmA, a_full(sa), p.a_coff[c], row0 + j * p.dil, b);
+                }
                 if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
               }
               if (!p.w_resident) {
                 mbar_wait(w_empty(sw), pw ^ 1, p.error_flag);
-                mbar_expect_tx(w_full(sw), p.w_box_bytes);
-                tma_load_2d(w_base + sw * p.w_stage_bytes, &tmW, w_full(sw), p.w_coff[c][wp], j * p.CoutT + nt * p.n_tile);
+                if (elect_one()) {
+                  mbar_expect_tx(w_full(sw), p.w_box_bytes);
+                  tma_load_2d(w_base + sw * p.w_stage_bytes, &tmW, w_full(sw), p.w_coff[c][wp], j * p.CoutT + nt * p.n_tile);
+                }
                 if (++sw == p.stages_w) { sw = 0; pw ^= 1; }
               }
             }

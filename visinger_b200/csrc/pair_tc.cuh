@@ -143,7 +143,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer: activated input tiles for conv1 =====================
-    if (lane == 0) {
+    {
       int sa = 0;
       uint32_t pa = 0;
       const uint32_t a_base = smem_base + p1.a_off;
@@ -152,10 +152,12 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < p1.total_tiles; tile += gridDim.x, it.next()) {
         const int row0 = it.mt * p1.tile_stride + p1.in_off0;
         mbar_wait(bar1 + 8u * (kBarAEmpty + sa), pa ^ 1, p1.error_flag);
-        mbar_expect_tx(bar1 + 8u * (kBarAFull + sa), (uint32_t)p1.a_n_boxes * p1.a_box_bytes);
-        for (int bx = 0; bx < p1.a_n_boxes; ++bx)
-          tma_load_3d(a_base + sa * p1.a_stage_bytes + bx * p1.a_box_bytes, &tmA, bar1 + 8u * (kBarAFull + sa), 0,
-                      row0 + bx * p1.a_box_rows, it.b);
+        if (elect_one()) {
+          mbar_expect_tx(bar1 + 8u * (kBarAFull + sa), (uint32_t)p1.a_n_boxes * p1.a_box_bytes);
+          for (int bx = 0; bx < p1.a_n_boxes; ++bx)
+            tma_load_3d(a_base + sa * p1.a_stage_bytes + bx * p1.a_box_bytes, &tmA, bar1 + 8u * (kBarAFull + sa), 0,
+                        row0 + bx * p1.a_box_rows, it.b);
+        }
         if (++sa == p1.stages_a) { sa = 0; pa ^= 1; }
       }
     }

@@ -199,7 +199,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     } else if (q.halo_mode) {
       // One A stage feeds (passes x taps x mb x KC/16) MMAs; a TMA round trip is ~3000 cycles, so a short-kernel conv
       // (k = 3: ~1500 cycles of MMA per stage at C = 256) needs 3-4 stages in flight where k = 11 is fine with 2.
-      const double mma_cyc = std::max(mb >= 2 ? 40.0 : 80.0, NT / 2.0);
+      const double mma_cyc = std::max(40.0, NT / 2.0);
       const double stage_cyc = (double)(w.x3 ? 1.5 : 1.0) * w.ktaps * mb * (KC / 16) * mma_cyc;
       int want_a = std::min(4, std::max(2, (int)(3000.0 / stage_cyc) + 2));
       if (2 * (size_t)q.a_stage_bytes + e_bytes + 2 * (size_t)q.w_stage_bytes > budget) return false;
@@ -224,8 +224,8 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   };
   // Candidate plans: (blocks per tile) x (one or two CTAs per SM) x (epilogue chunk width), ranked by a small cycle
   // model of one 128-row block (constants measured on B200, tools/mma_bench.cu and the ncu source pages):
-  //   MMA issue   ~80 cycles per tcgen05.mma from one thread, ~40 with the second issuer (mb >= 2), never below the
-  //               tensor time N/2 of an M=128 x N MMA;
+  //   MMA         the tensor pipe needs max(40, N/2) cycles per M=128 x N x 16 MMA (tools/mma_bench2.cu); the converged
+  //               issue loop keeps up with it;
   //   epilogue    per chunk: ~400 cycles of CTA-wide synchronisation + TMA issue (shared by the mb blocks of the tile)
   //               plus ~150 + 4*cw cycles per block, scaled by the number of TMA-loaded / TMA-stored tensors;
   //   weights     streamed weight tiles cost their bytes / ~32 B per cycle per tile (shared by mb blocks) and want >= 3
@@ -265,7 +265,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
         ConvTC q;
         if (!plan(mb, cw, two ? half_budget : kSmemBudget, topt.force_resident, &q)) continue;
         if (topt.force_resident >= 0 && q.w_resident != topt.force_resident) continue;
-        const double mma = n_mma * std::max(mb >= 2 ? 40.0 : 80.0, NT / 2.0);
+        const double mma = n_mma * std::max(40.0, NT / 2.0);
         const double epi = (double)(NT / cw) * (400.0 / mb + 150.0 + 4.0 * cw) * (1.0 + 0.5 * n_adds + 0.5 * (n_outs - 1));
         double wcy = 0.0;
         if (!q.w_resident) {
