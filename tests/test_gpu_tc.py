@@ -73,8 +73,9 @@ def test_tc_conv1d_residual_from_activated_stream(cuda_device, cin, cout, k, dil
     x, w, b, ref, gen = _case(cin, cout, k, dil, B, L)
     res = torch.randn(B, L, cout, generator=gen)
     a = F.leaky_relu(res, 0.1).to(torch.bfloat16)
-    resid = torch.where(a.float() > 0, a.float(), a.float() * 10.0)      # what the kernel must reconstruct
-    assert maxabs(resid, res) <= 2e-2
+    # what the kernel reconstructs: min(a, a * 10) on packed bf16 pairs (one more bf16 rounding for negative values)
+    resid = torch.minimum(a, a * torch.tensor(10.0, dtype=torch.bfloat16)).float()
+    assert maxabs(resid, res) <= 4e-2
     d = cuda_device
     out = _lib.debug_conv1d_bf16(x.to(d).contiguous(), w, b, dil, flags=3 | 8, add0=a.to(d).contiguous())
     assert maxabs(out.cpu(), ref + resid.double()) <= CONV_TOL

@@ -294,6 +294,33 @@ __device__ __forceinline__ void epi_bar_sync(int id, int n_threads) {
 
 }  // namespace tc
 
+// Plain-bf16 epilogue shortcuts on packed pairs (one HMUL2 + one HMNMX2 per TWO elements instead of two fp32
+// instructions per element).  Both act on values that are already bf16, so they add one bf16 rounding of the scaled
+// copy, which only matters for negative inputs; the split-bf16 (fp32-tolerance) mode does not use them.
+__device__ __forceinline__ uint32_t bf16x2_scale_max(uint32_t a, float s) {   // max(a, a * s): leaky_relu for 0 < s < 1
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162 y = __hmax2(x, __hmul2(x, __float2bfloat162_rn(s)));
+  return *reinterpret_cast<uint32_t*>(&y);
+}
+__device__ __forceinline__ uint32_t bf16x2_scale_min(uint32_t a, float s) {   // min(a, a * s): inverse leaky_relu, s = 1 / slope > 1
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162 y = __hmin2(x, __hmul2(x, __float2bfloat162_rn(s)));
+  return *reinterpret_cast<uint32_t*>(&y);
+}
+
+// leaky_relu'd copy of OW fp32 values, plain bf16: pack, then max(r, r * slope) on the packed pairs.
+template <int OW>
+__device__ __forceinline__ void stage_out_act(const float* v, uint32_t base, uint32_t row_off, uint32_t swz_mask, float slope) {
+  using namespace tc;
+#pragma unroll
+  for (int c = 0; c < OW / 8; ++c) {
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = bf16x2_scale_max(pack_bf16x2(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]), slope);
+    sts128(base + swz(row_off + c * 16, swz_mask), make_uint4(h[0], h[1], h[2], h[3]));
+  }
+}
+
 // Write one row chunk of OW fp32 values into a swizzled bf16 staging tile: one plane (plain bf16) or two planes
 // hi = bf16(v), lo = bf16(v - hi) (split-bf16: the pair carries ~16 mantissa bits).
 template <int OW>
@@ -425,11 +452,9 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
         mbar_wait(add_bar0 + 8u * add_buf, (add_phase >> add_buf) & 1u, error_flag);
         add_phase ^= 1u << add_buf;
       }
+      // staging buffer (out_count & 1) was last stored by the unit two back; barrier B of the previous unit already
+      // published that store's read-completion (see below), so it can be overwritten without another barrier
       const uint32_t ob = (out_count & 1u) * e_buf_bytes;
-      if (has_out) {
-        if (lead && elect_one()) bulk_wait_read<1>();   // the store that last used this staging buffer (2 units ago) has drained
-        epi_bar_sync(1, epi_threads);      // barrier A: staging buffer free
-      }
       for (int bi = set; bi < mb; bi += n_sets) {
         const int srow = bi * 128 + quarter * 32 + lane;      // row inside the staging tile
         const int q = tile_row0 + srow;
@@ -479,16 +504,17 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
 #pragma unroll
             for (int c = 0; c < CW / 8; ++c) {
               float f[8];
-              unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
+              uint4 u = lds128(base + swz(row_off_in + c * 16, swz_in));
+              if (add0_is_act) {   // plain bf16 only: residual = a > 0 ? a : a / slope = min(a, a / slope)
+                u.x = bf16x2_scale_min(u.x, inv_slope); u.y = bf16x2_scale_min(u.y, inv_slope);
+                u.z = bf16x2_scale_min(u.z, inv_slope); u.w = bf16x2_scale_min(u.w, inv_slope);
+              }
+              unpack_bf16x8(u, f);
               if (n_parts == 2) {
                 float g2[8];
                 unpack_bf16x8(lds128(base + part_bytes + swz(row_off_in + c * 16, swz_in)), g2);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += g2[i];
-              }
-              if (add0_is_act) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * inv_slope;
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -545,13 +571,22 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
           const uint32_t row_off_out = (uint32_t)srow * (OW * 2);
           if (has_raw) stage_out<OW>(v, raw_b + ob, row_off_out, swz_out, n_parts, part_bytes);
           if (has_act) {
+            if (n_parts == 1) {
+              stage_out_act<OW>(v, act_b + ob, row_off_out, swz_out, slope);
+            } else {
 #pragma unroll
-            for (int i = 0; i < OW; ++i) v[i] = fmaxf(v[i], v[i] * slope);   // leaky_relu, 0 < slope < 1
-            stage_out<OW>(v, act_b + ob, row_off_out, swz_out, n_parts, part_bytes);
+              for (int i = 0; i < OW; ++i) v[i] = fmaxf(v[i], v[i] * slope);   // leaky_relu, 0 < slope < 1
+              stage_out<OW>(v, act_b + ob, row_off_out, swz_out, n_parts, part_bytes);
+            }
           }
         }
       }
-      if (has_out) fence_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
+      if (has_out) {
+        fence_async_smem();                // generic-proxy writes -> visible to the TMA (async proxy)
+        // the previous unit's store (issued a whole unit ago) has finished reading its staging buffer: after this barrier
+        // every warp may overwrite that buffer, which is the one the NEXT unit uses
+        if (lead && elect_one()) bulk_wait_read<0>();
+      }
       epi_bar_sync(2, epi_threads);        // barrier B: staging tile complete; add buffer fully consumed
       if (has_add) { if (++add_buf == n_add_bufs) add_buf = 0; }
       if (has_out) {
