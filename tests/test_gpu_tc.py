@@ -158,6 +158,38 @@ def test_hot_path_bf16_and_fp32(cuda_device):
     assert rel <= 0.15
 
 
+def test_hot_path_pipeline_matches_direct_calls(cuda_device):
+    """HotPath.pipeline (upload / run / download on three streams, double-buffered graph slots) must return, for a
+    stream of DIFFERENT host-resident requests, exactly what hp.infer returns for each of them (fp32 mode: the
+    same kernels, so bit-identical) -- i.e. no slot is overwritten while a neighbouring request still uses it."""
+    from helpers import flow_shapes, FLOW_FULL
+    from visinger_b200.models.visinger import HotPath
+    fsd = O.synth_state_dict(flow_shapes(FLOW_FULL), 1234)
+    gsd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
+    d = cuda_device
+    hp = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, d, precision="fp32")
+    B, T, n_req = 2, 40, 5
+    pipe = hp.pipeline(B, T, d)
+    reqs = []
+    for r in range(n_req):
+        mu, mask, g = make_inputs(300 + r, B, 192, T, 256, [40, 17 + r])
+        gen = torch.Generator().manual_seed(r)
+        logs = 0.3 * torch.randn(B, 192, T, generator=gen) - 1.0
+        noise = torch.randn(B, 192, T, generator=gen)
+        reqs.append([t.contiguous().pin_memory() for t in (mu, logs, noise, mask, g)])
+    tickets, got = [], {}
+    for r, host in enumerate(reqs):
+        tickets.append(pipe.submit(*host))
+        if r >= 1:                                   # collect with one request of lag, like a server would
+            got[r - 1] = pipe.result(tickets[r - 1]).clone()
+    got[n_req - 1] = pipe.result(tickets[-1]).clone()
+    with pytest.raises(RuntimeError):
+        pipe.result(tickets[0])                      # its slot has been reused
+    for r, host in enumerate(reqs):
+        wav, _ = hp.infer(*[t.to(d) for t in host])
+        assert torch.equal(wav.cpu().view(B, -1), got[r]), f"request {r}"
+
+
 @pytest.mark.parametrize("cin,cout,k,dil,B,L", [(256, 256, 3, 1, 2, 300), (128, 128, 11, 5, 1, 700), (64, 64, 7, 3, 2, 513),
                                                 (32, 32, 11, 1, 1, 1000), (16, 16, 3, 5, 2, 4100), (192, 512, 7, 1, 1, 100)])
 def test_tc_conv1d_split_bf16(cuda_device, cin, cout, k, dil, B, L):

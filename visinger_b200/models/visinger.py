@@ -107,6 +107,11 @@ class HotPath(PackedModuleMixin, nn.Module):
         return cache[key]
 
     @torch.no_grad()
+    def pipeline(self, B: int, T: int, device=None, depth: int = 2) -> "HotPathPipeline":
+        """Double-buffered serving loop for host-resident requests (see HotPathPipeline)."""
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        return HotPathPipeline(self, B, T, dev, depth)
+
     def decode(self, z, g):
         """Generator only, through the shared pack (used by bench.py for the decoder roofline)."""
         _lib.require_cuda(z, "z")
@@ -177,6 +182,74 @@ class HotPathGraph:
         if g is not None:
             self.g.copy_(g, non_blocking=True)
         return self.replay()
+
+
+class HotPathPipeline:
+    """Serving loop around `HotPathGraph` for host-resident requests: the host->device copy of request i+1 and the
+    device->host copy of waveform i-1 overlap the kernels of request i.
+
+    `depth` graph instances (own static inputs, outputs and workspace) and three streams -- upload, run, download --
+    chained with events per slot:  upload(i) waits for run(i - depth) (the graph that last read this slot's inputs),
+    run(i) waits for upload(i) and download(i - depth) (the copy that last read this slot's waveform), download(i)
+    waits for run(i).  Inputs must be pinned host tensors (or device tensors); `result(ticket)` blocks until that
+    request's waveform is in its pinned host buffer.  Nothing here is specific to a benchmark: it is the loop a
+    synthesis server would run."""
+
+    def __init__(self, hp: "HotPath", B: int, T: int, device: torch.device, depth: int = 2):
+        self.device = torch.device(device)
+        self.B, self.T, self.depth = B, T, depth
+        self.slots = [HotPathGraph(hp, B, T, self.device) for _ in range(depth)]
+        hop = hp.decoder.hop_size
+        self.wav_host = [torch.empty(B, T * hop, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        with torch.cuda.device(self.device):
+            self.s_up, self.s_run, self.s_down = (torch.cuda.Stream(self.device) for _ in range(3))
+        self._ran = [None] * depth       # event: graph of this slot finished
+        self._down = [None] * depth      # event: waveform of this slot is in host memory
+        self._n = 0
+
+    def submit(self, mu_p, logs_p, noise, mask, g=None) -> int:
+        """Enqueue one request; returns a ticket for `result`."""
+        s = self._n % self.depth
+        slot = self.slots[s]
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.s_up):
+            self.s_up.wait_stream(cur)             # inputs produced on the caller's stream (device tensors) are complete
+            if self._ran[s] is not None:
+                self.s_up.wait_event(self._ran[s])
+            slot.mu_p.copy_(mu_p, non_blocking=True)
+            slot.logs_p.copy_(logs_p, non_blocking=True)
+            slot.noise.copy_(noise, non_blocking=True)
+            slot.mask.copy_(mask, non_blocking=True)
+            if g is not None:
+                slot.g.copy_(g, non_blocking=True)
+            up = self.s_up.record_event()
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(up)
+            if self._down[s] is not None:
+                self.s_run.wait_event(self._down[s])
+            slot.replay()
+            self._ran[s] = self.s_run.record_event()
+        with torch.cuda.stream(self.s_down):
+            self.s_down.wait_event(self._ran[s])
+            self.wav_host[s].copy_(slot.wav.view(self.B, -1), non_blocking=True)
+            self._down[s] = self.s_down.record_event()
+        self._n += 1
+        return self._n - 1
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Pinned host waveform [B, T*hop] of request `ticket` (valid until `depth` more requests are submitted)."""
+        if ticket < self._n - self.depth or ticket >= self._n:
+            raise RuntimeError("ticket is no longer (or not yet) held by the pipeline")
+        s = ticket % self.depth
+        self._down[s].synchronize()
+        return self.wav_host[s]
+
+    def flush(self) -> None:
+        """Make the caller's current stream wait for every outstanding request (upload, kernels and download)."""
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self._down:
+            if ev is not None:
+                cur.wait_event(ev)
 
 
 class VISinger(nn.Module):
