@@ -919,4 +919,52 @@ __global__ void conv_post_bf16_kernel(const __nv_bfloat16* __restrict__ x, const
   wav[(long long)b * L + n] = tanhf(s);
 }
 
+// conv_post for the shapes the model actually has (C = 16 channels, k = 7), plain bf16: every thread produces S
+// consecutive samples from a sliding window of S + K - 1 input rows, so each row is fetched once per thread (two
+// 16-byte loads at C = 16) and the inner loop is pure FFMA on weights the compiler keeps in registers / reloads from
+// L1.  The one-thread-per-sample kernel above re-reads every row K times and spends one shared-memory load per FMA
+// (165 us -> 94 us at B = 16, L = 300 000; HBM time is ~25 us).
+template <int C, int K, int S>
+__global__ void __launch_bounds__(128) conv_post_bf16_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[C][K]*/,
+                                                                 float* __restrict__ wav, int L, int groups_per_b, int total_groups) {
+  float wr[K][C];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int j = 0; j < K; ++j) wr[j][c] = __ldg(w + c * K + j);
+  constexpr int pad = (K - 1) / 2;
+  for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < total_groups; gidx += gridDim.x * blockDim.x) {
+    const int b = gidx / groups_per_b, n0 = (gidx - b * groups_per_b) * S;
+    const __nv_bfloat16* xb = x + (long long)b * L * C;
+    float acc[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < S + K - 1; ++r) {
+      const int pos = n0 + r - pad;
+      float f[C];
+      if (pos >= 0 && pos < L) {
+        const uint4* row = reinterpret_cast<const uint4*>(xb + (long long)pos * C);
+#pragma unroll
+        for (int c8 = 0; c8 < C / 8; ++c8) tc::unpack_bf16x8(__ldg(row + c8), f + 8 * c8);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) f[c] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        const int j = r - i;                       // tap of sample i that reads this row
+        if (j >= 0 && j < K) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[i] = fmaf(wr[j][c], f[c], acc[i]);
+        }
+      }
+    }
+    float* out = wav + (long long)b * L + n0;
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+      if (n0 + i < L) out[i] = tanhf(acc[i]);
+  }
+}
+
 }  // namespace vsg

@@ -796,10 +796,18 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
     cur_io ^= 1;
   }
   {  // wav = tanh(conv_post(leaky_relu(x)))   (decoder.py:55-57); the stage output already holds leaky_relu(x)
-    dim3 grid((L + 255) / 256, B);
-    conv_post_bf16_kernel<<<grid, 256, (size_t)ch * P->conv_post_k * sizeof(float), st>>>(io[cur_io], P->conv_post_w, wav,
-                                                                                           ch, L, P->conv_post_k, x3 ? 1 : 0);
-    VSG_LAUNCH_CHECK("conv_post_bf16_kernel");
+    if (!x3 && ch == 16 && P->conv_post_k == 7) {   // the model's shape: sliding-window kernel
+      constexpr int S = 8;
+      const int gpb = (L + S - 1) / S, total = gpb * B;
+      const int blocks = std::min((total + 127) / 128, 8 * P->sm_count);
+      conv_post_bf16_win_kernel<16, 7, S><<<blocks, 128, 0, st>>>(io[cur_io], P->conv_post_w, wav, L, gpb, total);
+      VSG_LAUNCH_CHECK("conv_post_bf16_win_kernel");
+    } else {
+      dim3 grid((L + 255) / 256, B);
+      conv_post_bf16_kernel<<<grid, 256, (size_t)ch * P->conv_post_k * sizeof(float), st>>>(io[cur_io], P->conv_post_w, wav,
+                                                                                             ch, L, P->conv_post_k, x3 ? 1 : 0);
+      VSG_LAUNCH_CHECK("conv_post_bf16_kernel");
+    }
   }
   return VSG_OK;
 }
