@@ -264,10 +264,11 @@ def main():
         value = world * audio_per_step * args.steps / (ms * 1e-3)
         e2e_value = world * audio_per_step * args.steps / (ms_e2e * 1e-3)
         dec_tflops = DEC_FLOP_PER_FRAME * B * T * args.steps / (ms_dec * 1e-3) / 1e12
-        traffic = None          # DRAM bytes of the decoder's conv kernels per pass, from the committed ncu capture
+        traffic, traffic_launches = None, 0   # DRAM bytes of the decoder's conv kernels per pass, from the committed ncu capture
         tp = os.path.join(ROOT, "profiles", "r1_decoder_traffic.json")
         if os.path.exists(tp) and args.precision == "bf16" and (B, T) == (16, 1000):
-            traffic = json.load(open(tp))["traffic_bytes"]
+            tj = json.load(open(tp))
+            traffic, traffic_launches = tj["traffic_bytes"], tj["launches"]
         peak = pk["bf16_sustained"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -289,8 +290,8 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": dec_tflops / peak, "traffic": traffic,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the 108 conv_tc_kernel launches of "
-                                         "one decoder pass (profiles/r1_decoder_traffic.json)",
+                         "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum over the {traffic_launches} conv_tc / pair_tc / "
+                                         "conv_post launches of one decoder pass (profiles/r1_decoder_traffic.json)",
                          "kernel": "decoder convolutions (vsg_generator_forward region)",
                          "algorithmic": f"{DEC_FLOP_PER_FRAME} FLOP/frame x {B * T} frames",
                          "ms": ms_dec / args.steps, "peak_source": pk["src"] + ", sustained bf16"},
