@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-merge-ups", action="store_true", help="one launch per polyphase of the transposed convs")
     ap.add_argument("--no-split-n", action="store_true", help="keep N = 256 tiles whole (no 2 x 128 split)")
     ap.add_argument("--one-epi-set", action="store_true", help="a single set of 4 epilogue warps per CTA")
+    ap.add_argument("--generic-epilogue", action="store_true", help="never use the signature-specialised kernels")
     ap.add_argument("--two-streams", action="store_true", help="store raw and activated copies of the resblock stream")
     return ap.parse_args()
 
@@ -181,10 +182,10 @@ def main():
     fsd = O.synth_state_dict(flow_shapes(FLOW_FULL), 1234)
     gsd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
     hp = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, dev, precision=args.precision)
-    if args.l2_mb >= 0 or args.no_pdl or args.no_fuse or args.no_merge_ups or args.no_split_n or args.two_streams or args.one_epi_set:
+    if args.l2_mb >= 0 or args.no_pdl or args.no_fuse or args.no_merge_ups or args.no_split_n or args.two_streams or args.generic_epilogue:
         from visinger_b200 import _lib
         _lib.set_tc_options(halo_mode=1 | (256 if args.no_pdl else 0) | (512 if args.no_fuse else 0) |
-                            (1024 if args.no_merge_ups else 0) | (2048 if args.no_split_n else 0) | (4096 if args.two_streams else 0) | (8192 if args.one_epi_set else 0), l2_tensor_mb=args.l2_mb)
+                            (1024 if args.no_merge_ups else 0) | (2048 if args.no_split_n else 0) | (4096 if args.two_streams else 0) | (8192 if args.generic_epilogue else 0), l2_tensor_mb=args.l2_mb)
 
     x, mask, g = make_inputs(rank, B, 192, T, 256)
     logs = torch.full_like(x, -1.0)

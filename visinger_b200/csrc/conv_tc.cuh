@@ -99,6 +99,15 @@ struct ConvTC {
 
 enum : int { EPI_TC_LINEAR = 0, EPI_TC_GATE = 1, EPI_TC_COUPLE = 2 };
 
+// Epilogue signatures: the decoder's two dominant epilogues get their own kernel instantiations in which every feature
+// flag is a compile-time constant.  The generic kernel carries 12 epilogue variants (3 chunk widths x 4 modes; ~15 k SASS
+// instructions, a quarter of a megabyte of code fetched by five different warp roles) and tests ~30 runtime flags per
+// unit; a specialised one is a fifth of that.
+//   EPI_SIG_GENERIC  everything decided at run time (flow, split-bf16, last conv of a resblock, debug hooks)
+//   EPI_SIG_ACT      out_act = leaky_relu(acc + bias)                          (conv1 of a pair, merged upsamplers)
+//   EPI_SIG_RES_ACT  out_act = leaky_relu(acc + bias + residual(add0_is_act))   (conv2 of a non-final pair)
+enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2 };
+
 namespace tc {
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -352,7 +361,7 @@ __device__ __forceinline__ void stage_out(const float* v, uint32_t base, uint32_
 //                      out[c] = tanh(a) * sigmoid(s)  -- fused_add_tanh_sigmoid_multiply, encoder.py:206-213;
 //                      the output tensor has Cout / 2 channels
 //       EPI_TC_COUPLE  m = (acc + bias) * mask; out = (add0 - m) * mask | m + add0 * mask  (flow.py:78,83)
-template <int CW, int MODE, int NP>
+template <int CW, int MODE, int NP, int SIG = EPI_SIG_GENERIC>
 __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, const CUtensorMap& tmAdd1,
                                                  const CUtensorMap& tmRaw, const CUtensorMap& tmAct, const ConvTC& p,
                                                  uint32_t smem_base, uint32_t bar_base, uint32_t tmem_base, int warp,
@@ -373,20 +382,25 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const int part_coff = p.part_coff;
   const uint32_t e_buf_bytes = p.e_buf_bytes, swz_in = p.e_swz_mask, swz_out = p.e_out_swz_mask;
   const uint32_t part_bytes = p.e_part_bytes;     // one bf16 plane (hi or lo) of a staging buffer
-  const bool has_add0 = p.has_add0, has_add1 = p.has_add1 && MODE == EPI_TC_LINEAR, has_raw = p.has_raw,
-             has_act = p.has_act && MODE == EPI_TC_LINEAR;
-  const float scale = p.scale, slope = p.slope;
-  const bool add0_is_act = p.add0_is_act != 0;
+  constexpr bool kGen = SIG == EPI_SIG_GENERIC;
+  static_assert(kGen || (MODE == EPI_TC_LINEAR && NP == 1), "specialised signatures are plain-bf16 linear epilogues");
+  const bool has_add0 = kGen ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT);
+  const bool has_add1 = kGen ? (p.has_add1 && MODE == EPI_TC_LINEAR) : false;
+  const bool has_raw = kGen ? (p.has_raw != 0) : false;
+  const bool has_act = kGen ? (p.has_act && MODE == EPI_TC_LINEAR) : true;
+  const float scale = kGen ? p.scale : 1.0f, slope = p.slope;
+  const bool add0_is_act = kGen ? (p.add0_is_act != 0) : true;
   const float inv_slope = 1.0f / p.slope;
   const float* const bias = p.bias;
-  const float* const bcond = p.bcond;
-  const float* const maskp = p.mask;
+  const float* const bcond = kGen ? p.bcond : nullptr;
+  const float* const maskp = kGen ? p.mask : nullptr;
+  float* const out_f32 = kGen ? p.out_f32 : nullptr;
   int* const error_flag = p.error_flag;
   // staging carve-up: [add0 x n_add_bufs][add1 x n_add_bufs][raw x 2][act x 2], each e_buf_bytes
   const uint32_t add0_b = smem_base + p.e_off;
-  const uint32_t add1_b = add0_b + (p.has_add0 ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
-  const uint32_t raw_b = add1_b + (p.has_add1 ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
-  const uint32_t act_b = raw_b + (p.has_raw ? 2u * e_buf_bytes : 0u);
+  const uint32_t add1_b = add0_b + (has_add0 ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
+  const uint32_t raw_b = add1_b + ((kGen && p.has_add1) ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
+  const uint32_t act_b = raw_b + (has_raw ? 2u * e_buf_bytes : 0u);
   const bool has_add = has_add0 || has_add1;
   const bool has_out = has_raw || has_act;
   const uint32_t add_box_bytes = (uint32_t)e_box_rows * CW * 2u, out_box_bytes = (uint32_t)e_box_rows * OW * 2u;
@@ -558,11 +572,11 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
             v[c] = t * sg;
           }
         }
-        if (p.out_f32) {   // debug / parity hook only: plain per-thread stores
+        if (out_f32) {   // debug / parity hook only: plain per-thread stores
           const int n = q * p.out_stride + p.out_phase;
           const int oc_total = (MODE == EPI_TC_GATE) ? p.Cout / 2 : p.Cout;
           if (srow < tile_stride && q < p.Lq && n < p.Lout && och < oc_total) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((long long)b * p.Lout + n) * oc_total + och);
+            float4* dst = reinterpret_cast<float4*>(out_f32 + ((long long)b * p.Lout + n) * oc_total + och);
 #pragma unroll
             for (int i = 0; i < OW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
@@ -692,7 +706,7 @@ __device__ __forceinline__ void conv_tc_mma_loop(const ConvTC& p, uint32_t a_bas
 
 // SMALL = true: the low-channel instantiation (epilogue chunks of <= 32 channels): register budget for TWO
 // resident CTAs per SM, which doubles the single-thread MMA issue rate and the epilogue warps in flight.
-template <bool SMALL>
+template <bool SMALL, int SIG = EPI_SIG_GENERIC>
 __global__ void __launch_bounds__(tc::kThreads, SMALL ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmAdd0, const __grid_constant__ CUtensorMap tmAdd1,
@@ -826,9 +840,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else                                                                                                          \
       conv_tc_epilogue<CWV, EPI_TC_COUPLE, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp); \
   } while (0)
-    if (!SMALL && p.cw == 64) VSG_EPI(64);
-    else if (p.cw == 32) VSG_EPI(32);
-    else VSG_EPI(16);
+    if constexpr (SIG == EPI_SIG_GENERIC) {
+      if (!SMALL && p.cw == 64) VSG_EPI(64);
+      else if (p.cw == 32) VSG_EPI(32);
+      else VSG_EPI(16);
+    } else {   // specialised signature: plain-bf16 linear epilogue with compile-time feature flags
+      if (!SMALL && p.cw == 64)
+        conv_tc_epilogue<64, EPI_TC_LINEAR, 1, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
+      else if (p.cw == 32)
+        conv_tc_epilogue<32, EPI_TC_LINEAR, 1, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
+      else
+        conv_tc_epilogue<16, EPI_TC_LINEAR, 1, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
+    }
 #undef VSG_EPI
   }
 

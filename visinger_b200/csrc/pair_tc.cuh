@@ -92,7 +92,7 @@ __device__ __forceinline__ void pair_mid_epilogue(const ConvTC& p1, const ConvTC
   }
 }
 
-template <int C>
+template <int C, int SIG = EPI_SIG_GENERIC>
 __global__ void __launch_bounds__(tc::kPairThreads, 1)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmAdd0,
@@ -170,7 +170,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     const int set = warp >= 11 ? 1 : 0;
     if (set < p2.epi_sets)
-      conv_tc_epilogue<C, EPI_TC_LINEAR, 1>(tmAdd0, tmAdd1, tmRaw, tmAct, p2, smem_base, bar_base, tmem_base, warp, lane, set, 2);
+      conv_tc_epilogue<C, EPI_TC_LINEAR, 1, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p2, smem_base, bar_base, tmem_base, warp, lane, set, 2);
   }
 
   fence_before_sync();

@@ -110,6 +110,7 @@ struct TCOptions {
   int merge_ups = 1;
   int split_n = 1;
   int single_stream = 1;
+  int epi_sigs = 1;
   int epi_sets = 2;
 };
 
@@ -342,11 +343,23 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1, n_parts * w.Cout, p.cw));
   if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw, n_parts * cout_eff, ow));
   if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act, n_parts * cout_eff, ow));
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvTC);
+  static const KernelFn kernels[2][3] = {
+      {conv_tc_kernel<false, EPI_SIG_GENERIC>, conv_tc_kernel<false, EPI_SIG_ACT>, conv_tc_kernel<false, EPI_SIG_RES_ACT>},
+      {conv_tc_kernel<true, EPI_SIG_GENERIC>, conv_tc_kernel<true, EPI_SIG_ACT>, conv_tc_kernel<true, EPI_SIG_RES_ACT>}};
   static bool attr_set = false;
   if (!attr_set) {
-    VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    VSG_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 3; ++b)
+        VSG_CUDA_TRY(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
+  }
+  // the decoder's two dominant epilogues run kernels specialised on their feature flags (conv_tc.cuh, EPI_SIG_*)
+  int sig = EPI_SIG_GENERIC;
+  if (opt.epi_sigs && e.mode == EPI_TC_LINEAR && !w.x3 && e.bias && !e.bcond && !e.mask && !e.out_f32 && !e.out_raw && e.out_act &&
+      !e.add1 && e.scale == 1.0f) {
+    if (!e.add0) sig = EPI_SIG_ACT;
+    else if (e.add0_is_act) sig = EPI_SIG_RES_ACT;
   }
   // Programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, resident-weight fetch) may
   // overlap the tail of the previous kernel in the stream; it executes griddepcontrol.wait before touching activations.
@@ -365,10 +378,10 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     // two CTAs per SM when two copies of the shared-memory carve-up (+1 KB reserved each) and of the TMEM fit
     const bool two = 2 * (smem + 1024) <= 228 * 1024 && 2 * p.tmem_cols <= 512;
     cfg.gridDim = dim3(std::min(p.total_tiles, (two ? 2 : 1) * P->sm_count));
-    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, tmA, tmW, tmAdd0, tmAdd1, tmRaw, tmAct, p);
+    le = cudaLaunchKernelEx(&cfg, kernels[1][sig], tmA, tmW, tmAdd0, tmAdd1, tmRaw, tmAct, p);
   } else {
     cfg.gridDim = dim3(std::min(p.total_tiles, P->sm_count));
-    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, tmA, tmW, tmAdd0, tmAdd1, tmRaw, tmAct, p);
+    le = cudaLaunchKernelEx(&cfg, kernels[0][sig], tmA, tmW, tmAdd0, tmAdd1, tmRaw, tmAct, p);
   }
   if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of conv_tc_kernel failed: %s", cudaGetErrorString(le));
   VSG_LAUNCH_CHECK("conv_tc_kernel");
@@ -476,6 +489,7 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   if (!attr_set) {
     VSG_CUDA_TRY(cudaFuncSetAttribute(pair_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     VSG_CUDA_TRY(cudaFuncSetAttribute(pair_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    VSG_CUDA_TRY(cudaFuncSetAttribute((pair_tc_kernel<32, EPI_SIG_RES_ACT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -489,8 +503,11 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = opt.use_pdl ? 1 : 0;
+  const bool res_act = opt.epi_sigs && C == 32 && e.add0 && e.add0_is_act && !e.add1 && e.out_act && !e.out_raw && !e.out_f32 &&
+                       e.scale == 1.0f && e.bias;
   cudaError_t le = C == 16 ? cudaLaunchKernelEx(&cfg, pair_tc_kernel<16>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2)
-                           : cudaLaunchKernelEx(&cfg, pair_tc_kernel<32>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2);
+                   : res_act ? cudaLaunchKernelEx(&cfg, pair_tc_kernel<32, EPI_SIG_RES_ACT>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2)
+                             : cudaLaunchKernelEx(&cfg, pair_tc_kernel<32>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2);
   if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of pair_tc_kernel failed: %s", cudaGetErrorString(le));
   VSG_LAUNCH_CHECK("pair_tc_kernel");
   return VSG_OK;
@@ -966,6 +983,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.merge_ups = (halo_mode & 1024) ? 0 : 1;                            // bit 10: one launch per polyphase
   g_default_opts.split_n = (halo_mode & 2048) ? 0 : 1;                              // bit 11: never split N = 256 tiles
   g_default_opts.single_stream = (halo_mode & 4096) ? 0 : 1;                        // bit 12: store raw + activated copies
+  g_default_opts.epi_sigs = (halo_mode & 8192) ? 0 : 1;                             // bit 13: generic epilogue kernels only
   g_default_opts.epi_sets = (halo_mode & 8192) ? 1 : 2;                             // bit 13: one set of epilogue warps
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
