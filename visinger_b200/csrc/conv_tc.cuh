@@ -106,7 +106,11 @@ enum : int { EPI_TC_LINEAR = 0, EPI_TC_GATE = 1, EPI_TC_COUPLE = 2 };
 //   EPI_SIG_GENERIC  everything decided at run time (flow, split-bf16, last conv of a resblock, debug hooks)
 //   EPI_SIG_ACT      out_act = leaky_relu(acc + bias)                          (conv1 of a pair, merged upsamplers)
 //   EPI_SIG_RES_ACT  out_act = leaky_relu(acc + bias + residual(add0_is_act))   (conv2 of a non-final pair)
-enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2 };
+//   EPI_SIG_LINEAR   plain-bf16 linear epilogue with run-time adds / outputs / scale but no speaker condition, mask or
+//                    fp32 debug copy                                              (last conv2 of a resblock)
+// (Separate images pay off for the decoder's long launches; the flow's ~20 us launches are better off sharing ONE warm
+// image -- splitting the generic kernel per mode made the step slower.)
+enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2, EPI_SIG_LINEAR = 3 };
 
 namespace tc {
 
@@ -384,12 +388,13 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const uint32_t part_bytes = p.e_part_bytes;     // one bf16 plane (hi or lo) of a staging buffer
   constexpr bool kGen = SIG == EPI_SIG_GENERIC;
   static_assert(kGen || (MODE == EPI_TC_LINEAR && NP == 1), "specialised signatures are plain-bf16 linear epilogues");
-  const bool has_add0 = kGen ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT);
-  const bool has_add1 = kGen ? (p.has_add1 && MODE == EPI_TC_LINEAR) : false;
-  const bool has_raw = kGen ? (p.has_raw != 0) : false;
-  const bool has_act = kGen ? (p.has_act && MODE == EPI_TC_LINEAR) : true;
-  const float scale = kGen ? p.scale : 1.0f, slope = p.slope;
-  const bool add0_is_act = kGen ? (p.add0_is_act != 0) : true;
+  constexpr bool kRt = kGen || SIG == EPI_SIG_LINEAR;      // adds / outputs / scale decided at run time
+  const bool has_add0 = kRt ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT);
+  const bool has_add1 = kRt ? (p.has_add1 && MODE == EPI_TC_LINEAR) : false;
+  const bool has_raw = kRt ? (p.has_raw != 0) : false;
+  const bool has_act = kRt ? (p.has_act && MODE == EPI_TC_LINEAR) : true;
+  const float scale = kRt ? p.scale : 1.0f, slope = p.slope;
+  const bool add0_is_act = kRt ? (p.add0_is_act != 0) : true;
   const float inv_slope = 1.0f / p.slope;
   const float* const bias = p.bias;
   const float* const bcond = kGen ? p.bcond : nullptr;
@@ -399,7 +404,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   // staging carve-up: [add0 x n_add_bufs][add1 x n_add_bufs][raw x 2][act x 2], each e_buf_bytes
   const uint32_t add0_b = smem_base + p.e_off;
   const uint32_t add1_b = add0_b + (has_add0 ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
-  const uint32_t raw_b = add1_b + ((kGen && p.has_add1) ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
+  const uint32_t raw_b = add1_b + ((kRt && p.has_add1) ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
   const uint32_t act_b = raw_b + (has_raw ? 2u * e_buf_bytes : 0u);
   const bool has_add = has_add0 || has_add1;
   const bool has_out = has_raw || has_act;

@@ -344,22 +344,26 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw, n_parts * cout_eff, ow));
   if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act, n_parts * cout_eff, ow));
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvTC);
-  static const KernelFn kernels[2][3] = {
-      {conv_tc_kernel<false, EPI_SIG_GENERIC>, conv_tc_kernel<false, EPI_SIG_ACT>, conv_tc_kernel<false, EPI_SIG_RES_ACT>},
-      {conv_tc_kernel<true, EPI_SIG_GENERIC>, conv_tc_kernel<true, EPI_SIG_ACT>, conv_tc_kernel<true, EPI_SIG_RES_ACT>}};
+  static const KernelFn kernels[2][4] = {
+      {conv_tc_kernel<false, EPI_SIG_GENERIC>, conv_tc_kernel<false, EPI_SIG_ACT>, conv_tc_kernel<false, EPI_SIG_RES_ACT>,
+       conv_tc_kernel<false, EPI_SIG_LINEAR>},
+      {conv_tc_kernel<true, EPI_SIG_GENERIC>, conv_tc_kernel<true, EPI_SIG_ACT>, conv_tc_kernel<true, EPI_SIG_RES_ACT>,
+       conv_tc_kernel<true, EPI_SIG_LINEAR>}};
   static bool attr_set = false;
   if (!attr_set) {
     for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 3; ++b)
+      for (int b = 0; b < 4; ++b)
         VSG_CUDA_TRY(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
   // the decoder's two dominant epilogues run kernels specialised on their feature flags (conv_tc.cuh, EPI_SIG_*)
   int sig = EPI_SIG_GENERIC;
-  if (opt.epi_sigs && e.mode == EPI_TC_LINEAR && !w.x3 && e.bias && !e.bcond && !e.mask && !e.out_f32 && !e.out_raw && e.out_act &&
-      !e.add1 && e.scale == 1.0f) {
-    if (!e.add0) sig = EPI_SIG_ACT;
-    else if (e.add0_is_act) sig = EPI_SIG_RES_ACT;
+  if (opt.epi_sigs && e.mode == EPI_TC_LINEAR && !w.x3 && e.bias && !e.bcond && !e.mask && !e.out_f32) {
+    sig = EPI_SIG_LINEAR;
+    if (!e.out_raw && e.out_act && !e.add1 && e.scale == 1.0f) {
+      if (!e.add0) sig = EPI_SIG_ACT;
+      else if (e.add0_is_act) sig = EPI_SIG_RES_ACT;
+    }
   }
   // Programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, resident-weight fetch) may
   // overlap the tail of the previous kernel in the stream; it executes griddepcontrol.wait before touching activations.
@@ -490,6 +494,7 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
     VSG_CUDA_TRY(cudaFuncSetAttribute(pair_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     VSG_CUDA_TRY(cudaFuncSetAttribute(pair_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     VSG_CUDA_TRY(cudaFuncSetAttribute((pair_tc_kernel<32, EPI_SIG_RES_ACT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    VSG_CUDA_TRY(cudaFuncSetAttribute((pair_tc_kernel<32, EPI_SIG_LINEAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -507,7 +512,9 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
                        e.scale == 1.0f && e.bias;
   cudaError_t le = C == 16 ? cudaLaunchKernelEx(&cfg, pair_tc_kernel<16>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2)
                    : res_act ? cudaLaunchKernelEx(&cfg, pair_tc_kernel<32, EPI_SIG_RES_ACT>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2)
-                             : cudaLaunchKernelEx(&cfg, pair_tc_kernel<32>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2);
+                   : (opt.epi_sigs && !e.out_f32 && e.bias)
+                       ? cudaLaunchKernelEx(&cfg, pair_tc_kernel<32, EPI_SIG_LINEAR>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2)
+                       : cudaLaunchKernelEx(&cfg, pair_tc_kernel<32>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2);
   if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of pair_tc_kernel failed: %s", cudaGetErrorString(le));
   VSG_LAUNCH_CHECK("pair_tc_kernel");
   return VSG_OK;
