@@ -22,7 +22,7 @@ for C, Lq in shapes:
         ms_pair = float(L.vsg_debug_last_ms())
         o1 = _lib.debug_conv1d_bf16(x, w, b, d1, flags=3, want_bf16=True, want_f32=False, want_raw=False)
         ms1 = float(L.vsg_debug_last_ms())
-        o2 = _lib.debug_conv1d_bf16(x, w, b, 1, flags=3, add0=x, want_bf16=True, want_f32=False, want_raw=False)
+        o2 = _lib.debug_conv1d_bf16(x, w, b, 1, flags=3 | 8, add0=x, want_bf16=True, want_f32=False, want_raw=False)
         ms2 = float(L.vsg_debug_last_ms())
         print(f"C={C} k={k} d1={d1}: pair {ms_pair*1e3:.0f} us | unfused c1 {ms1*1e3:.0f} + c2 {ms2*1e3:.0f} = {(ms1+ms2)*1e3:.0f} us", flush=True)
         del x, out, raw, act, o1, o2
