@@ -393,25 +393,33 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
 }
 
 // ---- fused ResBlock1 pair (pair_tc.cuh) ---------------------------------------------------------------------------
+// 128-row blocks per tile of the fused pair: tiles of the same byte size at both channel counts (per-tile costs are what
+// the low-channel stages are bound by)
+static inline int pair_mb(int C) { return C == 16 ? 4 : 2; }
+
 bool pair_supported(const ConvWTC& w1, const ConvWTC& w2, int d1, int L, int n_adds, int n_outs) {
   const int C = w1.Cin, k = w1.ktaps;
   if (!w1.has_tmap || !w2.has_tmap || w1.x3 || w2.x3) return false;
   if (w1.Cout != C || w2.Cin != C || w2.Cout != C || w2.ktaps != k || (C != 16 && C != 32) || k % 2 == 0) return false;
-  if (256 + (k - 1) * d1 > 512 || L < 256) return false;
+  const int rows_t = 128 * pair_mb(C);          // rows per tile: 512 at C = 16, 256 at C = 32 (same bytes per tile)
+  if ((k - 1) * d1 > 256 || L < rows_t) return false;
   // shared-memory footprint (mirrors launch_pair_tc): 2 input stages + both weight sets + 2 intermediate tiles + staging
   auto r1k = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
-  const int rows1 = 256 + (k - 1) * d1, nb = (rows1 + 255) / 256, box = (((rows1 + nb - 1) / nb) + 7) & ~7;
+  const int rows1 = rows_t + (k - 1) * d1, nb = (rows1 + 255) / 256, box = (((rows1 + nb - 1) / nb) + 7) & ~7;
   const size_t a1 = r1k((size_t)nb * box * C * 2), wb = (size_t)k * r1k((size_t)C * C * 2);
-  const size_t tb = r1k((size_t)((256 + k - 1 + 7) & ~7) * C * 2), eb = (size_t)(n_adds * 2 + n_outs * 2) * r1k(256 * C * 2);
+  const size_t tb = r1k((size_t)((rows_t + k - 1 + 7) & ~7) * C * 2), eb = (size_t)(n_adds * 2 + n_outs * 2) * r1k(rows_t * C * 2);
   return 2 * a1 + 2 * wb + 2 * tb + eb <= kSmemBudget;
 }
 
 // x_new = conv2(leaky_relu(conv1(xa) + b1)) + b2 [+ add0 + add1] [* scale]; xa = leaky_relu(x) [B, L, C] bf16.
 int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const __nv_bfloat16* xa, int B, int L, int d1,
                    const EpiTC& e, const TCOptions& opt, int* error_flag, cudaStream_t st) {
-  const int C = w1.Cin, k = w1.ktaps, mb = 2;
+  const int C = w1.Cin, k = w1.ktaps, mb = pair_mb(C);
   const int h2 = (k - 1) / 2, pad1 = (k - 1) * d1 / 2, halo1 = (k - 1) * d1;
-  const int V = 128 * mb - (k - 1);
+  // valid output rows per tile.  One TMA box holds <= 256 rows; with two boxes the box height must be a multiple of 8
+  // rows so that both start on a swizzle-atom boundary of the staging tile (a few more halo rows are recomputed).
+  const int n_eboxes = (128 * mb + 255) / 256;
+  const int V = n_eboxes == 1 ? 128 * mb - (k - 1) : ((128 * mb - (k - 1)) / (8 * n_eboxes)) * (8 * n_eboxes);
   const int n_adds = (e.add0 ? 1 : 0) + (e.add1 ? 1 : 0), n_outs = (e.out_raw ? 1 : 0) + (e.out_act ? 1 : 0);
   ConvTC p1, p2;
   memset(&p1, 0, sizeof(p1));
@@ -439,7 +447,7 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   p2.a_stage_bytes = ((uint32_t)rows2 * C * 2 + 1023u) & ~1023u;
   p2.stages_a = 2;
   p2.bar_slot0 = tc::kNumBars; p2.tmem_col0 = 2 * mb * C;
-  p2.e_box_rows = V; p2.e_n_boxes = 1;
+  p2.e_box_rows = V / n_eboxes; p2.e_n_boxes = n_eboxes;
   p2.e_part_bytes = (uint32_t)((128 * mb * C * 2 + 1023) & ~1023); p2.e_buf_bytes = p2.e_part_bytes;
   p2.n_add_bufs = 2;          // raised below to as many as fit (residual loads come from HBM: ~1.5 us of latency to cover)
   p2.epi_sets = opt.epi_sets; p1.epi_sets = 1;
@@ -482,21 +490,14 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   VSG_TRY(encode_3d(&tmA, xa, (uint64_t)C, (uint64_t)L, (uint64_t)B, (uint64_t)C, (uint64_t)L * C, (uint32_t)C,
                     (uint32_t)p1.a_box_rows, C));
   auto emap = [&](CUtensorMap* m, const __nv_bfloat16* base) -> int {
-    return encode_3d(m, base, (uint64_t)C, (uint64_t)L, (uint64_t)B, (uint64_t)C, (uint64_t)L * C, (uint32_t)C, (uint32_t)V, C);
+    return encode_3d(m, base, (uint64_t)C, (uint64_t)L, (uint64_t)B, (uint64_t)C, (uint64_t)L * C, (uint32_t)C,
+                     (uint32_t)p2.e_box_rows, C);
   };
   tmAdd0 = tmAdd1 = tmRaw = tmAct = tmA;
   if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0));
   if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1));
   if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw));
   if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act));
-  static bool attr_set = false;
-  if (!attr_set) {
-    VSG_CUDA_TRY(cudaFuncSetAttribute(pair_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    VSG_CUDA_TRY(cudaFuncSetAttribute(pair_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    VSG_CUDA_TRY(cudaFuncSetAttribute((pair_tc_kernel<32, EPI_SIG_RES_ACT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    VSG_CUDA_TRY(cudaFuncSetAttribute((pair_tc_kernel<32, EPI_SIG_LINEAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    attr_set = true;
-  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -508,13 +509,24 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = opt.use_pdl ? 1 : 0;
-  const bool res_act = opt.epi_sigs && C == 32 && e.add0 && e.add0_is_act && !e.add1 && e.out_act && !e.out_raw && !e.out_f32 &&
-                       e.scale == 1.0f && e.bias;
-  cudaError_t le = C == 16 ? cudaLaunchKernelEx(&cfg, pair_tc_kernel<16>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2)
-                   : res_act ? cudaLaunchKernelEx(&cfg, pair_tc_kernel<32, EPI_SIG_RES_ACT>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2)
-                   : (opt.epi_sigs && !e.out_f32 && e.bias)
-                       ? cudaLaunchKernelEx(&cfg, pair_tc_kernel<32, EPI_SIG_LINEAR>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2)
-                       : cudaLaunchKernelEx(&cfg, pair_tc_kernel<32>, tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2);
+  // kernel image by channel count and epilogue signature (conv_tc.cuh, EPI_SIG_*)
+  using PairFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvTC, ConvTC);
+  static const PairFn pair_kernels[2][3] = {
+      {pair_tc_kernel<16, EPI_SIG_GENERIC>, pair_tc_kernel<16, EPI_SIG_RES_ACT>, pair_tc_kernel<16, EPI_SIG_LINEAR>},
+      {pair_tc_kernel<32, EPI_SIG_GENERIC>, pair_tc_kernel<32, EPI_SIG_RES_ACT>, pair_tc_kernel<32, EPI_SIG_LINEAR>}};
+  static bool pair_attr_set = false;
+  if (!pair_attr_set) {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 3; ++b)
+        VSG_CUDA_TRY(cudaFuncSetAttribute(pair_kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    pair_attr_set = true;
+  }
+  int pv = 0;
+  if (opt.epi_sigs && !e.out_f32 && e.bias) {
+    pv = 2;
+    if (e.add0 && e.add0_is_act && !e.add1 && e.out_act && !e.out_raw && e.scale == 1.0f) pv = 1;
+  }
+  cudaError_t le = cudaLaunchKernelEx(&cfg, pair_kernels[C == 16 ? 0 : 1][pv], tmA, w1.tmap, w2.tmap, tmAdd0, tmAdd1, tmRaw, tmAct, p1, p2);
   if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of pair_tc_kernel failed: %s", cudaGetErrorString(le));
   VSG_LAUNCH_CHECK("pair_tc_kernel");
   return VSG_OK;
@@ -790,7 +802,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
           // epilogue warp set of the one-CTA-per-SM pair kernel is slower (239-275 us) than two co-resident un-fused CTAs
           // (210-235 us), so only C=32 is fused by default (fuse_pairs == 2 forces both).
           const int n_outs_pair = last ? 1 : (one_stream ? 1 : 2);
-          const bool fuse = c.dec_resblock == 1 && !x3 && opt.fuse_pairs && (ch == 32 || opt.fuse_pairs == 2) &&
+          const bool fuse = c.dec_resblock == 1 && !x3 && opt.fuse_pairs && (ch == 32 || ch == 16 || opt.fuse_pairs == 2) &&
                             pair_supported(rb.c1_tc[q], rb.c2_tc[q], d, L, 1 + (e2.add1 ? 1 : 0), n_outs_pair);
           if (fuse) {
             // low-channel stages: both convs of the pair in ONE kernel, the intermediate never leaves the SM
