@@ -349,7 +349,9 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
        conv_tc_kernel<false, EPI_SIG_LINEAR>},
       {conv_tc_kernel<true, EPI_SIG_GENERIC>, conv_tc_kernel<true, EPI_SIG_ACT>, conv_tc_kernel<true, EPI_SIG_RES_ACT>,
        conv_tc_kernel<true, EPI_SIG_LINEAR>}};
-  static bool attr_set = false;
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+  static bool attr_set_dev[64] = {false};
+  bool& attr_set = attr_set_dev[P->device & 63];
   if (!attr_set) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 4; ++b)
@@ -514,7 +516,8 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   static const PairFn pair_kernels[2][3] = {
       {pair_tc_kernel<16, EPI_SIG_GENERIC>, pair_tc_kernel<16, EPI_SIG_RES_ACT>, pair_tc_kernel<16, EPI_SIG_LINEAR>},
       {pair_tc_kernel<32, EPI_SIG_GENERIC>, pair_tc_kernel<32, EPI_SIG_RES_ACT>, pair_tc_kernel<32, EPI_SIG_LINEAR>}};
-  static bool pair_attr_set = false;
+  static bool pair_attr_set_dev[64] = {false};
+  bool& pair_attr_set = pair_attr_set_dev[P->device & 63];
   if (!pair_attr_set) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 3; ++b)
