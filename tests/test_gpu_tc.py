@@ -107,6 +107,32 @@ def test_generator_bf16_deterministic_and_batch_invariant(cuda_device):
     assert torch.equal(a[2:3], m(xd[2:3], g=gd[2:3]))
 
 
+def test_generator_bf16_full_length_fused_equals_unfused(cuda_device):
+    """BASELINE-size utterances (T = 1000 frames = 300 000 samples: thousands of 256- / 512-row tiles per utterance in the
+    fused-pair stages) are beyond what the CPU oracle finishes in seconds, so the full-length check is a property: the
+    fused ResBlock-pair kernels, the merged upsamplers, the N-split and the signature-specialised images must reproduce
+    what the plain one-kernel-per-conv path computes.  The two paths accumulate in different orders, every bf16 rounding
+    that flips is re-amplified by the following layers, so they differ by about sqrt(2) x the bf16-vs-fp32 error of
+    either (3.7e-3) -- a tiling / halo / indexing bug shows up as O(1).  Together with the small-size oracle tests above
+    this ties the full-length run to the reference."""
+    from visinger_b200 import _lib
+    sd = O.synth_state_dict(gen_shapes(GEN_FULL), 99)
+    m = build_gen(GEN_FULL, sd, cuda_device, precision="bf16")
+    x, _, g = make_inputs(901, 2, 192, 1000, 256)
+    xd, gd = x.to(cuda_device), g.to(cuda_device)
+    try:
+        fast = m(xd, g=gd).clone()
+        # bit 9 no fused pairs, bit 10 one launch per polyphase, bit 11 no N split, bit 13 generic epilogue images
+        _lib.set_tc_options(halo_mode=1 | 512 | 1024 | 2048 | 8192)
+        plain = m(xd, g=gd).clone()
+    finally:
+        _lib.set_tc_options(halo_mode=1)
+    assert fast.shape == (2, 1, 300000) and bool(torch.isfinite(fast).all())
+    rel = float((fast - plain).norm() / plain.norm())
+    print(f"full-length bf16 generator, fused vs plain path: rel-L2 {rel:.3e}, max-abs {maxabs(fast, plain):.3e}")
+    assert rel <= 1e-2          # measured 5.6e-3 = sqrt(2) x 3.7e-3 (two independent bf16 roundings of the same function)
+
+
 @pytest.mark.parametrize("B,T,lengths", [(1, 1, None), (2, 300, [300, 211]), (3, 130, [130, 128, 5])])
 def test_flow_bf16_vs_oracle(cuda_device, B, T, lengths):
     """bf16 tensor-core flow (gate / residual-skip / coupling epilogues) against the fp32 oracle.  bf16 storage of
