@@ -131,6 +131,14 @@ def test_generator_bf16_full_length_fused_equals_unfused(cuda_device):
     rel = float((fast - plain).norm() / plain.norm())
     print(f"full-length bf16 generator, fused vs plain path: rel-L2 {rel:.3e}, max-abs {maxabs(fast, plain):.3e}")
     assert rel <= 1e-2          # measured 5.6e-3 = sqrt(2) x 3.7e-3 (two independent bf16 roundings of the same function)
+    # the fp32 FFMA path (pinned to the oracle at small sizes, different kernels and layout) at the same full length
+    ref32 = build_gen(GEN_FULL, sd, cuda_device, precision="fp32")(xd, g=gd)
+    rel16 = float((fast - ref32).norm() / ref32.norm())
+    rel16p = float((plain - ref32).norm() / ref32.norm())
+    x3 = build_gen(GEN_FULL, sd, cuda_device, precision="bf16x3")(xd, g=gd)
+    print(f"full length vs fp32 path: bf16 rel-L2 {rel16:.3e} (plain path {rel16p:.3e}); bf16x3 max-abs {maxabs(x3, ref32):.3e}")
+    assert rel16 <= 1e-2 and rel16 <= 1.5 * rel16p   # bf16 noise floor of this network; the fast path adds none of its own
+    assert maxabs(x3, ref32) <= 1e-4          # north_star's fp32 tolerance, at full length
 
 
 @pytest.mark.parametrize("B,T,lengths", [(1, 1, None), (2, 300, [300, 211]), (3, 130, [130, 128, 5])])
