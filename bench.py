@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-split-n", action="store_true", help="keep N = 256 tiles whole (no 2 x 128 split)")
     ap.add_argument("--one-epi-set", action="store_true", help="a single set of 4 epilogue warps per CTA")
     ap.add_argument("--generic-epilogue", action="store_true", help="never use the signature-specialised kernels")
+    ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 / fp32 cross-check block")
     ap.add_argument("--two-streams", action="store_true", help="store raw and activated copies of the resblock stream")
     return ap.parse_args()
 
@@ -260,6 +261,34 @@ def main():
         step_decoder()
     ms_dec = timed(step_decoder, args.steps)
 
+    # The headline mode is bf16 (north_star reports it as rel-L2 against the reference).  The mode that meets the fp32
+    # tolerances (waveform max-abs <= 1e-4, z <= 1e-5) on the same tensor-core kernels is bf16x3: time it on the same
+    # workload and measure both modes' distance to the fp32 path right here, so the line carries its own parity evidence.
+    parity = None
+    if args.precision == "bf16" and world == 1 and not args.no_parity_mode:
+        hp3 = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, dev, precision="bf16x3")
+        nb = min(B, 2)
+        sub = [t[:nb].contiguous() for t in devin]
+        wav3, z3 = hp3.infer(*sub)
+        hp32 = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, dev, precision="fp32")
+        wav32, z32 = hp32.infer(*sub)
+        wav16, _ = hp.infer(*sub)
+        err3 = float((wav3 - wav32).abs().max())
+        errz = float((z3 - z32).abs().max())
+        rel16 = float((wav16 - wav32).norm() / wav32.norm())
+        del hp32
+        for _ in range(2):
+            hp3.infer(*devin)
+        k3 = max(3, min(args.steps, 5))
+        ms3 = timed(lambda: hp3.infer(*devin), k3)
+        parity = {"precision": "bf16x3", "value": audio_per_step * k3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / k3,
+                  "wav_max_abs_err_vs_fp32_path": err3, "z_max_abs_err_vs_fp32_path": errz,
+                  "bf16_wav_rel_l2_vs_fp32_path": rel16,
+                  "note": f"errors on {nb} of the {B} full-length utterances against this library's fp32 mode, which the tests "
+                          "pin to the reference (oracle) at waveform 3.5e-8 / z 7e-7"}
+        del hp3
+        torch.cuda.empty_cache()
+
     if rank == 0:
         pk = peaks()
         value = world * audio_per_step * args.steps / (ms * 1e-3)
@@ -297,6 +326,8 @@ def main():
                          "algorithmic": f"{DEC_FLOP_PER_FRAME} FLOP/frame x {B * T} frames",
                          "ms": ms_dec / args.steps, "peak_source": pk["src"] + ", sustained bf16"},
         }
+        if parity is not None:
+            line["parity_mode"] = parity
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
             ts = oracle_hot_path_time(1, T, 4, cores)[1:]
