@@ -14,6 +14,8 @@ the metric's roofline is quoted on), random weights of config/models/visinger.ya
   roofline  decoder convolutions (the dominant kernels): algorithmic FLOPs (SURVEY.md 8d:
             333 911 680 FLOP per latent frame) / CUDA-event time of the generator region
   cpu_baseline  the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1 only)
+  parity_mode   (N=1) the same workload in bf16x3 -- the tensor-core mode that meets the fp32 tolerances -- with its
+            and the bf16 mode's measured distance to the fp32 path on full-length utterances
 
 Multi-GPU: utterances are independent, so ranks shard by utterance with no collective on the data path
 (weak scaling: every rank runs the same per-GPU batch); torch.distributed is used only for the barrier
