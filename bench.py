@@ -169,8 +169,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import visinger_oracle as O            # weights generator only (shared with the tests)
-    from helpers import FLOW_FULL, GEN_FULL, flow_shapes, gen_shapes, make_inputs
+    # this arm never touches oracle/: random-init weights come from the module mirrors themselves
+    from visinger_b200.configs import VISINGER_FLOW as FLOW_FULL, VISINGER_GENERATOR as GEN_FULL
     from visinger_b200.models.visinger import HotPath
     import visinger_b200
 
@@ -182,15 +182,16 @@ def main():
     B, T = args.batch, args.frames
     audio_per_step = B * T * FRAME_SEC
 
-    fsd = O.synth_state_dict(flow_shapes(FLOW_FULL), 1234)
-    gsd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
-    hp = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, dev, precision=args.precision)
+    hp = HotPath.random_init(FLOW_FULL, GEN_FULL, dev, precision=args.precision, seed=1234)
     if args.l2_mb >= 0 or args.no_pdl or args.no_fuse or args.no_merge_ups or args.no_split_n or args.two_streams or args.generic_epilogue:
         from visinger_b200 import _lib
         _lib.set_tc_options(halo_mode=1 | (256 if args.no_pdl else 0) | (512 if args.no_fuse else 0) |
                             (1024 if args.no_merge_ups else 0) | (2048 if args.no_split_n else 0) | (4096 if args.two_streams else 0) | (8192 if args.generic_epilogue else 0), l2_tensor_mb=args.l2_mb)
 
-    x, mask, g = make_inputs(rank, B, 192, T, 256)
+    gen_in = torch.Generator().manual_seed(rank)
+    x = torch.randn(B, 192, T, generator=gen_in)                 # prior mean
+    g = 0.1 * torch.randn(B, 256, 1, generator=gen_in)           # speaker embedding
+    mask = torch.ones(B, 1, T)                                   # full-length utterances
     logs = torch.full_like(x, -1.0)
     noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + rank))
     host = [t.pin_memory() for t in (x, logs, noise, mask, g)]
@@ -268,11 +269,11 @@ def main():
     # workload and measure both modes' distance to the fp32 path right here, so the line carries its own parity evidence.
     parity = None
     if args.precision == "bf16" and world == 1 and not args.no_parity_mode:
-        hp3 = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, dev, precision="bf16x3")
+        hp3 = HotPath(hp.flow, hp.decoder, precision="bf16x3")       # same modules, own weight pack
         nb = min(B, 2)
         sub = [t[:nb].contiguous() for t in devin]
         wav3, z3 = hp3.infer(*sub)
-        hp32 = HotPath.from_configs(FLOW_FULL, GEN_FULL, fsd, gsd, dev, precision="fp32")
+        hp32 = HotPath(hp.flow, hp.decoder, precision="fp32")
         wav32, z32 = hp32.infer(*sub)
         wav16, _ = hp.infer(*sub)
         err3 = float((wav3 - wav32).abs().max())

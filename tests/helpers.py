@@ -9,9 +9,7 @@ from oracle import visinger_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-FLOW_FULL = dict(channels=192, hidden=192, kernel_size=5, dilation_rate=1, n_layers=4, n_flows=4, gin=256)
-GEN_FULL = dict(initial_channel=192, resblock="1", rk=[3, 7, 11], rd=[[1, 3, 5]] * 3, ur=[5, 5, 3, 2, 2], uic=512,
-                uk=[11, 11, 7, 4, 4], gin=256)
+from visinger_b200.configs import VISINGER_FLOW as FLOW_FULL, VISINGER_GENERATOR as GEN_FULL  # noqa: E402
 
 
 def load_npz(name):

@@ -45,6 +45,24 @@ class HotPath(PackedModuleMixin, nn.Module):
         dec.load_state_dict(gen_sd)
         return cls(flow, dec, precision).to(device).eval()
 
+    @classmethod
+    def random_init(cls, flow_cfg, gen_cfg, device, precision="fp32", seed=0, post_std=0.05):
+        """Randomly initialised hot path of the given architecture (benchmarks, smoke runs without a checkpoint).
+        PyTorch's default initialisation of the mirrors, except that the coupling layers' `post` convolutions -- which the
+        reference zero-initialises (flow.py:63-64), making an untrained flow the identity -- get N(0, post_std) weights so
+        that every kernel of the flow computes on non-trivial data."""
+        with torch.random.fork_rng(devices=[]):
+            torch.manual_seed(seed)
+            flow = ResidualCouplingBlock(flow_cfg["channels"], flow_cfg["hidden"], flow_cfg["kernel_size"],
+                                         flow_cfg["dilation_rate"], flow_cfg["n_layers"], n_flows=flow_cfg["n_flows"],
+                                         gin_channels=flow_cfg["gin"])
+            dec = Generator(gen_cfg["initial_channel"], gen_cfg["resblock"], gen_cfg["rk"], gen_cfg["rd"], gen_cfg["ur"],
+                            gen_cfg["uic"], gen_cfg["uk"], gin_channels=gen_cfg["gin"])
+            for name, prm in flow.named_parameters():
+                if ".post." in name:
+                    nn.init.normal_(prm, std=post_std)
+        return cls(flow, dec, precision).to(device).eval()
+
     # -- packing: both modules in one pack, reference checkpoint prefixes ------------------------
     def _vsg_config(self):
         c = self.decoder._vsg_config()
