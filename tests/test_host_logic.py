@@ -59,3 +59,23 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("no CPU or", ""), f"{f} mentions the oracle"
+
+
+def test_random_init_matches_reference_parameter_layout():
+    """HotPath.random_init (what bench.py's own arm uses instead of oracle weights) builds the reference architecture:
+    same parameter names and shapes as the oracle's shape tables (= the reference's state dict), non-zero `post` layers."""
+    from oracle import visinger_oracle as O
+    from visinger_b200.configs import VISINGER_FLOW as F, VISINGER_GENERATOR as G
+    from visinger_b200.models.visinger import HotPath
+    hp = HotPath.random_init(F, G, "cpu", precision="bf16", seed=7)
+    sd = hp.state_dict()
+    want = {"flow." + k: v for k, v in O.flow_param_shapes(F["channels"], F["hidden"], F["kernel_size"], F["n_layers"],
+                                                            F["n_flows"], F["gin"]).items()}
+    want.update({"decoder." + k: v for k, v in O.generator_param_shapes(G["initial_channel"], G["resblock"], G["rk"], G["rd"],
+                                                                        G["ur"], G["uic"], G["uk"], G["gin"]).items()})
+    assert set(sd) == set(want)
+    for k, shp in want.items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    assert all(float(sd[k].abs().max()) > 0 for k in sd if ".post.weight" in k)
+    again = HotPath.random_init(F, G, "cpu", precision="bf16", seed=7).state_dict()
+    assert all(torch.equal(sd[k], again[k]) for k in sd)
