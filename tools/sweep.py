@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--max-frames-per-batch", type=int, default=16000)
     ap.add_argument("--max-batch", type=int, default=64)
+    ap.add_argument("--eager", action="store_true", help="plain forward() per batch instead of one CUDA graph per batch shape")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -57,7 +58,10 @@ def main():
         outs = []
         for hb in host_batches:
             d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-            out = model(d["text_tokens"], d["note_pitch"], d["note_dur"], d["mel2ph"], spk_id=d["spk_ids"], infer=True)
+            if args.eager:
+                out = model(d["text_tokens"], d["note_pitch"], d["note_dur"], d["mel2ph"], spk_id=d["spk_ids"], infer=True)
+            else:   # one CUDA graph per batch shape (captured in the warm-up pass)
+                out = model.forward_graphed(d["text_tokens"], d["note_pitch"], d["note_dur"], d["mel2ph"], spk_id=d["spk_ids"])
             outs.append(out["wav_out"].to("cpu", non_blocking=True))
         torch.cuda.synchronize()
         return outs

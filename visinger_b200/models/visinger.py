@@ -339,15 +339,58 @@ class VISinger(nn.Module):
             ret["z_q"] = z_q
             return ret
 
+    def forward_graphed(self, text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed=None, spk_id=None, noise=None):
+        """`forward(..., infer=True)` replayed from one CUDA graph per input shape (prior network + prior sampling + flow +
+        decoder: ~600 eager launches and ~12 ms of CPU issue time at B=16 x T=1000 become one cudaGraphLaunch).
+        The first call with a new (shape, precision) captures; later calls copy the inputs into the graph's static
+        buffers and replay.  The returned tensors are the graph's static outputs: valid until the next call with the
+        same shape.  Without `noise` the prior noise comes from the CUDA generator inside the graph (fresh per replay).
+        The hot path's scratch buffer is allocated during capture, i.e. in the graph's private memory pool."""
+        ins = {"text_tokens": text_tokens, "pitch_tokens": pitch_tokens, "dur_tokens": dur_tokens, "mel2ph": mel2ph,
+               "spk_embed": spk_embed, "spk_id": spk_id, "noise": noise}
+        ins = {k: v for k, v in ins.items() if v is not None}
+        for k, v in ins.items():
+            _lib.require_cuda(v, k)
+        key = (self.precision,) + tuple((k, tuple(v.shape), v.dtype) for k, v in ins.items())
+        cache = self.__dict__.setdefault("_fw_graphs", {})
+        if key not in cache:
+            static = {k: v.clone() for k, v in ins.items()}
+            dev = mel2ph.device
+            with torch.cuda.device(dev):
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):          # warm-up outside capture: weight pack, workspaces, cuDNN plans
+                    for _ in range(2):
+                        self.forward(infer=True, **static)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self.forward(infer=True, **static)
+            cache[key] = (graph, static, out)
+        graph, static, out = cache[key]
+        for k, v in ins.items():
+            static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        return out
+
     def prior(self, text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed=None, spk_id=None, f0=None, uv=None,
               ret=None):
         """models/visinger.py:75-90: everything upstream of z_p (plain PyTorch, any device).
         Returns (mu_p, logs_p, tgt_nonpadding [B, 1, T], spk_emb [B, gin, 1]); fills ret["f0_pred"]."""
         ret = {} if ret is None else ret
-        # cuDNN convolutions default to TF32 on the GPU, which alone costs ~1e-4 on mu_p (SURVEY.md 8c); the prior runs in
-        # true fp32 so that the whole forward stays inside the reference's fp32 tolerance.
-        with torch.backends.cudnn.flags(enabled=torch.backends.cudnn.enabled, allow_tf32=False):
-            return self._prior(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret)
+        # cuDNN convolutions default to TF32 on the GPU, which alone costs ~1e-4 on mu_p (SURVEY.md 8c): in the parity
+        # modes ("fp32", "bf16x3") the prior runs in true fp32 so that the whole forward stays inside the reference's fp32
+        # tolerance.  The throughput mode ("bf16") lets the prior's convolutions and matmuls use TF32 tensor cores as
+        # well -- far below that mode's own bf16 rounding, and the fp32 prior is otherwise 3x the cost of the whole hot path.
+        fast = self.precision == "bf16" and getattr(self, "prior_tf32", True)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = fast
+        try:
+            with torch.backends.cudnn.flags(enabled=torch.backends.cudnn.enabled, allow_tf32=fast):
+                return self._prior(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
 
     def _prior(self, text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret):
         mask = (mel2ph > 0).float().unsqueeze(1)
