@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--one-epi-set", action="store_true", help="a single set of 4 epilogue warps per CTA")
     ap.add_argument("--generic-epilogue", action="store_true", help="never use the signature-specialised kernels")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 / fp32 cross-check block")
+    ap.add_argument("--no-chain-streams", action="store_true", help="run the resblock chains of a stage one after the other")
     ap.add_argument("--two-streams", action="store_true", help="store raw and activated copies of the resblock stream")
     return ap.parse_args()
 
@@ -183,10 +184,10 @@ def main():
     audio_per_step = B * T * FRAME_SEC
 
     hp = HotPath.random_init(FLOW_FULL, GEN_FULL, dev, precision=args.precision, seed=1234)
-    if args.l2_mb >= 0 or args.no_pdl or args.no_fuse or args.no_merge_ups or args.no_split_n or args.two_streams or args.generic_epilogue:
+    if args.l2_mb >= 0 or args.no_pdl or args.no_fuse or args.no_merge_ups or args.no_split_n or args.two_streams or args.generic_epilogue or args.no_chain_streams:
         from visinger_b200 import _lib
         _lib.set_tc_options(halo_mode=1 | (256 if args.no_pdl else 0) | (512 if args.no_fuse else 0) |
-                            (1024 if args.no_merge_ups else 0) | (2048 if args.no_split_n else 0) | (4096 if args.two_streams else 0) | (8192 if args.generic_epilogue else 0), l2_tensor_mb=args.l2_mb)
+                            (1024 if args.no_merge_ups else 0) | (2048 if args.no_split_n else 0) | (4096 if args.two_streams else 0) | (8192 if args.generic_epilogue else 0) | (16384 if args.no_chain_streams else 0), l2_tensor_mb=args.l2_mb)
 
     gen_in = torch.Generator().manual_seed(rank)
     x = torch.randn(B, 192, T, generator=gen_in)                 # prior mean

@@ -110,6 +110,7 @@ struct TCOptions {
   int merge_ups = 1;
   int split_n = 1;
   int single_stream = 1;
+  int chain_streams = 1;
   int epi_sigs = 1;
   int epi_sets = 2;
 };
@@ -700,11 +701,38 @@ SubBatchPlan plan_sub_batches(const VsgPack* P, int B, int T) {
   return pl;
 }
 
+// The NK resblocks of a stage read the same input and only meet in the running sum, so their conv chains run on
+// separate streams (chain 0 on the caller's stream): a persistent kernel's tail -- SMs idle while the last tiles finish,
+// up to 14 % of the launch at C = 256 -- is filled by CTAs of the other chains.  Streams and events are created once per
+// device; under CUDA-graph capture the fork / join events turn into graph edges.
+constexpr int kMaxChains = 3;
+struct ChainStreams {
+  cudaStream_t s[kMaxChains - 1] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[kMaxChains - 1] = {nullptr, nullptr}, sum_done[kMaxChains] = {nullptr, nullptr, nullptr};
+  bool ready = false;
+};
+static ChainStreams g_chain_streams[64];
+
+static int chain_streams_for(int device, ChainStreams** out) {
+  ChainStreams& cs = g_chain_streams[device & 63];
+  if (!cs.ready) {
+    for (int i = 0; i < kMaxChains - 1; ++i) {
+      VSG_CUDA_TRY(cudaStreamCreateWithFlags(&cs.s[i], cudaStreamNonBlocking));
+      VSG_CUDA_TRY(cudaEventCreateWithFlags(&cs.join[i], cudaEventDisableTiming));
+    }
+    VSG_CUDA_TRY(cudaEventCreateWithFlags(&cs.fork, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxChains; ++i) VSG_CUDA_TRY(cudaEventCreateWithFlags(&cs.sum_done[i], cudaEventDisableTiming));
+    cs.ready = true;
+  }
+  *out = &cs;
+  return VSG_OK;
+}
+
 size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T, bool x3) {
   const SubBatchPlan pl = plan_sub_batches(P, B, T);
   const size_t np = x3 ? 2 : 1;
   return align256((size_t)B * T * P->cfg.dec_initial_channel * 2 * np) + align256((size_t)B * P->cfg.dec_upsample_initial_channel * 4) +
-         2 * align256(pl.io_elems * 2 * np) + 7 * align256(pl.inter_elems * 2 * np) + 512;
+         2 * align256(pl.io_elems * 2 * np) + (7 + 4 * (kMaxChains - 1)) * align256(pl.inter_elems * 2 * np) + 512;
 }
 
 // Generator.forward (modules/visinger/decoder.py:40-59) on the tensor-core kernels.
@@ -724,15 +752,22 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
   bf* io[2] = {ws.take<bf>(pl.io_elems * np), ws.take<bf>(pl.io_elems * np)};   // leaky_relu'd stage input / output
   bf* bU = ws.take<bf>(pl.inter_elems * np);    // upsampled x (residual for the first pair of every resblock)
   bf* bUA = ws.take<bf>(pl.inter_elems * np);   // leaky_relu(x)
-  bf* bR = ws.take<bf>(pl.inter_elems * np);    // resblock running x
-  bf* bRA = ws.take<bf>(pl.inter_elems * np);   // leaky_relu of it
-  bf* bT = ws.take<bf>(pl.inter_elems * np);    // leaky_relu(conv1 output)  (ResBlock2: ping-pong partner of bR)
-  bf* bTA = ws.take<bf>(pl.inter_elems * np);   // (ResBlock2 only)
+  // per resblock chain (they run concurrently): running x, leaky_relu of it, leaky_relu(conv1 output), its ResBlock2 partner
+  bf *cR[kMaxChains], *cRA[kMaxChains], *cT[kMaxChains], *cTA[kMaxChains];
+  for (int j = 0; j < kMaxChains; ++j) {
+    cR[j] = ws.take<bf>(pl.inter_elems * np);
+    cRA[j] = ws.take<bf>(pl.inter_elems * np);
+    cT[j] = ws.take<bf>(pl.inter_elems * np);
+    cTA[j] = ws.take<bf>(pl.inter_elems * np);
+  }
   bf* bS = ws.take<bf>(pl.inter_elems * np);    // running sum over the NK resblocks
   int* err = ws.take<int>(1);
   if (ws.overflow) return fail(VSG_ENOMEM, "generator workspace too small: need %zu bytes", ws.off);
   VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
   const TCOptions opt = g_default_opts;
+  const bool chains = opt.chain_streams && NK > 1 && NK <= kMaxChains;
+  ChainStreams* cs = nullptr;
+  if (chains) VSG_TRY(chain_streams_for(P->device, &cs));
 
   if (c.dec_gin > 0) {
     if (!g) return fail(VSG_EINVAL, "generator was built with gin_channels=%d but g is NULL", c.dec_gin);
@@ -786,13 +821,23 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       // consumer's epilogue (a > 0 ? a : a / slope -- as exact in bf16 as a second, raw copy), so the upsampler and every
       // non-final conv2 write one tensor instead of two.  Split-bf16 keeps the raw copy (exactness of the lo plane).
       const bool one_stream = !x3 && opt.single_stream;
+      const cudaStream_t st_main = st;
+      if (chains) {   // fork: the other chains start once the upsampled input is complete
+        VSG_CUDA_TRY(cudaEventRecord(cs->fork, st_main));
+        for (int j = 1; j < NK; ++j) VSG_CUDA_TRY(cudaStreamWaitEvent(cs->s[j - 1], cs->fork, 0));
+      }
       for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
         const ResBlockPack& rb = us.blocks[j];
         const int nd = (int)rb.dilations.size(), k = rb.kernel;
         const bf* cur = one_stream ? bUA : bU; const bf* curA = bUA;
+        const int cj = chains ? j : 0;
+        bf *bR = cR[cj], *bRA = cRA[cj], *bT = cT[cj], *bTA = cTA[cj];
+        if (chains) st = j == 0 ? st_main : cs->s[j - 1];
         for (int q = 0; q < nd; ++q) {
           const bool last = (q == nd - 1);
           const int d = rb.dilations[q];
+          // the running sum is read-modify-written by the last conv of every chain, in chain order
+          const bool sum_wait = chains && last && j > 0;
           EpiTC e2;
           e2.add0 = cur;
           e2.add0_is_act = one_stream ? 1 : 0;
@@ -811,6 +856,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
             // low-channel stages: both convs of the pair in ONE kernel, the intermediate never leaves the SM
             e2.bias = rb.c2_tc[q].bias;
             if (!last) { e2.out_act = bRA; if (!one_stream) e2.out_raw = bR; }
+            if (sum_wait) VSG_CUDA_TRY(cudaStreamWaitEvent(st, cs->sum_done[j - 1], 0));
             VSG_TRY(launch_pair_tc(P, rb.c1_tc[q], rb.c2_tc[q], curA, nb, L, d, e2, opt, err, st));
             cur = one_stream ? bRA : bR; curA = bRA;
           } else if (c.dec_resblock == 1) {        // ResBlock1 (decoder.py:91-104)
@@ -819,6 +865,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
             VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
             e2.bias = rb.c2_tc[q].bias;
             if (!last) { e2.out_act = bRA; if (!one_stream) e2.out_raw = bR; }
+            if (sum_wait) VSG_CUDA_TRY(cudaStreamWaitEvent(st, cs->sum_done[j - 1], 0));
             VSG_TRY(launch_conv_tc(P, W(rb.c2_tc[q], rb.c2_x3[q]), bT, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
             cur = one_stream ? bRA : bR; curA = bRA;
           } else {                           // ResBlock2 (decoder.py:124-133)
@@ -826,10 +873,19 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
             bf* nr = (cur == bR || cur == bRA) ? bT : bR;
             bf* nra = (cur == bR || cur == bRA) ? bTA : bRA;
             if (!last) { e2.out_act = nra; if (!one_stream) e2.out_raw = nr; }
+            if (sum_wait) VSG_CUDA_TRY(cudaStreamWaitEvent(st, cs->sum_done[j - 1], 0));
             VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e2, opt, err, st));
             cur = one_stream ? nra : nr; curA = nra;
           }
         }
+        if (chains && j < NK - 1) VSG_CUDA_TRY(cudaEventRecord(cs->sum_done[j], st));
+      }
+      if (chains) {   // join: the stage output (written by the last chain) and every scratch buffer are settled
+        for (int j = 1; j < NK; ++j) {
+          VSG_CUDA_TRY(cudaEventRecord(cs->join[j - 1], cs->s[j - 1]));
+          VSG_CUDA_TRY(cudaStreamWaitEvent(st_main, cs->join[j - 1], 0));
+        }
+        st = st_main;
       }
     }
     cur_io ^= 1;
@@ -1006,6 +1062,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.split_n = (halo_mode & 2048) ? 0 : 1;                              // bit 11: never split N = 256 tiles
   g_default_opts.single_stream = (halo_mode & 4096) ? 0 : 1;                        // bit 12: store raw + activated copies
   g_default_opts.epi_sigs = (halo_mode & 8192) ? 0 : 1;                             // bit 13: generic epilogue kernels only
+  g_default_opts.chain_streams = (halo_mode & 16384) ? 0 : 1;                       // bit 14: resblock chains on one stream
   g_default_opts.epi_sets = (halo_mode & 8192) ? 1 : 2;                             // bit 13: one set of epilogue warps
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
