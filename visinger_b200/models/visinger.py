@@ -19,7 +19,7 @@ from ..modules.visinger.flow import ResidualCouplingBlock
 from ..modules.visinger.decoder import Generator
 from ..modules.visinger.encoder import (DEFAULT_MAX_TARGET_POSITIONS, Embedding, FramePriorNetwork, PosteriorEncoder,
                                         TextEncoder)
-from ..modules.visinger.predictor import PhonemePredictor, PitchPredictor
+from ..modules.visinger.encoder import PhonemePredictor, PitchPredictor
 
 
 class HotPath(PackedModuleMixin, nn.Module):

@@ -90,3 +90,35 @@ class PosteriorEncoder(nn.Module):
 
     def forward(self, *a, **k):
         raise NotImplementedError("PosteriorEncoder is training-only; visinger_b200 implements the inference path")
+
+
+# ---- predictors (reference: modules/visinger/predictor.py) ------------------------------------------------------------
+
+class PitchPredictor(nn.Module):
+    """Frame-level (log-f0, voiced/unvoiced) head: a relative-position encoder conditioned on the speaker embedding,
+    followed by a 1x1 projection (reference predictor.py:7-19).  Returns [B, T, out_dim]."""
+
+    def __init__(self, in_dim, filter_channels, n_heads, n_layers, kernel_size, p_dropout, gin_channels, out_dim=2):
+        super().__init__()
+        self.pitch_predictor = RelativeEncoder(in_dim, filter_channels, n_heads, n_layers=n_layers, gin_channels=gin_channels,
+                                               kernel_size=kernel_size, p_dropout=p_dropout)
+        self.linear = nn.Conv1d(in_dim, out_dim, 1)
+
+    def forward(self, x, x_mask, spk_emb):
+        hidden = self.pitch_predictor(x, x_mask, g=spk_emb)
+        return self.linear(hidden).transpose(1, 2)
+
+
+class PhonemePredictor(nn.Module):
+    """Parameter container for the training-only CTC head (reference predictor.py:22-35): present so that reference
+    checkpoints load with strict key matching; it has no inference role."""
+
+    def __init__(self, dict_size, hidden_channels, filter_channels, n_heads, n_layers, kernel_size, p_dropout):
+        super().__init__()
+        self.phoneme_predictor = RelativeEncoder(hidden_channels, filter_channels, n_heads, n_layers=n_layers,
+                                                 kernel_size=kernel_size, p_dropout=p_dropout)
+        self.ph_proj = nn.Conv1d(hidden_channels, dict_size, 1)
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("PhonemePredictor is training-only; visinger_b200 implements the inference path")
+
