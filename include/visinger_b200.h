@@ -161,6 +161,18 @@ int vsg_infer(const VsgPack* pack, const float* mu_p, const float* logs_p, const
               int32_t B, int32_t T, int32_t precision,
               void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Output stage, `save_wav(wav, path, sr, norm)` up to the file write        utils/audio/io.py:8-14
+ * (called with norm = out_wav_norm: true at inference/visinger.py:100, tasks/visinger.py:258):
+ *   pcm = int16( (norm ? wav / max|wav| : wav) * 32767 )     fp32 arithmetic, conversion truncating toward zero
+ * -- the integers numpy produces, bit for bit.  wav: device fp32 [B, L] (the Generator's output); `lengths` (device
+ * int32 [B], valid SAMPLES per utterance, or NULL = L): the peak is taken over the valid samples of each utterance
+ * only (the reference runs one utterance per call) and samples beyond them are written as 0; pcm: device int16 [B, L];
+ * peak: device fp32 [B], receives max|wav| per utterance.  Asynchronous on `stream`, no allocation, capturable.
+ */
+int vsg_wav_to_int16(const float* wav, const int32_t* lengths, int16_t* pcm, float* peak, int32_t B, int32_t L,
+                     int32_t norm, void* stream);
+
 /* Samples produced per latent frame (prod(upsample_rates)); 0 if the pack has no decoder. */
 int32_t vsg_hop_size(const VsgPack* pack);
 

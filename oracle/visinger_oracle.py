@@ -221,6 +221,74 @@ def infer_hot_path(sd: StateDict, mu_p, logs_p, noise, mask, g, *, flow_kw=None,
 
 
 # --------------------------------------------------------------------------------------
+# bf16-mode report metric: the reference's own log-mel spectrogram
+# --------------------------------------------------------------------------------------
+MEL_KW = dict(sample_rate=24000, n_fft=2048, win_length=1200, hop_length=300, f_min=20.0, f_max=12000.0, n_mels=128)
+"""Parameters of `MelSpectrogramFixed` as the reference task builds it (tasks/visinger.py:32-35 with
+config/datasets/svs/csd/preprocess.yaml:6-15: sample_rate 24000, fft_size 2048, win_size 1200, hop_size 300,
+fmin 20, fmax 12000, num_mel_bins 128)."""
+
+
+def _hz_to_mel_htk(f: float) -> float:
+    import math
+    return 2595.0 * math.log10(1.0 + f / 700.0)
+
+
+def mel_filterbank(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int) -> torch.Tensor:
+    """torchaudio.functional.melscale_fbanks(norm=None, mel_scale="htk") -- the filterbank behind
+    torchaudio.transforms.MelSpectrogram's defaults, which utils/audio/mel_processing.py:33 instantiates."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_pts = torch.linspace(_hz_to_mel_htk(f_min), _hz_to_mel_htk(f_max), n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.clamp(torch.min(down, up), min=0.0)            # [n_freqs, n_mels]
+
+
+def mel_spectrogram_fixed(wav: torch.Tensor, *, sample_rate=24000, n_fft=2048, win_length=1200, hop_length=300,
+                          f_min=20.0, f_max=12000.0, n_mels=128) -> torch.Tensor:
+    """`MelSpectrogramFixed.forward` (utils/audio/mel_processing.py:28-38):
+    log(MelSpectrogram(...)(x) + 0.001)[..., :-1], with torchaudio's defaults spelled out -- power spectrogram of a
+    centred, reflect-padded STFT with a periodic Hann window of win_length zero-padded to n_fft, HTK mel filterbank
+    without normalisation.  wav [..., L] -> [..., n_mels, L // hop_length]."""
+    window = torch.hann_window(win_length, periodic=True, dtype=wav.dtype, device=wav.device)
+    shape = wav.shape
+    x = wav.reshape(-1, shape[-1])
+    spec = torch.stft(x, n_fft, hop_length=hop_length, win_length=win_length, window=window, center=True,
+                      pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    power = spec.abs().pow(2.0)                                 # [N, n_freqs, frames]
+    fb = mel_filterbank(n_fft // 2 + 1, f_min, f_max, n_mels, sample_rate).to(wav.dtype).to(wav.device)
+    mel = torch.matmul(power.transpose(-1, -2), fb).transpose(-1, -2)
+    out = torch.log(mel + 0.001)[..., :-1]
+    return out.reshape(shape[:-1] + out.shape[-2:])
+
+
+def mel_l1(wav: torch.Tensor, wav_ref: torch.Tensor) -> float:
+    """Mean absolute difference of the two log-mel spectrograms: the reference's own mel loss without its weight
+    (tasks/visinger.py: F.l1_loss(mel_fn(wav_out), mel)); the bf16-mode report metric north_star names."""
+    return float((mel_spectrogram_fixed(wav.float()) - mel_spectrogram_fixed(wav_ref.float())).abs().mean())
+
+
+# --------------------------------------------------------------------------------------
+# output stage (SURVEY.md 8f, f3): utils/audio/io.py:8-14 up to the file write
+# --------------------------------------------------------------------------------------
+def wav_to_int16(wav, norm: bool = True):
+    """`save_wav` (utils/audio/io.py:8-14) without the file write: `wav / np.abs(wav).max()` when norm
+    (out_wav_norm: true, config/models/base_task.yaml:53), `* 32767`, `.astype(np.int16)` -- float32 numpy
+    arithmetic, conversion truncating toward zero.  wav: 1-D float32 array (ONE utterance, valid samples only:
+    the reference runs batch 1, tasks/visinger.py:246).  Returns (int16 array, peak)."""
+    import numpy as np
+    w = np.asarray(wav, dtype=np.float32)
+    peak = np.abs(w).max() if w.size else np.float32(0)
+    if norm:
+        w = w / peak
+    w = w * 32767
+    return w.astype(np.int16), float(peak)
+
+
+# --------------------------------------------------------------------------------------
 # deterministic synthetic weights (used by tests, smoke and bench on both sides)
 # --------------------------------------------------------------------------------------
 def flow_param_shapes(channels=192, hidden=192, kernel_size=5, n_layers=4, n_flows=4, gin=256):

@@ -23,7 +23,7 @@ _CSRC = os.path.join(_HERE, "csrc")
 _LIBDIR = os.path.join(_HERE, "lib")
 _LIBPATH = os.path.join(_LIBDIR, "libvisinger_b200.so")
 _HEADER = os.path.join(os.path.dirname(_HERE), "include", "visinger_b200.h")
-_SOURCES = ["api.cu", "pack.cu", "run_f32.cu", "run_tc.cu"]
+_SOURCES = ["api.cu", "pack.cu", "run_f32.cu", "run_tc.cu", "output.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
@@ -100,16 +100,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if nvcc is None:
         raise RuntimeError("visinger_b200: libvisinger_b200.so is missing or stale and nvcc was not found; "
                            "there is no fallback path")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", _LIBPATH + ".tmp"] + [os.path.join(_CSRC, s) for s in _SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), flush=True)
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+    # one nvcc per translation unit, in parallel, then one link: run_tc.cu alone is most of the serial build time
+    objdir = os.path.join(os.path.dirname(_HERE), "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(_CSRC, src)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, proc
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(_SOURCES)) as pool:
+        results = list(pool.map(compile_one, _SOURCES))
+    for src, _, proc in results:
+        if proc.returncode != 0:
+            raise RuntimeError(f"visinger_b200: nvcc failed on {src}\n" + proc.stdout + proc.stderr)
+        if verbose:
+            print(proc.stdout + proc.stderr, flush=True)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", _LIBPATH + ".tmp"] + [o for _, o, _ in results]
+    proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("visinger_b200: nvcc failed\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stdout + proc.stderr, flush=True)
+        raise RuntimeError("visinger_b200: link failed\n" + proc.stdout + proc.stderr)
     os.replace(_LIBPATH + ".tmp", _LIBPATH)
     with open(stamp, "w") as fh:
         fh.write(want)
@@ -152,6 +167,8 @@ def lib() -> ctypes.CDLL:
         L.vsg_generator_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
         L.vsg_infer.restype = ctypes.c_int
         L.vsg_infer.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+        L.vsg_wav_to_int16.restype = ctypes.c_int
+        L.vsg_wav_to_int16.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
         L.vsg_debug_conv1d_bf16.restype = ctypes.c_int
         L.vsg_debug_conv1d_bf16.argtypes = [vp, vp, vp, vp, vp, ctypes.c_float, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
                                             i32]

@@ -57,6 +57,9 @@ struct Loader {
       double ss = 0.0;
       for (int64_t i = 0; i < inner; ++i) { double t = v->data[r * inner + i]; ss += t * t; }
       const float norm = (float)sqrt(ss);
+      if (!(norm > 0.f))
+        return fail(VSG_EINVAL, "%s.weight_v row %lld has zero norm: weight-norm w = g * v / ||v|| is undefined",
+                    prefix.c_str(), (long long)r);
       const float scale = g->data[r] / norm;
       for (int64_t i = 0; i < inner; ++i) out[r * inner + i] = v->data[r * inner + i] * scale;
     }
@@ -331,8 +334,9 @@ extern "C" int vsg_pack_create(const VsgConfig* cfg, const VsgTensor* weights, i
   int ndev = 0;
   VSG_CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(VSG_EINVAL, "device %d out of range (%d visible)", device, ndev);
-  int prev = 0;
-  VSG_CUDA_TRY(cudaGetDevice(&prev));
+  // every exit below restores the caller's current device
+  struct Restore { int prev = -1; ~Restore() { if (prev >= 0) cudaSetDevice(prev); } } restore;
+  VSG_CUDA_TRY(cudaGetDevice(&restore.prev));
   VSG_CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   VSG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -359,7 +363,6 @@ extern "C" int vsg_pack_create(const VsgConfig* cfg, const VsgTensor* weights, i
   if (cfg->flow_n_flows > 0) rc = pack_flow(L, flow_prefix ? flow_prefix : "", P);
   if (rc == VSG_OK && cfg->dec_n_ups > 0) rc = pack_decoder(L, dec_prefix ? dec_prefix : "", P);
   if (rc == VSG_OK && !P->has_flow && !P->has_dec) rc = fail(VSG_EINVAL, "config selects neither flow nor decoder");
-  cudaSetDevice(prev);
   if (rc != VSG_OK) {
     vsg_pack_destroy(P);
     return rc;

@@ -9,6 +9,9 @@ int prior_sample(const float* mu, const float* logs, const float* noise, const f
                  int T, cudaStream_t st);
 int mask_mul(const float* x, const float* mask, float* y, int B, int C, int T, cudaStream_t st);
 
+// output stage (output.cu): peak-normalise -> x 32767 -> int16 (utils/audio/io.py:8-14)
+int wav_to_int16(const float* wav, const int32_t* lengths, int16_t* pcm, float* peak, int B, int L, int norm, cudaStream_t st);
+
 // fp32 parity mode (run_f32.cu)
 size_t flow_ws_bytes_f32(const VsgPack* P, int B, int T);
 size_t dec_ws_bytes_f32(const VsgPack* P, int B, int T);

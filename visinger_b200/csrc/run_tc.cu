@@ -6,7 +6,9 @@
 #include "pair_tc.cuh"
 
 #include <algorithm>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <stdlib.h>
 
 namespace vsg {
@@ -133,6 +135,9 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (!w.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 16 "
                                                  "(conv %d -> %d)", w.Cin, w.Cout);
   if (Lq <= 0 || B <= 0) return VSG_OK;
+  // a convolution with taps reads rows that other CTAs' output tiles cover: it must not write over its own input
+  if (w.ktaps > 1 && ((const void*)x == (const void*)e.out_act || (const void*)x == (const void*)e.out_raw))
+    return fail(VSG_EINVAL, "a k > 1 convolution must not run in place (output aliases the input)");
   const int KC = pick_kc(w.Cin);
   int NT = pick_ntile(w.Cout);                 // output-channel tile; N = 256 convs may also run as 2 x 128 (see below)
   const int halo = (w.ktaps - 1) * dil;
@@ -419,6 +424,9 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
                    const EpiTC& e, const TCOptions& opt, int* error_flag, cudaStream_t st) {
   const int C = w1.Cin, k = w1.ktaps, mb = pair_mb(C);
   const int h2 = (k - 1) / 2, pad1 = (k - 1) * d1 / 2, halo1 = (k - 1) * d1;
+  // the input is read with a halo that other CTAs' output tiles cover: an aliased output is a data race
+  if ((const void*)xa == (const void*)e.out_act || (const void*)xa == (const void*)e.out_raw)
+    return fail(VSG_EINVAL, "fused pair must not run in place (output aliases the activated input)");
   // valid output rows per tile.  One TMA box holds <= 256 rows; with two boxes the box height must be a multiple of 8
   // rows so that both start on a swizzle-atom boundary of the staging tile (a few more halo rows are recomputed).
   const int n_eboxes = (128 * mb + 255) / 256;
@@ -703,28 +711,65 @@ SubBatchPlan plan_sub_batches(const VsgPack* P, int B, int T) {
 
 // The NK resblocks of a stage read the same input and only meet in the running sum, so their conv chains run on
 // separate streams (chain 0 on the caller's stream): a persistent kernel's tail -- SMs idle while the last tiles finish,
-// up to 14 % of the launch at C = 256 -- is filled by CTAs of the other chains.  Streams and events are created once per
-// device; under CUDA-graph capture the fork / join events turn into graph edges.
+// up to 14 % of the launch at C = 256 -- is filled by CTAs of the other chains.  Under CUDA-graph capture the fork / join
+// events turn into graph edges.
+// Helper streams and events belong to ONE (device, caller stream): two calls on different caller streams (two serving
+// pipelines, two host threads) never share an event or a side stream, so the header's promise that a pack may be used
+// from several streams of its device holds.  Calls on the SAME caller stream are ordered by that stream, as for any
+// CUDA library.  The table is mutex-protected and bounded; beyond kMaxChainCtx distinct caller streams a call simply
+// runs its chains back to back on its own stream.
 constexpr int kMaxChains = 3;
+constexpr size_t kMaxChainCtx = 256;
+constexpr int kChainPool = 8;
 struct ChainStreams {
   cudaStream_t s[kMaxChains - 1] = {nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[kMaxChains - 1] = {nullptr, nullptr}, sum_done[kMaxChains] = {nullptr, nullptr, nullptr};
-  bool ready = false;
 };
-static ChainStreams g_chain_streams[64];
+static std::mutex g_chain_mu;
+static std::map<std::pair<int, cudaStream_t>, ChainStreams*> g_chain_ctx;   // bound contexts
+static std::map<int, std::vector<ChainStreams*>> g_chain_free;               // created, not yet bound (per device)
 
-static int chain_streams_for(int device, ChainStreams** out) {
-  ChainStreams& cs = g_chain_streams[device & 63];
-  if (!cs.ready) {
-    for (int i = 0; i < kMaxChains - 1; ++i) {
-      VSG_CUDA_TRY(cudaStreamCreateWithFlags(&cs.s[i], cudaStreamNonBlocking));
-      VSG_CUDA_TRY(cudaEventCreateWithFlags(&cs.join[i], cudaEventDisableTiming));
+static ChainStreams* chain_ctx_create() {
+  ChainStreams* cs = new ChainStreams();
+  bool ok = true;
+  for (int i = 0; i < kMaxChains - 1 && ok; ++i)
+    ok = cudaStreamCreateWithFlags(&cs->s[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&cs->join[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&cs->fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < kMaxChains && ok; ++i) ok = cudaEventCreateWithFlags(&cs->sum_done[i], cudaEventDisableTiming) == cudaSuccess;
+  if (ok) return cs;
+  for (int i = 0; i < kMaxChains - 1; ++i) { if (cs->s[i]) cudaStreamDestroy(cs->s[i]); if (cs->join[i]) cudaEventDestroy(cs->join[i]); }
+  if (cs->fork) cudaEventDestroy(cs->fork);
+  for (int i = 0; i < kMaxChains; ++i) if (cs->sum_done[i]) cudaEventDestroy(cs->sum_done[i]);
+  delete cs;
+  cudaGetLastError();
+  return nullptr;
+}
+
+// nullptr in *out (with VSG_OK) = no context available: the caller runs its chains back to back on its own stream.
+// Streams and events are only ever CREATED outside graph capture (the first eager call on a device fills a small pool);
+// a capturing stream binds a pooled context, so the warm-up-then-capture pattern of HotPathGraph keeps its chains.
+static int chain_streams_for(int device, cudaStream_t caller, ChainStreams** out) {
+  std::lock_guard<std::mutex> lock(g_chain_mu);
+  *out = nullptr;
+  const auto key = std::make_pair(device, caller);
+  auto it = g_chain_ctx.find(key);
+  if (it != g_chain_ctx.end()) { *out = it->second; return VSG_OK; }
+  if (g_chain_ctx.size() >= kMaxChainCtx) return VSG_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(caller, &cap) != cudaSuccess) { cudaGetLastError(); return VSG_OK; }
+  std::vector<ChainStreams*>& pool = g_chain_free[device];
+  if (cap == cudaStreamCaptureStatusNone)
+    while ((int)pool.size() < kChainPool) {
+      ChainStreams* cs = chain_ctx_create();
+      if (!cs) break;
+      pool.push_back(cs);
     }
-    VSG_CUDA_TRY(cudaEventCreateWithFlags(&cs.fork, cudaEventDisableTiming));
-    for (int i = 0; i < kMaxChains; ++i) VSG_CUDA_TRY(cudaEventCreateWithFlags(&cs.sum_done[i], cudaEventDisableTiming));
-    cs.ready = true;
-  }
-  *out = &cs;
+  if (pool.empty()) return VSG_OK;
+  ChainStreams* cs = pool.back();
+  pool.pop_back();
+  g_chain_ctx[key] = cs;
+  *out = cs;
   return VSG_OK;
 }
 
@@ -765,9 +810,12 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
   if (ws.overflow) return fail(VSG_ENOMEM, "generator workspace too small: need %zu bytes", ws.off);
   VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
   const TCOptions opt = g_default_opts;
-  const bool chains = opt.chain_streams && NK > 1 && NK <= kMaxChains;
+  bool chains = opt.chain_streams && NK > 1 && NK <= kMaxChains;
   ChainStreams* cs = nullptr;
-  if (chains) VSG_TRY(chain_streams_for(P->device, &cs));
+  if (chains) {
+    VSG_TRY(chain_streams_for(P->device, st, &cs));
+    if (!cs) chains = false;
+  }
 
   if (c.dec_gin > 0) {
     if (!g) return fail(VSG_EINVAL, "generator was built with gin_channels=%d but g is NULL", c.dec_gin);
@@ -826,6 +874,9 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
         VSG_CUDA_TRY(cudaEventRecord(cs->fork, st_main));
         for (int j = 1; j < NK; ++j) VSG_CUDA_TRY(cudaStreamWaitEvent(cs->s[j - 1], cs->fork, 0));
       }
+      // every failure between fork and join must still join the side streams (a capture would otherwise be left with
+      // un-joined branches), so the chains run inside a lambda and the join below is unconditional
+      auto run_resblocks = [&]() -> int {
       for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
         const ResBlockPack& rb = us.blocks[j];
         const int nd = (int)rb.dilations.size(), k = rb.kernel;
@@ -854,20 +905,32 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
                             pair_supported(rb.c1_tc[q], rb.c2_tc[q], d, L, 1 + (e2.add1 ? 1 : 0), n_outs_pair);
           if (fuse) {
             // low-channel stages: both convs of the pair in ONE kernel, the intermediate never leaves the SM
+            // The pair kernel reads its input with a halo (rows of the NEIGHBOUR tiles) while other CTAs store their
+            // output tiles: it must never run in place.  The running stream ping-pongs between the chain's R and T buffers
+            // (the T buffers are otherwise unused on the fused path).
             e2.bias = rb.c2_tc[q].bias;
-            if (!last) { e2.out_act = bRA; if (!one_stream) e2.out_raw = bR; }
+            bf* nr = (curA == bRA) ? bT : bR;
+            bf* nra = (curA == bRA) ? bTA : bRA;
+            if (!last) { e2.out_act = nra; if (!one_stream) e2.out_raw = nr; }
             if (sum_wait) VSG_CUDA_TRY(cudaStreamWaitEvent(st, cs->sum_done[j - 1], 0));
             VSG_TRY(launch_pair_tc(P, rb.c1_tc[q], rb.c2_tc[q], curA, nb, L, d, e2, opt, err, st));
-            cur = one_stream ? bRA : bR; curA = bRA;
+            cur = one_stream ? nra : nr; curA = nra;
           } else if (c.dec_resblock == 1) {        // ResBlock1 (decoder.py:91-104)
+            // conv1 writes a scratch tensor of the OTHER buffer pair; conv2 reads that scratch (with a halo) and updates
+            // the running stream, in place when it already lives in this chain's buffers: its add0 / output tiles are
+            // the same rows of the same CTA, so only the scratch is ever read across tile borders.
+            const bool in_t = (curA == bTA);          // a preceding fused pair may have left the stream in the T pair
+            bf* tmp = in_t ? bR : bT;
+            bf* nr = in_t ? bT : bR;
+            bf* nra = in_t ? bTA : bRA;
             EpiTC e1;
-            e1.bias = rb.c1_tc[q].bias; e1.out_act = bT;
+            e1.bias = rb.c1_tc[q].bias; e1.out_act = tmp;
             VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
             e2.bias = rb.c2_tc[q].bias;
-            if (!last) { e2.out_act = bRA; if (!one_stream) e2.out_raw = bR; }
+            if (!last) { e2.out_act = nra; if (!one_stream) e2.out_raw = nr; }
             if (sum_wait) VSG_CUDA_TRY(cudaStreamWaitEvent(st, cs->sum_done[j - 1], 0));
-            VSG_TRY(launch_conv_tc(P, W(rb.c2_tc[q], rb.c2_x3[q]), bT, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
-            cur = one_stream ? bRA : bR; curA = bRA;
+            VSG_TRY(launch_conv_tc(P, W(rb.c2_tc[q], rb.c2_x3[q]), tmp, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
+            cur = one_stream ? nra : nr; curA = nra;
           } else {                           // ResBlock2 (decoder.py:124-133)
             e2.bias = rb.c1_tc[q].bias;
             bf* nr = (cur == bR || cur == bRA) ? bT : bR;
@@ -880,13 +943,21 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
         }
         if (chains && j < NK - 1) VSG_CUDA_TRY(cudaEventRecord(cs->sum_done[j], st));
       }
+      return VSG_OK;
+      };
+      const int rc_chains = run_resblocks();
       if (chains) {   // join: the stage output (written by the last chain) and every scratch buffer are settled
-        for (int j = 1; j < NK; ++j) {
-          VSG_CUDA_TRY(cudaEventRecord(cs->join[j - 1], cs->s[j - 1]));
-          VSG_CUDA_TRY(cudaStreamWaitEvent(st_main, cs->join[j - 1], 0));
-        }
         st = st_main;
+        cudaError_t je = cudaSuccess;
+        for (int j = 1; j < NK; ++j) {
+          cudaError_t e1 = cudaEventRecord(cs->join[j - 1], cs->s[j - 1]);
+          cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(st_main, cs->join[j - 1], 0) : e1;
+          if (je == cudaSuccess) je = e2;
+        }
+        if (rc_chains == VSG_OK && je != cudaSuccess)
+          return fail(VSG_ECUDA, "joining the resblock chains failed: %s", cudaGetErrorString(je));
       }
+      VSG_TRY(rc_chains);
     }
     cur_io ^= 1;
   }

@@ -29,6 +29,10 @@ class HotPath(PackedModuleMixin, nn.Module):
         super().__init__()
         if flow.channels != decoder.initial_channel:
             raise ValueError("flow channels must equal the decoder's initial_channel")
+        if flow.gin_channels != decoder.gin_channels:
+            raise ValueError(f"flow.gin_channels ({flow.gin_channels}) must equal decoder.gin_channels "
+                             f"({decoder.gin_channels}): both are conditioned on the same speaker embedding "
+                             "(models/visinger.py:109,111)")
         self.flow = flow
         self.decoder = decoder
         self.precision = precision
@@ -86,11 +90,7 @@ class HotPath(PackedModuleMixin, nn.Module):
             raise RuntimeError(f"expected {self.flow.channels} channels, got {C}")
         if logs_p.shape != mu_p.shape or noise.shape != mu_p.shape or mask.numel() != B * T:
             raise RuntimeError("mu_p, logs_p, noise must share a shape and mask must be [B, 1, T]")
-        use_g = self.flow.gin_channels != 0
-        if use_g:
-            if g is None:
-                raise RuntimeError("g is required (gin_channels != 0)")
-            _lib.require_cuda(g, "g")
+        use_g = self._check_g(g, B)
         pack = self._pack()
         prec = _lib.precision_code(self.precision)
         a = [_lib.as_f32c(t) for t in (mu_p, logs_p, noise, mask)]
@@ -109,6 +109,19 @@ class HotPath(PackedModuleMixin, nn.Module):
         self.last_launches = _lib.last_launch_count()
         return wav, z_q
 
+    def _check_g(self, g, B: int) -> bool:
+        """The reference broadcasts g [B, gin, 1] over time (models/visinger.py:84); anything else would be misread
+        as B*gin floats through the raw pointer, so it is rejected here.  Returns whether g is used."""
+        gin = self.flow.gin_channels
+        if gin == 0:
+            return False
+        if g is None:
+            raise RuntimeError("g is required (gin_channels != 0)")
+        _lib.require_cuda(g, "g")
+        if g.numel() != B * gin or g.shape[0] != B:
+            raise RuntimeError(f"g must be [B={B}, gin={gin}, 1]; got {tuple(g.shape)}")
+        return True
+
     # -- CUDA-graph replay of the whole path -----------------------------------------------------
     @torch.no_grad()
     def graph(self, B: int, T: int, device=None) -> "HotPathGraph":
@@ -118,8 +131,13 @@ class HotPath(PackedModuleMixin, nn.Module):
         pass (more with L2-resident batch tiling) replay from a single cudaGraphLaunch.  Inputs are written into
         the graph's static buffers (`.mu_p, .logs_p, .noise, .mask, .g`), outputs read from `.wav, .z_q`."""
         dev = torch.device(device) if device is not None else next(self.parameters()).device
-        key = (B, T, _lib.precision_code(self.precision), str(dev))
+        self._pack()
+        # the graph bakes the pack's device pointers in: key on the parameter identity / version the pack was built from,
+        # so load_state_dict / .to() / remove_weight_norm get a fresh capture instead of stale (or freed) weights
+        key = (B, T, _lib.precision_code(self.precision), str(dev), self._vsg_key)
         cache = self.__dict__.setdefault("_graphs", {})
+        for k in [k for k in cache if k[4] != self._vsg_key]:
+            del cache[k]
         if key not in cache:
             cache[key] = HotPathGraph(self, B, T, dev)
         return cache[key]
@@ -137,7 +155,7 @@ class HotPath(PackedModuleMixin, nn.Module):
         pack = self._pack()
         prec = _lib.precision_code(self.precision)
         zc = _lib.as_f32c(z)
-        use_g = self.decoder.gin_channels != 0
+        use_g = self._check_g(g, B)
         gc = _lib.as_f32c(g) if use_g else None
         wav = torch.empty(B, 1, T * self.decoder.hop_size, dtype=torch.float32, device=z.device)
         with torch.cuda.device(z.device):
@@ -166,7 +184,8 @@ class HotPathGraph:
         pack = hp._pack()
         prec = _lib.precision_code(hp.precision)
         self._ws = torch.empty(pack.workspace_bytes(B, T, prec), dtype=torch.uint8, device=device)  # private: pointers are baked
-        self._pack = pack
+        self._pack = pack                      # keeps the device weights alive for as long as the graph exists
+        self._gin, self._B = gin, B
         L = _lib.lib()
 
         def run():
@@ -192,7 +211,12 @@ class HotPathGraph:
         self._graph.replay()
         return self.wav, self.z_q
 
+    def check_g(self, g) -> None:
+        if self._gin and (g is None or g.numel() != self._B * self._gin):
+            raise RuntimeError(f"g must be [B={self._B}, gin={self._gin}, 1] (gin_channels != 0)")
+
     def __call__(self, mu_p, logs_p, noise, mask, g=None):
+        self.check_g(g)
         self.mu_p.copy_(mu_p, non_blocking=True)
         self.logs_p.copy_(logs_p, non_blocking=True)
         self.noise.copy_(noise, non_blocking=True)
@@ -229,6 +253,7 @@ class HotPathPipeline:
         """Enqueue one request; returns a ticket for `result`."""
         s = self._n % self.depth
         slot = self.slots[s]
+        slot.check_g(g)
         cur = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.s_up):
             self.s_up.wait_stream(cur)             # inputs produced on the caller's stream (device tensors) are complete
@@ -351,8 +376,13 @@ class VISinger(nn.Module):
         ins = {k: v for k, v in ins.items() if v is not None}
         for k, v in ins.items():
             _lib.require_cuda(v, k)
-        key = (self.precision,) + tuple((k, tuple(v.shape), v.dtype) for k, v in ins.items())
+        # weight identity is part of the key (the graph bakes device pointers of the pack and of every prior-network
+        # parameter in); the entry also holds the pack so that the weights it replays from cannot be freed under it
+        wkey = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (self.precision, wkey) + tuple((k, tuple(v.shape), v.dtype) for k, v in ins.items())
         cache = self.__dict__.setdefault("_fw_graphs", {})
+        for k in [k for k in cache if k[1] != wkey]:
+            del cache[k]
         if key not in cache:
             static = {k: v.clone() for k, v in ins.items()}
             dev = mel2ph.device
@@ -367,8 +397,8 @@ class VISinger(nn.Module):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     out = self.forward(infer=True, **static)
-            cache[key] = (graph, static, out)
-        graph, static, out = cache[key]
+            cache[key] = (graph, static, out, self._hot._pack())
+        graph, static, out, _pack = cache[key]
         for k, v in ins.items():
             static[k].copy_(v, non_blocking=True)
         graph.replay()
