@@ -106,13 +106,14 @@ def test_generator_resblock2_tensor_core(cuda_device, B, T):
     rel = float((got - ref).norm() / ref.norm())
     print(f"ResBlock2 tcgen05 B={B} T={T}: bf16 rel-L2 {rel:.3e} max-abs {maxabs(got, ref):.3e}; bf16x3 max-abs {e3:.3e}")
     assert e3 <= 1e-4
-    assert rel <= 1.5e-2 and maxabs(got, ref) <= 3e-2 * float(ref.abs().max())
+    assert rel <= 1.0e-2 and maxabs(got, ref) <= 1.1e-3       # floors 6.9e-3 / 7.2e-4
 
 
-# Measured floors on B200 (round 2, seed 1234 weights, T = 1000): see the printed line.  Gates = 1.5 x floor.
-FULL_BF16_REL_L2 = 9e-3
-FULL_BF16_MAXABS = 2e-3
-FULL_BF16_MEL_L1 = 6e-2
+# Measured floors on B200 (round 2, seed 1234 weights, T = 1000; gpurun_out/r2_gputest_full_1.log): rel-L2 3.76e-3,
+# max-abs 3.64e-4 (|ref|max 0.038), log-mel L1 3.23e-2, worst 64-sample window rms 1.4 x the median.  Gates = 1.5 x floor.
+FULL_BF16_REL_L2 = 5.7e-3
+FULL_BF16_MAXABS = 5.5e-4
+FULL_BF16_MEL_L1 = 4.9e-2
 
 
 def test_generator_bf16_full_length_vs_oracle(cuda_device):
@@ -136,7 +137,7 @@ def test_generator_bf16_full_length_vs_oracle(cuda_device):
           f"bf16x3 max-abs {maxabs(x3, ref):.3e} mel-L1 {O.mel_l1(x3, ref):.3e}")
     assert maxabs(x3, ref) <= 1e-4
     assert rel <= FULL_BF16_REL_L2 and float(err.max()) <= FULL_BF16_MAXABS and mel <= FULL_BF16_MEL_L1
-    assert float(win.max()) <= 12.0 * float(win.median())
+    assert float(win.max()) <= 3.0 * float(win.median())
 
 
 def test_hot_path_bf16_full_length_vs_oracle(cuda_device):
@@ -163,7 +164,9 @@ def test_hot_path_bf16_full_length_vs_oracle(cuda_device):
     zrel = float((z16.cpu() - z_ref).norm() / z_ref.norm())
     print(f"full-length bf16 hot path vs oracle: wav rel-L2 {rel:.3e} max-abs {maxabs(w16, wav_ref):.3e} mel-L1 "
           f"{O.mel_l1(w16, wav_ref):.3e}; z rel-L2 {zrel:.3e} max-abs {maxabs(z16.cpu(), z_ref):.3e}")
-    assert rel <= 3e-2 and zrel <= 1e-2 and maxabs(z16.cpu(), z_ref) <= 8e-2
+    # floors: wav rel-L2 3.78e-3 / max-abs 3.6e-4, z rel-L2 3.03e-3 / max-abs 3.1e-2 (|z|max ~4.7)
+    assert rel <= FULL_BF16_REL_L2 and maxabs(w16, wav_ref) <= FULL_BF16_MAXABS and O.mel_l1(w16, wav_ref) <= FULL_BF16_MEL_L1
+    assert zrel <= 4.6e-3 and maxabs(z16.cpu(), z_ref) <= 4.8e-2
     assert float(z16[0, :, 937:].abs().max()) == 0.0
 
 

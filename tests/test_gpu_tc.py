@@ -92,7 +92,7 @@ def test_generator_bf16_vs_oracle(cuda_device, B, T):
     assert got.shape == ref.shape
     rel = float((got - ref).norm() / ref.norm())
     print(f"bf16 generator B={B} T={T}: rel-L2 {rel:.3e}, max-abs {maxabs(got, ref):.3e}, |ref|max {float(ref.abs().max()):.3e}")
-    assert rel <= 3e-2
+    assert rel <= 5.7e-3 and maxabs(got, ref) <= 5.5e-4      # 1.5 x the measured floor (3.8e-3 / 3.5e-4; |ref|max 0.038)
     m32 = build_gen(GEN_FULL, sd, cuda_device, precision="fp32")
     assert maxabs(m32(x.to(cuda_device), g=g.to(cuda_device)).cpu(), ref) <= 1e-4
 
@@ -154,7 +154,7 @@ def test_generator_bf16_odd_shapes_vs_fp32_path(cuda_device, B, T):
     fast, ref = m16(xd, g=gd), m32(xd, g=gd)
     assert bool(torch.isfinite(fast).all()) and torch.equal(fast, m16(xd, g=gd))
     rel = float((fast - ref).norm() / ref.norm())
-    assert rel <= 1.5e-2, rel        # 8.1e-3 for these weights at every shape (tools/stress_shapes.py)
+    assert rel <= 1.2e-2, rel        # 8.1e-3 for these weights at every shape (tools/stress_shapes.py)
 
 
 @pytest.mark.parametrize("B,T,lengths", [(1, 1, None), (2, 300, [300, 211]), (3, 130, [130, 128, 5])])
@@ -175,7 +175,8 @@ def test_flow_bf16_vs_oracle(cuda_device, B, T, lengths):
     rel = float((rev - ref_rev).norm() / ref_rev.norm())
     print(f"bf16 flow B={B} T={T}: reverse rel-L2 {rel:.3e} max-abs {maxabs(rev, ref_rev):.3e}; "
           f"forward max-abs {maxabs(fwd, ref_fwd):.3e}; |z|max {float(ref_rev.abs().max()):.2f}")
-    assert rel <= 2e-2 and maxabs(rev, ref_rev) <= 0.15 and maxabs(fwd, ref_fwd) <= 0.15
+    # 1.5 x the measured floors (rel-L2 3.2e-3; max-abs 3.0e-2 reverse, 4.1e-2 forward at |z|max ~4.7)
+    assert rel <= 4.8e-3 and maxabs(rev, ref_rev) <= 4.5e-2 and maxabs(fwd, ref_fwd) <= 6.2e-2
     if lengths is not None:
         for b, n in enumerate(lengths):
             assert float(rev[b, :, n:].abs().max()) == 0.0 if n < T else True
@@ -205,7 +206,7 @@ def test_hot_path_bf16_and_fp32(cuda_device):
     wav16, z16 = hp16.infer(*args)
     rel = float((wav16.cpu().squeeze(1) - wav_ref).norm() / wav_ref.norm())
     print(f"bf16 hot path: wav rel-L2 {rel:.3e}, z max-abs {maxabs(z16.cpu(), z_ref):.3e}")
-    assert rel <= 0.15
+    assert rel <= 5.7e-3 and maxabs(z16.cpu(), z_ref) <= 4.5e-2      # 1.5 x floor (3.79e-3 / 2.9e-2)
 
 
 def test_hot_path_pipeline_matches_direct_calls(cuda_device):
