@@ -15,7 +15,12 @@ the metric's roofline is quoted on), random weights of config/models/visinger.ya
             333 911 680 FLOP per latent frame) / CUDA-event time of the generator region
   cpu_baseline  the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1 only)
   parity_mode   (N=1) the same workload in bf16x3 -- the tensor-core mode that meets the fp32 tolerances -- with its
-            and the bf16 mode's measured distance to the fp32 path on full-length utterances
+            measured distance to the CPU oracle on a full-length utterance
+  bf16      (N=1) the headline mode's distance to the CPU oracle on the same full-length utterance: relative L2,
+            max-abs and the reference's own log-mel L1 (MelSpectrogramFixed, utils/audio/mel_processing.py:28-38)
+  sharded   BASELINE.json configs[4]: 512 mixed-length utterances (log-normal lengths, seed 1234) -> LPT shard by
+            utterance -> length buckets -> per-rank serving loop -> pinned host results; strong scaling (fixed total
+            work), with padding overhead and per-rank imbalance
 
 Multi-GPU: utterances are independent, so ranks shard by utterance with no collective on the data path
 (weak scaling: every rank runs the same per-GPU batch); torch.distributed is used only for the barrier
@@ -57,7 +62,8 @@ def parse():
     ap.add_argument("--no-split-n", action="store_true", help="keep N = 256 tiles whole (no 2 x 128 split)")
     ap.add_argument("--one-epi-set", action="store_true", help="a single set of 4 epilogue warps per CTA")
     ap.add_argument("--generic-epilogue", action="store_true", help="never use the signature-specialised kernels")
-    ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 / fp32 cross-check block")
+    ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 timing / parity block")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the 512-utterance sharded sweep (configs[4])")
     ap.add_argument("--no-chain-streams", action="store_true", help="run the resblock chains of a stage one after the other")
     ap.add_argument("--two-streams", action="store_true", help="store raw and activated copies of the resblock stream")
     return ap.parse_args()
@@ -112,51 +118,166 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
-def oracle_hot_path_time(B, T, reps, threads):
-    """Times the oracle port of the reference CPU path (flow reverse + generator, fp32, eval, no_grad)."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")     # vendored by __graft_entry__.build() (git-ignored; travels with gpurun)
+
+
+def bench_weights_and_inputs(B, T, rank=0):
+    """The workload both arms run: random-init weights of config/models/visinger.yaml shape (torch default init through
+    the module mirrors' constructors, seed 1234, `post` re-randomised) and the seeded inputs of `rank`."""
     import torch
-    from oracle import visinger_oracle as O
-    from helpers import FLOW_FULL, GEN_FULL, flow_shapes, gen_shapes, make_inputs
-    torch.set_num_threads(threads)
-    fsd = O.synth_state_dict(flow_shapes(FLOW_FULL), 1234)
-    gsd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
-    sd = {"flow." + k: v for k, v in fsd.items()}
-    sd.update({"decoder." + k: v for k, v in gsd.items()})
-    x, mask, g = make_inputs(0, B, 192, T, 256)
+    from visinger_b200.configs import VISINGER_FLOW as FLOW_FULL, VISINGER_GENERATOR as GEN_FULL
+    from visinger_b200.models.visinger import HotPath
+    hp = HotPath.random_init(FLOW_FULL, GEN_FULL, "cpu", precision="fp32", seed=1234)
+    gen_in = torch.Generator().manual_seed(rank)
+    x = torch.randn(B, 192, T, generator=gen_in)                 # prior mean
+    g = 0.1 * torch.randn(B, 256, 1, generator=gen_in)           # speaker embedding
+    mask = torch.ones(B, 1, T)                                   # full-length utterances
     logs = torch.full_like(x, -1.0)
-    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(1))
-    times = []
-    with torch.no_grad():
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            O.infer_hot_path(sd, x, logs, noise, mask, g)
-            times.append(time.perf_counter() - t0)
-    return times
+    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + rank))
+    return hp, (x, logs, noise, mask, g)
+
+
+class CpuHotPath:
+    """The reference's CPU implementation of the path for one batch: the REAL reference modules when the vendored copy
+    (baseline/_ref) is present -- `ResidualCouplingBlock` (modules/visinger/flow.py:15) and `Generator`
+    (modules/visinger/decoder.py:13) driven exactly as models/visinger.py:107-111 drives them -- else the oracle port."""
+
+    def __init__(self, state_dict):
+        import torch
+        self.kind = "port"
+        self.sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        if os.path.isdir(os.path.join(REF_DIR, "modules", "visinger")):
+            import warnings
+            warnings.filterwarnings("ignore")
+            sys.path.insert(0, REF_DIR)
+            try:
+                from modules.visinger.flow import ResidualCouplingBlock      # the unmodified reference
+                from modules.visinger.decoder import Generator
+                self.flow = ResidualCouplingBlock(192, 192, 5, 1, 4, gin_channels=256).eval()       # models/visinger.py:65
+                self.dec = Generator(192, "1", [3, 7, 11], [[1, 3, 5]] * 3, [5, 5, 3, 2, 2], 512, [11, 11, 7, 4, 4],
+                                     gin_channels=256).eval()                                      # models/visinger.py:67-69
+                self.flow.load_state_dict({k[5:]: v for k, v in self.sd.items() if k.startswith("flow.")})
+                self.dec.load_state_dict({k[8:]: v for k, v in self.sd.items() if k.startswith("decoder.")})
+                self.kind = "reference"
+            finally:
+                sys.path.remove(REF_DIR)
+
+    def __call__(self, mu, logs, noise, mask, g):
+        import torch
+        with torch.no_grad():
+            if self.kind == "reference":
+                z_p = (mu + noise * torch.exp(logs)) * mask                          # models/visinger.py:107
+                z_q = self.flow(z_p, mask, g=g, reverse=True) * mask                 # :109
+                return self.dec(z_q * mask, g=g).squeeze(1), z_q                     # :111
+            from oracle import visinger_oracle as O
+            return O.infer_hot_path(self.sd, mu, logs, noise, mask, g)
+
+
+def cpu_hot_path_time(cpu, inputs, reps, threads):
+    import torch
+    torch.set_num_threads(threads)
+    times, out = [], None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = cpu(*inputs)
+        times.append(time.perf_counter() - t0)
+    return times, out
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference is
-    Python and cannot travel to the GPU box) on all host threads, each step a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path (the vendored reference modules when
+    present, else the oracle port) on all host threads, same weights and inputs as the B200 arm; each step a bounded
+    sample of the arm's workload (one of its B utterances)."""
     import torch
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    Bs, Ts = 1, args.frames     # bounded sample of the arm's workload: one of its B utterances per step
-    times = oracle_hot_path_time(Bs, Ts, args.warmup + args.steps, cores)[args.warmup:]
-    audio = Bs * Ts * FRAME_SEC
+    Ts = args.frames
+    hp, inputs = bench_weights_and_inputs(args.batch, Ts)
+    cpu = CpuHotPath(hp.state_dict())
+    one = [t[:1].contiguous() for t in inputs]
+    times, _ = cpu_hot_path_time(cpu, one, args.warmup + args.steps, cores)
+    times = times[args.warmup:]
+    audio = Ts * FRAME_SEC
     tot = sum(times)
     val = audio * len(times) / tot
+    t1, _ = cpu_hot_path_time(cpu, one, 1, 1)                    # the reference's own launcher pins OMP_NUM_THREADS=1 (tasks/runs/run.py:3)
+    what = "the unmodified reference modules (baseline/_ref)" if cpu.kind == "reference" else "oracle port of the reference CPU path"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "hot path (prior sample -> flow reverse -> HiFi-GAN generator), oracle port of the "
-                                   "reference CPU path; bounded sample per step: 1 of the " + str(args.batch) + f" utterances of the B={args.batch} x T={Ts} workload ({Ts * FRAME_SEC:.1f} s audio)",
-                       "threads": torch.get_num_threads()},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps of 1 utterance x T={Ts} frames ({Ts * FRAME_SEC:.1f} s audio each), fp32, all host threads"},
+            "config": {"workload": f"hot path (prior sample -> flow reverse -> HiFi-GAN generator), {what}; bounded sample per "
+                                   f"step: utterance 0 of the B={args.batch} x T={Ts} workload ({audio:.1f} s audio), same weights "
+                                   "and inputs as the B200 arm",
+                       "threads": cores},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": cpu.kind,
+                             "sample": f"{args.steps} steps of 1 utterance x T={Ts} frames ({audio:.1f} s audio each), fp32, all host threads",
+                             "one_thread": {"value": audio / t1[0], "unit": UNIT, "cores": 1,
+                                            "sample": "1 step of the same utterance with torch.set_num_threads(1) "
+                                                      "(the reference launcher's OMP_NUM_THREADS=1, tasks/runs/run.py:3)"}},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def sharded_leg(hp, dev, rank, world, barrier, max_over_ranks, n_utt=512, frames_per_batch=16000):
+    """BASELINE.json configs[4] through the hot path: 512 synthetic utterances with the CSD-like length distribution of
+    SURVEY.md 8(d) (seed 1234) are sharded by utterance over the ranks (LPT on frame count, reference analogue: the rank
+    slicing of tasks/base.py:130-133), length-bucketed within each shard (utils/commons/dataset_utils.py:69-118) and run
+    through the per-rank serving loop.  Timed from "padded batches in pinned host memory" (what the reference's collater
+    hands over) to "all int16 / fp32 results in pinned host memory"; device time, max over ranks."""
+    import numpy as np
+    import torch
+    from visinger_b200.sharding import HostBatchRunner, bucket_by_length, shard_utterances
+    rng = np.random.default_rng(1234)
+    lengths = np.clip(np.round(80 * rng.lognormal(np.log(5.6), 0.45, n_utt)), 120, 1280).astype(int).tolist()
+    shards = shard_utterances(lengths, world)
+    plans = [bucket_by_length(sh, lengths, frames_per_batch, 64) for sh in shards]
+    loads = [sum(lengths[i] for i in sh) for sh in shards]
+    padded = [sum(len(b) * max(lengths[i] for i in b) for b in pl) for pl in plans]
+    gen = torch.Generator().manual_seed(4000 + rank)
+    pool = torch.randn(3, 192 * 1280 * 64 // 8, generator=gen)       # one pool of random values, sliced per batch (host time)
+    batches, lens = [], []
+    for b in plans[rank]:
+        T, B = max(lengths[i] for i in b), len(b)
+        n = B * 192 * T
+        mu, noise = (pool[k, :1].expand(n) if n > pool.shape[1] else pool[k, :n] for k in (0, 1))
+        mask = torch.zeros(B, 1, T)
+        for r, i in enumerate(b):
+            mask[r, :, :lengths[i]] = 1
+        batches.append({"mu_p": mu.reshape(B, 192, T).contiguous().pin_memory(),
+                        "logs_p": torch.full((B, 192, T), -1.0).pin_memory(),
+                        "noise": noise.reshape(B, 192, T).contiguous().pin_memory(), "mask": mask.pin_memory(),
+                        "g": (0.1 * pool[2, :B * 256]).reshape(B, 256, 1).contiguous().pin_memory()})
+        lens.append(torch.tensor([lengths[i] * 300 for i in b], dtype=torch.int32).pin_memory())
+    res = {}
+    for pcm in (False, True):
+        runner = HostBatchRunner(hp, dev, n_streams=2, pcm=pcm)
+        outs = runner.alloc_outputs(batches)
+        runner.run(batches, outs, lens)          # warm-up: workspaces grow to the largest batch, lazy module load
+        runner.wait()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        runner.run(batches, outs, lens)
+        e1.record()
+        barrier()
+        res["int16" if pcm else "fp32"] = (max_over_ranks(e0.elapsed_time(e1)), sum(o.numel() * o.element_size() for o in outs))
+        finite = all(bool(torch.isfinite(o).all()) for o in outs) if not pcm else all(int(o.abs().max()) == 32767 for o in outs)
+        assert finite, "sharded leg produced a non-finite / un-normalised result"
+    audio = sum(lengths) * FRAME_SEC
+    ms, d2h = res["fp32"]
+    ms16, d2h16 = res["int16"]
+    return {"workload": f"{n_utt} utterances, T_i = clip(round(80 * LogNormal(ln 5.6, 0.45)), 120, 1280) frames (seed 1234), "
+                        f"{audio:.0f} s audio in total; LPT shard by utterance -> buckets of <= {frames_per_batch} padded frames "
+                        "-> HotPath.infer per batch on 2 streams -> pinned host results",
+            "scaling": "strong", "value": audio / (ms * 1e-3), "unit": UNIT, "ms": ms,
+            "value_int16_output": audio / (ms16 * 1e-3), "ms_int16_output": ms16,
+            "d2h_bytes_rank0": d2h, "d2h_bytes_rank0_int16": d2h16,
+            "batches_per_rank": [len(pl) for pl in plans],
+            "padding_overhead": max(p / l for p, l in zip(padded, loads)),
+            "imbalance_max_over_mean": max(loads) / (sum(loads) / len(loads)),
+            "timed": "padded batches in pinned host memory -> results in pinned host memory, CUDA events, max over ranks"}
 
 
 def main():
@@ -183,18 +304,13 @@ def main():
     B, T = args.batch, args.frames
     audio_per_step = B * T * FRAME_SEC
 
-    hp = HotPath.random_init(FLOW_FULL, GEN_FULL, dev, precision=args.precision, seed=1234)
+    hp_cpu, (x, logs, noise, mask, g) = bench_weights_and_inputs(B, T, rank)
+    hp = HotPath(hp_cpu.flow, hp_cpu.decoder, precision=args.precision).to(dev).eval()
     if args.l2_mb >= 0 or args.no_pdl or args.no_fuse or args.no_merge_ups or args.no_split_n or args.two_streams or args.generic_epilogue or args.no_chain_streams:
         from visinger_b200 import _lib
         _lib.set_tc_options(halo_mode=1 | (256 if args.no_pdl else 0) | (512 if args.no_fuse else 0) |
                             (1024 if args.no_merge_ups else 0) | (2048 if args.no_split_n else 0) | (4096 if args.two_streams else 0) | (8192 if args.generic_epilogue else 0) | (16384 if args.no_chain_streams else 0), l2_tensor_mb=args.l2_mb)
 
-    gen_in = torch.Generator().manual_seed(rank)
-    x = torch.randn(B, 192, T, generator=gen_in)                 # prior mean
-    g = 0.1 * torch.randn(B, 256, 1, generator=gen_in)           # speaker embedding
-    mask = torch.ones(B, 1, T)                                   # full-length utterances
-    logs = torch.full_like(x, -1.0)
-    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + rank))
     host = [t.pin_memory() for t in (x, logs, noise, mask, g)]
     devin = [t.to(dev) for t in host]
     wav_host = torch.empty(B, T * 300, dtype=torch.float32).pin_memory()
@@ -265,33 +381,52 @@ def main():
     sampler.stop_flag = True        # clocks are sampled across all three timed regions (resident, e2e, decoder)
     sampler.join()
 
-    # The headline mode is bf16 (north_star reports it as rel-L2 against the reference).  The mode that meets the fp32
-    # tolerances (waveform max-abs <= 1e-4, z <= 1e-5) on the same tensor-core kernels is bf16x3: time it on the same
-    # workload and measure both modes' distance to the fp32 path right here, so the line carries its own parity evidence.
-    parity = None
-    if args.precision == "bf16" and world == 1 and not args.no_parity_mode:
-        hp3 = HotPath(hp.flow, hp.decoder, precision="bf16x3")       # same modules, own weight pack
-        nb = min(B, 2)
-        sub = [t[:nb].contiguous() for t in devin]
-        wav3, z3 = hp3.infer(*sub)
-        hp32 = HotPath(hp.flow, hp.decoder, precision="fp32")
-        wav32, z32 = hp32.infer(*sub)
-        wav16, _ = hp.infer(*sub)
-        err3 = float((wav3 - wav32).abs().max())
-        errz = float((z3 - z32).abs().max())
-        rel16 = float((wav16 - wav32).norm() / wav32.norm())
-        del hp32
-        for _ in range(2):
-            hp3.infer(*devin)
-        k3 = max(3, min(args.steps, 5))
-        ms3 = timed(lambda: hp3.infer(*devin), k3)
-        parity = {"precision": "bf16x3", "value": audio_per_step * k3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / k3,
-                  "wav_max_abs_err_vs_fp32_path": err3, "z_max_abs_err_vs_fp32_path": errz,
-                  "bf16_wav_rel_l2_vs_fp32_path": rel16,
-                  "note": f"errors on {nb} of the {B} full-length utterances against this library's fp32 mode, which the tests "
-                          "pin to the reference (oracle) at waveform 3.5e-8 / z 7e-7"}
-        del hp3
-        torch.cuda.empty_cache()
+    # CPU leg (N=1): the reference's CPU path on utterance 0 of the batch -- timed (cpu_baseline) and, because it runs the
+    # same weights and inputs, also the CHECKER of this run: the bf16 mode's relative L2 / max-abs / log-mel L1 and the
+    # bf16x3 mode's max-abs error against it, on a full-length utterance.
+    cpu_line, bf16_report, parity = None, None, None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import visinger_oracle as O          # checker + baseline only; never on the product path
+        cores = len(os.sched_getaffinity(0))
+        cpu = CpuHotPath(hp_cpu.state_dict())
+        one = [t[:1].contiguous() for t in (x, logs, noise, mask, g)]
+        ts, (wav_ref, z_ref) = cpu_hot_path_time(cpu, one, 4, cores)
+        t1, _ = cpu_hot_path_time(cpu, one, 1, 1)
+        cpu_line = {"value": T * FRAME_SEC / min(ts[1:]), "unit": UNIT, "cores": cores, "kind": cpu.kind,
+                    "sample": f"utterance 0 of the {B} (T={T} frames, {T * FRAME_SEC:.1f} s audio), best of 3 after 1 warm-up, "
+                              "fp32, " + ("the unmodified reference modules (baseline/_ref)" if cpu.kind == "reference"
+                                          else "oracle port of the reference CPU path") + " on all host threads",
+                    "one_thread": {"value": T * FRAME_SEC / t1[0], "unit": UNIT, "cores": 1,
+                                   "sample": "1 pass of the same utterance with torch.set_num_threads(1) (tasks/runs/run.py:3)"}}
+        sub = [t[:1].contiguous() for t in devin]
+        if args.precision == "bf16":
+            w16, z16 = hp.infer(*sub)
+            w16, z16 = w16.cpu().squeeze(1), z16.cpu()
+            bf16_report = {"rel_l2": float((w16 - wav_ref).norm() / wav_ref.norm()), "max_abs": float((w16 - wav_ref).abs().max()),
+                           "mel_l1": O.mel_l1(w16, wav_ref), "z_rel_l2": float((z16 - z_ref).norm() / z_ref.norm()),
+                           "ref_max_abs": float(wav_ref.abs().max()),
+                           "vs": f"CPU {cpu.kind} (fp32) on utterance 0 of the batch, T={T}: waveform relative L2, max-abs, "
+                                 "L1 of log-mel spectrograms (MelSpectrogramFixed, utils/audio/mel_processing.py:28-38)"}
+        if args.precision == "bf16" and not args.no_parity_mode:
+            # the mode that meets north_star's fp32 tolerances (waveform <= 1e-4, z <= 1e-5) on the tensor-core kernels
+            hp3 = HotPath(hp.flow, hp.decoder, precision="bf16x3")       # same modules, own weight pack
+            wav3, z3 = hp3.infer(*sub)
+            err3, errz = float((wav3.cpu().squeeze(1) - wav_ref).abs().max()), float((z3.cpu() - z_ref).abs().max())
+            mel3 = O.mel_l1(wav3.cpu().squeeze(1), wav_ref)
+            for _ in range(2):
+                hp3.infer(*devin)
+            k3 = max(3, min(args.steps, 5))
+            ms3 = timed(lambda: hp3.infer(*devin), k3)
+            parity = {"precision": "bf16x3", "value": audio_per_step * k3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / k3,
+                      "wav_max_abs_err": err3, "z_max_abs_err": errz, "mel_l1": mel3,
+                      "meets_fp32_tolerance": bool(err3 <= 1e-4 and errz <= 1e-5),
+                      "vs": f"CPU {cpu.kind} (fp32) on utterance 0 of the batch, T={T}"}
+            del hp3
+            torch.cuda.empty_cache()
+
+    sharded = None
+    if args.precision == "bf16" and not args.no_sharded:
+        sharded = sharded_leg(hp, dev, rank, world, barrier, max_over_ranks)
 
     if rank == 0:
         pk = peaks()
@@ -323,21 +458,21 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": dec_tflops / peak, "traffic": traffic,
+                         "frac": dec_tflops / peak, "frac_of_burst_peak": dec_tflops / pk["bf16_burst"], "traffic": traffic,
                          "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum over the {traffic_launches} conv_tc / pair_tc / "
                                          "conv_post launches of one decoder pass (profiles/r1_decoder_traffic.json)",
                          "kernel": "decoder convolutions (vsg_generator_forward region)",
                          "algorithmic": f"{DEC_FLOP_PER_FRAME} FLOP/frame x {B * T} frames",
                          "ms": ms_dec / args.steps, "peak_source": pk["src"] + ", sustained bf16"},
         }
+        if bf16_report is not None:
+            line["bf16"] = bf16_report
         if parity is not None:
             line["parity_mode"] = parity
-        if world == 1 and not args.no_cpu_baseline:
-            cores = len(os.sched_getaffinity(0))
-            ts = oracle_hot_path_time(1, T, 4, cores)[1:]
-            line["cpu_baseline"] = {"value": T * FRAME_SEC / min(ts), "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"1 of the {B} utterances (T={T} frames, {T * FRAME_SEC:.1f} s audio), best of 3 "
-                                              "after 1 warm-up, fp32, oracle port of the reference CPU path on all host threads"}
+        if sharded is not None:
+            line["sharded"] = sharded
+        if cpu_line is not None:
+            line["cpu_baseline"] = cpu_line
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

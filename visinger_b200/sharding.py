@@ -69,3 +69,54 @@ def gather_lengths(local: Sequence[int]) -> List[List[int]]:
     out: List[List[int]] = [None] * dist.get_world_size()  # type: ignore[list-item]
     dist.all_gather_object(out, list(local))
     return out
+
+
+class HostBatchRunner:
+    """Runs a list of padded, HOST-resident batches of different shapes through `HotPath.infer` and leaves every result
+    in pinned host memory: the per-rank loop of the utterance-sharded sweep (BASELINE.json configs[4]).
+
+    Batches go round-robin over `n_streams` CUDA streams, so the host->device copy of batch i+1 and the device->host
+    copy of batch i-1 overlap the kernels of batch i (each stream has its own scratch workspace; the weights pack is
+    shared).  With `pcm=True` the int16 output stage (utils/audio/io.py:8-14, `vsg_wav_to_int16`) runs on the device and
+    only int16 PCM is downloaded -- half the device->host bytes.  The reference runs one utterance per call and pulls fp32
+    (`inference/visinger.py:95-100`); padding semantics follow its collater (right padding, mask from `mel2ph > 0`)."""
+
+    def __init__(self, hp, device, n_streams: int = 2, pcm: bool = False):
+        import torch
+        self.hp, self.device, self.pcm = hp, torch.device(device), pcm
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, n_streams))]
+
+    def alloc_outputs(self, batches):
+        """Pinned host result buffers, one per batch ([B, T * hop] fp32, or int16 with pcm=True)."""
+        import torch
+        hop = self.hp.decoder.hop_size
+        dt = torch.int16 if self.pcm else torch.float32
+        return [torch.empty(b["mu_p"].shape[0], b["mu_p"].shape[2] * hop, dtype=dt).pin_memory() for b in batches]
+
+    def run(self, batches, outs, lengths=None) -> None:
+        """batches: dicts of pinned host tensors mu_p, logs_p, noise [B, C, T], mask [B, 1, T], g [B, gin, 1];
+        outs: from alloc_outputs; lengths (pcm only): per batch, valid SAMPLES per utterance (host int tensors).
+        Returns with all results in `outs` being written; call `wait()` before reading them."""
+        import torch
+        from .utils.audio.io import wav_to_int16
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        for s in self.streams:
+            s.wait_stream(cur)
+        for i, (b, out) in enumerate(zip(batches, outs)):
+            s = self.streams[i % len(self.streams)]
+            with torch.cuda.stream(s):
+                d = {k: v.to(dev, non_blocking=True) for k, v in b.items()}
+                wav, _ = self.hp.infer(d["mu_p"], d["logs_p"], d["noise"], d["mask"], d.get("g"))
+                if self.pcm:
+                    pcm, _ = wav_to_int16(wav, None if lengths is None else lengths[i].to(dev, non_blocking=True), norm=True)
+                    out.copy_(pcm, non_blocking=True)
+                else:
+                    out.copy_(wav.view(out.shape), non_blocking=True)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def wait(self) -> None:
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()
