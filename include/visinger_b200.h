@@ -208,6 +208,20 @@ int vsg_debug_pair_bf16(const void* xa_bf16, const float* w1, const float* b1, c
                         const void* add0_bf16, const void* add1_bf16, float scale, float* out_f32, void* out_raw_bf16,
                         void* out_act_bf16, int32_t B, int32_t L, int32_t C, int32_t k, int32_t d1, int32_t device);
 
+/*
+ * Per-layer parity hook for the whole-ResBlock1 kernel (tests and tuning only; allocates and synchronises):
+ *   for q in 0..n_pairs-1:  x = conv1d(leaky_relu(conv1d(leaky_relu(x), w[2q], dilation d_q) + b[2q]), w[2q+1]) + b[2q+1] + x
+ *   out = (x [+ add1]) * scale
+ * -- ResBlock1.forward (modules/visinger/decoder.py:91-104) in ONE kernel.  xa_bf16 = leaky_relu(x_0), add1, out_raw,
+ * out_act: device bf16 [B, L, C] channels-last; w: HOST fp32 [2 * n_pairs][C][C][k]; b: HOST fp32 [2 * n_pairs][C];
+ * dilations: HOST int32 [n_pairs]; out_f32: device fp32 [B, L, C] or NULL.  C in {16, 32, 64}.
+ * max_mb caps the 128-row blocks per tile (0 = as many as fit), sets = epilogue warp sets (0 = default).
+ */
+int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, const float* b, int32_t n_pairs,
+                            const int32_t* dilations, const void* add1_bf16, float scale, float* out_f32,
+                            void* out_raw_bf16, void* out_act_bf16, int32_t B, int32_t L, int32_t C, int32_t k,
+                            int32_t max_mb, int32_t sets, int32_t device);
+
 /* Tuning aids for tools/tune_plans.py: force the tile plan (0 / -1 = automatic) and the number of timed repetitions of
  * the following vsg_debug_conv1d_bf16 calls; average kernel milliseconds of the last such call. */
 int vsg_debug_set_plan(int32_t mb, int32_t cw, int32_t two_ctas, int32_t resident, int32_t reps);
@@ -224,7 +238,9 @@ int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32
  *   bit 0 HALO activation tiles | bits 4-7 cap on 128-row blocks per tile | bit 8 no programmatic dependent launch |
  *   bit 9 no fused resblock pairs | bit 10 one launch per upsampler polyphase | bit 11 never split N = 256 tiles |
  *   bit 12 store raw AND activated resblock streams | bit 13 generic epilogue images only |
- *   bit 14 resblock chains of a stage on one stream. */
+ *   bit 14 resblock chains of a stage on one stream | bit 15 no whole-resblock kernel (C <= 64 stages fall back to the
+ *   fused pairs / per-conv kernels) | bits 16-20 cap on 128-row blocks per resblock tile | bits 21-23 resblock epilogue
+ *   warp sets (0 = 4). */
 int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t l2_tensor_mb, int32_t min_tiles);
 
 #ifdef __cplusplus

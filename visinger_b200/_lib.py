@@ -176,6 +176,11 @@ def lib() -> ctypes.CDLL:
         L.vsg_set_tc_options.argtypes = [i32, i32, i32, i32]
         L.vsg_debug_pair_bf16.restype = ctypes.c_int
         L.vsg_debug_pair_bf16.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_float, vp, vp, vp, i32, i32, i32, i32, i32, i32]
+        L.vsg_debug_resblock_bf16.restype = ctypes.c_int
+        L.vsg_debug_resblock_bf16.argtypes = [vp, vp, vp, i32, vp, vp, ctypes.c_float, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32]
+        L.vsg_debug_set_plan.restype = ctypes.c_int
+        L.vsg_debug_set_plan.argtypes = [i32, i32, i32, i32, i32]
+        L.vsg_debug_last_ms.restype = ctypes.c_float
         if L.vsg_abi_version() != 1:
             raise RuntimeError("visinger_b200: ABI version mismatch between _lib.py and the shared library")
         _lib = L
@@ -326,6 +331,41 @@ def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, ad
                                    dev.index or 0)
     check(rc, "vsg_debug_pair_bf16")
     return out, raw, act
+
+
+def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scale: float = 1.0, max_mb: int = 0, sets: int = 0,
+                        want_raw: bool = True, want_act: bool = True, reps: int = 1):
+    """Per-layer parity hook of the whole-ResBlock1 kernel (csrc/rb_tc.cuh).  xa_bld / add1: CUDA bf16 [B, L, C];
+    ws / bs: lists [c1_0, c2_0, c1_1, c2_1, ...] of fp32 [C, C, k] / [C].  Returns (out_f32, out_raw_bf16, out_act_bf16[, ms])."""
+    require_cuda(xa_bld, "xa")
+    assert xa_bld.dtype == torch.bfloat16 and xa_bld.is_contiguous()
+    B, Lx, C = xa_bld.shape
+    k = ws[0].shape[2]
+    n_pairs = len(dilations)
+    assert len(ws) == 2 * n_pairs and len(bs) == 2 * n_pairs
+    wh = torch.stack([w.detach().to("cpu", torch.float32) for w in ws]).contiguous()
+    bh = torch.stack([b.detach().to("cpu", torch.float32) for b in bs]).contiguous()
+    dl = (ctypes.c_int32 * n_pairs)(*[int(d) for d in dilations])
+    dev = xa_bld.device
+    out = torch.zeros(B, Lx, C, dtype=torch.float32, device=dev)
+    raw = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev) if want_raw else None
+    act = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev) if want_act else None
+    assert add1 is None or (add1.is_cuda and add1.dtype == torch.bfloat16 and add1.is_contiguous())
+    torch.cuda.synchronize(dev)
+    if reps > 1:
+        lib().vsg_debug_set_plan(0, 0, -1, -1, reps)
+    try:
+        rc = lib().vsg_debug_resblock_bf16(xa_bld.data_ptr(), wh.data_ptr(), bh.data_ptr(), n_pairs, dl,
+                                           add1.data_ptr() if add1 is not None else None, float(scale), out.data_ptr(),
+                                           raw.data_ptr() if raw is not None else None,
+                                           act.data_ptr() if act is not None else None, B, Lx, C, k, int(max_mb), int(sets),
+                                           dev.index or 0)
+        ms = float(lib().vsg_debug_last_ms()) if reps > 1 else None
+    finally:
+        if reps > 1:
+            lib().vsg_debug_set_plan(0, 0, -1, -1, 1)
+    check(rc, "vsg_debug_resblock_bf16")
+    return (out, raw, act, ms) if reps > 1 else (out, raw, act)
 
 
 def split_bf16(x: torch.Tensor) -> torch.Tensor:

@@ -4,6 +4,7 @@
 #include "pack_tc.cuh"
 #include "conv_tc.cuh"
 #include "pair_tc.cuh"
+#include "rb_tc.cuh"
 
 #include <algorithm>
 #include <map>
@@ -115,6 +116,10 @@ struct TCOptions {
   int chain_streams = 1;
   int epi_sigs = 1;
   int epi_sets = 2;
+  int fuse_rb = 0;          // whole-ResBlock1 kernel (rb_tc.cuh) for the C <= 64 stages (opt-in: bit 15)
+  int rb_max_mb = 0;        // cap on 128-row blocks per resblock tile (0 = as many as fit)
+  int rb_sets = 4;          // epilogue warp sets of the resblock kernel
+  int rb_issuers = 0;       // MMA issuer warps of the resblock kernel (0 = by channel count)
 };
 
 TCOptions g_default_opts;
@@ -544,6 +549,126 @@ int launch_pair_tc(const VsgPack* P, const ConvWTC& w1, const ConvWTC& w2, const
   return VSG_OK;
 }
 
+// ---- whole ResBlock1 in one kernel (rb_tc.cuh) --------------------------------------------------------------------
+struct RbPlan { int mb, H, V, M, G, n_groups, stages_w; uint32_t tap_bytes, w_stage_bytes, buf_bytes; size_t smem; };
+
+bool rb_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RbPlan* out) {
+  const int k = rb.kernel, nd = (int)rb.dilations.size();
+  if ((C != 16 && C != 32 && C != 64) || k % 2 == 0 || nd < 1 || 2 * nd > kRbMaxConvs) return false;
+  if ((int)rb.c1_tc.size() != nd || (int)rb.c2_tc.size() != nd) return false;
+  int H = 0, reach = (k - 1) / 2;
+  for (int q = 0; q < nd; ++q) {
+    const ConvWTC &w1 = rb.c1_tc[q], &w2 = rb.c2_tc[q];
+    if (!w1.has_tmap || !w2.has_tmap || w1.x3 || w2.x3 || w1.Cin != C || w1.Cout != C || w2.Cin != C || w2.Cout != C ||
+        w1.ktaps != k || w2.ktaps != k || rb.dilations[q] < 1) return false;
+    H += (k - 1) / 2 * (rb.dilations[q] + 1);
+    reach = std::max(reach, (k - 1) / 2 * rb.dilations[q]);
+  }
+  RbPlan p;
+  p.H = H;
+  p.M = std::max(8, (int)(1024 / (C * 2)));                 // margins keep the tile's first row 1024-byte aligned
+  while (p.M < reach) p.M *= 2;
+  const int mb_cap = std::min(kRbMaxBlocks, 512 / (2 * C));  // tensor memory: accumulators + fp32 residual stream
+  int mb_max = opt.rb_max_mb > 0 ? std::min(opt.rb_max_mb, mb_cap) : mb_cap;
+  p.tap_bytes = (uint32_t)((C * C * 2 + 1023) & ~1023);
+  p.G = std::min(k, std::max(1, (int)(24576 / p.tap_bytes)));
+  p.n_groups = (k + p.G - 1) / p.G;
+  p.w_stage_bytes = (uint32_t)p.G * p.tap_bytes;
+  // the tallest tile that fits (with >= 2 weight stages); a short utterance takes the smallest tile that covers it
+  for (int mb = mb_max; mb >= 2; mb >>= 1) {
+    const int V = 128 * mb - 2 * H;
+    if (V < 64) return false;
+    p.mb = mb; p.V = V;
+    p.buf_bytes = (uint32_t)(((size_t)(2 * p.M + 128 * mb) * C * 2 + 1023) & ~(size_t)1023);
+    const size_t fixed = 2 * (size_t)p.buf_bytes + 8 * tc::kRbNumBars + 64 + 1024;
+    if (fixed + 2 * (size_t)p.w_stage_bytes > kSmemMax) continue;
+    p.stages_w = (int)std::min<size_t>(kRbMaxWStages, (kSmemMax - fixed) / p.w_stage_bytes);
+    p.smem = fixed + (size_t)p.stages_w * p.w_stage_bytes;
+    const int half = mb >> 1;
+    if (half >= 2 && 128 * half - 2 * H >= 64 && 128 * half - 2 * H >= L) continue;   // a smaller tile covers the utterance
+    *out = p;
+    return true;
+  }
+  return false;
+}
+
+// One ResBlock1 (decoder.py:91-104) on a channels-last activated input xa = leaky_relu(x) [B, L, C]:
+//   out = (resblock(x) [+ add1]) * scale  ->  out_raw (bf16) and / or out_act = leaky_relu(out) (bf16) [, out_f32]
+int launch_rb_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfloat16* xa, int B, int L,
+                 const __nv_bfloat16* add1, __nv_bfloat16* out_raw, __nv_bfloat16* out_act, float* out_f32, float scale,
+                 const TCOptions& opt, int* error_flag, cudaStream_t st) {
+  RbPlan pl;
+  if (!rb_plan(rb, C, L, opt, &pl)) return fail(VSG_EUNSUPPORTED, "resblock shape not supported by the fused kernel");
+  if ((const void*)xa == (const void*)out_raw || (const void*)xa == (const void*)out_act)
+    return fail(VSG_EINVAL, "fused resblock must not run in place (tiles read halo rows of their neighbours)");
+  const int nd = (int)rb.dilations.size();
+  RbTC p;
+  memset(&p, 0, sizeof(p));
+  RbMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.B = B; p.L = L; p.k = rb.kernel; p.n_convs = 2 * nd;
+  for (int q = 0; q < nd; ++q) {
+    p.dil[2 * q] = rb.dilations[q]; p.dil[2 * q + 1] = 1;
+    p.bias[2 * q] = rb.c1_tc[q].bias; p.bias[2 * q + 1] = rb.c2_tc[q].bias;
+    maps.w[2 * q] = rb.c1_tc[q].tmap; maps.w[2 * q + 1] = rb.c2_tc[q].tmap;
+  }
+  p.mb = pl.mb; p.H = pl.H; p.V = pl.V; p.M = pl.M;
+  p.m_tiles_per_b = (L + pl.V - 1) / pl.V;
+  p.total_tiles = p.m_tiles_per_b * B;
+  p.G = pl.G; p.n_groups = pl.n_groups; p.stages_w = pl.stages_w;
+  p.tap_bytes = pl.tap_bytes; p.w_stage_bytes = pl.w_stage_bytes; p.buf_bytes = pl.buf_bytes;
+  p.p_off = 0; p.q_off = pl.buf_bytes; p.w_off = 2 * pl.buf_bytes;
+  p.bar_off = p.w_off + (uint32_t)pl.stages_w * pl.w_stage_bytes;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < (uint32_t)(2 * pl.mb * C)) p.tmem_cols <<= 1;
+  p.swizzle_code = C == 64 ? 2u : C == 32 ? 4u : 6u;
+  p.sbo_bytes = 8u * C * 2u;
+  // epilogue sets: a power of two <= 4; the (block, chunk) units of a tile must cover every set
+  p.n_sets = std::max(1, std::min(opt.rb_sets, tc::kRbMaxSets));
+  while (p.n_sets & (p.n_sets - 1)) --p.n_sets;
+  while (p.n_sets > 1 && p.n_sets > pl.mb * (C / 16)) p.n_sets >>= 1;
+  p.n_issuers = opt.rb_issuers > 0 ? opt.rb_issuers : (C == 64 ? 1 : 2);
+  p.n_issuers = std::max(1, std::min(std::min(p.n_issuers, tc::kRbMaxIssuers), pl.mb));
+  while (p.n_issuers & (p.n_issuers - 1)) --p.n_issuers;
+  p.add1 = add1; p.out_raw = out_raw; p.out_act = out_act; p.out_f32 = out_f32;
+  p.scale = scale; p.slope = 0.1f;
+  p.error_flag = error_flag;
+  static const bool debug_plan = getenv("VSG_DEBUG_PLAN") != nullptr;
+  if (debug_plan || opt.plan_only)
+    fprintf(stderr, "[vsg plan] RESBLOCK C%d k%d pairs%d B%d L%d | mb%d H%d V%d M%d G%d groups%d stagesW%d sets%d smem %zu KB "
+                    "issuers%d tmem %u tiles %d\n", C, rb.kernel, nd, B, L, pl.mb, pl.H, pl.V, pl.M, pl.G, pl.n_groups, pl.stages_w,
+            p.n_sets, pl.smem / 1024, p.n_issuers, p.tmem_cols, p.total_tiles);
+  if (opt.plan_only) return VSG_OK;
+  CUtensorMap tmA;
+  const int R = 128 * pl.mb;
+  VSG_TRY(encode_3d(&tmA, xa, (uint64_t)C, (uint64_t)L, (uint64_t)B, (uint64_t)C, (uint64_t)L * C, (uint32_t)C,
+                    (uint32_t)std::min(R, 256), C));
+  using RbFn = void (*)(CUtensorMap, RbMaps, RbTC);
+  RbFn fn = C == 16 ? rb_tc_kernel<16> : C == 32 ? rb_tc_kernel<32> : rb_tc_kernel<64>;
+  static bool rb_attr_set_dev[64] = {false};
+  bool& attr_set = rb_attr_set_dev[P->device & 63];
+  if (!attr_set) {
+    for (RbFn f : {(RbFn)rb_tc_kernel<16>, (RbFn)rb_tc_kernel<32>, (RbFn)rb_tc_kernel<64>})
+      VSG_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = dim3(std::min(p.total_tiles, P->sm_count));
+  cfg.blockDim = dim3((4 + 4 * p.n_sets + (p.n_issuers > 2 ? 2 : 0)) * 32);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = opt.use_pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, tmA, maps, p);
+  if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of rb_tc_kernel failed: %s", cudaGetErrorString(le));
+  VSG_LAUNCH_CHECK("rb_tc_kernel");
+  return VSG_OK;
+}
+
 size_t dec_max_elems(const VsgPack* P, int B, int T) {
   size_t m = (size_t)B * P->cfg.dec_upsample_initial_channel * T;
   long long L = T;
@@ -870,6 +995,21 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       // non-final conv2 write one tensor instead of two.  Split-bf16 keeps the raw copy (exactness of the lo plane).
       const bool one_stream = !x3 && opt.single_stream;
       const cudaStream_t st_main = st;
+      // C <= 64 stages: every ResBlock1 is ONE kernel (rb_tc.cuh); the three launches of a stage are chained through the
+      // running sum, so they stay on the caller's stream (their CTAs own all of tensor memory and cannot co-reside anyway)
+      bool rb_stage = c.dec_resblock == 1 && !x3 && opt.fuse_rb && ch <= 64;
+      for (int j = 0; j < NK && rb_stage; ++j) {
+        RbPlan rp;
+        rb_stage = rb_plan(us.blocks[j], ch, L, opt, &rp) && L >= 256;
+      }
+      if (rb_stage) {
+        for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
+          const bool lastj = (j == NK - 1);
+          VSG_TRY(launch_rb_tc(P, us.blocks[j], ch, bUA, nb, L, j > 0 ? bS : nullptr, lastj ? nullptr : bS, lastj ? xout : nullptr,
+                               nullptr, lastj ? 1.0f / (float)NK : 1.0f, opt, err, st));
+        }
+        continue;
+      }
       if (chains) {   // fork: the other chains start once the upsampled input is complete
         VSG_CUDA_TRY(cudaEventRecord(cs->fork, st_main));
         for (int j = 1; j < NK; ++j) VSG_CUDA_TRY(cudaStreamWaitEvent(cs->s[j - 1], cs->fork, 0));
@@ -1105,6 +1245,65 @@ extern "C" int vsg_debug_pair_bf16(const void* xa_bf16, const float* w1, const f
   return rc;
 }
 
+// Per-layer parity hook for the whole-ResBlock1 kernel (tests and tuning only; allocates and synchronises).
+//   xa: device bf16 [B, L, C] = leaky_relu(x); w: HOST fp32 [2 * n_pairs][C][C][k] in the order c1_0, c2_0, c1_1, ...;
+//   b: HOST fp32 [2 * n_pairs][C]; out = (resblock1(x) [+ add1]) * scale.
+extern "C" int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, const float* b, int32_t n_pairs,
+                                       const int32_t* dilations, const void* add1_bf16, float scale, float* out_f32,
+                                       void* out_raw_bf16, void* out_act_bf16, int32_t B, int32_t L, int32_t C, int32_t k,
+                                       int32_t max_mb, int32_t sets, int32_t device) {
+  g_launches = 0;
+  if (!xa_bf16 || !w || !b || !dilations || n_pairs < 1 || n_pairs > VSG_MAX_RESBLOCK_DILATIONS) return fail(VSG_EINVAL, "bad argument");
+  VSG_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VSG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  VsgPack tmp;
+  tmp.device = device;
+  tmp.sm_count = prop.multiProcessorCount;
+  ResBlockPack rb;
+  rb.kernel = k;
+  rb.dilations.assign(dilations, dilations + n_pairs);
+  rb.c1_tc.resize(n_pairs); rb.c2_tc.resize(n_pairs);
+  int rc = VSG_OK;
+  const size_t wn = (size_t)C * C * k;
+  for (int q = 0; q < n_pairs && rc == VSG_OK; ++q) {
+    std::vector<float> W1(w + (2 * q) * wn, w + (2 * q + 1) * wn), W2(w + (2 * q + 1) * wn, w + (2 * q + 2) * wn);
+    std::vector<float> B1(b + (2 * q) * C, b + (2 * q + 1) * C), B2(b + (2 * q + 1) * C, b + (2 * q + 2) * C);
+    rc = pack_conv_tc(&tmp, W1, B1, C, C, k, &rb.c1_tc[q]);
+    if (rc == VSG_OK) rc = pack_conv_tc(&tmp, W2, B2, C, C, k, &rb.c2_tc[q]);
+  }
+  int* err = nullptr;
+  if (rc == VSG_OK && cudaMalloc(&err, sizeof(int)) != cudaSuccess) rc = fail(VSG_ECUDA, "cudaMalloc failed");
+  if (rc == VSG_OK) {
+    cudaMemset(err, 0, sizeof(int));
+    TCOptions opt;
+    opt.rb_max_mb = max_mb;
+    if ((sets & 15) > 0) opt.rb_sets = sets & 15;       // bits 0-3: epilogue sets, bits 4-7: MMA issuer warps
+    opt.rb_issuers = (sets >> 4) & 15;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto run = [&]() {
+      return launch_rb_tc(&tmp, rb, C, (const __nv_bfloat16*)xa_bf16, B, L, (const __nv_bfloat16*)add1_bf16,
+                          (__nv_bfloat16*)out_raw_bf16, (__nv_bfloat16*)out_act_bf16, out_f32, scale, opt, err, 0);
+    };
+    rc = run();
+    if (rc == VSG_OK && g_debug_reps > 1) {
+      cudaEventRecord(e0, 0);
+      for (int r = 0; r < g_debug_reps && rc == VSG_OK; ++r) rc = run();
+      cudaEventRecord(e1, 0);
+    }
+    if (rc == VSG_OK) {
+      cudaError_t ce = cudaDeviceSynchronize();
+      if (ce != cudaSuccess) rc = fail(VSG_ECUDA, "rb_tc_kernel execution failed: %s", cudaGetErrorString(ce));
+      else if (g_debug_reps > 1) { cudaEventElapsedTime(&g_debug_ms, e0, e1); g_debug_ms /= g_debug_reps; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  if (err) cudaFree(err);
+  for (void* q : tmp.allocs) cudaFree(q);
+  return rc;
+}
+
 // Host-only: print the tile plan the launcher would choose for one convolution (tuning aid; no GPU needed).
 extern "C" int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t B, int32_t L, int32_t n_adds,
                               int32_t n_outs, int32_t x3) {
@@ -1135,6 +1334,9 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.epi_sigs = (halo_mode & 8192) ? 0 : 1;                             // bit 13: generic epilogue kernels only
   g_default_opts.chain_streams = (halo_mode & 16384) ? 0 : 1;                       // bit 14: resblock chains on one stream
   g_default_opts.epi_sets = (halo_mode & 8192) ? 1 : 2;                             // bit 13: one set of epilogue warps
+  g_default_opts.fuse_rb = (halo_mode & 32768) ? 1 : 0;                             // bit 15: whole-resblock kernel
+  g_default_opts.rb_max_mb = (halo_mode >> 16) & 31;                                // bits 16-20: cap on blocks per resblock tile
+  g_default_opts.rb_sets = ((halo_mode >> 21) & 7) ? ((halo_mode >> 21) & 7) : 4;   // bits 21-23: resblock epilogue warp sets
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;
