@@ -207,46 +207,78 @@ def _resblock_case(C, k, dils, B, L, seed):
     return xa, ws, bs, add1
 
 
-def _resblock_reference(xa, ws, bs, k, dils, add1, scale):
+def _resblock_reference(xa, ws, bs, k, dils, add1, scale, packed_leaky=False):
     """ResBlock1.forward (decoder.py:91-104) with the kernel's roundings: bf16 A operands (leaky_relu'd stream and
-    intermediate), fp32 residual stream recovered from the activated input, wide accumulation."""
+    intermediate), fp32 residual stream recovered from the activated input, wide accumulation.  packed_leaky: the
+    row-packed kernel rounds to bf16 first and applies max(h, h * bf16(0.1)) on packed pairs (one more bf16 rounding of
+    the negative values), like the per-conv kernels' plain-bf16 epilogue."""
+    slope_b = float(torch.tensor(0.1).to(torch.bfloat16))
+
+    def act(v):
+        if not packed_leaky:
+            return F.leaky_relu(v, 0.1).float().to(torch.bfloat16).double()
+        h = v.float().to(torch.bfloat16)
+        return torch.maximum(h, (h.float() * slope_b).to(torch.bfloat16)).double()
+
     a = xa.float()
     x = torch.minimum(a, a * 10.0).double()
     a = a.double()
     for q, d in enumerate(dils):
         t = F.conv1d(a.transpose(1, 2), ws[2 * q].double(), bs[2 * q].double(), dilation=d, padding=(k - 1) * d // 2)
-        ta = F.leaky_relu(t, 0.1).float().to(torch.bfloat16).double()
+        ta = act(t)
         y = F.conv1d(ta, ws[2 * q + 1].double(), bs[2 * q + 1].double(), padding=(k - 1) // 2).transpose(1, 2)
         x = x + y
-        a = F.leaky_relu(x, 0.1).float().to(torch.bfloat16).double()
+        a = act(x)
     if add1 is not None:
         x = x + add1.double()
     return x * scale
 
 
-@pytest.mark.parametrize("C,k,dils,B,L,max_mb", [
+RB_CASES = [
     (16, 3, (1, 3, 5), 2, 5000, 0), (16, 11, (1, 3, 5), 1, 2049, 0), (16, 7, (1, 3, 5), 3, 700, 4),
     (32, 3, (1, 3, 5), 2, 3000, 0), (32, 11, (1, 3, 5), 1, 1500, 0), (32, 7, (1, 3, 5), 2, 1024, 2),
     (64, 3, (1, 3, 5), 2, 1500, 0), (64, 7, (1, 3, 5), 1, 999, 0), (64, 11, (1, 3, 5), 2, 777, 0),
-    (32, 5, (1, 2), 1, 600, 0), (16, 3, (1,), 1, 300, 0)])
-def test_fused_resblock_kernel(cuda_device, C, k, dils, B, L, max_mb):
-    """Whole ResBlock1 in one kernel (rb_tc.cuh): tile borders (halo recompute), utterance borders (zero padding of every
-    intermediate), ragged last tiles, running-sum add, scale, both bf16 outputs."""
+    (32, 5, (1, 2), 1, 600, 0), (16, 3, (1,), 1, 300, 0)]
+# row-packed kernel (rp_tc.cuh): L must be a multiple of 64 / C; tiles of 1 .. 4 blocks, several tiles per utterance,
+# utterances shorter than the halo, every (C, k) of the model's C <= 32 stages, C = 64 (direct form only)
+RP_CASES = [
+    (16, 3, (1, 3, 5), 2, 5000, 0), (16, 7, (1, 3, 5), 3, 700, 0), (16, 11, (1, 3, 5), 1, 6148, 0),
+    (16, 11, (1, 3, 5), 2, 2052, 2), (16, 5, (1, 2), 1, 600, 1), (16, 3, (1,), 1, 300, 0), (16, 7, (1, 3, 5), 2, 40, 0),
+    (32, 3, (1, 3, 5), 2, 3000, 0), (32, 7, (1, 3, 5), 2, 1024, 2), (32, 11, (1, 3, 5), 1, 2502, 0),
+    (32, 9, (2, 1), 1, 1200, 3), (64, 3, (1, 3, 5), 2, 1500, 0), (64, 7, (1, 3, 5), 1, 999, 0)]
+
+
+def _run_resblock_case(cuda_device, C, k, dils, B, L, max_mb, variant):
     from visinger_b200 import _lib
     xa, ws, bs, add1 = _resblock_case(C, k, dils, B, L, C * 13 + k + L)
     d = cuda_device
     for use_add, scale in ((True, 1.0 / 3.0), (False, 1.0)):
-        want = _resblock_reference(xa, ws, bs, k, dils, add1 if use_add else None, scale)
+        want = _resblock_reference(xa, ws, bs, k, dils, add1 if use_add else None, scale, packed_leaky=bool(variant & 256))
         out, raw, act = _lib.debug_resblock_bf16(xa.to(d).contiguous(), ws, bs, dils, add1=add1.to(d).contiguous() if use_add else None,
-                                                 scale=scale, max_mb=max_mb)
+                                                 scale=scale, max_mb=max_mb, sets=variant)
         err = (out.cpu().double() - want).abs()
         rel = float((out.cpu().double() - want).norm() / want.norm())
-        print(f"resblock C={C} k={k} L={L}: max err {float(err.max()):.3e} mean {float(err.mean()):.3e} rel-L2 {rel:.3e}")
+        print(f"resblock[{variant}] C={C} k={k} L={L}: max err {float(err.max()):.3e} mean {float(err.mean()):.3e} rel-L2 {rel:.3e}")
         # an intermediate that sits on a bf16 rounding boundary may round the other way (fp32 vs fp64 accumulation):
         # a few elements move by one bf16 ulp of an O(1) value, everything else agrees to fp32 accumulation order
         assert float(err.max()) <= 3e-2 * max(scale, 0.34) and float(err.mean()) <= 1e-3 * max(scale, 0.34) and rel <= 2e-3
         assert torch.equal(raw.cpu(), out.cpu().to(torch.bfloat16))
         assert maxabs(act.cpu().double(), F.leaky_relu(out.cpu().double(), 0.1)) <= 2e-2
     # deterministic
-    out2, _, _ = _lib.debug_resblock_bf16(xa.to(d).contiguous(), ws, bs, dils, scale=1.0, max_mb=max_mb)
+    out2, _, _ = _lib.debug_resblock_bf16(xa.to(d).contiguous(), ws, bs, dils, scale=1.0, max_mb=max_mb, sets=variant)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("C,k,dils,B,L,max_mb", RB_CASES)
+def test_fused_resblock_kernel(cuda_device, C, k, dils, B, L, max_mb):
+    """Whole ResBlock1 in one kernel (rb_tc.cuh): tile borders (halo recompute), utterance borders (zero padding of every
+    intermediate), ragged last tiles, running-sum add, scale, both bf16 outputs."""
+    _run_resblock_case(cuda_device, C, k, dils, B, L, max_mb, 0)
+
+
+@pytest.mark.parametrize("C,k,dils,B,L,max_mb", RP_CASES)
+@pytest.mark.parametrize("variant", [256, 256 | 512])
+def test_rowpacked_resblock_kernel(cuda_device, C, k, dils, B, L, max_mb, variant):
+    """Row-packed whole ResBlock1 (rp_tc.cuh), with the dilation-1 convolutions in the block-Toeplitz form (256) and with
+    every convolution tap by tap (256 | 512): same checks as the per-row kernel."""
+    _run_resblock_case(cuda_device, C, k, dils, B, L, max_mb, variant)

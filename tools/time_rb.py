@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--sets", type=int, default=0, help="epilogue sets | (MMA issuer warps << 4)")
     ap.add_argument("--issuers", type=int, default=0)
+    ap.add_argument("--rp", type=int, default=0, help="1: row-packed kernel (rp_tc.cuh); 2: row-packed, no Toeplitz form")
     ap.add_argument("--max-mb", type=int, default=0)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--frames", type=int, default=1000)
@@ -28,6 +29,8 @@ def main():
     dev = torch.device("cuda:0")
     dils = (1, 3, 5)
     for C, rate in ((64, 75), (32, 150), (16, 300)):
+        if args.rp and C == 64 and not args.only:
+            continue
         for k in (3, 7, 11):
             if args.only and args.only != f"{C},{k}":
                 continue
@@ -38,7 +41,7 @@ def main():
             bs = [torch.randn(C, generator=gen) * 0.1 for _ in range(6)]
             add1 = torch.randn(args.batch, L, C, generator=gen).to(torch.bfloat16).to(dev).contiguous()
             out, raw, act, ms = _lib.debug_resblock_bf16(xa, ws, bs, dils, add1=add1, scale=1 / 3, max_mb=args.max_mb,
-                                                         sets=args.sets | (args.issuers << 4), want_raw=False, reps=args.reps)
+                                                         sets=args.sets | (args.issuers << 4) | (256 if args.rp else 0) | (512 if args.rp == 2 else 0), want_raw=False, want_f32=False, reps=args.reps)
             mb = args.max_mb or 512 // (2 * C)
             H = (k - 1) // 2 * 12
             V = 128 * mb - 2 * H

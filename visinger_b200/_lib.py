@@ -319,7 +319,7 @@ def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, ad
     k = w1.shape[2]
     h = [t.detach().to("cpu", torch.float32).contiguous() for t in (w1, b1, w2, b2)]
     dev = xa_bld.device
-    out = torch.zeros(B, Lx, C, dtype=torch.float32, device=dev)
+    out = torch.zeros(B, Lx, C, dtype=torch.float32, device=dev) if want_f32 else None
     raw = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev) if want_raw else None
     act = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev)
     torch.cuda.synchronize(dev)
@@ -334,7 +334,7 @@ def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, ad
 
 
 def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scale: float = 1.0, max_mb: int = 0, sets: int = 0,
-                        want_raw: bool = True, want_act: bool = True, reps: int = 1):
+                        want_raw: bool = True, want_act: bool = True, reps: int = 1, want_f32: bool = True):
     """Per-layer parity hook of the whole-ResBlock1 kernel (csrc/rb_tc.cuh).  xa_bld / add1: CUDA bf16 [B, L, C];
     ws / bs: lists [c1_0, c2_0, c1_1, c2_1, ...] of fp32 [C, C, k] / [C].  Returns (out_f32, out_raw_bf16, out_act_bf16[, ms])."""
     require_cuda(xa_bld, "xa")
@@ -347,7 +347,7 @@ def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scal
     bh = torch.stack([b.detach().to("cpu", torch.float32) for b in bs]).contiguous()
     dl = (ctypes.c_int32 * n_pairs)(*[int(d) for d in dilations])
     dev = xa_bld.device
-    out = torch.zeros(B, Lx, C, dtype=torch.float32, device=dev)
+    out = torch.zeros(B, Lx, C, dtype=torch.float32, device=dev) if want_f32 else None
     raw = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev) if want_raw else None
     act = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev) if want_act else None
     assert add1 is None or (add1.is_cuda and add1.dtype == torch.bfloat16 and add1.is_contiguous())
@@ -356,8 +356,8 @@ def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scal
         lib().vsg_debug_set_plan(0, 0, -1, -1, reps)
     try:
         rc = lib().vsg_debug_resblock_bf16(xa_bld.data_ptr(), wh.data_ptr(), bh.data_ptr(), n_pairs, dl,
-                                           add1.data_ptr() if add1 is not None else None, float(scale), out.data_ptr(),
-                                           raw.data_ptr() if raw is not None else None,
+                                           add1.data_ptr() if add1 is not None else None, float(scale),
+                                           out.data_ptr() if out is not None else None, raw.data_ptr() if raw is not None else None,
                                            act.data_ptr() if act is not None else None, B, Lx, C, k, int(max_mb), int(sets),
                                            dev.index or 0)
         ms = float(lib().vsg_debug_last_ms()) if reps > 1 else None

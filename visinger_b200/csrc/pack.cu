@@ -290,7 +290,8 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
       rb.dilations.assign(c.dec_resblock_dilations[j], c.dec_resblock_dilations[j] + nd);
       const std::string pb = pre + "resblocks." + std::to_string(i * c.dec_n_kernels + j) + ".";
       rb.c1.resize(nd); rb.c1_tc.resize(nd); rb.c1_x3.resize(nd);
-      if (c.dec_resblock == 1) { rb.c2.resize(nd); rb.c2_tc.resize(nd); rb.c2_x3.resize(nd); }
+      if (c.dec_resblock == 1) { rb.c2.resize(nd); rb.c2_tc.resize(nd); rb.c2_x3.resize(nd); rb.c1_rp.resize(nd); rb.c2_rp.resize(nd); }
+      std::vector<std::vector<float>> b2s;
       for (int q = 0; q < nd; ++q) {
         const std::string n1 = pb + (c.dec_resblock == 1 ? "convs1." : "convs.") + std::to_string(q);
         VSG_TRY(L.eff_weight(n1, ch, ch, rb.kernel, W));
@@ -298,6 +299,7 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
         VSG_TRY(pack_conv_f32(L, W, b, ch, ch, rb.kernel, Identity{}, &rb.c1[q]));
         VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_tc[q]));
         VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_x3[q], true));
+        if (c.dec_resblock == 1 && rb.dilations[q] == 1) VSG_TRY(pack_conv_rowpacked(P, W, ch, rb.kernel, &rb.c1_rp[q]));
         if (c.dec_resblock == 1) {
           const std::string n2 = pb + "convs2." + std::to_string(q);
           VSG_TRY(L.eff_weight(n2, ch, ch, rb.kernel, W));
@@ -305,8 +307,11 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
           VSG_TRY(pack_conv_f32(L, W, b, ch, ch, rb.kernel, Identity{}, &rb.c2[q]));
           VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_tc[q]));
           VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_x3[q], true));
+          VSG_TRY(pack_conv_rowpacked(P, W, ch, rb.kernel, &rb.c2_rp[q]));
+          b2s.push_back(b);
         }
       }
+      if (c.dec_resblock == 1 && ch <= 64) VSG_TRY(pack_resblock_bias_sums(P, b2s, &rb));
     }
   }
   // conv_post: Conv1d(ch -> 1, 7, padding 3, bias=False)                    decoder.py:34

@@ -5,6 +5,7 @@
 #include "conv_tc.cuh"
 #include "pair_tc.cuh"
 #include "rb_tc.cuh"
+#include "rp_tc.cuh"
 
 #include <algorithm>
 #include <map>
@@ -120,6 +121,11 @@ struct TCOptions {
   int rb_max_mb = 0;        // cap on 128-row blocks per resblock tile (0 = as many as fit)
   int rb_sets = 4;          // epilogue warp sets of the resblock kernel
   int rb_issuers = 0;       // MMA issuer warps of the resblock kernel (0 = by channel count)
+  int fuse_rp = 1;          // row-packed whole-ResBlock1 kernel (rp_tc.cuh) for the C <= 32 stages
+  int rp_max_c = 32;        // widest stage the row-packed kernel takes
+  int rp_packed = 1;        // dilation-1 convolutions in the block-Toeplitz form (0: every conv tap by tap)
+  int rp_max_mb = 0;        // cap on 128-row blocks per row-packed tile (0 = as many as fit)
+  uint32_t* rp_trace = nullptr;   // tuning aid (vsg_debug_resblock_bf16 with VSG_RP_TRACE set): pipeline event clocks of CTA 0
 };
 
 TCOptions g_default_opts;
@@ -669,6 +675,137 @@ int launch_rb_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   return VSG_OK;
 }
 
+// ---- row-packed whole ResBlock1 (rp_tc.cuh) ------------------------------------------------------------------------
+struct RpPlan {
+  int S, mb, H, V, n_k, packed_stages, tps, direct_stages, n_wst;
+  uint32_t packed_mask, margin_bytes, buf_bytes;
+  size_t smem;
+};
+
+bool rp_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RpPlan* out) {
+  const int k = rb.kernel, nd = (int)rb.dilations.size();
+  if ((C != 16 && C != 32 && C != 64) || k % 2 == 0 || nd < 1 || 2 * nd > kRpMaxConvs) return false;
+  if ((int)rb.c1_tc.size() != nd || (int)rb.c2_tc.size() != nd || (int)rb.c2_bsum.size() != nd) return false;
+  RpPlan p;
+  p.S = 64 / C;
+  if (L % p.S) return false;
+  const int cen = (k - 1) / 2;
+  int H = 0, dmax = 1;
+  p.packed_mask = 0;
+  for (int q = 0; q < nd; ++q) {
+    const ConvWTC &w1 = rb.c1_tc[q], &w2 = rb.c2_tc[q];
+    if (!w1.has_tmap || !w2.has_tmap || w1.x3 || w2.x3 || w1.Cin != C || w1.Cout != C || w2.Cin != C || w2.Cout != C ||
+        w1.ktaps != k || w2.ktaps != k || rb.dilations[q] < 1) return false;
+    H += cen * (rb.dilations[q] + 1);
+    dmax = std::max(dmax, rb.dilations[q]);
+    if (opt.rp_packed && p.S > 1) {
+      if (rb.dilations[q] == 1 && (int)rb.c1_rp.size() == nd && rb.c1_rp[q].has_tmap) p.packed_mask |= 1u << (2 * q);
+      if ((int)rb.c2_rp.size() == nd && rb.c2_rp[q].has_tmap) p.packed_mask |= 1u << (2 * q + 1);
+    }
+  }
+  p.H = (H + p.S - 1) / p.S * p.S;
+  p.n_k = (k + p.S - 1) * (C / 16);
+  p.packed_stages = (p.n_k + 3) / 4;
+  const uint32_t slot_bytes = std::max(1024, C * C * 2);
+  p.tps = (int)(kRpStageBytes / slot_bytes);
+  p.direct_stages = (k + p.tps - 1) / p.tps;
+  const int reach_bytes = cen * dmax * C * 2 + 128;
+  p.margin_bytes = (uint32_t)((reach_bytes + 1023) & ~1023);
+  int need = 0;
+  for (int c = 0; c < 2 * nd; ++c) need = std::max(need, ((p.packed_mask >> c) & 1u) ? p.packed_stages : p.direct_stages);
+  const int mb_max = opt.rp_max_mb > 0 ? std::min(opt.rp_max_mb, kRpMaxBlocks) : kRpMaxBlocks;
+  for (int mb = mb_max; mb >= 1; --mb) {
+    const int V = 128 * p.S * mb - 2 * p.H;
+    if (V < 32 * p.S) return false;
+    p.mb = mb; p.V = V;
+    p.buf_bytes = 2 * p.margin_bytes + 16384u * (uint32_t)mb;
+    const size_t fixed = 2 * (size_t)p.buf_bytes + 8 * tc::kRpNumBars + 64 + kRpMaxConvs * 64 * sizeof(float) + 1024;
+    if (fixed + (size_t)need * kRpStageBytes > kSmemMax) continue;
+    // a convolution's stages are released by its last block: twice the largest need keeps a whole convolution of prefetch
+    p.n_wst = (int)std::min<size_t>({(size_t)kRpMaxWStages, (size_t)2 * need, (kSmemMax - fixed) / kRpStageBytes});
+    p.smem = fixed + (size_t)p.n_wst * kRpStageBytes;
+    if (mb > 1 && 128 * p.S * (mb - 1) - 2 * p.H >= L) continue;   // a smaller tile covers the utterance
+    *out = p;
+    return true;
+  }
+  return false;
+}
+
+// One ResBlock1 (decoder.py:91-104) on a channels-last activated input xa = leaky_relu(x) [B, L, C]:
+//   out = (resblock(x) [+ add1]) * scale  ->  out_raw (bf16) and / or out_act = leaky_relu(out) (bf16) [, out_f32]
+int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfloat16* xa, int B, int L,
+                 const __nv_bfloat16* add1, __nv_bfloat16* out_raw, __nv_bfloat16* out_act, float* out_f32, float scale,
+                 const TCOptions& opt, int* error_flag, cudaStream_t st) {
+  RpPlan pl;
+  if (!rp_plan(rb, C, L, opt, &pl)) return fail(VSG_EUNSUPPORTED, "resblock shape not supported by the row-packed kernel");
+  if ((const void*)xa == (const void*)out_raw || (const void*)xa == (const void*)out_act)
+    return fail(VSG_EINVAL, "fused resblock must not run in place (tiles read halo rows of their neighbours)");
+  const int nd = (int)rb.dilations.size();
+  RpTC p;
+  memset(&p, 0, sizeof(p));
+  RpMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.B = B; p.L = L; p.k = rb.kernel; p.n_convs = 2 * nd;
+  for (int q = 0; q < nd; ++q) {
+    p.dil[2 * q] = rb.dilations[q]; p.dil[2 * q + 1] = 1;
+    p.bias[2 * q] = rb.c1_tc[q].bias; p.bias[2 * q + 1] = rb.c2_bsum[q];
+    maps.w[2 * q] = ((pl.packed_mask >> (2 * q)) & 1u) ? rb.c1_rp[q].tmap : rb.c1_tc[q].tmap;
+    maps.w[2 * q + 1] = ((pl.packed_mask >> (2 * q + 1)) & 1u) ? rb.c2_rp[q].tmap : rb.c2_tc[q].tmap;
+  }
+  p.packed_mask = pl.packed_mask; p.n_k = pl.n_k; p.packed_stages = pl.packed_stages;
+  p.tps = pl.tps; p.direct_stages = pl.direct_stages;
+  p.mb = pl.mb; p.H = pl.H; p.V = pl.V;
+  p.m_tiles_per_b = (L + pl.V - 1) / pl.V;
+  p.total_tiles = p.m_tiles_per_b * B;
+  p.n_wst = pl.n_wst;
+  p.margin_bytes = pl.margin_bytes; p.buf_bytes = pl.buf_bytes;
+  p.p_off = 0; p.q_off = pl.buf_bytes; p.w_off = 2 * pl.buf_bytes;
+  p.bar_off = p.w_off + (uint32_t)pl.n_wst * kRpStageBytes;
+  p.bias_off = p.bar_off + 8 * tc::kRpNumBars + 64;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < (uint32_t)(2 * pl.mb * 64)) p.tmem_cols <<= 1;
+  p.add1 = add1; p.out_raw = out_raw; p.out_act = out_act; p.out_f32 = out_f32;
+  p.scale = scale; p.slope = 0.1f;
+  p.error_flag = error_flag;
+  p.trace = opt.rp_trace;
+  static const bool debug_plan = getenv("VSG_DEBUG_PLAN") != nullptr;
+  if (debug_plan || opt.plan_only)
+    fprintf(stderr, "[vsg plan] ROWPACKED RESBLOCK C%d k%d pairs%d B%d L%d | S%d mb%d H%d V%d packed 0x%x K slices %d (stages %d) "
+                    "direct stages %d ring %d margin %u smem %zu KB tmem %u tiles %d\n", C, rb.kernel, nd, B, L, pl.S, pl.mb,
+            pl.H, pl.V, pl.packed_mask, pl.n_k, pl.packed_stages, pl.direct_stages, pl.n_wst,
+            pl.margin_bytes, pl.smem / 1024, p.tmem_cols, p.total_tiles);
+  if (opt.plan_only) return VSG_OK;
+  // the input as rows of 64 channels = S time steps: [B, L, C] == [B, L / S, 64]
+  CUtensorMap tmA;
+  VSG_TRY(encode_3d(&tmA, xa, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
+  maps.add1 = tmA;
+  if (add1) VSG_TRY(encode_3d(&maps.add1, add1, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
+  using RpFn = void (*)(CUtensorMap, RpMaps, RpTC);
+  RpFn fn = C == 16 ? rp_tc_kernel<16> : C == 32 ? rp_tc_kernel<32> : rp_tc_kernel<64>;
+  static bool rp_attr_set_dev[64] = {false};
+  bool& attr_set = rp_attr_set_dev[P->device & 63];
+  if (!attr_set) {
+    for (RpFn f : {(RpFn)rp_tc_kernel<16>, (RpFn)rp_tc_kernel<32>, (RpFn)rp_tc_kernel<64>})
+      VSG_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = dim3(std::min(p.total_tiles, P->sm_count));
+  cfg.blockDim = dim3(tc::kRpThreads);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = opt.use_pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, tmA, maps, p);
+  if (le != cudaSuccess) return fail(VSG_ECUDA, "launch of rp_tc_kernel failed: %s", cudaGetErrorString(le));
+  VSG_LAUNCH_CHECK("rp_tc_kernel");
+  return VSG_OK;
+}
+
 size_t dec_max_elems(const VsgPack* P, int B, int T) {
   size_t m = (size_t)B * P->cfg.dec_upsample_initial_channel * T;
   long long L = T;
@@ -711,6 +848,44 @@ int pack_conv_tc(VsgPack* P, const std::vector<float>& W, const std::vector<floa
   out->bias = (float*)db;
   VSG_TRY(encode_2d(&out->tmap, dw, (uint64_t)CinT, (uint64_t)k * Cout, (uint32_t)KC, (uint32_t)NT, KC));
   out->has_tmap = true;
+  return VSG_OK;
+}
+
+// Dilation-1 Conv1d(C -> C, k) in the row-packed form of rp_tc.cuh: S = 64 / C consecutive time steps are one row of 64
+// channels; output column n = s' * C + co of a row is fed by the 16-wide K slices m = 0 .. (k + S - 1) * C / 16 - 1 of the
+// input, slice m = channels 16 (m % KK) .. of input sub-step sigma = m / KK - (k-1)/2 (KK = C / 16), through tap
+// j = sigma - s' + (k-1)/2:   W'[m][n][ci'] = W[co][16 (m % KK) + ci'][j]   (zero outside the k taps).
+// Four slices share one [64 x 64] SWIZZLE_128B tile (K index = 16 (m % 4) + ci'): packed as Conv1d(64 -> 64, ceil(n_k / 4) taps).
+int pack_conv_rowpacked(VsgPack* P, const std::vector<float>& W, int C, int k, ConvWTC* out) {
+  out->has_tmap = false;
+  if ((C != 16 && C != 32) || k % 2 == 0) return VSG_OK;
+  const int S = 64 / C, KK = C / 16, cen = (k - 1) / 2, n_k = (k + S - 1) * KK, n_g = (n_k + 3) / 4;
+  std::vector<float> Wp((size_t)64 * 64 * n_g, 0.f), bz(64, 0.f);
+  for (int m = 0; m < n_k; ++m) {
+    const int sigma = m / KK - cen, c_lo = 16 * (m % KK);
+    for (int sp = 0; sp < S; ++sp) {
+      const int j = sigma - sp + cen;
+      if (j < 0 || j >= k) continue;
+      for (int co = 0; co < C; ++co)
+        for (int ci = 0; ci < 16; ++ci)
+          Wp[((size_t)(sp * C + co) * 64 + 16 * (m % 4) + ci) * n_g + m / 4] = W[((size_t)co * C + c_lo + ci) * k + j];
+    }
+  }
+  return pack_conv_tc(P, Wp, bz, 64, 64, n_g, out);
+}
+
+int pack_resblock_bias_sums(VsgPack* P, const std::vector<std::vector<float>>& b2, ResBlockPack* rb) {
+  rb->c2_bsum.assign(b2.size(), nullptr);
+  std::vector<float> acc;
+  for (size_t q = 0; q < b2.size(); ++q) {
+    if (q == 0) acc = b2[0];
+    else for (size_t i = 0; i < acc.size() && i < b2[q].size(); ++i) acc[i] += b2[q][i];
+    void* d = nullptr;
+    VSG_CUDA_TRY(cudaMalloc(&d, acc.size() * sizeof(float) + 256));
+    P->allocs.push_back(d);
+    VSG_CUDA_TRY(cudaMemcpy(d, acc.data(), acc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    rb->c2_bsum[q] = (float*)d;
+  }
   return VSG_OK;
 }
 
@@ -1002,11 +1177,22 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
         RbPlan rp;
         rb_stage = rb_plan(us.blocks[j], ch, L, opt, &rp) && L >= 256;
       }
-      if (rb_stage) {
+      static const int rp_max_c_env = getenv("VSG_RP_MAX_C") ? atoi(getenv("VSG_RP_MAX_C")) : -1;   // A/B aid
+      const int rp_max_c = rp_max_c_env >= 0 ? rp_max_c_env : opt.rp_max_c;
+      bool rp_stage = c.dec_resblock == 1 && !x3 && opt.fuse_rp && ch <= rp_max_c;
+      for (int j = 0; j < NK && rp_stage; ++j) {
+        RpPlan rp;
+        rp_stage = rp_plan(us.blocks[j], ch, L, opt, &rp) && L >= 256;
+      }
+      if (rb_stage || rp_stage) {
         for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
           const bool lastj = (j == NK - 1);
-          VSG_TRY(launch_rb_tc(P, us.blocks[j], ch, bUA, nb, L, j > 0 ? bS : nullptr, lastj ? nullptr : bS, lastj ? xout : nullptr,
-                               nullptr, lastj ? 1.0f / (float)NK : 1.0f, opt, err, st));
+          if (rp_stage)
+            VSG_TRY(launch_rp_tc(P, us.blocks[j], ch, bUA, nb, L, j > 0 ? bS : nullptr, lastj ? nullptr : bS, lastj ? xout : nullptr,
+                                 nullptr, lastj ? 1.0f / (float)NK : 1.0f, opt, err, st));
+          else
+            VSG_TRY(launch_rb_tc(P, us.blocks[j], ch, bUA, nb, L, j > 0 ? bS : nullptr, lastj ? nullptr : bS, lastj ? xout : nullptr,
+                                 nullptr, lastj ? 1.0f / (float)NK : 1.0f, opt, err, st));
         }
         continue;
       }
@@ -1264,13 +1450,20 @@ extern "C" int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, cons
   rb.kernel = k;
   rb.dilations.assign(dilations, dilations + n_pairs);
   rb.c1_tc.resize(n_pairs); rb.c2_tc.resize(n_pairs);
+  rb.c1_rp.resize(n_pairs); rb.c2_rp.resize(n_pairs);
+  const bool row_packed = (sets & 256) != 0;              // bit 8: the row-packed kernel (rp_tc.cuh); bit 9: no Toeplitz form
   int rc = VSG_OK;
   const size_t wn = (size_t)C * C * k;
+  std::vector<std::vector<float>> b2s;
+  for (int q = 0; q < n_pairs; ++q) b2s.emplace_back(b + (2 * q + 1) * C, b + (2 * q + 2) * C);
+  if (row_packed) rc = pack_resblock_bias_sums(&tmp, b2s, &rb);
   for (int q = 0; q < n_pairs && rc == VSG_OK; ++q) {
     std::vector<float> W1(w + (2 * q) * wn, w + (2 * q + 1) * wn), W2(w + (2 * q + 1) * wn, w + (2 * q + 2) * wn);
     std::vector<float> B1(b + (2 * q) * C, b + (2 * q + 1) * C), B2(b + (2 * q + 1) * C, b + (2 * q + 2) * C);
     rc = pack_conv_tc(&tmp, W1, B1, C, C, k, &rb.c1_tc[q]);
     if (rc == VSG_OK) rc = pack_conv_tc(&tmp, W2, B2, C, C, k, &rb.c2_tc[q]);
+    if (rc == VSG_OK && row_packed && dilations[q] == 1) rc = pack_conv_rowpacked(&tmp, W1, C, k, &rb.c1_rp[q]);
+    if (rc == VSG_OK && row_packed) rc = pack_conv_rowpacked(&tmp, W2, C, k, &rb.c2_rp[q]);
   }
   int* err = nullptr;
   if (rc == VSG_OK && cudaMalloc(&err, sizeof(int)) != cudaSuccess) rc = fail(VSG_ECUDA, "cudaMalloc failed");
@@ -1280,9 +1473,20 @@ extern "C" int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, cons
     opt.rb_max_mb = max_mb;
     if ((sets & 15) > 0) opt.rb_sets = sets & 15;       // bits 0-3: epilogue sets, bits 4-7: MMA issuer warps
     opt.rb_issuers = (sets >> 4) & 15;
+    opt.rp_max_mb = max_mb;
+    opt.rp_packed = (sets & 512) ? 0 : 1;
+    uint32_t* d_trace = nullptr;
+    if (row_packed && getenv("VSG_RP_TRACE")) {
+      cudaMalloc(&d_trace, 5 * 1024 * sizeof(uint32_t));
+      cudaMemset(d_trace, 0, 5 * 1024 * sizeof(uint32_t));
+      opt.rp_trace = d_trace;
+    }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto run = [&]() {
+      if (row_packed)
+        return launch_rp_tc(&tmp, rb, C, (const __nv_bfloat16*)xa_bf16, B, L, (const __nv_bfloat16*)add1_bf16,
+                            (__nv_bfloat16*)out_raw_bf16, (__nv_bfloat16*)out_act_bf16, out_f32, scale, opt, err, 0);
       return launch_rb_tc(&tmp, rb, C, (const __nv_bfloat16*)xa_bf16, B, L, (const __nv_bfloat16*)add1_bf16,
                           (__nv_bfloat16*)out_raw_bf16, (__nv_bfloat16*)out_act_bf16, out_f32, scale, opt, err, 0);
     };
@@ -1298,6 +1502,17 @@ extern "C" int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, cons
       else if (g_debug_reps > 1) { cudaEventElapsedTime(&g_debug_ms, e0, e1); g_debug_ms /= g_debug_reps; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (d_trace) {   // issuer: (after waits, after commit) per block; epilogue sets: (before wait, after wait, before fence, after arrive)
+      std::vector<uint32_t> h(5 * 1024);
+      cudaMemcpy(h.data(), d_trace, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+      const uint32_t t0 = h[0];
+      for (int r = 0; r < 5; ++r) {
+        fprintf(stderr, "[rp trace] role %d:", r);
+        for (int i = 0; i < 160 && h[r * 1024 + i]; ++i) fprintf(stderr, " %u", h[r * 1024 + i] - t0);
+        fprintf(stderr, "\n");
+      }
+      cudaFree(d_trace);
+    }
   }
   if (err) cudaFree(err);
   for (void* q : tmp.allocs) cudaFree(q);
@@ -1337,6 +1552,9 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.fuse_rb = (halo_mode & 32768) ? 1 : 0;                             // bit 15: whole-resblock kernel
   g_default_opts.rb_max_mb = (halo_mode >> 16) & 31;                                // bits 16-20: cap on blocks per resblock tile
   g_default_opts.rb_sets = ((halo_mode >> 21) & 7) ? ((halo_mode >> 21) & 7) : 4;   // bits 21-23: resblock epilogue warp sets
+  g_default_opts.fuse_rp = (halo_mode & (1 << 24)) ? 0 : 1;                         // bit 24: no row-packed resblock kernel
+  g_default_opts.rp_max_c = (halo_mode & (1 << 25)) ? 64 : 32;                      // bit 25: row-packed kernel at C = 64 too
+  g_default_opts.rp_packed = (halo_mode & (1 << 26)) ? 0 : 1;                       // bit 26: no block-Toeplitz form
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;

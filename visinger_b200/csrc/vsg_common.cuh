@@ -92,6 +92,8 @@ struct ResBlockPack {
   std::vector<ConvW32> c1, c2;      // ResBlock2 uses c1 only
   std::vector<ConvWTC> c1_tc, c2_tc;
   std::vector<ConvWTC> c1_x3, c2_x3;   // split-bf16 packs
+  std::vector<ConvWTC> c1_rp, c2_rp;   // row-packed block-Toeplitz packs of the dilation-1 convolutions (C <= 32; rp_tc.cuh)
+  std::vector<float*> c2_bsum;         // running bias of the residual stream: b2_0 + ... + b2_q, fp32 [C] each (rp_tc.cuh)
 };
 
 struct UpStage {
