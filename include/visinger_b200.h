@@ -173,6 +173,41 @@ int vsg_infer(const VsgPack* pack, const float* mu_p, const float* logs_p, const
 int vsg_wav_to_int16(const float* wav, const int32_t* lengths, int16_t* pcm, float* peak, int32_t B, int32_t L,
                      int32_t norm, void* stream);
 
+/*
+ * PosteriorEncoder(in_channels, out_channels, hidden_channels, kernel_size, dilation_rate, n_layers, gin_channels)
+ *                                                                         modules/visinger/encoder.py:76-101
+ * (constructed at models/visinger.py:59-60 as (num_linear_bins, 192, 192, 5, 1, 16, gin); the training / voice-conversion
+ * side of the model: SURVEY.md section 8 row f4).  It re-uses the WaveNet kernels of the flow.
+ */
+typedef struct VsgEncConfig {
+  int32_t in_channels;
+  int32_t out_channels;
+  int32_t hidden_channels;
+  int32_t kernel_size;
+  int32_t dilation_rate;
+  int32_t n_layers;
+  int32_t gin_channels;
+} VsgEncConfig;
+
+/* Pre-pack of a PosteriorEncoder's state-dict entries (`prefix` + "pre.weight", "enc.in_layers.0.weight_v", ...,
+ * "proj.bias"); the result is an ordinary VsgPack (vsg_pack_destroy frees it) that only vsg_posterior_* accept. */
+int vsg_enc_pack_create(const VsgEncConfig* cfg, const VsgTensor* weights, int32_t n_weights, const char* prefix,
+                        int32_t device, VsgPack** out);
+size_t vsg_posterior_workspace_bytes(const VsgPack* pack, int32_t B, int32_t T, int32_t precision);
+
+/*
+ * PosteriorEncoder.forward(x, nonpadding, g)                              modules/visinger/encoder.py:92-98
+ *   h = pre(x) * mask ; h = WaveNet(h, mask, g) ; stats = proj(h) * mask ; (mu_q, logs_q) = split(stats)
+ *   z_q = (mu_q + noise * exp(logs_q)) * mask
+ * x: [B, in_channels, T]; noise: [B, out_channels, T] (the reference draws torch.randn_like(mu_q));
+ * stats: [B, 2 * out_channels, T] receives proj(h) * mask -- mu_q and logs_q are its two channel halves, the views
+ * torch.split returns; z_q: [B, out_channels, T].  FP32: FFMA kernels (reference parity); BF16: tcgen05 kernels
+ * (BF16X3 runs as FP32, like the flow).
+ */
+int vsg_posterior_forward(const VsgPack* pack, const float* x, const float* mask, const float* g, const float* noise,
+                          float* z_q, float* stats, int32_t B, int32_t T, int32_t precision,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Samples produced per latent frame (prod(upsample_rates)); 0 if the pack has no decoder. */
 int32_t vsg_hop_size(const VsgPack* pack);
 

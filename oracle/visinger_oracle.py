@@ -117,6 +117,22 @@ def wavenet(sd: StateDict, prefix: str, x, x_mask, g, *, hidden: int, kernel_siz
 
 
 # --------------------------------------------------------------------------------------
+# f4: posterior encoder
+# --------------------------------------------------------------------------------------
+def posterior_encoder(sd: StateDict, x, x_mask, g, noise, *, out_channels: int = 192, hidden: int = 192,
+                      kernel_size: int = 5, dilation_rate: int = 1, n_layers: int = 16, prefix: str = ""):
+    """modules/visinger/encoder.py:92-98 PosteriorEncoder.forward with the noise injected (the reference draws
+    torch.randn_like(mu_q) at :97).  Returns (z_q, mu_q, logs_q)."""
+    h = F.conv1d(x, sd[prefix + "pre.weight"], sd[prefix + "pre.bias"]) * x_mask
+    h = wavenet(sd, prefix + "enc.", h, x_mask, g, hidden=hidden, kernel_size=kernel_size, dilation_rate=dilation_rate,
+                n_layers=n_layers)
+    stats = F.conv1d(h, sd[prefix + "proj.weight"], sd[prefix + "proj.bias"]) * x_mask
+    mu_q, logs_q = torch.split(stats, out_channels, dim=1)
+    z_q = (mu_q + noise * torch.exp(logs_q)) * x_mask
+    return z_q, mu_q, logs_q
+
+
+# --------------------------------------------------------------------------------------
 # a2/a3/a4: residual coupling block
 # --------------------------------------------------------------------------------------
 def coupling_layer(sd: StateDict, prefix: str, x, x_mask, g, reverse: bool, *, channels: int, hidden: int,
@@ -313,6 +329,25 @@ def flow_param_shapes(channels=192, hidden=192, kernel_size=5, n_layers=4, n_flo
             shapes[p + f"enc.res_skip_layers.{i}.weight_v"] = (rs, hidden, 1)
         shapes[p + "post.weight"] = (half, hidden, 1)
         shapes[p + "post.bias"] = (half,)
+    return shapes
+
+
+def posterior_param_shapes(in_channels=1025, out_channels=192, hidden=192, kernel_size=5, n_layers=16, gin=256):
+    """State-dict layout of PosteriorEncoder (modules/visinger/encoder.py:77-90)."""
+    shapes = {"pre.weight": (hidden, in_channels, 1), "pre.bias": (hidden,),
+              "proj.weight": (2 * out_channels, hidden, 1), "proj.bias": (2 * out_channels,)}
+    if gin:
+        shapes["enc.cond_layer.bias"] = (2 * hidden * n_layers,)
+        shapes["enc.cond_layer.weight_g"] = (2 * hidden * n_layers, 1, 1)
+        shapes["enc.cond_layer.weight_v"] = (2 * hidden * n_layers, gin, 1)
+    for i in range(n_layers):
+        shapes[f"enc.in_layers.{i}.bias"] = (2 * hidden,)
+        shapes[f"enc.in_layers.{i}.weight_g"] = (2 * hidden, 1, 1)
+        shapes[f"enc.in_layers.{i}.weight_v"] = (2 * hidden, hidden, kernel_size)
+        rs = 2 * hidden if i < n_layers - 1 else hidden
+        shapes[f"enc.res_skip_layers.{i}.bias"] = (rs,)
+        shapes[f"enc.res_skip_layers.{i}.weight_g"] = (rs, 1, 1)
+        shapes[f"enc.res_skip_layers.{i}.weight_v"] = (rs, hidden, 1)
     return shapes
 
 

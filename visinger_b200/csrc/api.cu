@@ -124,3 +124,25 @@ extern "C" int vsg_infer(const VsgPack* pack, const float* mu_p, const float* lo
   (void)launches;
   return VSG_OK;
 }
+
+extern "C" size_t vsg_posterior_workspace_bytes(const VsgPack* pack, int32_t B, int32_t T, int32_t precision) {
+  if (check_common(pack, B, T, precision) != VSG_OK || !pack->has_enc) return 0;
+  return (precision == VSG_PRECISION_BF16 ? posterior_ws_bytes_tc(pack, B, T) : posterior_ws_bytes_f32(pack, B, T)) + 1024;
+}
+
+extern "C" int vsg_posterior_forward(const VsgPack* pack, const float* x, const float* mask, const float* g,
+                                     const float* noise, float* z_q, float* stats, int32_t B, int32_t T, int32_t precision,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  VSG_TRY(check_common(pack, B, T, precision));
+  if (!pack->has_enc) return fail(VSG_EINVAL, "pack has no posterior encoder (create it with vsg_enc_pack_create)");
+  if (B == 0 || T == 0) return VSG_OK;
+  if (!x || !mask || !noise || !z_q || !stats) return fail(VSG_EINVAL, "null pointer");
+  if (!workspace) return fail(VSG_ENOMEM, "workspace is NULL");
+  DeviceGuard dg(pack->device);
+  if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
+  Workspace ws(workspace, workspace_bytes);
+  if (precision != VSG_PRECISION_BF16)
+    return posterior_forward_f32(pack, x, mask, g, noise, z_q, stats, B, T, ws, (cudaStream_t)stream);
+  return posterior_forward_tc(pack, x, mask, g, noise, z_q, stats, B, T, ws, (cudaStream_t)stream);
+}

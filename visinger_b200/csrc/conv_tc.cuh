@@ -901,6 +901,34 @@ __global__ void transpose_to_bf16_kernel(const float* __restrict__ x, __nv_bfloa
   }
 }
 
+// [B, C, T] fp32 -> [B, T, Cp] bf16 with channels [C, Cp) written as zeros (rows padded to the kernels' channel chunks).
+__global__ void transpose_pad_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int Cp, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? x[((long long)b * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < T && c < Cp) y[((long long)b * T + t) * Cp + c] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+// z = (mu + noise * exp(logs)) * mask with mu / logs the channel halves of stats [B, 2C, T]   (encoder.py:96-97)
+__global__ void posterior_sample_from_stats_kernel(const float* __restrict__ stats, const float* __restrict__ noise,
+                                                   const float* __restrict__ mask, float* __restrict__ z, int C, int T,
+                                                   long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long CT = (long long)C * T;
+  const long long b = i / CT, r = i - b * CT;
+  const int t = (int)(r % T);
+  z[i] = (stats[b * 2 * CT + r] + noise[i] * expf(stats[b * 2 * CT + CT + r])) * mask[b * T + t];
+}
+
 // [B, T, C] bf16 -> [B, C, T] fp32; flip != 0 reverses the channel order (an odd number of Flips).
 __global__ void transpose_from_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int T,
                                            int flip) {

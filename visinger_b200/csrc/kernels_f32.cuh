@@ -202,6 +202,19 @@ __global__ void prior_sample_kernel(const float* __restrict__ mu, const float* _
   z[i] = (mu[i] + noise[i] * expf(logs[i])) * mask[bt * T + t];
 }
 
+// ---- posterior sampling, modules/visinger/encoder.py:96-97: z = (mu + noise * exp(logs)) * mask with mu / logs the two
+// channel halves of stats [B, 2C, T]
+__global__ void posterior_sample_kernel(const float* __restrict__ stats, const float* __restrict__ noise,
+                                        const float* __restrict__ mask, float* __restrict__ z, int C, int T, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long CT = (long long)C * T;
+  const long long b = i / CT, r = i - b * CT;
+  const int t = (int)(r % T);
+  const float mu = stats[b * 2 * CT + r], logs = stats[b * 2 * CT + CT + r];
+  z[i] = (mu + noise[i] * expf(logs)) * mask[b * T + t];
+}
+
 // ---- y = x * mask (z_q * mask before the decoder, models/visinger.py:109-111) -----------------
 __global__ void mask_mul_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ y,
                                 int C, int T, long long total) {

@@ -199,6 +199,82 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
   return VSG_OK;
 }
 
+// PosteriorEncoder: pre Conv1d(in -> H, 1), WaveNet(H, k, dilation_rate, n_layers, gin), proj Conv1d(H -> 2 out, 1)
+// (modules/visinger/encoder.py:77-90; WaveNet layout encoder.py:131-165 as in pack_flow).
+int pack_enc(const Loader& L, const std::string& p, VsgPack* P) {
+  EncPack& e = P->enc;
+  const int Cin = e.in_channels, Co = e.out_channels, H = e.hidden, K = e.kernel, NL = e.n_layers;
+  if (Cin <= 0 || Co <= 0 || H <= 0 || NL <= 0 || K % 2 == 0 || e.dil_rate < 1 || e.gin < 0)
+    return fail(VSG_EINVAL, "bad posterior encoder config (in %d out %d hidden %d kernel %d layers %d)", Cin, Co, H, K, NL);
+  std::vector<float> W, b;
+  VSG_TRY(L.eff_weight(p + "pre", H, Cin, 1, W));
+  VSG_TRY(L.bias(p + "pre", H, b, true));
+  VSG_TRY(pack_conv_f32(L, W, b, H, Cin, 1, Identity{}, &e.pre));
+  e.in_pad = round_up(Cin, 64);
+  for (int c0 = 0; c0 < e.in_pad; c0 += 1024) {   // tensor-core packs: slabs of <= 1024 (zero-padded) input channels
+    const int cs = std::min(1024, e.in_pad - c0);
+    std::vector<float> Ws((size_t)H * cs, 0.f), bs(H, 0.f);
+    for (int co = 0; co < H; ++co)
+      for (int ci = 0; ci < cs && c0 + ci < Cin; ++ci) Ws[(size_t)co * cs + ci] = W[(size_t)co * Cin + c0 + ci];
+    if (c0 == 0) bs = b;
+    ConvWTC wt;
+    VSG_TRY(pack_conv_tc(P, Ws, bs, H, cs, 1, &wt));
+    e.pre_tc.push_back(wt);
+    e.pre_c0.push_back(c0);
+  }
+  FlowLayer& fl = e.wn;
+  fl.in_layers.resize(NL); fl.res_skip.resize(NL); fl.in_tc.resize(NL); fl.res_tc.resize(NL); fl.skip_tc.resize(NL);
+  for (int i = 0; i < NL; ++i) {
+    const std::string pi = p + "enc.in_layers." + std::to_string(i);
+    VSG_TRY(L.eff_weight(pi, 2 * H, H, K, W));
+    VSG_TRY(L.bias(pi, 2 * H, b, true));
+    VSG_TRY(pack_conv_f32(L, W, b, 2 * H, H, K, GateInterleave{H}, &fl.in_layers[i]));
+    {
+      GateInterleave gi{H};
+      std::vector<float> Wg(W.size()), bg(b.size());
+      for (int co = 0; co < 2 * H; ++co) {
+        bg[gi(co)] = b[co];
+        memcpy(&Wg[(size_t)gi(co) * H * K], &W[(size_t)co * H * K], (size_t)H * K * sizeof(float));
+      }
+      VSG_TRY(pack_conv_tc(P, Wg, bg, 2 * H, H, K, &fl.in_tc[i]));
+    }
+    const int rs = (i < NL - 1) ? 2 * H : H;
+    const std::string pr = p + "enc.res_skip_layers." + std::to_string(i);
+    VSG_TRY(L.eff_weight(pr, rs, H, 1, W));
+    VSG_TRY(L.bias(pr, rs, b, true));
+    VSG_TRY(pack_conv_f32(L, W, b, rs, H, 1, Identity{}, &fl.res_skip[i]));
+    if (i < NL - 1) {
+      std::vector<float> Wr(W.begin(), W.begin() + (size_t)H * H), br(b.begin(), b.begin() + H);
+      std::vector<float> Ws(W.begin() + (size_t)H * H, W.end()), bs(b.begin() + H, b.end());
+      VSG_TRY(pack_conv_tc(P, Wr, br, H, H, 1, &fl.res_tc[i]));
+      VSG_TRY(pack_conv_tc(P, Ws, bs, H, H, 1, &fl.skip_tc[i]));
+    } else {
+      VSG_TRY(pack_conv_tc(P, W, b, H, H, 1, &fl.skip_tc[i]));
+    }
+  }
+  if (e.gin > 0) {
+    const int O = 2 * H * NL, I = e.gin;
+    VSG_TRY(L.eff_weight(p + "enc.cond_layer", O, I, 1, W));
+    VSG_TRY(L.bias(p + "enc.cond_layer", O, b, true));
+    std::vector<float> Wp(W.size()), bp(b.size());
+    GateInterleave gi{H};
+    for (int l = 0; l < NL; ++l)
+      for (int cc = 0; cc < 2 * H; ++cc) {
+        const int src = l * 2 * H + cc, dst = l * 2 * H + gi(cc);
+        bp[dst] = b[src];
+        memcpy(&Wp[(size_t)dst * I], &W[(size_t)src * I], I * sizeof(float));
+      }
+    VSG_TRY(L.upload(Wp, &fl.cond_w));
+    VSG_TRY(L.upload(bp, &fl.cond_b));
+  }
+  VSG_TRY(L.eff_weight(p + "proj", 2 * Co, H, 1, W));
+  VSG_TRY(L.bias(p + "proj", 2 * Co, b, true));
+  VSG_TRY(pack_conv_f32(L, W, b, 2 * Co, H, 1, Identity{}, &e.proj));
+  VSG_TRY(pack_conv_tc(P, W, b, 2 * Co, H, 1, &e.proj_tc));
+  P->has_enc = true;
+  return VSG_OK;
+}
+
 int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
   const VsgConfig& c = P->cfg;
   const int C0 = c.dec_initial_channel, UIC = c.dec_upsample_initial_channel;
@@ -368,6 +444,49 @@ extern "C" int vsg_pack_create(const VsgConfig* cfg, const VsgTensor* weights, i
   if (cfg->flow_n_flows > 0) rc = pack_flow(L, flow_prefix ? flow_prefix : "", P);
   if (rc == VSG_OK && cfg->dec_n_ups > 0) rc = pack_decoder(L, dec_prefix ? dec_prefix : "", P);
   if (rc == VSG_OK && !P->has_flow && !P->has_dec) rc = fail(VSG_EINVAL, "config selects neither flow nor decoder");
+  if (rc != VSG_OK) {
+    vsg_pack_destroy(P);
+    return rc;
+  }
+  *out = P;
+  return VSG_OK;
+}
+
+extern "C" int vsg_enc_pack_create(const VsgEncConfig* cfg, const VsgTensor* weights, int32_t n_weights, const char* prefix,
+                                   int32_t device, VsgPack** out) {
+  if (!cfg || !out || (!weights && n_weights > 0)) return fail(VSG_EINVAL, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  VSG_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(VSG_EINVAL, "device %d out of range (%d visible)", device, ndev);
+  struct Restore { int prev = -1; ~Restore() { if (prev >= 0) cudaSetDevice(prev); } } restore;
+  VSG_CUDA_TRY(cudaGetDevice(&restore.prev));
+  VSG_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VSG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(VSG_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  VsgPack* P = new VsgPack();
+  memset(&P->cfg, 0, sizeof(P->cfg));
+  P->device = device;
+  P->sm_count = prop.multiProcessorCount;
+  P->enc.in_channels = cfg->in_channels; P->enc.out_channels = cfg->out_channels; P->enc.hidden = cfg->hidden_channels;
+  P->enc.kernel = cfg->kernel_size; P->enc.dil_rate = cfg->dilation_rate; P->enc.n_layers = cfg->n_layers;
+  P->enc.gin = cfg->gin_channels;
+  Loader L;
+  L.pack = P;
+  for (int i = 0; i < n_weights; ++i) {
+    if (!weights[i].name || !weights[i].data || weights[i].ndim < 0 || weights[i].ndim > 4) {
+      delete P;
+      return fail(VSG_EINVAL, "weight table entry %d is malformed", i);
+    }
+    HostTensor t;
+    t.data = weights[i].data;
+    t.shape.assign(weights[i].shape, weights[i].shape + weights[i].ndim);
+    L.m[weights[i].name] = t;
+  }
+  const int rc = pack_enc(L, prefix ? prefix : "", P);
   if (rc != VSG_OK) {
     vsg_pack_destroy(P);
     return rc;

@@ -28,4 +28,13 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
 int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float* wav, int B, int T, Workspace& ws,
                          cudaStream_t st, bool x3);
 
+
+// PosteriorEncoder (f32: run_f32.cu, bf16: run_tc.cu)
+size_t posterior_ws_bytes_f32(const VsgPack* P, int B, int T);
+size_t posterior_ws_bytes_tc(const VsgPack* P, int B, int T);
+int posterior_forward_f32(const VsgPack* P, const float* x, const float* mask, const float* g, const float* noise,
+                          float* z, float* stats, int B, int T, Workspace& ws, cudaStream_t st);
+int posterior_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, const float* noise,
+                         float* z, float* stats, int B, int T, Workspace& ws, cudaStream_t st);
+
 }  // namespace vsg

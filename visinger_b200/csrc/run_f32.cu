@@ -134,6 +134,66 @@ int flow_forward_f32(const VsgPack* P, const float* x, const float* mask, const 
   return VSG_OK;
 }
 
+size_t posterior_ws_bytes_f32(const VsgPack* P, int B, int T) {
+  const EncPack& e = P->enc;
+  return align256((size_t)B * 2 * e.hidden * e.n_layers * sizeof(float)) + 3 * align256((size_t)B * e.hidden * T * sizeof(float));
+}
+
+// PosteriorEncoder.forward, modules/visinger/encoder.py:92-98.
+int posterior_forward_f32(const VsgPack* P, const float* x, const float* mask, const float* g, const float* noise,
+                          float* z, float* stats, int B, int T, Workspace& ws, cudaStream_t st) {
+  const EncPack& e = P->enc;
+  const int H = e.hidden, NL = e.n_layers, K = e.kernel, Cin = e.in_channels, Co = e.out_channels;
+  const int condO = 2 * H * NL;
+  float* cond = ws.take<float>((size_t)B * condO);
+  float* h = ws.take<float>((size_t)B * H * T);
+  float* acts = ws.take<float>((size_t)B * H * T);
+  float* out = ws.take<float>((size_t)B * H * T);
+  if (ws.overflow) return fail(VSG_ENOMEM, "posterior workspace too small: need %zu bytes", ws.off);
+  if (e.gin > 0) {
+    if (!g) return fail(VSG_EINVAL, "posterior encoder was built with gin_channels=%d but g is NULL", e.gin);
+    VSG_TRY(launch_cond(e.wn.cond_w, e.wn.cond_b, g, cond, condO, e.gin, B, st));
+  }
+  const long long HT = (long long)H * T;
+  {  // h = pre(x) * mask                                            encoder.py:93
+    ConvF32 p = base_conv(e.pre, x, (long long)Cin * T, T, T, 0, 1);
+    p.y = h; p.y_bs = HT; p.y_cs = T; p.mask = mask; p.mask_bs = T;
+    VSG_TRY(launch_conv_f32(p, B, st));
+  }
+  int dil = 1;
+  for (int i = 0; i < NL; ++i) {   // WaveNet                        encoder.py:174-195
+    const int pad = (K * dil - dil) / 2;
+    {
+      ConvF32 p = base_conv(e.wn.in_layers[i], h, HT, T, T, -pad, dil);
+      p.epi = EPI_GATE;
+      if (e.gin > 0) { p.bcond = cond + (size_t)i * 2 * H; p.bcond_bs = condO; }
+      p.y = acts; p.y_bs = HT; p.y_cs = T;
+      VSG_TRY(launch_conv_f32(p, B, st));
+    }
+    {
+      ConvF32 p = base_conv(e.wn.res_skip[i], acts, HT, T, T, 0, 1);
+      p.epi = EPI_RES_SKIP;
+      const bool last = (i == NL - 1);
+      p.rs_split = last ? 0 : H;
+      p.y = h; p.y_bs = HT; p.y_cs = T;
+      p.y2 = out; p.y2_bs = HT; p.y2_cs = T;
+      p.y2_first = (i == 0); p.y2_mask = last;
+      p.mask = mask; p.mask_bs = T;
+      VSG_TRY(launch_conv_f32(p, B, st));
+    }
+    dil *= e.dil_rate;
+  }
+  {  // stats = proj(h) * mask                                        encoder.py:95
+    ConvF32 p = base_conv(e.proj, out, HT, T, T, 0, 1);
+    p.y = stats; p.y_bs = (long long)2 * Co * T; p.y_cs = T; p.mask = mask; p.mask_bs = T;
+    VSG_TRY(launch_conv_f32(p, B, st));
+  }
+  const long long n = (long long)B * Co * T;   // z = (mu + noise * exp(logs)) * mask   encoder.py:96-97
+  posterior_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats, noise, mask, z, Co, T, n);
+  VSG_LAUNCH_CHECK("posterior_sample_kernel");
+  return VSG_OK;
+}
+
 static size_t dec_max_elems(const VsgPack* P, int B, int T) {
   size_t m = (size_t)B * P->cfg.dec_upsample_initial_channel * T;
   long long L = T;

@@ -977,6 +977,92 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
   return VSG_OK;
 }
 
+size_t posterior_ws_bytes_tc(const VsgPack* P, int B, int T) {
+  const EncPack& e = P->enc;
+  size_t n = 0;
+  n += align256((size_t)B * 2 * e.hidden * e.n_layers * sizeof(float));          // cond
+  n += align256((size_t)B * T * e.in_pad * 2);                                     // input, channels-last, padded rows
+  n += 3 * align256((size_t)B * T * e.hidden * 2);                                 // h, acts, out
+  n += align256((size_t)B * T * 2 * e.out_channels * 2);                           // stats, channels-last
+  return n + 512;
+}
+
+// PosteriorEncoder.forward (modules/visinger/encoder.py:92-98) on the tensor-core kernels: the same WaveNet launches as
+// the flow; `pre` contracts the (padded) input channels in slabs of <= 1024, chained through the residual input.
+int posterior_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, const float* noise,
+                         float* z, float* stats, int B, int T, Workspace& ws, cudaStream_t st) {
+  const EncPack& en = P->enc;
+  const int H = en.hidden, NL = en.n_layers, K = en.kernel, Cin = en.in_channels, CinP = en.in_pad, Co = en.out_channels;
+  if (en.pre_tc.empty() || !en.pre_tc[0].has_tmap || !en.proj_tc.has_tmap || (int)en.wn.in_tc.size() != NL ||
+      !en.wn.in_tc[0].has_tmap)
+    return fail(VSG_EUNSUPPORTED, "bf16 posterior encoder needs hidden and 2 * out channels to be multiples of 16");
+  const int condO = 2 * H * NL;
+  typedef __nv_bfloat16 bf;
+  float* cond = ws.take<float>((size_t)B * condO);
+  bf* u = ws.take<bf>((size_t)B * T * CinP);
+  bf* h = ws.take<bf>((size_t)B * T * H);
+  bf* acts = ws.take<bf>((size_t)B * T * H);
+  bf* out = ws.take<bf>((size_t)B * T * H);
+  bf* sb = ws.take<bf>((size_t)B * T * 2 * Co);
+  int* err = ws.take<int>(1);
+  if (ws.overflow) return fail(VSG_ENOMEM, "posterior workspace too small: need %zu bytes", ws.off);
+  VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+  const TCOptions opt = g_default_opts;
+  if (en.gin > 0) {
+    if (!g) return fail(VSG_EINVAL, "posterior encoder was built with gin_channels=%d but g is NULL", en.gin);
+    VSG_TRY(launch_cond(en.wn.cond_w, en.wn.cond_b, g, cond, condO, en.gin, B, st));
+  }
+  {
+    dim3 grid((T + 31) / 32, (CinP + 31) / 32, B), block(32, 8);
+    transpose_pad_to_bf16_kernel<<<grid, block, 0, st>>>(x, u, Cin, CinP, T);
+    VSG_LAUNCH_CHECK("transpose_pad_to_bf16_kernel");
+  }
+  for (size_t s = 0; s < en.pre_tc.size(); ++s) {   // h = pre(x) * mask, one launch per input-channel slab
+    const bool last = (s + 1 == en.pre_tc.size());
+    EpiTC e;
+    e.bias = en.pre_tc[s].bias;                      // (only slab 0 carries the bias)
+    e.add0 = s > 0 ? h : nullptr;
+    e.mask = last ? mask : nullptr;
+    e.out_raw = h;
+    VSG_TRY(launch_conv_tc(P, en.pre_tc[s], u + en.pre_c0[s], B, T, 0, 1, T, 1, 0, T, e, opt, err, st, CinP));
+  }
+  int dil = 1;
+  for (int i = 0; i < NL; ++i) {
+    const bool last = (i == NL - 1);
+    {
+      EpiTC e;
+      e.mode = EPI_TC_GATE; e.bias = en.wn.in_tc[i].bias; e.out_raw = acts;
+      if (en.gin > 0) { e.bcond = cond + (size_t)i * 2 * H; e.bcond_bs = condO; }
+      VSG_TRY(launch_conv_tc(P, en.wn.in_tc[i], h, B, T, -((K * dil - dil) / 2), dil, T, 1, 0, T, e, opt, err, st));
+    }
+    if (!last) {
+      EpiTC e;
+      e.bias = en.wn.res_tc[i].bias; e.add0 = h; e.mask = mask; e.out_raw = h;
+      VSG_TRY(launch_conv_tc(P, en.wn.res_tc[i], acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+    }
+    {
+      EpiTC e;
+      e.bias = en.wn.skip_tc[i].bias; e.add0 = (i > 0) ? out : nullptr; e.mask = last ? mask : nullptr; e.out_raw = out;
+      VSG_TRY(launch_conv_tc(P, en.wn.skip_tc[i], acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+    }
+    dil *= en.dil_rate;
+  }
+  {  // stats = proj(h) * mask
+    EpiTC e;
+    e.bias = en.proj_tc.bias; e.mask = mask; e.out_raw = sb;
+    VSG_TRY(launch_conv_tc(P, en.proj_tc, out, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+  }
+  {
+    dim3 grid((T + 31) / 32, (2 * Co + 31) / 32, B), block(32, 8);
+    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(sb, stats, 2 * Co, T, 0);
+    VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
+  }
+  const long long n = (long long)B * Co * T;
+  posterior_sample_from_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats, noise, mask, z, Co, T, n);
+  VSG_LAUNCH_CHECK("posterior_sample_from_stats_kernel");
+  return VSG_OK;
+}
+
 // ---- L2-resident batch tiling --------------------------------------------------------------------------------
 // Un-fused, one stage of the decoder streams 54 tensor passes through memory.  The stage tensors of
 // ONE utterance are small (<= 9.6 MB in bf16), so each upsampling stage is run over sub-batches whose intermediates

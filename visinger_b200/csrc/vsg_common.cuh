@@ -86,6 +86,17 @@ struct FlowLayer {
   std::vector<ConvWTC> skip_tc;     // res_skip rows [H, 2H) (all H rows for the last layer)
 };
 
+// PosteriorEncoder (modules/visinger/encoder.py:76-101): pre (1x1) -> WaveNet -> proj (1x1) -> reparameterised sample.
+struct EncPack {
+  int in_channels = 0, out_channels = 0, hidden = 0, kernel = 0, dil_rate = 1, n_layers = 0, gin = 0;
+  int in_pad = 0;                   // in_channels rounded up to a multiple of 64: row width of the bf16 channels-last input
+  ConvW32 pre, proj;
+  FlowLayer wn;                     // in_layers / res_skip / cond and their tensor-core packs (pre / post unused)
+  std::vector<ConvWTC> pre_tc;      // pre split into input-channel slabs of <= 1024 channels (the kernel's chunk table)
+  std::vector<int> pre_c0;          // first input channel of each slab
+  ConvWTC proj_tc;
+};
+
 struct ResBlockPack {
   int kernel = 0;
   std::vector<int> dilations;
@@ -113,7 +124,8 @@ struct VsgPack {
   int device = 0;
   int hop = 0;
   int sm_count = 148;
-  bool has_flow = false, has_dec = false;
+  bool has_flow = false, has_dec = false, has_enc = false;
+  vsg::EncPack enc;
   std::vector<void*> allocs;
   // flow
   std::vector<vsg::FlowLayer> flow_layers;

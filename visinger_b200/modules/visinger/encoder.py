@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ... import _lib
 from ..rel_transformer import RelativeEncoder, SinusoidalPositionalEmbedding
 from .flow import WaveNet
 
@@ -79,17 +80,80 @@ class FramePriorNetwork(nn.Module):
 
 
 class PosteriorEncoder(nn.Module):
-    """Training-only in the reference (models/visinger.py:94).  Parameter container so full checkpoints load."""
+    """Reference `PosteriorEncoder` (modules/visinger/encoder.py:76-101) on the B200 kernels: `pre` (1x1) -> WaveNet ->
+    `proj` (1x1) -> reparameterised sample, one `vsg_posterior_forward` call.  Same
+    constructor, state-dict keys and `forward(x, nonpadding, g)` -> `(z_q, mu_q, logs_q)` contract; `noise` (defaults to
+    `torch.randn_like(mu_q)`, encoder.py:97) can be injected for parity tests.  `precision`: "fp32" (FFMA parity
+    kernels) or "bf16" (tcgen05)."""
 
-    def __init__(self, in_channels, out_channels, hidden_channels, kernel_size, dilation_rate, n_layers, gin_channels):
+    def __init__(self, in_channels, out_channels, hidden_channels, kernel_size, dilation_rate, n_layers, gin_channels,
+                 precision="fp32"):
         super().__init__()
+        self.in_channels = in_channels
         self.out_channels = out_channels
+        self.hidden_channels = hidden_channels
+        self.kernel_size = kernel_size
+        self.dilation_rate = dilation_rate
+        self.n_layers = n_layers
+        self.gin_channels = gin_channels
+        self.precision = precision
         self.pre = nn.Conv1d(in_channels, hidden_channels, 1)
         self.enc = WaveNet(hidden_channels, kernel_size, dilation_rate, n_layers, gin_channels=gin_channels)
         self.proj = nn.Conv1d(hidden_channels, out_channels * 2, 1)
+        self._vsg_pack = None
+        self._vsg_key = None
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("PosteriorEncoder is training-only; visinger_b200 implements the inference path")
+    def _pack(self):
+        params = list(self.parameters())
+        dev = params[0].device
+        key = (str(dev),) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._vsg_pack is None or self._vsg_key != key:
+            c = _lib.VsgEncConfig(self.in_channels, self.out_channels, self.hidden_channels, self.kernel_size,
+                                  self.dilation_rate, self.n_layers, self.gin_channels)
+            self._vsg_pack = _lib.EncPack(c, dict(self.state_dict()), "", dev)
+            self._vsg_key = key
+        return self._vsg_pack
+
+    @torch.no_grad()
+    def forward(self, x, nonpadding, g=None, noise=None):
+        """x [B, in_channels, T], nonpadding [B, 1, T], g [B, gin, 1] -> (z_q, mu_q, logs_q), each [B, out_channels, T]."""
+        _lib.require_cuda(x, "x")
+        _lib.require_cuda(nonpadding, "nonpadding")
+        if x.dim() != 3 or x.shape[1] != self.in_channels:
+            raise RuntimeError(f"expected x of shape [B, {self.in_channels}, T], got {tuple(x.shape)}")
+        B, _, T = x.shape
+        if nonpadding.numel() != B * T:
+            raise RuntimeError(f"expected nonpadding of shape [B, 1, T] = [{B}, 1, {T}], got {tuple(nonpadding.shape)}")
+        if self.gin_channels != 0:
+            if g is None:
+                raise RuntimeError("this encoder was built with gin_channels != 0; g is required")
+            _lib.require_cuda(g, "g")
+            if g.numel() != B * self.gin_channels:
+                raise RuntimeError(f"expected g of shape [B, {self.gin_channels}, 1], got {tuple(g.shape)}")
+        if noise is None:
+            noise = torch.randn(B, self.out_channels, T, device=x.device, dtype=torch.float32)
+        elif tuple(noise.shape) != (B, self.out_channels, T):
+            raise RuntimeError(f"expected noise of shape {(B, self.out_channels, T)}, got {tuple(noise.shape)}")
+        pack = self._pack()
+        prec = _lib.precision_code(self.precision)
+        xc, mc, nc = _lib.as_f32c(x), _lib.as_f32c(nonpadding), _lib.as_f32c(noise)
+        gc = _lib.as_f32c(g) if (g is not None and self.gin_channels != 0) else None
+        z = torch.empty(B, self.out_channels, T, device=x.device, dtype=torch.float32)
+        stats = torch.empty(B, 2 * self.out_channels, T, device=x.device, dtype=torch.float32)
+        if B and T:
+            with torch.cuda.device(x.device):
+                ws = _lib.workspace(x.device, pack.workspace_bytes(B, T, prec))
+                rc = _lib.lib().vsg_posterior_forward(pack.handle, xc.data_ptr(), mc.data_ptr(),
+                                                      gc.data_ptr() if gc is not None else None, nc.data_ptr(), z.data_ptr(),
+                                                      stats.data_ptr(), B, T, prec, ws.data_ptr(), ws.numel(),
+                                                      _lib.stream_ptr(x.device))
+            _lib.check(rc, "vsg_posterior_forward")
+        mu_q, logs_q = torch.split(stats, self.out_channels, dim=1)
+        return z, mu_q, logs_q
+
+    def remove_weight_norm(self):
+        self.enc.remove_weight_norm()
+        self._vsg_pack = None
 
 
 # ---- predictors (reference: modules/visinger/predictor.py) ------------------------------------------------------------
