@@ -208,6 +208,38 @@ int vsg_posterior_forward(const VsgPack* pack, const float* x, const float* mask
                           float* z_q, float* stats, int32_t B, int32_t T, int32_t precision,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * RelativeEncoder(hidden_channels, filter_channels, n_heads, n_layers, kernel_size, p_dropout, window_size, block_length,
+ * pre_ln=False, gin_channels)                                             modules/rel_transformer.py:257-320
+ * -- the frame-rate stacks of the prior network (PitchPredictor, modules/visinger/predictor.py:7-19; FramePriorNetwork,
+ * modules/visinger/encoder.py:58-73) and the phoneme-rate stack of the TextEncoder.  Post-LN
+ * only (pre_ln = False, the reference's default and the only variant VISinger builds), block_length = None, eval mode.
+ */
+typedef struct VsgRelEncConfig {
+  int32_t hidden_channels;
+  int32_t filter_channels;
+  int32_t n_heads;
+  int32_t n_layers;
+  int32_t kernel_size;     /* FFN conv_1 taps */
+  int32_t window_size;     /* relative-position window (4) */
+  int32_t gin_channels;    /* 0 = no pre_net */
+} VsgRelEncConfig;
+
+int vsg_relenc_pack_create(const VsgRelEncConfig* cfg, const VsgTensor* weights, int32_t n_weights, const char* prefix,
+                           int32_t device, VsgPack** out);
+size_t vsg_relenc_workspace_bytes(const VsgPack* pack, int32_t B, int32_t T, int32_t g_per_frame, int32_t precision);
+
+/*
+ * RelativeEncoder.forward(x, x_mask, g)                                    modules/rel_transformer.py:286-320
+ * x, y: [B, hidden, T] (y may alias x); mask: [B, 1, T]; g: NULL, or the condition the reference feeds to pre_net:
+ * [B, gin, 1] (g_per_frame == 0, e.g. the speaker embedding of the PitchPredictor) or [B, gin, T] (g_per_frame != 0,
+ * e.g. the frame-level f0 of the FramePriorNetwork).  Attention: full T x T softmax per head with +-window relative-
+ * position key / value embeddings, masked scores filled with -1e4 (:167), channel LayerNorm eps 1e-4.
+ */
+int vsg_relenc_forward(const VsgPack* pack, const float* x, const float* mask, const float* g, int32_t g_per_frame,
+                       float* y, int32_t B, int32_t T, int32_t precision, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* Samples produced per latent frame (prod(upsample_rates)); 0 if the pack has no decoder. */
 int32_t vsg_hop_size(const VsgPack* pack);
 

@@ -31,6 +31,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
+import math
+
 import torch
 import torch.nn.functional as F
 
@@ -114,6 +116,113 @@ def wavenet(sd: StateDict, prefix: str, x, x_mask, g, *, hidden: int, kernel_siz
         else:
             out = out + rs
     return out * x_mask
+
+
+# --------------------------------------------------------------------------------------
+# f1: relative-position transformer encoder
+# --------------------------------------------------------------------------------------
+def channel_layer_norm(x, gamma, beta, eps: float = 1e-4):
+    """modules/rel_transformer.py:33-42 LayerNorm.forward over dim 1 of [B, C, T]."""
+    mean = torch.mean(x, 1, keepdim=True)
+    variance = torch.mean((x - mean) ** 2, 1, keepdim=True)
+    x = (x - mean) * torch.rsqrt(variance + eps)
+    return x * gamma.view(1, -1, 1) + beta.view(1, -1, 1)
+
+
+def rel_attention(sd: StateDict, prefix: str, x, attn_mask, *, n_heads: int, window: int):
+    """modules/rel_transformer.py:123-177 MultiHeadAttention.forward (self-attention, heads_share=True, eval mode).  The
+    reference moves the relative-position logits / weights between relative and absolute indexing with a pad-and-
+    reshape trick (:218-243); stated directly: s_ij += q_i . Ek[j-i+w] and o_i += p_ij Ev[j-i+w] for |j-i| <= w."""
+    q = F.conv1d(x, sd[prefix + "conv_q.weight"], sd[prefix + "conv_q.bias"])
+    k = F.conv1d(x, sd[prefix + "conv_k.weight"], sd[prefix + "conv_k.bias"])
+    v = F.conv1d(x, sd[prefix + "conv_v.weight"], sd[prefix + "conv_v.bias"])
+    b, d, t = q.shape
+    dk = d // n_heads
+    q = q.view(b, n_heads, dk, t).transpose(2, 3)
+    k = k.view(b, n_heads, dk, t).transpose(2, 3)
+    v = v.view(b, n_heads, dk, t).transpose(2, 3)
+    scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(dk)
+    ek, ev = sd[prefix + "emb_rel_k"][0], sd[prefix + "emb_rel_v"][0]           # [2w+1, dk]
+    idx = torch.arange(t)
+    rel = idx[None, :] - idx[:, None] + window                                   # [t, t]: j - i + w
+    inside = (rel >= 0) & (rel <= 2 * window)
+    relc = rel.clamp(0, 2 * window)
+    qe = torch.matmul(q, ek.t())                                                 # [b, h, t, 2w+1]
+    local = torch.gather(qe, 3, relc.expand(b, n_heads, t, t)) * inside
+    scores = scores + local / math.sqrt(dk)
+    scores = scores.masked_fill(attn_mask == 0, -1e4)
+    p = F.softmax(scores, dim=-1)
+    out = torch.matmul(p, v)
+    pw = torch.zeros(b, n_heads, t, 2 * window + 1, dtype=p.dtype)
+    pw.scatter_add_(3, relc.expand(b, n_heads, t, t), p * inside)
+    out = out + torch.matmul(pw, ev)
+    out = out.transpose(2, 3).contiguous().view(b, d, t)
+    return F.conv1d(out, sd[prefix + "conv_o.weight"], sd[prefix + "conv_o.bias"])
+
+
+def rel_encoder(sd: StateDict, x, x_mask, g=None, *, n_heads: int = 2, n_layers: int = 4, kernel_size: int = 9,
+                window: int = 4, prefix: str = ""):
+    """modules/rel_transformer.py:286-320 RelativeEncoder.forward (pre_ln=False) with FFN :337-345 (ReLU)."""
+    attn_mask = x_mask.unsqueeze(2) * x_mask.unsqueeze(-1)
+    if g is not None:
+        g = F.conv1d(g, sd[prefix + "pre_net.weight"], sd[prefix + "pre_net.bias"])
+    for i in range(n_layers):
+        if g is not None:
+            x = x + g
+        x = x * x_mask
+        y = rel_attention(sd, f"{prefix}attn_layers.{i}.", x, attn_mask, n_heads=n_heads, window=window)
+        x = channel_layer_norm(x + y, sd[f"{prefix}norm_layers_1.{i}.gamma"], sd[f"{prefix}norm_layers_1.{i}.beta"])
+        h = F.conv1d(x * x_mask, sd[f"{prefix}ffn_layers.{i}.conv_1.weight"], sd[f"{prefix}ffn_layers.{i}.conv_1.bias"],
+                     padding=kernel_size // 2)
+        h = torch.relu(h)
+        y = F.conv1d(h * x_mask, sd[f"{prefix}ffn_layers.{i}.conv_2.weight"], sd[f"{prefix}ffn_layers.{i}.conv_2.bias"])
+        x = channel_layer_norm(x + y, sd[f"{prefix}norm_layers_2.{i}.gamma"], sd[f"{prefix}norm_layers_2.{i}.beta"])
+    return x * x_mask
+
+
+def rel_encoder_param_shapes(hidden=192, filter_channels=768, n_heads=2, n_layers=4, kernel_size=9, window=4, gin=None):
+    """State-dict layout of RelativeEncoder (modules/rel_transformer.py:272-284)."""
+    dk = hidden // n_heads
+    shapes = {}
+    for i in range(n_layers):
+        a = f"attn_layers.{i}."
+        for nm in ("conv_q", "conv_k", "conv_v", "conv_o"):
+            shapes[a + nm + ".weight"] = (hidden, hidden, 1)
+            shapes[a + nm + ".bias"] = (hidden,)
+        shapes[a + "emb_rel_k"] = (1, 2 * window + 1, dk)
+        shapes[a + "emb_rel_v"] = (1, 2 * window + 1, dk)
+        shapes[f"ffn_layers.{i}.conv_1.weight"] = (filter_channels, hidden, kernel_size)
+        shapes[f"ffn_layers.{i}.conv_1.bias"] = (filter_channels,)
+        shapes[f"ffn_layers.{i}.conv_2.weight"] = (hidden, filter_channels, 1)
+        shapes[f"ffn_layers.{i}.conv_2.bias"] = (hidden,)
+        for j in (1, 2):
+            shapes[f"norm_layers_{j}.{i}.gamma"] = (hidden,)
+            shapes[f"norm_layers_{j}.{i}.beta"] = (hidden,)
+    if gin:
+        shapes["pre_net.weight"] = (hidden, gin, 1)
+        shapes["pre_net.bias"] = (hidden,)
+    return shapes
+
+
+def synth_rel_encoder_state_dict(shapes: Dict[str, tuple], seed: int) -> StateDict:
+    """Deterministic weights for the encoder: conv weights U(+-1/sqrt(fan_in)), biases U(+-0.05), relative embeddings
+    N(0, 1/dk), LayerNorm gamma around 1 / beta around 0 (non-trivial, unlike the ones / zeros default init)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: StateDict = {}
+    for name in sorted(shapes):
+        shp = shapes[name]
+        if name.endswith(".gamma"):
+            sd[name] = 1.0 + 0.1 * (torch.rand(shp, generator=gen) * 2 - 1)
+        elif name.endswith(".beta") or name.endswith(".bias"):
+            sd[name] = (torch.rand(shp, generator=gen) * 2 - 1) * 0.05
+        elif "emb_rel" in name:
+            sd[name] = torch.randn(shp, generator=gen) * shp[-1] ** -0.5
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            sd[name] = (torch.rand(shp, generator=gen) * 2 - 1) * (1.0 / fan_in) ** 0.5
+    return sd
 
 
 # --------------------------------------------------------------------------------------

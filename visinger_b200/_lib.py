@@ -70,6 +70,12 @@ class VsgEncConfig(ctypes.Structure):
                 ("gin_channels", ctypes.c_int32)]
 
 
+class VsgRelEncConfig(ctypes.Structure):
+    _fields_ = [("hidden_channels", ctypes.c_int32), ("filter_channels", ctypes.c_int32), ("n_heads", ctypes.c_int32),
+                ("n_layers", ctypes.c_int32), ("kernel_size", ctypes.c_int32), ("window_size", ctypes.c_int32),
+                ("gin_channels", ctypes.c_int32)]
+
+
 class VsgTensor(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.c_void_p), ("ndim", ctypes.c_int32),
                 ("shape", ctypes.c_int64 * 4)]
@@ -189,6 +195,13 @@ def lib() -> ctypes.CDLL:
         L.vsg_posterior_workspace_bytes.argtypes = [vp, i32, i32, i32]
         L.vsg_posterior_forward.restype = ctypes.c_int
         L.vsg_posterior_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, ctypes.c_size_t, vp]
+        L.vsg_relenc_pack_create.restype = ctypes.c_int
+        L.vsg_relenc_pack_create.argtypes = [ctypes.POINTER(VsgRelEncConfig), ctypes.POINTER(VsgTensor), i32, ctypes.c_char_p,
+                                             i32, ctypes.POINTER(ctypes.c_void_p)]
+        L.vsg_relenc_workspace_bytes.restype = ctypes.c_size_t
+        L.vsg_relenc_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
+        L.vsg_relenc_forward.restype = ctypes.c_int
+        L.vsg_relenc_forward.argtypes = [vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, ctypes.c_size_t, vp]
         L.vsg_debug_resblock_bf16.restype = ctypes.c_int
         L.vsg_debug_resblock_bf16.argtypes = [vp, vp, vp, i32, vp, vp, ctypes.c_float, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32]
         L.vsg_debug_set_plan.restype = ctypes.c_int
@@ -307,6 +320,37 @@ class EncPack:
 
     def workspace_bytes(self, B: int, T: int, precision: int) -> int:
         return int(lib().vsg_posterior_workspace_bytes(self._h, B, T, precision))
+
+    def __del__(self):
+        try:
+            if self._h and _lib is not None:
+                _lib.vsg_pack_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+class RelEncPack:
+    """Owner of the VsgPack* of a RelativeEncoder (vsg_relenc_pack_create)."""
+
+    def __init__(self, cfg: VsgRelEncConfig, state_dict: Dict[str, torch.Tensor], prefix: str, device: torch.device):
+        self._h = ctypes.c_void_p()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("visinger_b200: weights must live on a CUDA device; there is no CPU fallback")
+        host = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items() if k.startswith(prefix)}
+        arr, keep = _weight_table(host)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        rc = lib().vsg_relenc_pack_create(ctypes.byref(cfg), arr, len(host), prefix.encode(), idx, ctypes.byref(self._h))
+        check(rc, "vsg_relenc_pack_create")
+        self.index = idx
+
+    @property
+    def handle(self):
+        return self._h
+
+    def workspace_bytes(self, B: int, T: int, g_per_frame: int, precision: int) -> int:
+        return int(lib().vsg_relenc_workspace_bytes(self._h, B, T, g_per_frame, precision))
 
     def __del__(self):
         try:

@@ -146,3 +146,23 @@ extern "C" int vsg_posterior_forward(const VsgPack* pack, const float* x, const 
     return posterior_forward_f32(pack, x, mask, g, noise, z_q, stats, B, T, ws, (cudaStream_t)stream);
   return posterior_forward_tc(pack, x, mask, g, noise, z_q, stats, B, T, ws, (cudaStream_t)stream);
 }
+
+extern "C" size_t vsg_relenc_workspace_bytes(const VsgPack* pack, int32_t B, int32_t T, int32_t g_per_frame, int32_t precision) {
+  if (check_common(pack, B, T, precision) != VSG_OK || !pack->has_relenc) return 0;
+  return relenc_ws_bytes_f32(pack, B, T, g_per_frame) + 1024;
+}
+
+extern "C" int vsg_relenc_forward(const VsgPack* pack, const float* x, const float* mask, const float* g, int32_t g_per_frame,
+                                  float* y, int32_t B, int32_t T, int32_t precision, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  g_launches = 0;
+  VSG_TRY(check_common(pack, B, T, precision));
+  if (!pack->has_relenc) return fail(VSG_EINVAL, "pack has no relative-position encoder (create it with vsg_relenc_pack_create)");
+  if (B == 0 || T == 0) return VSG_OK;
+  if (!x || !mask || !y) return fail(VSG_EINVAL, "null pointer");
+  if (!workspace) return fail(VSG_ENOMEM, "workspace is NULL");
+  DeviceGuard dg(pack->device);
+  if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
+  Workspace ws(workspace, workspace_bytes);
+  return relenc_forward_f32(pack, x, mask, g, g_per_frame, y, B, T, ws, (cudaStream_t)stream);
+}

@@ -275,6 +275,67 @@ int pack_enc(const Loader& L, const std::string& p, VsgPack* P) {
   return VSG_OK;
 }
 
+// RelativeEncoder state-dict (modules/rel_transformer.py:272-284): attn_layers.N.{conv_q,conv_k,conv_v,conv_o}.{weight,bias},
+// attn_layers.N.{emb_rel_k,emb_rel_v} [1][2w+1][dk], norm_layers_{1,2}.N.{gamma,beta}, ffn_layers.N.{conv_1,conv_2}.{weight,
+// bias}, pre_net.{weight,bias}.  No weight-norm anywhere.
+int pack_relenc(const Loader& L, const std::string& p, VsgPack* P) {
+  RelEncPack& e = P->relenc;
+  const int H = e.hidden, F = e.filter, NL = e.n_layers, K = e.kernel, nh = e.n_heads, w = e.window;
+  if (H <= 0 || F <= 0 || NL <= 0 || nh <= 0 || H % nh || K % 2 == 0 || w < 0 || w > 16)
+    return fail(VSG_EINVAL, "bad encoder config (hidden %d filter %d heads %d layers %d kernel %d window %d)", H, F, nh, NL, K, w);
+  const int dk = H / nh, nrel = 2 * w + 1;
+  e.layers.resize(NL);
+  std::vector<float> W, b, Wq, bq;
+  auto vec = [&](const std::string& name, int64_t n, float** out) -> int {
+    const HostTensor* t = L.find(name);
+    if (!t || t->numel() != n) return fail(VSG_EINVAL, "missing or mis-shaped %s (expected %lld elements)", name.c_str(), (long long)n);
+    std::vector<float> h(t->data, t->data + n);
+    return L.upload(h, out);
+  };
+  for (int i = 0; i < NL; ++i) {
+    RelEncLayer& l = e.layers[i];
+    const std::string pa = p + "attn_layers." + std::to_string(i) + ".";
+    Wq.assign((size_t)3 * H * H, 0.f); bq.assign((size_t)3 * H, 0.f);
+    const char* names[3] = {"conv_q", "conv_k", "conv_v"};
+    for (int s = 0; s < 3; ++s) {
+      VSG_TRY(L.eff_weight(pa + names[s], H, H, 1, W));
+      VSG_TRY(L.bias(pa + names[s], H, b, true));
+      memcpy(&Wq[(size_t)s * H * H], W.data(), (size_t)H * H * sizeof(float));
+      memcpy(&bq[(size_t)s * H], b.data(), (size_t)H * sizeof(float));
+    }
+    VSG_TRY(pack_conv_f32(L, Wq, bq, 3 * H, H, 1, Identity{}, &l.qkv));
+    VSG_TRY(pack_conv_tc(P, Wq, bq, 3 * H, H, 1, &l.qkv_tc));
+    VSG_TRY(L.eff_weight(pa + "conv_o", H, H, 1, W));
+    VSG_TRY(L.bias(pa + "conv_o", H, b, true));
+    VSG_TRY(pack_conv_f32(L, W, b, H, H, 1, Identity{}, &l.o));
+    VSG_TRY(pack_conv_tc(P, W, b, H, H, 1, &l.o_tc));
+    VSG_TRY(vec(pa + "emb_rel_k", (int64_t)nrel * dk, &l.ek));      // heads_share = True: [1][2w+1][dk]
+    VSG_TRY(vec(pa + "emb_rel_v", (int64_t)nrel * dk, &l.ev));
+    const std::string pf = p + "ffn_layers." + std::to_string(i) + ".";
+    VSG_TRY(L.eff_weight(pf + "conv_1", F, H, K, W));
+    VSG_TRY(L.bias(pf + "conv_1", F, b, true));
+    VSG_TRY(pack_conv_f32(L, W, b, F, H, K, Identity{}, &l.ffn1));
+    VSG_TRY(pack_conv_tc(P, W, b, F, H, K, &l.ffn1_tc));
+    VSG_TRY(L.eff_weight(pf + "conv_2", H, F, 1, W));
+    VSG_TRY(L.bias(pf + "conv_2", H, b, true));
+    VSG_TRY(pack_conv_f32(L, W, b, H, F, 1, Identity{}, &l.ffn2));
+    VSG_TRY(pack_conv_tc(P, W, b, H, F, 1, &l.ffn2_tc));
+    VSG_TRY(vec(p + "norm_layers_1." + std::to_string(i) + ".gamma", H, &l.g1));
+    VSG_TRY(vec(p + "norm_layers_1." + std::to_string(i) + ".beta", H, &l.b1));
+    VSG_TRY(vec(p + "norm_layers_2." + std::to_string(i) + ".gamma", H, &l.g2));
+    VSG_TRY(vec(p + "norm_layers_2." + std::to_string(i) + ".beta", H, &l.b2));
+  }
+  if (e.gin > 0) {
+    VSG_TRY(L.eff_weight(p + "pre_net", H, e.gin, 1, W));
+    VSG_TRY(L.bias(p + "pre_net", H, b, true));
+    VSG_TRY(pack_conv_f32(L, W, b, H, e.gin, 1, Identity{}, &e.pre_net));
+    VSG_TRY(L.upload(W, &e.pre_w));
+    VSG_TRY(L.upload(b, &e.pre_b));
+  }
+  P->has_relenc = true;
+  return VSG_OK;
+}
+
 int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
   const VsgConfig& c = P->cfg;
   const int C0 = c.dec_initial_channel, UIC = c.dec_upsample_initial_channel;
@@ -487,6 +548,49 @@ extern "C" int vsg_enc_pack_create(const VsgEncConfig* cfg, const VsgTensor* wei
     L.m[weights[i].name] = t;
   }
   const int rc = pack_enc(L, prefix ? prefix : "", P);
+  if (rc != VSG_OK) {
+    vsg_pack_destroy(P);
+    return rc;
+  }
+  *out = P;
+  return VSG_OK;
+}
+
+extern "C" int vsg_relenc_pack_create(const VsgRelEncConfig* cfg, const VsgTensor* weights, int32_t n_weights,
+                                      const char* prefix, int32_t device, VsgPack** out) {
+  if (!cfg || !out || (!weights && n_weights > 0)) return fail(VSG_EINVAL, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  VSG_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(VSG_EINVAL, "device %d out of range (%d visible)", device, ndev);
+  struct Restore { int prev = -1; ~Restore() { if (prev >= 0) cudaSetDevice(prev); } } restore;
+  VSG_CUDA_TRY(cudaGetDevice(&restore.prev));
+  VSG_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VSG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(VSG_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  VsgPack* P = new VsgPack();
+  memset(&P->cfg, 0, sizeof(P->cfg));
+  P->device = device;
+  P->sm_count = prop.multiProcessorCount;
+  RelEncPack& e = P->relenc;
+  e.hidden = cfg->hidden_channels; e.filter = cfg->filter_channels; e.n_heads = cfg->n_heads; e.n_layers = cfg->n_layers;
+  e.kernel = cfg->kernel_size; e.window = cfg->window_size; e.gin = cfg->gin_channels;
+  Loader L;
+  L.pack = P;
+  for (int i = 0; i < n_weights; ++i) {
+    if (!weights[i].name || !weights[i].data || weights[i].ndim < 0 || weights[i].ndim > 4) {
+      delete P;
+      return fail(VSG_EINVAL, "weight table entry %d is malformed", i);
+    }
+    HostTensor t;
+    t.data = weights[i].data;
+    t.shape.assign(weights[i].shape, weights[i].shape + weights[i].ndim);
+    L.m[weights[i].name] = t;
+  }
+  const int rc = pack_relenc(L, prefix ? prefix : "", P);
   if (rc != VSG_OK) {
     vsg_pack_destroy(P);
     return rc;

@@ -37,4 +37,10 @@ int posterior_forward_f32(const VsgPack* P, const float* x, const float* mask, c
 int posterior_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, const float* noise,
                          float* z, float* stats, int B, int T, Workspace& ws, cudaStream_t st);
 
+
+// RelativeEncoder (f32: run_f32.cu)
+size_t relenc_ws_bytes_f32(const VsgPack* P, int B, int T, int g_t);
+int relenc_forward_f32(const VsgPack* P, const float* x, const float* mask, const float* g, int g_t, float* y, int B, int T,
+                       Workspace& ws, cudaStream_t st);
+
 }  // namespace vsg

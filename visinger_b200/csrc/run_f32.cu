@@ -1,6 +1,7 @@
 // fp32 parity-mode drivers: sequence the fused FFMA kernels of kernels_f32.cuh over one batch.
 #include "vsg_common.cuh"
 #include "kernels_f32.cuh"
+#include "relenc_f32.cuh"
 #include "run.cuh"
 
 namespace vsg {
@@ -191,6 +192,99 @@ int posterior_forward_f32(const VsgPack* P, const float* x, const float* mask, c
   const long long n = (long long)B * Co * T;   // z = (mu + noise * exp(logs)) * mask   encoder.py:96-97
   posterior_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats, noise, mask, z, Co, T, n);
   VSG_LAUNCH_CHECK("posterior_sample_kernel");
+  return VSG_OK;
+}
+
+size_t relenc_ws_bytes_f32(const VsgPack* P, int B, int T, int g_t) {
+  const RelEncPack& e = P->relenc;
+  size_t n = align256((size_t)B * 3 * e.hidden * T * sizeof(float)) + align256((size_t)B * e.hidden * T * sizeof(float)) +
+             align256((size_t)B * e.filter * T * sizeof(float));
+  n += align256((size_t)B * e.hidden * (g_t ? T : 1) * sizeof(float));
+  return n;
+}
+
+namespace {
+template <int DK>
+int launch_attention_f32(const float* qkv, const float* mask, const float* ek, const float* ev, float* o, int B, int n_heads,
+                         int T, int w, cudaStream_t st) {
+  const size_t sm = relenc_attention_f32_smem(DK, w);
+  if (sm > 200 * 1024) return fail(VSG_EUNSUPPORTED, "attention tile does not fit shared memory (%zu B)", sm);
+  VSG_CUDA_TRY(cudaFuncSetAttribute(relenc_attention_f32_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid((T + kAttTile - 1) / kAttTile, n_heads, B);
+  relenc_attention_f32_kernel<DK><<<grid, 256, sm, st>>>(qkv, mask, ek, ev, o, n_heads, T, w);
+  VSG_LAUNCH_CHECK("relenc_attention_f32_kernel");
+  return VSG_OK;
+}
+}  // namespace
+
+// RelativeEncoder.forward, modules/rel_transformer.py:286-320 (post-LN; dropout is the identity in eval mode).
+// g: NULL, [B, gin] (g_t == 0: one condition vector per utterance, e.g. the speaker embedding) or [B, gin, T] (g_t != 0).
+int relenc_forward_f32(const VsgPack* P, const float* x, const float* mask, const float* g, int g_t, float* y, int B, int T,
+                       Workspace& ws, cudaStream_t st) {
+  const RelEncPack& e = P->relenc;
+  const int H = e.hidden, F = e.filter, NL = e.n_layers, K = e.kernel, dk = H / e.n_heads;
+  float* qkv = ws.take<float>((size_t)B * 3 * H * T);
+  float* o = ws.take<float>((size_t)B * H * T);
+  float* f = ws.take<float>((size_t)B * F * T);
+  float* gp = ws.take<float>((size_t)B * H * (g_t ? T : 1));
+  if (ws.overflow) return fail(VSG_ENOMEM, "encoder workspace too small: need %zu bytes", ws.off);
+  const long long HT = (long long)H * T, n = (long long)B * H * T;
+  if (g && e.gin <= 0) return fail(VSG_EINVAL, "this encoder has no pre_net (gin_channels is None) but g was given");
+  const float* gadd = nullptr;
+  if (g) {   // g = pre_net(g)                                        :289-290
+    if (g_t) {
+      ConvF32 p = base_conv(e.pre_net, g, (long long)e.gin * T, T, T, 0, 1);
+      p.y = gp; p.y_bs = HT; p.y_cs = T;
+      VSG_TRY(launch_conv_f32(p, B, st));
+    } else {
+      VSG_TRY(launch_cond(e.pre_w, e.pre_b, g, gp, H, e.gin, B, st));
+    }
+    gadd = gp;
+  }
+  if (y != x) VSG_CUDA_TRY(cudaMemcpyAsync(y, x, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  relenc_addg_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, gadd, g_t, mask, H, T, n);   // x = (x + g) * mask
+  VSG_LAUNCH_CHECK("relenc_addg_mask_kernel");
+  const unsigned ln_blocks = (unsigned)(((long long)B * T + 127) / 128);
+  for (int i = 0; i < NL; ++i) {
+    const RelEncLayer& L = e.layers[i];
+    {  // q | k | v = conv_{q,k,v}(x)                                :124-126
+      ConvF32 p = base_conv(L.qkv, y, HT, T, T, 0, 1);
+      p.y = qkv; p.y_bs = 3 * HT; p.y_cs = T;
+      VSG_TRY(launch_conv_f32(p, B, st));
+    }
+    switch (dk) {                                                   // attention :137-177
+      case 16: VSG_TRY(launch_attention_f32<16>(qkv, mask, L.ek, L.ev, o, B, e.n_heads, T, e.window, st)); break;
+      case 32: VSG_TRY(launch_attention_f32<32>(qkv, mask, L.ek, L.ev, o, B, e.n_heads, T, e.window, st)); break;
+      case 48: VSG_TRY(launch_attention_f32<48>(qkv, mask, L.ek, L.ev, o, B, e.n_heads, T, e.window, st)); break;
+      case 64: VSG_TRY(launch_attention_f32<64>(qkv, mask, L.ek, L.ev, o, B, e.n_heads, T, e.window, st)); break;
+      case 96: VSG_TRY(launch_attention_f32<96>(qkv, mask, L.ek, L.ev, o, B, e.n_heads, T, e.window, st)); break;
+      case 128: VSG_TRY(launch_attention_f32<128>(qkv, mask, L.ek, L.ev, o, B, e.n_heads, T, e.window, st)); break;
+      default: return fail(VSG_EUNSUPPORTED, "attention head width %d (supported: 16, 32, 48, 64, 96, 128)", dk);
+    }
+    {  // x = x + conv_o(attn)                                        :130, :301
+      ConvF32 p = base_conv(L.o, o, HT, T, T, 0, 1);
+      p.res = y; p.res_bs = HT; p.res_cs = T;
+      p.y = y; p.y_bs = HT; p.y_cs = T;
+      VSG_TRY(launch_conv_f32(p, B, st));
+    }
+    relenc_layernorm_kernel<<<ln_blocks, 128, 0, st>>>(y, L.g1, L.b1, nullptr, 0, mask, 1e-4f, H, T, B);   // :303
+    VSG_LAUNCH_CHECK("relenc_layernorm_kernel");
+    {  // FFN: conv_1(x * mask) -> relu -> conv_2(. * mask)            :337-345
+      ConvF32 p = base_conv(L.ffn1, y, HT, T, T, -(K / 2), 1);
+      p.y = f; p.y_bs = (long long)F * T; p.y_cs = T; p.mask = mask; p.mask_bs = T;   // relu(h) * mask == relu(h * mask)
+      VSG_TRY(launch_conv_f32(p, B, st));
+    }
+    {
+      ConvF32 p = base_conv(L.ffn2, f, (long long)F * T, T, T, 0, 1);
+      p.pre_lrelu = 1; p.slope = 0.f;                               // relu on load
+      p.res = y; p.res_bs = HT; p.res_cs = T;
+      p.y = y; p.y_bs = HT; p.y_cs = T;
+      VSG_TRY(launch_conv_f32(p, B, st));
+    }
+    // x = LayerNorm(x); then the next layer's `x = (x + g) * mask` (:293-295) or the final `x * mask` (:318)
+    relenc_layernorm_kernel<<<ln_blocks, 128, 0, st>>>(y, L.g2, L.b2, (i + 1 < NL) ? gadd : nullptr, g_t, mask, 1e-4f, H, T, B);
+    VSG_LAUNCH_CHECK("relenc_layernorm_kernel");
+  }
   return VSG_OK;
 }
 

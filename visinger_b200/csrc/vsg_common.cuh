@@ -97,6 +97,21 @@ struct EncPack {
   ConvWTC proj_tc;
 };
 
+// RelativeEncoder (modules/rel_transformer.py:257-320): n_layers x {windowed relative-position self-attention, channel
+// LayerNorm, FFN (Conv1d k -> ReLU -> Conv1d 1), LayerNorm}, optional condition through pre_net.
+struct RelEncLayer {
+  ConvW32 qkv, o, ffn1, ffn2;          // conv_q | conv_k | conv_v stacked into one 1x1 convolution H -> 3H
+  ConvWTC qkv_tc, o_tc, ffn1_tc, ffn2_tc;
+  float *ek = nullptr, *ev = nullptr;  // emb_rel_k / emb_rel_v [2w+1][dk]
+  float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;   // LayerNorm gamma / beta
+};
+struct RelEncPack {
+  int hidden = 0, filter = 0, n_heads = 0, n_layers = 0, kernel = 0, window = 0, gin = 0;
+  std::vector<RelEncLayer> layers;
+  ConvW32 pre_net;                     // Conv1d(gin -> hidden, 1) as a convolution (per-frame condition)
+  float *pre_w = nullptr, *pre_b = nullptr;   // the same weights [hidden][gin] for the per-utterance GEMV
+};
+
 struct ResBlockPack {
   int kernel = 0;
   std::vector<int> dilations;
@@ -124,8 +139,9 @@ struct VsgPack {
   int device = 0;
   int hop = 0;
   int sm_count = 148;
-  bool has_flow = false, has_dec = false, has_enc = false;
+  bool has_flow = false, has_dec = false, has_enc = false, has_relenc = false;
   vsg::EncPack enc;
+  vsg::RelEncPack relenc;
   std::vector<void*> allocs;
   // flow
   std::vector<vsg::FlowLayer> flow_layers;

@@ -147,12 +147,22 @@ class FFN(nn.Module):
 
 
 class RelativeEncoder(nn.Module):
-    """Post-LN transformer encoder over [B, C, T] with an optional broadcast condition `g` (reference :257-320)."""
+    """Post-LN transformer encoder over [B, C, T] with an optional condition `g` (reference :257-320).
+
+    On a CUDA device `forward` is ONE call into the native library (`vsg_relenc_forward`: fused QKV projection, windowed
+    relative-position attention kernel, fused residual + channel-LayerNorm + condition + mask, FFN on the convolution
+    kernels).  The PyTorch formulation below (`forward_torch`) is kept as the readable
+    statement of the same arithmetic and for CPU-side tooling; set `native = False` to force it."""
+
+    native = True
+    precision = "fp32"
 
     def __init__(self, hidden_channels, filter_channels, n_heads, n_layers, kernel_size=1, p_dropout=0.0, window_size=4,
                  block_length=None, pre_ln=False, gin_channels=None, **kwargs):
         super().__init__()
         self.hidden_channels, self.n_layers, self.pre_ln = hidden_channels, n_layers, pre_ln
+        self.filter_channels, self.n_heads, self.kernel_size = filter_channels, n_heads, kernel_size
+        self.window_size, self.block_length, self.gin_channels = window_size, block_length, gin_channels
         self.attn_layers = nn.ModuleList()
         self.norm_layers_1 = nn.ModuleList()
         self.ffn_layers = nn.ModuleList()
@@ -167,8 +177,64 @@ class RelativeEncoder(nn.Module):
             self.last_ln = LayerNorm(hidden_channels)
         if gin_channels is not None:
             self.pre_net = nn.Conv1d(gin_channels, hidden_channels, 1)
+        self._vsg_pack = None
+        self._vsg_key = None
+
+    # -- native path -----------------------------------------------------------------------------
+    def _native_supported(self):
+        return not self.pre_ln and self.block_length is None and self.window_size is not None and self.kernel_size % 2 == 1
+
+    def _pack(self):
+        from .. import _lib
+        params = list(self.parameters())
+        dev = params[0].device
+        key = (str(dev),) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._vsg_pack is None or self._vsg_key != key:
+            c = _lib.VsgRelEncConfig(self.hidden_channels, self.filter_channels, self.n_heads, self.n_layers, self.kernel_size,
+                                     self.window_size, self.gin_channels or 0)
+            self._vsg_pack = _lib.RelEncPack(c, dict(self.state_dict()), "", dev)
+            self._vsg_key = key
+        return self._vsg_pack
+
+    @torch.no_grad()
+    def forward_native(self, x, x_mask, g=None):
+        from .. import _lib
+        if x.dim() != 3 or x.shape[1] != self.hidden_channels:
+            raise RuntimeError(f"expected x of shape [B, {self.hidden_channels}, T], got {tuple(x.shape)}")
+        B, _, T = x.shape
+        if x_mask.numel() != B * T:
+            raise RuntimeError(f"expected x_mask of shape [B, 1, T] = [{B}, 1, {T}], got {tuple(x_mask.shape)}")
+        g_t = 0
+        if g is not None:
+            if self.gin_channels is None:
+                raise RuntimeError("this encoder was built without gin_channels; g must be None")
+            if g.dim() != 3 or g.shape[0] != B or g.shape[1] != self.gin_channels or g.shape[2] not in (1, T):
+                raise RuntimeError(f"expected g of shape [B, {self.gin_channels}, 1 or T], got {tuple(g.shape)}")
+            g_t = 1 if (g.shape[2] == T and T > 1) else 0
+        pack = self._pack()
+        prec = _lib.precision_code(self.precision)
+        xc, mc = _lib.as_f32c(x), _lib.as_f32c(x_mask)
+        gc = _lib.as_f32c(g) if g is not None else None
+        y = torch.empty_like(xc)
+        if B and T:
+            with torch.cuda.device(x.device):
+                ws = _lib.workspace(x.device, pack.workspace_bytes(B, T, g_t, prec))
+                rc = _lib.lib().vsg_relenc_forward(pack.handle, xc.data_ptr(), mc.data_ptr(),
+                                                   gc.data_ptr() if gc is not None else None, g_t, y.data_ptr(), B, T, prec,
+                                                   ws.data_ptr(), ws.numel(), _lib.stream_ptr(x.device))
+            _lib.check(rc, "vsg_relenc_forward")
+        return y
 
     def forward(self, x, x_mask, g=None):
+        if x.is_cuda and self.native and not self.training:
+            if not self._native_supported():      # no silent fallback on the GPU: say what is missing
+                raise RuntimeError("visinger_b200 RelativeEncoder: the native kernels implement post-LN (pre_ln=False), "
+                                   "block_length=None, odd FFN kernel sizes; set `native = False` for the PyTorch statement")
+            return self.forward_native(x, x_mask, g)
+        return self.forward_torch(x, x_mask, g)
+
+    # -- PyTorch statement of the same arithmetic --------------------------------------------------
+    def forward_torch(self, x, x_mask, g=None):
         attn_mask = x_mask.unsqueeze(2) * x_mask.unsqueeze(-1)
         if g is not None:
             g = self.pre_net(g)
