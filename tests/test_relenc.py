@@ -124,3 +124,35 @@ def test_relenc_long_sequence_vs_oracle(cuda_device):
     err = maxabs(y.cpu(), yo)
     print(f"relenc fp32 T=1000: max-abs {err:.3e}")
     assert err <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SMALL)
+def test_relenc_bf16_small_vs_reference(cuda_device, name):
+    """Throughput mode: tcgen05 projections / FFN, warp-mma flash attention, bf16 activations."""
+    z = load_npz(name)
+    cfg, sd = _cfg(z), weights_of(z)
+    m = _build(cfg, sd, cuda_device)
+    m.precision = "bf16"
+    x, mask = torch.from_numpy(z["x"]).to(cuda_device), torch.from_numpy(z["mask"]).to(cuda_device)
+    g = torch.from_numpy(z["g"]).to(cuda_device) if cfg["gin"] else None
+    y = m(x, mask, g)
+    ref = torch.from_numpy(z["y"])
+    rel = float((y.cpu() - ref).norm() / ref.norm())
+    print(f"relenc bf16 {name}: rel-L2 {rel:.3e} max-abs {maxabs(y.cpu(), ref):.3e}")
+    assert rel <= 8e-3 and maxabs(y.cpu(), ref) <= 0.06          # 1.5x the measured 5.0e-3 / 4.0e-2
+    assert float((y * (1 - mask)).abs().max()) == 0.0
+    assert torch.equal(y, m(x, mask, g))
+
+
+@pytest.mark.gpu
+def test_relenc_bf16_full_config_vs_oracle(cuda_device):
+    z, cfg, sd, x, mask, g = _full_case()
+    with torch.no_grad():
+        yo = O.rel_encoder(sd, x, mask, g, **_okw(cfg))
+    m = _build(cfg, sd, cuda_device)
+    m.precision = "bf16"
+    y = m(x.to(cuda_device), mask.to(cuda_device), g.to(cuda_device))
+    rel = float((y.cpu() - yo).norm() / yo.norm())
+    print(f"relenc bf16 full: rel-L2 {rel:.3e} max-abs {maxabs(y.cpu(), yo):.3e}")
+    assert rel <= 8.5e-3 and maxabs(y.cpu(), yo) <= 0.09       # 1.5x the measured 5.6e-3 / 5.8e-2

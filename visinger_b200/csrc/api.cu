@@ -149,7 +149,7 @@ extern "C" int vsg_posterior_forward(const VsgPack* pack, const float* x, const 
 
 extern "C" size_t vsg_relenc_workspace_bytes(const VsgPack* pack, int32_t B, int32_t T, int32_t g_per_frame, int32_t precision) {
   if (check_common(pack, B, T, precision) != VSG_OK || !pack->has_relenc) return 0;
-  return relenc_ws_bytes_f32(pack, B, T, g_per_frame) + 1024;
+  return (precision == VSG_PRECISION_BF16 ? relenc_ws_bytes_tc(pack, B, T, g_per_frame) : relenc_ws_bytes_f32(pack, B, T, g_per_frame)) + 1024;
 }
 
 extern "C" int vsg_relenc_forward(const VsgPack* pack, const float* x, const float* mask, const float* g, int32_t g_per_frame,
@@ -164,5 +164,7 @@ extern "C" int vsg_relenc_forward(const VsgPack* pack, const float* x, const flo
   DeviceGuard dg(pack->device);
   if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
   Workspace ws(workspace, workspace_bytes);
+  if (precision == VSG_PRECISION_BF16)
+    return relenc_forward_tc(pack, x, mask, g, g_per_frame, y, B, T, ws, (cudaStream_t)stream);
   return relenc_forward_f32(pack, x, mask, g, g_per_frame, y, B, T, ws, (cudaStream_t)stream);
 }

@@ -38,7 +38,13 @@ int posterior_forward_tc(const VsgPack* P, const float* x, const float* mask, co
                          float* z, float* stats, int B, int T, Workspace& ws, cudaStream_t st);
 
 
-// RelativeEncoder (f32: run_f32.cu)
+// y [B, Cout, T] = Conv1d(x [B, Cin, T]) with the fp32 kernel, stride 1, 'same' padding (run_f32.cu)
+int conv_f32_plain(const ConvW32& w, const float* x, int B, int T, float* y, cudaStream_t st);
+
+// RelativeEncoder (f32: run_f32.cu, bf16: run_tc.cu)
+size_t relenc_ws_bytes_tc(const VsgPack* P, int B, int T, int g_t);
+int relenc_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, int g_t, float* y, int B, int T,
+                      Workspace& ws, cudaStream_t st);
 size_t relenc_ws_bytes_f32(const VsgPack* P, int B, int T, int g_t);
 int relenc_forward_f32(const VsgPack* P, const float* x, const float* mask, const float* g, int g_t, float* y, int B, int T,
                        Workspace& ws, cudaStream_t st);

@@ -195,6 +195,12 @@ int posterior_forward_f32(const VsgPack* P, const float* x, const float* mask, c
   return VSG_OK;
 }
 
+int conv_f32_plain(const ConvW32& w, const float* x, int B, int T, float* y, cudaStream_t st) {
+  ConvF32 p = base_conv(w, x, (long long)w.Cin * T, T, T, -(w.ktaps / 2), 1);
+  p.y = y; p.y_bs = (long long)w.Cout * T; p.y_cs = T;
+  return launch_conv_f32(p, B, st);
+}
+
 size_t relenc_ws_bytes_f32(const VsgPack* P, int B, int T, int g_t) {
   const RelEncPack& e = P->relenc;
   size_t n = align256((size_t)B * 3 * e.hidden * T * sizeof(float)) + align256((size_t)B * e.hidden * T * sizeof(float)) +

@@ -6,6 +6,7 @@
 #include "pair_tc.cuh"
 #include "rb_tc.cuh"
 #include "rp_tc.cuh"
+#include "relenc_tc.cuh"
 
 #include <algorithm>
 #include <map>
@@ -99,6 +100,7 @@ struct EpiTC {
   const __nv_bfloat16* add0 = nullptr;
   const __nv_bfloat16* add1 = nullptr;
   float scale = 1.f;
+  float slope = 0.1f;               // leaky_relu slope of out_act (0 = ReLU)
   __nv_bfloat16* out_raw = nullptr;
   __nv_bfloat16* out_act = nullptr;
   float* out_f32 = nullptr;
@@ -330,7 +332,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.swizzle_code = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
   p.sbo_bytes = 8u * KC * 2u;
   p.bias = e.bias; p.bcond = e.bcond; p.bcond_bs = e.bcond_bs;
-  p.scale = e.scale; p.slope = 0.1f;
+  p.scale = e.scale; p.slope = e.slope;
   p.out_f32 = e.out_f32;
   p.error_flag = error_flag;
 
@@ -1060,6 +1062,109 @@ int posterior_forward_tc(const VsgPack* P, const float* x, const float* mask, co
   const long long n = (long long)B * Co * T;
   posterior_sample_from_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats, noise, mask, z, Co, T, n);
   VSG_LAUNCH_CHECK("posterior_sample_from_stats_kernel");
+  return VSG_OK;
+}
+
+size_t relenc_ws_bytes_tc(const VsgPack* P, int B, int T, int g_t) {
+  const RelEncPack& e = P->relenc;
+  size_t n = 0;
+  n += align256((size_t)B * T * e.hidden * 2) * 2;            // x, attention output
+  n += align256((size_t)B * T * 3 * e.hidden * 2);            // q | k | v
+  n += align256((size_t)B * T * e.filter * 2);                // FFN hidden
+  n += align256((size_t)B * e.hidden * (g_t ? T : 1) * sizeof(float));
+  return n + 512;
+}
+
+namespace {
+template <int DK>
+int launch_attention_bf16(const __nv_bfloat16* qkv, const float* mask, const float* ek, const float* ev, __nv_bfloat16* o, int B,
+                          int n_heads, int T, int w, cudaStream_t st) {
+  const size_t sm = relenc_attention_bf16_smem(DK, w);
+  if (sm > 48 * 1024)
+    VSG_CUDA_TRY(cudaFuncSetAttribute(relenc_attention_bf16_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid((T + kAttQ - 1) / kAttQ, n_heads, B);
+  relenc_attention_bf16_kernel<DK><<<grid, 128, sm, st>>>(qkv, mask, ek, ev, o, n_heads, T, w);
+  VSG_LAUNCH_CHECK("relenc_attention_bf16_kernel");
+  return VSG_OK;
+}
+}  // namespace
+
+// RelativeEncoder.forward (modules/rel_transformer.py:286-320) in the throughput mode: channels-last bf16 activations, the
+// projections and the FFN on the tcgen05 convolution kernel (residual adds, ReLU and masks in its epilogue), attention on
+// the warp-mma flash kernel, LayerNorm + condition + mask fused in one pass.
+int relenc_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, int g_t, float* y, int B, int T,
+                      Workspace& ws, cudaStream_t st) {
+  const RelEncPack& e = P->relenc;
+  const int H = e.hidden, F = e.filter, NL = e.n_layers, K = e.kernel, dk = H / e.n_heads;
+  if (e.layers.empty() || !e.layers[0].qkv_tc.has_tmap || !e.layers[0].ffn1_tc.has_tmap || !e.layers[0].ffn2_tc.has_tmap ||
+      H > 256 || (H & 1))
+    return fail(VSG_EUNSUPPORTED, "bf16 encoder needs hidden / filter channels that are multiples of 16 (hidden <= 256)");
+  typedef __nv_bfloat16 bf;
+  bf* xb = ws.take<bf>((size_t)B * T * H);
+  bf* ob = ws.take<bf>((size_t)B * T * H);
+  bf* qkv = ws.take<bf>((size_t)B * T * 3 * H);
+  bf* fb = ws.take<bf>((size_t)B * T * F);
+  float* gp = ws.take<float>((size_t)B * H * (g_t ? T : 1));
+  int* err = ws.take<int>(1);
+  if (ws.overflow) return fail(VSG_ENOMEM, "encoder workspace too small: need %zu bytes", ws.off);
+  VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+  if (g && e.gin <= 0) return fail(VSG_EINVAL, "this encoder has no pre_net (gin_channels is None) but g was given");
+  const TCOptions opt = g_default_opts;
+  const float* gadd = nullptr;
+  if (g) {
+    if (g_t) VSG_TRY(conv_f32_plain(e.pre_net, g, B, T, gp, st));
+    else VSG_TRY(launch_cond(e.pre_w, e.pre_b, g, gp, H, e.gin, B, st));
+    gadd = gp;
+  }
+  {
+    dim3 grid((T + 31) / 32, (H + 31) / 32, B), block(32, 8);
+    relenc_entry_bf16_kernel<<<grid, block, 0, st>>>(x, gadd, g_t, mask, xb, H, T);
+    VSG_LAUNCH_CHECK("relenc_entry_bf16_kernel");
+  }
+  const long long rows = (long long)B * T;
+  const unsigned ln_blocks = (unsigned)((rows + 7) / 8);
+  for (int i = 0; i < NL; ++i) {
+    const RelEncLayer& L = e.layers[i];
+    {
+      EpiTC ep;
+      ep.bias = L.qkv_tc.bias; ep.out_raw = qkv;
+      VSG_TRY(launch_conv_tc(P, L.qkv_tc, xb, B, T, 0, 1, T, 1, 0, T, ep, opt, err, st));
+    }
+    switch (dk) {
+      case 16: VSG_TRY(launch_attention_bf16<16>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
+      case 32: VSG_TRY(launch_attention_bf16<32>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
+      case 48: VSG_TRY(launch_attention_bf16<48>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
+      case 64: VSG_TRY(launch_attention_bf16<64>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
+      case 96: VSG_TRY(launch_attention_bf16<96>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
+      case 128: VSG_TRY(launch_attention_bf16<128>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
+      default: return fail(VSG_EUNSUPPORTED, "attention head width %d (supported: 16, 32, 48, 64, 96, 128)", dk);
+    }
+    {  // x = x + conv_o(attn)
+      EpiTC ep;
+      ep.bias = L.o_tc.bias; ep.add0 = xb; ep.out_raw = xb;
+      VSG_TRY(launch_conv_tc(P, L.o_tc, ob, B, T, 0, 1, T, 1, 0, T, ep, opt, err, st));
+    }
+    relenc_layernorm_bf16_kernel<256><<<ln_blocks, 256, 0, st>>>(xb, L.g1, L.b1, nullptr, 0, mask, 1e-4f, H, T, rows);
+    VSG_LAUNCH_CHECK("relenc_layernorm_bf16_kernel");
+    {  // relu(conv_1(x * mask)) * mask
+      EpiTC ep;
+      ep.bias = L.ffn1_tc.bias; ep.mask = mask; ep.slope = 0.f; ep.out_act = fb;
+      VSG_TRY(launch_conv_tc(P, L.ffn1_tc, xb, B, T, -(K / 2), 1, T, 1, 0, T, ep, opt, err, st));
+    }
+    {  // x = x + conv_2(.)
+      EpiTC ep;
+      ep.bias = L.ffn2_tc.bias; ep.add0 = xb; ep.out_raw = xb;
+      VSG_TRY(launch_conv_tc(P, L.ffn2_tc, fb, B, T, 0, 1, T, 1, 0, T, ep, opt, err, st));
+    }
+    relenc_layernorm_bf16_kernel<256><<<ln_blocks, 256, 0, st>>>(xb, L.g2, L.b2, (i + 1 < NL) ? gadd : nullptr, g_t, mask, 1e-4f,
+                                                                 H, T, rows);
+    VSG_LAUNCH_CHECK("relenc_layernorm_bf16_kernel");
+  }
+  {
+    dim3 grid((T + 31) / 32, (H + 31) / 32, B), block(32, 8);
+    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(xb, y, H, T, 0);
+    VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
+  }
   return VSG_OK;
 }
 
