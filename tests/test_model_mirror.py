@@ -82,7 +82,9 @@ def test_full_forward_matches_reference_golden(cuda_device, precision, tol):
     err = maxabs(out["wav_out"].cpu(), ref)
     print(f"full forward {precision}: waveform max-abs err {err:.3e} (|ref|max {float(ref.abs().max()):.3e})")
     assert err <= tol
-    assert maxabs(out["f0_pred"].cpu(), torch.from_numpy(z["f0_pred"])) <= 1e-3
+    # the pitch predictor runs in the path's arithmetic mode too (native RelativeEncoder): fp32 kernels in the parity
+    # modes, bf16 tensor-core kernels in the throughput mode (measured 1.04e-2 on log-f0 / uv logits of magnitude ~1)
+    assert maxabs(out["f0_pred"].cpu(), torch.from_numpy(z["f0_pred"])) <= (1.6e-2 if precision == "bf16" else 2e-5)
 
 
 @pytest.mark.gpu

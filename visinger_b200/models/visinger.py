@@ -13,7 +13,7 @@ import torch.nn as nn
 from copy import deepcopy
 
 from .. import _lib
-from ..modules.rel_transformer import SinusoidalPositionalEmbedding
+from ..modules.rel_transformer import RelativeEncoder, SinusoidalPositionalEmbedding
 from ..modules.visinger._packing import PackedModuleMixin
 from ..modules.visinger.flow import ResidualCouplingBlock
 from ..modules.visinger.decoder import Generator
@@ -414,6 +414,11 @@ class VISinger(nn.Module):
         # tolerance.  The throughput mode ("bf16") lets the prior's convolutions and matmuls use TF32 tensor cores as
         # well -- far below that mode's own bf16 rounding, and the fp32 prior is otherwise 3x the cost of the whole hot path.
         fast = self.precision == "bf16" and getattr(self, "prior_tf32", True)
+        # the transformer stacks (text encoder, pitch predictor, frame prior) are native: vsg_relenc_forward in the
+        # path's own arithmetic mode -- fp32 kernels for the parity modes, tcgen05 / warp-mma bf16 for the throughput mode
+        for m in self.modules():
+            if isinstance(m, RelativeEncoder):
+                m.precision = "bf16" if self.precision == "bf16" else "fp32"
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = fast
         try:
