@@ -240,6 +240,37 @@ int vsg_relenc_forward(const VsgPack* pack, const float* x, const float* mask, c
                        float* y, int32_t B, int32_t T, int32_t precision, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/*
+ * FramePriorNetwork(hidden, filter, n_heads, n_layers, kernel_size, gin_channels = 1, p_dropout)
+ *                                                                         modules/visinger/encoder.py:58-73
+ * with prior sampling fused behind it.  Weights: `prefix` + "encoder.*" (a RelativeEncoder)
+ * and `prefix` + "proj.{weight,bias}".
+ *   h = encoder(x, mask, g) ; stats = proj(h) * mask ; (mu_p, logs_p) = split(stats)        encoder.py:70-73
+ *   z_p = (mu_p + noise * exp(logs_p)) * mask                                               models/visinger.py:107
+ * x: [B, hidden, T]; g: [B, 1, T] frame-level condition (log-f0 of voiced frames) or NULL; noise, z_p: [B, hidden, T];
+ * stats: [B, 2 * hidden, T] or NULL (mu_p / logs_p are its channel halves).  z_p is what vsg_infer_zp consumes.
+ */
+int vsg_frame_prior_pack_create(const VsgRelEncConfig* cfg, const VsgTensor* weights, int32_t n_weights, const char* prefix,
+                                int32_t device, VsgPack** out);
+size_t vsg_frame_prior_workspace_bytes(const VsgPack* pack, int32_t B, int32_t T, int32_t precision);
+int vsg_frame_prior_forward(const VsgPack* pack, const float* x, const float* mask, const float* g, const float* noise,
+                            float* stats, float* z_p, int32_t B, int32_t T, int32_t precision,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Length regulator + frame positions, one kernel:
+ *   y[b, :, t] = enc[b, :, mel2ph[b, t] - 1]  (0 where mel2ph == 0)       expand_states, models/commons/align_ops.py:22-26
+ *   y[b, :, t] += pos_table[pos_t, :],  pos_t = running count of frames with y[b, 0, t] != 0 (0 on the others)
+ *                                                    models/visinger.py:79-82, modules/rel_transformer.py:78-100
+ * enc: [B, H, T_ph]; mel2ph: int64 [B, T]; pos_table: [pos_rows, H] sinusoidal table (row 0 zero) or NULL; y: [B, H, T].
+ */
+int vsg_length_regulate(const float* enc, const int64_t* mel2ph, const float* pos_table, int32_t pos_rows, float* y,
+                        int32_t B, int32_t H, int32_t T_ph, int32_t T, void* stream);
+
+/* vsg_infer from an already sampled z_p (models/visinger.py:109-111): z_q = flow(z_p, reverse) * mask; wav = decoder(z_q). */
+int vsg_infer_zp(const VsgPack* pack, const float* z_p, const float* mask, const float* g, float* wav, float* z_q_out,
+                 int32_t B, int32_t T, int32_t precision, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Samples produced per latent frame (prod(upsample_rates)); 0 if the pack has no decoder. */
 int32_t vsg_hop_size(const VsgPack* pack);
 

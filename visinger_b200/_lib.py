@@ -202,6 +202,16 @@ def lib() -> ctypes.CDLL:
         L.vsg_relenc_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
         L.vsg_relenc_forward.restype = ctypes.c_int
         L.vsg_relenc_forward.argtypes = [vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, ctypes.c_size_t, vp]
+        L.vsg_frame_prior_pack_create.restype = ctypes.c_int
+        L.vsg_frame_prior_pack_create.argtypes = L.vsg_relenc_pack_create.argtypes
+        L.vsg_frame_prior_workspace_bytes.restype = ctypes.c_size_t
+        L.vsg_frame_prior_workspace_bytes.argtypes = [vp, i32, i32, i32]
+        L.vsg_frame_prior_forward.restype = ctypes.c_int
+        L.vsg_frame_prior_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, ctypes.c_size_t, vp]
+        L.vsg_length_regulate.restype = ctypes.c_int
+        L.vsg_length_regulate.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, i32, vp]
+        L.vsg_infer_zp.restype = ctypes.c_int
+        L.vsg_infer_zp.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, ctypes.c_size_t, vp]
         L.vsg_debug_resblock_bf16.restype = ctypes.c_int
         L.vsg_debug_resblock_bf16.argtypes = [vp, vp, vp, i32, vp, vp, ctypes.c_float, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32]
         L.vsg_debug_set_plan.restype = ctypes.c_int
@@ -331,9 +341,11 @@ class EncPack:
 
 
 class RelEncPack:
-    """Owner of the VsgPack* of a RelativeEncoder (vsg_relenc_pack_create)."""
+    """Owner of the VsgPack* of a RelativeEncoder (vsg_relenc_pack_create) or, with frame_prior=True, of a whole
+    FramePriorNetwork (encoder + proj; vsg_frame_prior_pack_create)."""
 
-    def __init__(self, cfg: VsgRelEncConfig, state_dict: Dict[str, torch.Tensor], prefix: str, device: torch.device):
+    def __init__(self, cfg: VsgRelEncConfig, state_dict: Dict[str, torch.Tensor], prefix: str, device: torch.device,
+                 frame_prior: bool = False):
         self._h = ctypes.c_void_p()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -341,8 +353,9 @@ class RelEncPack:
         host = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items() if k.startswith(prefix)}
         arr, keep = _weight_table(host)
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        rc = lib().vsg_relenc_pack_create(ctypes.byref(cfg), arr, len(host), prefix.encode(), idx, ctypes.byref(self._h))
-        check(rc, "vsg_relenc_pack_create")
+        create = lib().vsg_frame_prior_pack_create if frame_prior else lib().vsg_relenc_pack_create
+        rc = create(ctypes.byref(cfg), arr, len(host), prefix.encode(), idx, ctypes.byref(self._h))
+        check(rc, "vsg_frame_prior_pack_create" if frame_prior else "vsg_relenc_pack_create")
         self.index = idx
 
     @property
@@ -359,6 +372,27 @@ class RelEncPack:
                 self._h = ctypes.c_void_p()
         except Exception:
             pass
+
+
+def length_regulate(enc: torch.Tensor, mel2ph: torch.Tensor, pos_table: Optional[torch.Tensor]) -> torch.Tensor:
+    """enc [B, H, T_ph] fp32, mel2ph [B, T] int64, pos_table [rows, H] fp32 or None -> [B, H, T]  (vsg_length_regulate)."""
+    require_cuda(enc, "enc")
+    require_cuda(mel2ph, "mel2ph")
+    ec = as_f32c(enc)
+    mc = mel2ph.to(torch.int64).contiguous()
+    B, H, T_ph = ec.shape
+    T = mc.shape[1]
+    tab = as_f32c(pos_table) if pos_table is not None else None
+    if tab is not None:
+        require_cuda(tab, "pos_table")
+    y = torch.empty(B, H, T, dtype=torch.float32, device=enc.device)
+    if B and T:
+        with torch.cuda.device(enc.device):
+            rc = lib().vsg_length_regulate(ec.data_ptr(), mc.data_ptr(), tab.data_ptr() if tab is not None else None,
+                                           tab.shape[0] if tab is not None else 0, y.data_ptr(), B, H, T_ph, T,
+                                           stream_ptr(enc.device))
+        check(rc, "vsg_length_regulate")
+    return y
 
 
 _ws_cache: Dict[tuple, torch.Tensor] = {}

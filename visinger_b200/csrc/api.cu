@@ -168,3 +168,66 @@ extern "C" int vsg_relenc_forward(const VsgPack* pack, const float* x, const flo
     return relenc_forward_tc(pack, x, mask, g, g_per_frame, y, B, T, ws, (cudaStream_t)stream);
   return relenc_forward_f32(pack, x, mask, g, g_per_frame, y, B, T, ws, (cudaStream_t)stream);
 }
+
+extern "C" size_t vsg_frame_prior_workspace_bytes(const VsgPack* pack, int32_t B, int32_t T, int32_t precision) {
+  if (check_common(pack, B, T, precision) != VSG_OK || !pack->has_relenc || !pack->relenc.proj_w) return 0;
+  return frame_prior_ws_bytes(pack, B, T, precision) + 1024;
+}
+
+extern "C" int vsg_frame_prior_forward(const VsgPack* pack, const float* x, const float* mask, const float* g,
+                                       const float* noise, float* stats, float* z_p, int32_t B, int32_t T, int32_t precision,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  VSG_TRY(check_common(pack, B, T, precision));
+  if (!pack->has_relenc || !pack->relenc.proj_w)
+    return fail(VSG_EINVAL, "pack has no frame prior network (create it with vsg_frame_prior_pack_create)");
+  if (B == 0 || T == 0) return VSG_OK;
+  if (!x || !mask || !noise || !z_p) return fail(VSG_EINVAL, "null pointer");
+  if (!workspace) return fail(VSG_ENOMEM, "workspace is NULL");
+  DeviceGuard dg(pack->device);
+  if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
+  Workspace ws(workspace, workspace_bytes);
+  if (precision == VSG_PRECISION_BF16)
+    return frame_prior_forward_tc(pack, x, mask, g, noise, stats, z_p, B, T, ws, (cudaStream_t)stream);
+  return frame_prior_forward_f32(pack, x, mask, g, noise, stats, z_p, B, T, ws, (cudaStream_t)stream);
+}
+
+extern "C" int vsg_length_regulate(const float* enc, const int64_t* mel2ph, const float* pos_table, int32_t pos_rows,
+                                   float* y, int32_t B, int32_t H, int32_t T_ph, int32_t T, void* stream) {
+  g_launches = 0;
+  if (B < 0 || H <= 0 || T_ph < 0 || T < 0) return fail(VSG_EINVAL, "bad dimension");
+  if (B == 0 || T == 0) return VSG_OK;
+  if (!enc || !mel2ph || !y || (pos_table && pos_rows <= 0)) return fail(VSG_EINVAL, "null pointer");
+  return length_regulate(enc, (const long long*)mel2ph, pos_table, pos_rows, y, B, H, T_ph, T, (cudaStream_t)stream);
+}
+
+extern "C" int vsg_infer_zp(const VsgPack* pack, const float* z_p, const float* mask, const float* g, float* wav,
+                            float* z_q_out, int32_t B, int32_t T, int32_t precision, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  g_launches = 0;
+  VSG_TRY(check_common(pack, B, T, precision));
+  if (!pack->has_flow || !pack->has_dec) return fail(VSG_EINVAL, "vsg_infer_zp needs a pack with both flow and decoder");
+  if (pack->cfg.flow_channels != pack->cfg.dec_initial_channel)
+    return fail(VSG_EINVAL, "flow channels (%d) != decoder initial_channel (%d)", pack->cfg.flow_channels,
+                pack->cfg.dec_initial_channel);
+  if (B == 0 || T == 0) return VSG_OK;
+  if (!z_p || !mask || !wav) return fail(VSG_EINVAL, "null pointer");
+  if (!workspace) return fail(VSG_ENOMEM, "workspace is NULL");
+  DeviceGuard dg(pack->device);
+  if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = pack->cfg.flow_channels;
+  Workspace ws(workspace, workspace_bytes);
+  float* z = ws.take<float>((size_t)B * C * T);
+  if (ws.overflow) return fail(VSG_ENOMEM, "workspace too small");
+  const size_t mark = ws.off;
+  if (precision != VSG_PRECISION_BF16) VSG_TRY(flow_forward_f32(pack, z_p, mask, g, z, B, T, 1, ws, st));
+  else VSG_TRY(flow_forward_tc(pack, z_p, mask, g, z, B, T, 1, ws, st));
+  VSG_TRY(mask_mul(z, mask, z, B, C, T, st));
+  if (z_q_out)
+    VSG_CUDA_TRY(cudaMemcpyAsync(z_q_out, z, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ws.off = mark;
+  if (precision == VSG_PRECISION_FP32) VSG_TRY(generator_forward_f32(pack, z, g, wav, B, T, ws, st));
+  else VSG_TRY(generator_forward_tc(pack, z, g, wav, B, T, ws, st, precision == VSG_PRECISION_BF16X3));
+  return VSG_OK;
+}

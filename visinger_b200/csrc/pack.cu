@@ -278,7 +278,7 @@ int pack_enc(const Loader& L, const std::string& p, VsgPack* P) {
 // RelativeEncoder state-dict (modules/rel_transformer.py:272-284): attn_layers.N.{conv_q,conv_k,conv_v,conv_o}.{weight,bias},
 // attn_layers.N.{emb_rel_k,emb_rel_v} [1][2w+1][dk], norm_layers_{1,2}.N.{gamma,beta}, ffn_layers.N.{conv_1,conv_2}.{weight,
 // bias}, pre_net.{weight,bias}.  No weight-norm anywhere.
-int pack_relenc(const Loader& L, const std::string& p, VsgPack* P) {
+int pack_relenc(const Loader& L, const std::string& p, VsgPack* P, const char* proj_prefix = nullptr) {
   RelEncPack& e = P->relenc;
   const int H = e.hidden, F = e.filter, NL = e.n_layers, K = e.kernel, nh = e.n_heads, w = e.window;
   if (H <= 0 || F <= 0 || NL <= 0 || nh <= 0 || H % nh || K % 2 == 0 || w < 0 || w > 16)
@@ -331,6 +331,14 @@ int pack_relenc(const Loader& L, const std::string& p, VsgPack* P) {
     VSG_TRY(pack_conv_f32(L, W, b, H, e.gin, 1, Identity{}, &e.pre_net));
     VSG_TRY(L.upload(W, &e.pre_w));
     VSG_TRY(L.upload(b, &e.pre_b));
+  }
+  if (proj_prefix) {   // FramePriorNetwork.proj: Conv1d(H -> 2H, 1)      modules/visinger/encoder.py:65
+    const std::string pp = std::string(proj_prefix) + "proj";
+    VSG_TRY(L.eff_weight(pp, 2 * H, H, 1, W));
+    VSG_TRY(L.bias(pp, 2 * H, b, true));
+    VSG_TRY(L.upload(W, &e.proj_w));
+    VSG_TRY(L.upload(b, &e.proj_b));
+    VSG_TRY(pack_conv_tc(P, W, b, 2 * H, H, 1, &e.proj_tc));
   }
   P->has_relenc = true;
   return VSG_OK;
@@ -556,8 +564,22 @@ extern "C" int vsg_enc_pack_create(const VsgEncConfig* cfg, const VsgTensor* wei
   return VSG_OK;
 }
 
+static int relenc_pack_create(const VsgRelEncConfig* cfg, const VsgTensor* weights, int32_t n_weights, const char* prefix,
+                              const char* proj_prefix, int32_t device, VsgPack** out);
+
 extern "C" int vsg_relenc_pack_create(const VsgRelEncConfig* cfg, const VsgTensor* weights, int32_t n_weights,
                                       const char* prefix, int32_t device, VsgPack** out) {
+  return relenc_pack_create(cfg, weights, n_weights, prefix, nullptr, device, out);
+}
+
+extern "C" int vsg_frame_prior_pack_create(const VsgRelEncConfig* cfg, const VsgTensor* weights, int32_t n_weights,
+                                           const char* prefix, int32_t device, VsgPack** out) {
+  const std::string p = prefix ? prefix : "";
+  return relenc_pack_create(cfg, weights, n_weights, (p + "encoder.").c_str(), p.c_str(), device, out);
+}
+
+static int relenc_pack_create(const VsgRelEncConfig* cfg, const VsgTensor* weights, int32_t n_weights, const char* prefix,
+                              const char* proj_prefix, int32_t device, VsgPack** out) {
   if (!cfg || !out || (!weights && n_weights > 0)) return fail(VSG_EINVAL, "null argument");
   *out = nullptr;
   int ndev = 0;
@@ -590,7 +612,7 @@ extern "C" int vsg_relenc_pack_create(const VsgRelEncConfig* cfg, const VsgTenso
     t.shape.assign(weights[i].shape, weights[i].shape + weights[i].ndim);
     L.m[weights[i].name] = t;
   }
-  const int rc = pack_relenc(L, prefix ? prefix : "", P);
+  const int rc = pack_relenc(L, prefix ? prefix : "", P, proj_prefix);
   if (rc != VSG_OK) {
     vsg_pack_destroy(P);
     return rc;

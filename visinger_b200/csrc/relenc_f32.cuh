@@ -211,6 +211,91 @@ __global__ void __launch_bounds__(256) relenc_attention_f32_kernel(const float* 
   }
 }
 
+// Length regulator + positional embedding, one CTA per utterance:
+//   y[b, :, t] = enc[b, :, mel2ph[b, t] - 1]   (0 where mel2ph == 0)      expand_states, models/commons/align_ops.py:22-26
+//   keep_t = (y[b, 0, t] != 0);  pos_t = cumsum(keep)_t * keep_t            make_positions, modules/rel_transformer.py:78-88
+//   y[b, :, t] += table[pos_t, :]                                           models/visinger.py:79-82 (table row 0 is zero)
+// -- the position of a frame is the running count of frames whose channel 0 is non-zero, the reference's data-dependent
+// definition.  enc: [B, H, T_ph]; mel2ph: int64 [B, T]; table: [rows, H] (SinusoidalPositionalEmbedding.weights) or null.
+__global__ void length_regulate_pos_kernel(const float* __restrict__ enc, const long long* __restrict__ mel2ph,
+                                           const float* __restrict__ table, int table_rows, float* __restrict__ y, int H,
+                                           int T_ph, int T) {
+  extern __shared__ int lr_sm[];                 // [T] token index (-1 = padding), then [T] position
+  int* tok = lr_sm;
+  int* pos = lr_sm + T;
+  __shared__ int warp_tot[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float* eb = enc + (long long)b * H * T_ph;
+  float* yb = y + (long long)b * H * T;
+  for (int t = tid; t < T; t += blockDim.x) {
+    const long long m = mel2ph[(long long)b * T + t];
+    tok[t] = (m > 0 && m <= T_ph) ? (int)(m - 1) : -1;
+  }
+  __syncthreads();
+  // inclusive scan of keep_t over the utterance, a chunk of blockDim.x frames at a time
+  int carry = 0;
+  for (int t0 = 0; t0 < T; t0 += blockDim.x) {
+    const int t = t0 + tid;
+    int keep = 0;
+    if (t < T && tok[t] >= 0) keep = (eb[tok[t]] != 0.f) ? 1 : 0;             // channel 0 of the gathered row
+    int v = keep;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, v, off);
+      if (lane >= off) v += n;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    int before = carry;
+    for (int wv = 0; wv < warp; ++wv) before += warp_tot[wv];
+    if (t < T) pos[t] = keep ? before + v : 0;
+    int chunk = 0;
+    for (int wv = 0; wv < nw; ++wv) chunk += warp_tot[wv];
+    carry += chunk;
+    __syncthreads();
+  }
+  for (int i = tid; i < H * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;
+    float v = tok[t] >= 0 ? eb[(long long)c * T_ph + tok[t]] : 0.f;
+    if (table && pos[t] < table_rows) v += table[(long long)pos[t] * H + c];
+    yb[i] = v;
+  }
+}
+
+// FramePriorNetwork head + prior sampling, fp32 layout:
+//   stats = proj(h) * mask  (Conv1d(H -> 2H, 1), modules/visinger/encoder.py:65,71);  (mu_p, logs_p) = split(stats)  (:72)
+//   z_p = (mu_p + noise * exp(logs_p)) * mask                                              models/visinger.py:107
+// One thread owns one (channel, frame): both dot products of length H, the sample, three stores (stats may be null).
+// W: [2H][H] row-major; h, noise, z: [B, H, T]; stats: [B, 2H, T].
+__global__ void prior_head_f32_kernel(const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ bias,
+                                      const float* __restrict__ noise, const float* __restrict__ mask, float* __restrict__ stats,
+                                      float* __restrict__ z, int H, int T) {
+  extern __shared__ float ph_sm[];              // [H][32] frames of h
+  const int b = blockIdx.y, t0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
+  const int t = t0 + tx;
+  for (int c = ty; c < H; c += nty) ph_sm[c * 32 + tx] = t < T ? h[((long long)b * H + c) * T + t] : 0.f;
+  __syncthreads();
+  if (t >= T) return;
+  const float mk = mask[(long long)b * T + t];
+  for (int c = ty; c < H; c += nty) {
+    float mu = bias[c], lg = bias[H + c];
+    const float* wm = W + (long long)c * H;
+    const float* wl = W + (long long)(H + c) * H;
+    for (int k = 0; k < H; ++k) {
+      const float hv = ph_sm[k * 32 + tx];
+      mu = fmaf(wm[k], hv, mu);
+      lg = fmaf(wl[k], hv, lg);
+    }
+    mu *= mk; lg *= mk;
+    const long long o = ((long long)b * H + c) * T + t;
+    if (stats) {
+      stats[((long long)b * 2 * H + c) * T + t] = mu;
+      stats[((long long)b * 2 * H + H + c) * T + t] = lg;
+    }
+    z[o] = (mu + noise[o] * expf(lg)) * mk;
+  }
+}
+
 inline size_t relenc_attention_f32_smem(int dk, int w) {
   const int NT = kAttTile, VS = NT + 1, nrel = 2 * w + 1;
   return sizeof(float) * ((size_t)2 * dk * NT + (size_t)dk * VS + (size_t)NT * VS + (size_t)2 * nrel * dk + (size_t)NT * nrel + 2 * NT);

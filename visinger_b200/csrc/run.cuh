@@ -49,4 +49,14 @@ size_t relenc_ws_bytes_f32(const VsgPack* P, int B, int T, int g_t);
 int relenc_forward_f32(const VsgPack* P, const float* x, const float* mask, const float* g, int g_t, float* y, int B, int T,
                        Workspace& ws, cudaStream_t st);
 
+
+// FramePriorNetwork + prior sampling (encoder -> proj -> sample); stats [B, 2H, T] may be null
+size_t frame_prior_ws_bytes(const VsgPack* P, int B, int T, int precision);
+int frame_prior_forward_f32(const VsgPack* P, const float* x, const float* mask, const float* g, const float* noise,
+                            float* stats, float* z, int B, int T, Workspace& ws, cudaStream_t st);
+int frame_prior_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, const float* noise,
+                           float* stats, float* z, int B, int T, Workspace& ws, cudaStream_t st);
+int length_regulate(const float* enc, const long long* mel2ph, const float* table, int table_rows, float* y, int B, int H,
+                    int T_ph, int T, cudaStream_t st);
+
 }  // namespace vsg

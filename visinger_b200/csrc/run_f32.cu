@@ -294,6 +294,32 @@ int relenc_forward_f32(const VsgPack* P, const float* x, const float* mask, cons
   return VSG_OK;
 }
 
+// FramePriorNetwork.forward (modules/visinger/encoder.py:67-73) + prior sampling (models/visinger.py:107), fp32 mode.
+int frame_prior_forward_f32(const VsgPack* P, const float* x, const float* mask, const float* g, const float* noise,
+                            float* stats, float* z, int B, int T, Workspace& ws, cudaStream_t st) {
+  const RelEncPack& e = P->relenc;
+  const int H = e.hidden;
+  float* h = ws.take<float>((size_t)B * H * T);
+  if (ws.overflow) return fail(VSG_ENOMEM, "frame prior workspace too small: need %zu bytes", ws.off);
+  VSG_TRY(relenc_forward_f32(P, x, mask, g, g ? 1 : 0, h, B, T, ws, st));
+  const size_t sm = (size_t)H * 32 * sizeof(float);
+  dim3 grid((T + 31) / 32, B);
+  prior_head_f32_kernel<<<grid, 256, sm, st>>>(h, e.proj_w, e.proj_b, noise, mask, stats, z, H, T);
+  VSG_LAUNCH_CHECK("prior_head_f32_kernel");
+  return VSG_OK;
+}
+
+int length_regulate(const float* enc, const long long* mel2ph, const float* table, int table_rows, float* y, int B, int H,
+                    int T_ph, int T, cudaStream_t st) {
+  const size_t sm = (size_t)2 * T * sizeof(int);
+  if (sm > 96 * 1024) return fail(VSG_EUNSUPPORTED, "sequence too long for the length regulator (%d frames)", T);
+  if (sm > 48 * 1024)
+    VSG_CUDA_TRY(cudaFuncSetAttribute(length_regulate_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  length_regulate_pos_kernel<<<B, 512, sm, st>>>(enc, mel2ph, table, table_rows, y, H, T_ph, T);
+  VSG_LAUNCH_CHECK("length_regulate_pos_kernel");
+  return VSG_OK;
+}
+
 static size_t dec_max_elems(const VsgPack* P, int B, int T) {
   size_t m = (size_t)B * P->cfg.dec_upsample_initial_channel * T;
   long long L = T;

@@ -1092,8 +1092,8 @@ int launch_attention_bf16(const __nv_bfloat16* qkv, const float* mask, const flo
 // RelativeEncoder.forward (modules/rel_transformer.py:286-320) in the throughput mode: channels-last bf16 activations, the
 // projections and the FFN on the tcgen05 convolution kernel (residual adds, ReLU and masks in its epilogue), attention on
 // the warp-mma flash kernel, LayerNorm + condition + mask fused in one pass.
-int relenc_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, int g_t, float* y, int B, int T,
-                      Workspace& ws, cudaStream_t st) {
+static int relenc_core_tc(const VsgPack* P, const float* x, const float* mask, const float* g, int g_t, int B, int T,
+                          Workspace& ws, cudaStream_t st, __nv_bfloat16** xb_out, int** err_out) {
   const RelEncPack& e = P->relenc;
   const int H = e.hidden, F = e.filter, NL = e.n_layers, K = e.kernel, dk = H / e.n_heads;
   if (e.layers.empty() || !e.layers[0].qkv_tc.has_tmap || !e.layers[0].ffn1_tc.has_tmap || !e.layers[0].ffn2_tc.has_tmap ||
@@ -1160,11 +1160,56 @@ int relenc_forward_tc(const VsgPack* P, const float* x, const float* mask, const
                                                                  H, T, rows);
     VSG_LAUNCH_CHECK("relenc_layernorm_bf16_kernel");
   }
+  *xb_out = xb;
+  *err_out = err;
+  return VSG_OK;
+}
+
+int relenc_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, int g_t, float* y, int B, int T,
+                      Workspace& ws, cudaStream_t st) {
+  __nv_bfloat16* xb = nullptr;
+  int* err = nullptr;
+  VSG_TRY(relenc_core_tc(P, x, mask, g, g_t, B, T, ws, st, &xb, &err));
+  const int H = P->relenc.hidden;
+  dim3 grid((T + 31) / 32, (H + 31) / 32, B), block(32, 8);
+  transpose_from_bf16_kernel<<<grid, block, 0, st>>>(xb, y, H, T, 0);
+  VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
+  return VSG_OK;
+}
+
+size_t frame_prior_ws_bytes(const VsgPack* P, int B, int T, int precision) {
+  const RelEncPack& e = P->relenc;
+  if (precision == VSG_PRECISION_BF16)
+    return relenc_ws_bytes_tc(P, B, T, 1) + align256((size_t)B * T * 2 * e.hidden * 2) + align256((size_t)B * 2 * e.hidden * T * 4);
+  return relenc_ws_bytes_f32(P, B, T, 1) + align256((size_t)B * e.hidden * T * sizeof(float));
+}
+
+// FramePriorNetwork.forward + prior sampling in the throughput mode: the encoder's channels-last bf16 output feeds proj
+// (tcgen05, mask in the epilogue) without leaving that layout; stats -> fp32 [B, 2H, T]; z_p = (mu + noise exp(logs)) mask.
+int frame_prior_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, const float* noise,
+                           float* stats, float* z, int B, int T, Workspace& ws, cudaStream_t st) {
+  const RelEncPack& e = P->relenc;
+  const int H = e.hidden;
+  if (!e.proj_tc.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 frame prior needs hidden channels that are a multiple of 16");
+  __nv_bfloat16* xb = nullptr;
+  int* err = nullptr;
+  VSG_TRY(relenc_core_tc(P, x, mask, g, g ? 1 : 0, B, T, ws, st, &xb, &err));
+  __nv_bfloat16* sb = ws.take<__nv_bfloat16>((size_t)B * T * 2 * H);
+  float* st32 = stats ? stats : ws.take<float>((size_t)B * 2 * H * T);
+  if (ws.overflow) return fail(VSG_ENOMEM, "frame prior workspace too small: need %zu bytes", ws.off);
   {
-    dim3 grid((T + 31) / 32, (H + 31) / 32, B), block(32, 8);
-    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(xb, y, H, T, 0);
+    EpiTC ep;
+    ep.bias = e.proj_tc.bias; ep.mask = mask; ep.out_raw = sb;
+    VSG_TRY(launch_conv_tc(P, e.proj_tc, xb, B, T, 0, 1, T, 1, 0, T, ep, g_default_opts, err, st));
+  }
+  {
+    dim3 grid((T + 31) / 32, (2 * H + 31) / 32, B), block(32, 8);
+    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(sb, st32, 2 * H, T, 0);
     VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
   }
+  const long long n = (long long)B * H * T;
+  posterior_sample_from_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(st32, noise, mask, z, H, T, n);
+  VSG_LAUNCH_CHECK("posterior_sample_from_stats_kernel");
   return VSG_OK;
 }
 

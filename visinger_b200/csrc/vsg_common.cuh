@@ -110,6 +110,9 @@ struct RelEncPack {
   std::vector<RelEncLayer> layers;
   ConvW32 pre_net;                     // Conv1d(gin -> hidden, 1) as a convolution (per-frame condition)
   float *pre_w = nullptr, *pre_b = nullptr;   // the same weights [hidden][gin] for the per-utterance GEMV
+  // FramePriorNetwork head: proj = Conv1d(hidden -> 2 hidden, 1) (modules/visinger/encoder.py:65); absent if proj_w is null
+  float *proj_w = nullptr, *proj_b = nullptr; // [2H][H], [2H]
+  ConvWTC proj_tc;
 };
 
 struct ResBlockPack {

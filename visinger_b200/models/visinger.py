@@ -109,6 +109,34 @@ class HotPath(PackedModuleMixin, nn.Module):
         self.last_launches = _lib.last_launch_count()
         return wav, z_q
 
+    @torch.no_grad()
+    def infer_zp(self, z_p, mask, g):
+        """models/visinger.py:109-111 from an already sampled z_p [B, C, T] (what the native frame-prior head emits):
+        z_q = flow(z_p, reverse) * mask; wav = decoder(z_q).  Returns (wav [B, 1, T*hop], z_q)."""
+        _lib.require_cuda(z_p, "z_p")
+        _lib.require_cuda(mask, "mask")
+        B, C, T = z_p.shape
+        if C != self.flow.channels or mask.numel() != B * T:
+            raise RuntimeError(f"expected z_p [B, {self.flow.channels}, T] and mask [B, 1, T]")
+        use_g = self._check_g(g, B)
+        pack = self._pack()
+        prec = _lib.precision_code(self.precision)
+        zc, mc = _lib.as_f32c(z_p), _lib.as_f32c(mask)
+        gc = _lib.as_f32c(g) if use_g else None
+        dev = z_p.device
+        wav = torch.empty(B, 1, T * self.decoder.hop_size, dtype=torch.float32, device=dev)
+        z_q = torch.empty(B, C, T, dtype=torch.float32, device=dev)
+        if B == 0 or T == 0:
+            return wav, z_q
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, pack.workspace_bytes(B, T, prec))
+            rc = _lib.lib().vsg_infer_zp(pack.handle, zc.data_ptr(), mc.data_ptr(), gc.data_ptr() if use_g else None,
+                                         wav.data_ptr(), z_q.data_ptr(), B, T, prec, ws.data_ptr(), ws.numel(),
+                                         _lib.stream_ptr(dev))
+        _lib.check(rc, "vsg_infer_zp")
+        self.last_launches = _lib.last_launch_count()
+        return wav, z_q
+
     def _check_g(self, g, B: int) -> bool:
         """The reference broadcasts g [B, gin, 1] over time (models/visinger.py:84); anything else would be misread
         as B*gin floats through the raw pointer, so it is rejected here.  Returns whether g is used."""
@@ -354,12 +382,19 @@ class VISinger(nn.Module):
             raise NotImplementedError("visinger_b200.VISinger implements forward(infer=True); training stays with the reference")
         with torch.no_grad():
             ret = {}
-            mu_p, logs_p, mask, spk_emb = self.prior(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id,
-                                                     f0, uv, ret)
-            if noise is None:
-                noise = torch.randn_like(mu_p)
             self._hot.precision = self.precision
-            wav, z_q = self._hot.infer(mu_p, logs_p, noise, mask, spk_emb)              # models/visinger.py:107-111
+            if mel2ph.is_cuda and getattr(self, "fused_prior_head", True):
+                # frame prior network + proj + prior sampling in one native call (vsg_frame_prior_forward), then
+                # flow + decoder from z_p (vsg_infer_zp): mu_p / logs_p never round-trip through PyTorch
+                z_p, mask, spk_emb = self.prior(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret,
+                                                noise=noise, sample=True)
+                wav, z_q = self._hot.infer_zp(z_p, mask, spk_emb)
+            else:
+                mu_p, logs_p, mask, spk_emb = self.prior(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id,
+                                                         f0, uv, ret)
+                if noise is None:
+                    noise = torch.randn_like(mu_p)
+                wav, z_q = self._hot.infer(mu_p, logs_p, noise, mask, spk_emb)          # models/visinger.py:107-111
             ret["wav_out"] = wav.squeeze(1)
             ret["z_q"] = z_q
             return ret
@@ -405,7 +440,7 @@ class VISinger(nn.Module):
         return out
 
     def prior(self, text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed=None, spk_id=None, f0=None, uv=None,
-              ret=None):
+              ret=None, noise=None, sample=False):
         """models/visinger.py:75-90: everything upstream of z_p (plain PyTorch, any device).
         Returns (mu_p, logs_p, tgt_nonpadding [B, 1, T], spk_emb [B, gin, 1]); fills ret["f0_pred"]."""
         ret = {} if ret is None else ret
@@ -423,20 +458,32 @@ class VISinger(nn.Module):
         torch.backends.cuda.matmul.allow_tf32 = fast
         try:
             with torch.backends.cudnn.flags(enabled=torch.backends.cudnn.enabled, allow_tf32=fast):
-                return self._prior(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret)
+                return self._prior(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret, noise, sample)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
 
-    def _prior(self, text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret):
+    def _prior(self, text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed, spk_id, f0, uv, ret, noise=None, sample=False):
         mask = (mel2ph > 0).float().unsqueeze(1)
-        prior_inp = self.text_encoder(text_tokens, pitch_tokens, dur_tokens, mel2ph) * mask
-        if self.use_pos_embed:                                                      # models/visinger.py:79-82
-            pos = self.embed_positions(prior_inp.shape[0], prior_inp.shape[2], prior_inp.transpose(1, 2)[..., 0])
-            prior_inp = prior_inp + pos.transpose(1, 2)
+        if mel2ph.is_cuda and getattr(self, "native_length_regulator", True):
+            # length regulator + frame positions in one kernel (vsg_length_regulate)
+            enc = self.text_encoder.encode_tokens(text_tokens, pitch_tokens, dur_tokens)              # [B, H, T_ph]
+            table = None
+            if self.use_pos_embed:
+                table = self.embed_positions.table(mel2ph.shape[1] + 1, enc.device)
+            prior_inp = _lib.length_regulate(enc, mel2ph, table)
+        else:
+            prior_inp = self.text_encoder(text_tokens, pitch_tokens, dur_tokens, mel2ph) * mask
+            if self.use_pos_embed:                                                  # models/visinger.py:79-82
+                pos = self.embed_positions(prior_inp.shape[0], prior_inp.shape[2], prior_inp.transpose(1, 2)[..., 0])
+                prior_inp = prior_inp + pos.transpose(1, 2)
         spk_emb = self.speaker_embedding(spk_embed, spk_id).transpose(1, 2)         # [B, gin, 1]
         cond_pitch = None
         if self.hparams["use_pitch_embed"]:
             cond_pitch = self.forward_pitch(prior_inp, f0, uv, spk_emb, mask, ret)
+        if sample:
+            self.frame_prior.precision = "bf16" if self.precision == "bf16" else "fp32"
+            z_p, _, _ = self.frame_prior.sample(prior_inp, mask, cond_pitch, noise)
+            return z_p, mask, spk_emb
         mu_p, logs_p = self.frame_prior(prior_inp, mask, cond_pitch)
         return mu_p, logs_p, mask, spk_emb
 

@@ -52,6 +52,15 @@ class SinusoidalPositionalEmbedding(nn.Module):
             table[padding_idx] = 0
         return table
 
+    def table(self, n_rows, device):
+        """The sinusoidal table with at least n_rows rows on `device` (row padding_idx is zero): what the native length
+        regulator indexes with the frame positions it computes itself."""
+        if self.weights is None or n_rows > self.weights.size(0):
+            self.weights = self.get_embedding(n_rows, self.embedding_dim, self.padding_idx)
+        if self.weights.device != torch.device(device) or self.weights.dtype != torch.float32:
+            self.weights = self.weights.to(device=device, dtype=torch.float32)
+        return self.weights
+
     def forward(self, bsz, seq_len, input):
         """`input` [B, T]: entries equal to padding_idx are padding.  Returns [bsz, seq_len, -1] exactly as the reference
         does (a `.view`, which only equals [B, T, dim] when seq_len == T -- reference encoder.py:51 relies on that)."""

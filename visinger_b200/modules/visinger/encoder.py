@@ -51,6 +51,11 @@ class TextEncoder(nn.Module):
             self.embed_positions = SinusoidalPositionalEmbedding(hidden_channels, 0, init_size=DEFAULT_MAX_TARGET_POSITIONS)
 
     def forward(self, text_tokens, pitch_tokens, dur_tokens, mel2ph):
+        enc = self.encode_tokens(text_tokens, pitch_tokens, dur_tokens)
+        return expand_states(enc.transpose(1, 2), mel2ph).transpose(1, 2)    # [B, H, T]
+
+    def encode_tokens(self, text_tokens, pitch_tokens, dur_tokens):
+        """Everything before the length regulator: [B, T_ph] tokens -> phoneme-rate states [B, H, T_ph]."""
         nonpad = (text_tokens > 0).float().unsqueeze(1)                      # [B, 1, T_ph]
         emb = torch.cat([self.ph_emb(text_tokens), self.pitch_emb(pitch_tokens), self.dur_emb(dur_tokens)], 2)
         tok = self.linear(emb * self.embed_scale) * nonpad.transpose(1, 2)   # [B, T_ph, H]
@@ -60,8 +65,7 @@ class TextEncoder(nn.Module):
             pos = self.embed_positions(tok.shape[0], tok.shape[2], tok[..., 0])
             tok = tok + pos.transpose(1, 2)
         tok = tok * nonpad.transpose(1, 2)
-        enc = self.text_encoder(tok.transpose(1, 2), nonpad)                 # [B, H, T_ph]
-        return expand_states(enc.transpose(1, 2), mel2ph).transpose(1, 2)    # [B, H, T]
+        return self.text_encoder(tok.transpose(1, 2), nonpad)                # [B, H, T_ph]
 
 
 class FramePriorNetwork(nn.Module):
@@ -77,6 +81,44 @@ class FramePriorNetwork(nn.Module):
         # (SURVEY.md Appendix B-1).  The evident intent -- condition every frame on its log-f0 -- is implemented.
         out = self.proj(self.encoder(x, x_mask, g)) * x_mask
         return torch.split(out, self.hidden_channels, dim=1)
+
+    precision = "fp32"
+
+    @torch.no_grad()
+    def sample(self, x, x_mask, g=None, noise=None):
+        """Native fused head (vsg_frame_prior_forward): encoder -> proj -> split -> prior sampling
+        (models/visinger.py:107) in one library call.  Returns (z_p, mu_p, logs_p), each [B, H, T]."""
+        _lib.require_cuda(x, "x")
+        B, H, T = x.shape
+        if noise is None:
+            noise = torch.randn(B, H, T, device=x.device, dtype=torch.float32)
+        enc = self.encoder
+        params = list(self.parameters())
+        key = (str(x.device),) + tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, "_vsg_pack", None) is None or self._vsg_key != key:
+            c = _lib.VsgRelEncConfig(enc.hidden_channels, enc.filter_channels, enc.n_heads, enc.n_layers, enc.kernel_size,
+                                     enc.window_size, enc.gin_channels or 0)
+            self._vsg_pack = _lib.RelEncPack(c, dict(self.state_dict()), "", x.device, frame_prior=True)
+            self._vsg_key = key
+        pack = self._vsg_pack
+        prec = _lib.precision_code(self.precision)
+        xc, mc, nc = _lib.as_f32c(x), _lib.as_f32c(x_mask), _lib.as_f32c(noise)
+        gc = _lib.as_f32c(g) if g is not None else None
+        if gc is not None and tuple(gc.shape) != (B, 1, T):
+            raise RuntimeError(f"expected g of shape [B, 1, T] = {(B, 1, T)}, got {tuple(gc.shape)}")
+        stats = torch.empty(B, 2 * H, T, device=x.device, dtype=torch.float32)
+        z = torch.empty(B, H, T, device=x.device, dtype=torch.float32)
+        if B and T:
+            with torch.cuda.device(x.device):
+                nbytes = int(_lib.lib().vsg_frame_prior_workspace_bytes(pack.handle, B, T, prec))
+                ws = _lib.workspace(x.device, nbytes)
+                rc = _lib.lib().vsg_frame_prior_forward(pack.handle, xc.data_ptr(), mc.data_ptr(),
+                                                        gc.data_ptr() if gc is not None else None, nc.data_ptr(),
+                                                        stats.data_ptr(), z.data_ptr(), B, T, prec, ws.data_ptr(), ws.numel(),
+                                                        _lib.stream_ptr(x.device))
+            _lib.check(rc, "vsg_frame_prior_forward")
+        mu_p, logs_p = torch.split(stats, H, dim=1)
+        return z, mu_p, logs_p
 
 
 class PosteriorEncoder(nn.Module):
