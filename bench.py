@@ -18,6 +18,9 @@ the metric's roofline is quoted on), random weights of config/models/visinger.ya
             measured distance to the CPU oracle on a full-length utterance
   bf16      (N=1) the headline mode's distance to the CPU oracle on the same full-length utterance: relative L2,
             max-abs and the reference's own log-mel L1 (MelSpectrogramFixed, utils/audio/mel_processing.py:28-38)
+  full_model  (N=1) BASELINE.json configs[3]: the whole VISinger.forward(infer=True) -- native transformer stacks of the prior
+            network, length regulator, fused frame-prior head, flow, decoder -- on 64 mixed-length utterances, host
+            tokens -> host waveforms, with the bf16 mode's distance to the fp32 mode on the same padded batch
   sharded   BASELINE.json configs[4]: 512 mixed-length utterances (log-normal lengths, seed 1234) -> LPT shard by
             utterance -> length buckets -> per-rank serving loop -> pinned host results; strong scaling (fixed total
             work), with padding overhead and per-rank imbalance
@@ -64,6 +67,7 @@ def parse():
     ap.add_argument("--generic-epilogue", action="store_true", help="never use the signature-specialised kernels")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 timing / parity block")
     ap.add_argument("--no-sharded", action="store_true", help="skip the 512-utterance sharded sweep (configs[4])")
+    ap.add_argument("--no-full-model", action="store_true", help="skip the 64-utterance full-model leg (configs[3])")
     ap.add_argument("--no-chain-streams", action="store_true", help="run the resblock chains of a stage one after the other")
     ap.add_argument("--two-streams", action="store_true", help="store raw and activated copies of the resblock stream")
     return ap.parse_args()
@@ -280,6 +284,85 @@ def sharded_leg(hp, dev, rank, world, barrier, max_over_ranks, n_utt=512, frames
             "timed": "padded batches in pinned host memory -> results in pinned host memory, CUDA events, max over ranks"}
 
 
+def full_model_leg(dev, mel_l1=None, steps=3, n_utt=64, frames_per_batch=16000):
+    """BASELINE.json configs[3]: full infer on 64 mixed-length synthetic utterances (note / lyric token tensors of the
+    collater, SURVEY.md 8(d) length distribution, seed 1234) on one GPU.  Utterances are length-sorted into buckets of
+    <= 16000 padded frames (the reference sorts by length too: base_config.yaml:15); each bucket is one
+    VISinger.forward_graphed call (the whole forward from one CUDA graph per bucket shape).  Timed from pinned host token
+    tensors to pinned host waveforms, CUDA events.  Parity: the fp32 mode of this model is pinned to the reference's
+    whole-model golden by tests/test_model_mirror.py; the leg reports the bf16 mode's distance to it on the identical padded
+    batch (the shortest bucket, so the 260 ms/16k-frame fp32 kernels stay within seconds)."""
+    import numpy as np
+    import torch
+    from model_inputs import full_hparams, synth_utterances
+    from visinger_b200.models.visinger import VISinger
+    rng = np.random.default_rng(1234)
+    lengths = np.clip(np.round(80 * rng.lognormal(np.log(5.6), 0.45, n_utt)), 120, 1280).astype(int).tolist()
+    order = sorted(range(n_utt), key=lambda i: -lengths[i])
+    buckets, cur = [], []
+    for i in order:
+        if cur and (len(cur) + 1) * lengths[cur[0]] > frames_per_batch:
+            buckets.append(cur)
+            cur = []
+        cur.append(i)
+    buckets.append(cur)
+    torch.manual_seed(1234)
+    m = VISinger(73, 117, 132, full_hparams(), precision="bf16").eval()
+    for name, prm in m.named_parameters():       # the reference zero-initialises flow `post` (flow.py:63-64): make it non-trivial
+        if ".post." in name:
+            torch.nn.init.normal_(prm, std=0.05)
+    m = m.to(dev)
+    host, noises, outs = [], [], []
+    for k, b in enumerate(buckets):
+        hb = synth_utterances(seed=100 + k, n=len(b), lengths=[lengths[i] for i in b])
+        host.append({kk: v.pin_memory() for kk, v in hb.items()})
+        T = hb["mel2ph"].shape[1]
+        noises.append(torch.randn(len(b), 192, T, generator=torch.Generator().manual_seed(200 + k)).to(dev))
+        outs.append(torch.empty(len(b), T * 300, dtype=torch.float32).pin_memory())
+
+    def run_all():
+        for hb, nz, o in zip(host, noises, outs):
+            d = {kk: v.to(dev, non_blocking=True) for kk, v in hb.items()}
+            r = m.forward_graphed(d["text_tokens"], d["note_pitch"], d["note_dur"], d["mel2ph"], spk_id=d["spk_ids"], noise=nz)
+            o.copy_(r["wav_out"], non_blocking=True)
+
+    with torch.no_grad():
+        run_all()                                 # captures one graph per bucket shape
+        run_all()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run_all()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        # parity on the identical padded batch: bf16 vs the fp32 mode of the same model (shortest bucket)
+        hb = host[-1]
+        d = {kk: v.to(dev) for kk, v in hb.items()}
+        w16 = m(d["text_tokens"], d["note_pitch"], d["note_dur"], d["mel2ph"], spk_id=d["spk_ids"], infer=True, noise=noises[-1])["wav_out"]
+        m.precision = "fp32"
+        w32 = m(d["text_tokens"], d["note_pitch"], d["note_dur"], d["mel2ph"], spk_id=d["spk_ids"], infer=True, noise=noises[-1])["wav_out"]
+        n0 = lengths[buckets[-1][0]] * 300        # valid samples of the bucket's first utterance
+        a, r = w16[0, :n0].cpu(), w32[0, :n0].cpu()
+        finite = all(bool(torch.isfinite(o).all()) for o in outs)
+    assert finite, "full-model leg produced a non-finite waveform"
+    audio = sum(lengths) * FRAME_SEC
+    padded = sum(len(b) * lengths[b[0]] for b in buckets)
+    del m
+    torch.cuda.empty_cache()
+    return {"workload": f"VISinger.forward(infer=True), {n_utt} utterances, T_i = clip(round(80 * LogNormal(ln 5.6, 0.45)), 120, 1280) "
+                        f"frames (seed 1234, {audio:.0f} s audio), length-sorted into {len(buckets)} buckets of <= {frames_per_batch} "
+                        "padded frames, one CUDA graph per bucket; pinned host tokens -> pinned host waveforms",
+            "value": audio / (ms * 1e-3), "unit": UNIT, "ms": ms, "padding_overhead": padded / sum(lengths),
+            "precision_mode": "bf16 (prior network: native bf16 encoder kernels; hot path: tcgen05)",
+            "bf16_vs_fp32_mode": {"rel_l2": float((a - r).norm() / r.norm()), "max_abs": float((a - r).abs().max()),
+                                  "mel_l1": mel_l1(a[None], r[None]) if mel_l1 is not None else None,
+                                  "ref_max_abs": float(r.abs().max()),
+                                  "on": f"utterance 0 of the last bucket ({len(buckets[-1])} x {lengths[buckets[-1][0]]} frames), the "
+                                        "identical padded batch and noise in both modes"}}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -427,6 +510,10 @@ def main():
     sharded = None
     if args.precision == "bf16" and not args.no_sharded:
         sharded = sharded_leg(hp, dev, rank, world, barrier, max_over_ranks)
+    full_model = None
+    if args.precision == "bf16" and not args.no_full_model and world == 1 and (B, T) == (16, 1000):
+        # (the mel metric is the checker's -- oracle/ -- and only available when the cpu_baseline leg imported it)
+        full_model = full_model_leg(dev, mel_l1=None if args.no_cpu_baseline else __import__("oracle.visinger_oracle", fromlist=["mel_l1"]).mel_l1)
 
     if rank == 0:
         pk = peaks()
@@ -434,7 +521,7 @@ def main():
         e2e_value = world * audio_per_step * args.steps / (ms_e2e * 1e-3)
         dec_tflops = DEC_FLOP_PER_FRAME * B * T * args.steps / (ms_dec * 1e-3) / 1e12
         traffic, traffic_launches = None, 0   # DRAM bytes of the decoder's conv kernels per pass, from the committed ncu capture
-        tp = os.path.join(ROOT, "profiles", "r1_decoder_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_decoder_traffic.json")
         if os.path.exists(tp) and args.precision == "bf16" and (B, T) == (16, 1000):
             tj = json.load(open(tp))
             traffic, traffic_launches = tj["traffic_bytes"], tj["launches"]
@@ -459,8 +546,8 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": dec_tflops / peak, "frac_of_burst_peak": dec_tflops / pk["bf16_burst"], "traffic": traffic,
-                         "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum over the {traffic_launches} conv_tc / pair_tc / "
-                                         "conv_post launches of one decoder pass (profiles/r1_decoder_traffic.json)",
+                         "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum over the {traffic_launches} conv_tc / rp_tc / "
+                                         "conv_post launches of one decoder pass (profiles/r2_decoder_traffic.json)",
                          "kernel": "decoder convolutions (vsg_generator_forward region)",
                          "algorithmic": f"{DEC_FLOP_PER_FRAME} FLOP/frame x {B * T} frames",
                          "ms": ms_dec / args.steps, "peak_source": pk["src"] + ", sustained bf16"},
@@ -471,6 +558,8 @@ def main():
             line["parity_mode"] = parity
         if sharded is not None:
             line["sharded"] = sharded
+        if full_model is not None:
+            line["full_model"] = full_model
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
         print(json.dumps(line), flush=True)
