@@ -46,12 +46,7 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     assert re.search(r"UTC\w*MMA", sass), "no tcgen05.mma (UTC*MMA) in SASS"
     assert "UTMALDG" in sass, "no TMA loads (UTMALDG) in SASS"
     assert "LDTM" in sass, "no tcgen05.ld (LDTM) in SASS"
-    # warp-level mma (HMMA) is allowed in ONE kernel: the flash attention of the transformer encoder (relenc_tc.cuh says
-    # why); every convolution of the hot path must be tcgen05
-    for fn in re.split(r"\n\s*Function : ", sass)[1:]:
-        name = fn.split("\n", 1)[0]
-        if re.search(r"(?<!UTC)HMMA", fn):
-            assert "relenc_attention_bf16_kernel" in name, f"legacy mma.sync in {name}"
+    assert not re.search(r"(?<!UTC)HMMA", sass), "legacy mma.sync path present"
 
 
 def test_pack_create_rejects_bad_arguments_without_gpu():

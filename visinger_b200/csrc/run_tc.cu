@@ -7,6 +7,7 @@
 #include "rb_tc.cuh"
 #include "rp_tc.cuh"
 #include "relenc_tc.cuh"
+#include "attn_tc.cuh"
 
 #include <algorithm>
 #include <map>
@@ -1078,13 +1079,27 @@ size_t relenc_ws_bytes_tc(const VsgPack* P, int B, int T, int g_t) {
 namespace {
 template <int DK>
 int launch_attention_bf16(const __nv_bfloat16* qkv, const float* mask, const float* ek, const float* ev, __nv_bfloat16* o, int B,
-                          int n_heads, int T, int w, cudaStream_t st) {
-  const size_t sm = relenc_attention_bf16_smem(DK, w);
-  if (sm > 48 * 1024)
-    VSG_CUDA_TRY(cudaFuncSetAttribute(relenc_attention_bf16_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  dim3 grid((T + kAttQ - 1) / kAttQ, n_heads, B);
-  relenc_attention_bf16_kernel<DK><<<grid, 128, sm, st>>>(qkv, mask, ek, ev, o, n_heads, T, w);
-  VSG_LAUNCH_CHECK("relenc_attention_bf16_kernel");
+                          int n_heads, int T, int w, int* err, cudaStream_t st) {
+  if (T > 128 * tc::kAtMaxTiles) return fail(VSG_EUNSUPPORTED, "attention: sequence of %d frames (supported: <= %d)", T, 128 * tc::kAtMaxTiles);
+  if (w > 7) return fail(VSG_EUNSUPPORTED, "attention: relative-position window %d (supported: <= 7)", w);
+  const int H = n_heads * DK;
+  constexpr int CW = AttnSmem<DK>::CW;
+  CUtensorMap tm;   // the fused projection's output [B, T, 3H] as (channels, frames, utterances)
+  VSG_TRY(encode_3d(&tm, qkv, (uint64_t)3 * H, (uint64_t)T, (uint64_t)B, (uint64_t)3 * H, (uint64_t)T * 3 * H, (uint32_t)CW, 128, CW));
+  AttnTC p;
+  p.B = B; p.T = T; p.n_heads = n_heads; p.w = w; p.n_tiles = (T + 127) / 128;
+  p.mask = mask; p.Ek = ek; p.Ev = ev; p.o = o; p.error_flag = err;
+  const size_t sm = AttnSmem<DK>::bytes;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  VSG_CUDA_TRY(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    VSG_CUDA_TRY(cudaFuncSetAttribute(relenc_attention_tc_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    attr_set[dev & 63] = true;
+  }
+  dim3 grid(p.n_tiles, n_heads, B);
+  relenc_attention_tc_kernel<DK><<<grid, tc::kAtThreads, sm, st>>>(tm, p);
+  VSG_LAUNCH_CHECK("relenc_attention_tc_kernel");
   return VSG_OK;
 }
 }  // namespace
@@ -1131,12 +1146,12 @@ static int relenc_core_tc(const VsgPack* P, const float* x, const float* mask, c
       VSG_TRY(launch_conv_tc(P, L.qkv_tc, xb, B, T, 0, 1, T, 1, 0, T, ep, opt, err, st));
     }
     switch (dk) {
-      case 16: VSG_TRY(launch_attention_bf16<16>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
-      case 32: VSG_TRY(launch_attention_bf16<32>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
-      case 48: VSG_TRY(launch_attention_bf16<48>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
-      case 64: VSG_TRY(launch_attention_bf16<64>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
-      case 96: VSG_TRY(launch_attention_bf16<96>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
-      case 128: VSG_TRY(launch_attention_bf16<128>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, st)); break;
+      case 16: VSG_TRY(launch_attention_bf16<16>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, err, st)); break;
+      case 32: VSG_TRY(launch_attention_bf16<32>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, err, st)); break;
+      case 48: VSG_TRY(launch_attention_bf16<48>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, err, st)); break;
+      case 64: VSG_TRY(launch_attention_bf16<64>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, err, st)); break;
+      case 96: VSG_TRY(launch_attention_bf16<96>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, err, st)); break;
+      case 128: VSG_TRY(launch_attention_bf16<128>(qkv, mask, L.ek, L.ev, ob, B, e.n_heads, T, e.window, err, st)); break;
       default: return fail(VSG_EUNSUPPORTED, "attention head width %d (supported: 16, 32, 48, 64, 96, 128)", dk);
     }
     {  // x = x + conv_o(attn)
