@@ -423,7 +423,7 @@ def debug_conv1d_bf16(x_bld: torch.Tensor, w: torch.Tensor, bias, dilation: int,
     require_cuda(x_bld, "x")
     assert x_bld.dtype == torch.bfloat16 and x_bld.is_contiguous()
     B, Lx, Cin = x_bld.shape
-    planes = 2 if (flags & 4) else 1           # split-bf16: [hi | lo] planes per row
+    planes = 3 if (flags & 256) else 2 if (flags & 4) else 1    # split-bf16: [hi | lo] ([hi | mid | lo]) planes per row
     Cin //= planes
     Cout, _, k = w.shape
     wh = w.detach().to("cpu", torch.float32).contiguous()

@@ -27,7 +27,19 @@ struct DeviceGuard {
 
 size_t flow_ws(const VsgPack* p, int B, int T, int prec) {
   if (!p->has_flow) return 0;
-  return prec == VSG_PRECISION_BF16 ? flow_ws_bytes_tc(p, B, T) : flow_ws_bytes_f32(p, B, T);
+  if (prec == VSG_PRECISION_BF16) return flow_ws_bytes_tc(p, B, T, 1);
+  if (prec == VSG_PRECISION_BF16X3) return std::max(flow_ws_bytes_tc(p, B, T, 3), flow_ws_bytes_f32(p, B, T));
+  return flow_ws_bytes_f32(p, B, T);
+}
+// fp32: CUDA-core FFMA kernels.  bf16: tcgen05, one bf16 plane.  bf16x3: tcgen05 on three bf16 planes per value (the
+// flow's z <= 1e-5 needs all 24 mantissa bits of its state; the decoder's 1e-4 is met by two planes).
+int run_flow(const VsgPack* pack, const float* x, const float* mask, const float* g, float* y, int B, int T, int reverse,
+             int precision, Workspace& ws, cudaStream_t st) {
+  if (precision == VSG_PRECISION_BF16) return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, st, 1);
+  if (precision == VSG_PRECISION_BF16X3 && x3_flow_on_tensor_cores() && !pack->flow_layers.empty() &&
+      pack->flow_layers[0].pre_x6[0].has_tmap)
+    return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, st, 3);
+  return flow_forward_f32(pack, x, mask, g, y, B, T, reverse, ws, st);
 }
 size_t dec_ws(const VsgPack* p, int B, int T, int prec) {
   if (!p->has_dec) return 0;
@@ -64,10 +76,7 @@ extern "C" int vsg_flow_forward(const VsgPack* pack, const float* x, const float
   DeviceGuard dg(pack->device);
   if (!dg.ok) return fail(VSG_ECUDA, "cannot select device %d", pack->device);
   Workspace ws(workspace, workspace_bytes);
-  // the flow's 1e-5 tolerance needs full fp32 state: only the plain bf16 mode runs it on the tensor cores
-  if (precision != VSG_PRECISION_BF16)
-    return flow_forward_f32(pack, x, mask, g, y, B, T, reverse, ws, (cudaStream_t)stream);
-  return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, (cudaStream_t)stream);
+  return run_flow(pack, x, mask, g, y, B, T, reverse, precision, ws, (cudaStream_t)stream);
 }
 
 extern "C" int vsg_generator_forward(const VsgPack* pack, const float* z, const float* g, float* wav, int32_t B,
@@ -112,8 +121,7 @@ extern "C" int vsg_infer(const VsgPack* pack, const float* mu_p, const float* lo
   // z_p = (mu_p + noise * exp(logs_p)) * mask                       models/visinger.py:107
   VSG_TRY(prior_sample(mu_p, logs_p, noise, mask, z, B, C, T, st));
   // z_q = flow(z_p, mask, g, reverse=True) * mask                    models/visinger.py:109
-  if (precision != VSG_PRECISION_BF16) VSG_TRY(flow_forward_f32(pack, z, mask, g, z, B, T, 1, ws, st));
-  else VSG_TRY(flow_forward_tc(pack, z, mask, g, z, B, T, 1, ws, st));
+  VSG_TRY(run_flow(pack, z, mask, g, z, B, T, 1, precision, ws, st));
   VSG_TRY(mask_mul(z, mask, z, B, C, T, st));
   if (z_q_out)
     VSG_CUDA_TRY(cudaMemcpyAsync(z_q_out, z, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -221,8 +229,7 @@ extern "C" int vsg_infer_zp(const VsgPack* pack, const float* z_p, const float* 
   float* z = ws.take<float>((size_t)B * C * T);
   if (ws.overflow) return fail(VSG_ENOMEM, "workspace too small");
   const size_t mark = ws.off;
-  if (precision != VSG_PRECISION_BF16) VSG_TRY(flow_forward_f32(pack, z_p, mask, g, z, B, T, 1, ws, st));
-  else VSG_TRY(flow_forward_tc(pack, z_p, mask, g, z, B, T, 1, ws, st));
+  VSG_TRY(run_flow(pack, z_p, mask, g, z, B, T, 1, precision, ws, st));
   VSG_TRY(mask_mul(z, mask, z, B, C, T, st));
   if (z_q_out)
     VSG_CUDA_TRY(cudaMemcpyAsync(z_q_out, z, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));

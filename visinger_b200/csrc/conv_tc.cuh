@@ -110,7 +110,9 @@ enum : int { EPI_TC_LINEAR = 0, EPI_TC_GATE = 1, EPI_TC_COUPLE = 2 };
 //                    fp32 debug copy                                              (last conv2 of a resblock)
 // (Separate images pay off for the decoder's long launches; the flow's ~20 us launches are better off sharing ONE warm
 // image -- splitting the generic kernel per mode made the step slower.)
-enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2, EPI_SIG_LINEAR = 3 };
+//   EPI_SIG_X6       the generic epilogue on THREE bf16 planes per tensor (hi, mid, lo = 24 mantissa bits: every fp32 value
+//                    exactly), linear / gate / coupling with full-precision tanh / sigmoid: the flow at the fp32 tolerance
+enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2, EPI_SIG_LINEAR = 3, EPI_SIG_X6 = 4 };
 
 namespace tc {
 
@@ -340,8 +342,8 @@ __device__ __forceinline__ void stage_out_act(const float* v, uint32_t base, uin
   }
 }
 
-// Write one row chunk of OW fp32 values into a swizzled bf16 staging tile: one plane (plain bf16) or two planes
-// hi = bf16(v), lo = bf16(v - hi) (split-bf16: the pair carries ~16 mantissa bits).
+// Write one row chunk of OW fp32 values into a swizzled bf16 staging tile: one plane (plain bf16), two planes
+// hi = bf16(v), lo = bf16(v - hi) (split-bf16: the pair carries ~16 mantissa bits) or three (the fp32 value exactly).
 template <int OW>
 __device__ __forceinline__ void stage_out(const float* v, uint32_t base, uint32_t row_off, uint32_t swz_mask, int n_parts,
                                           uint32_t part_bytes) {
@@ -353,15 +355,23 @@ __device__ __forceinline__ void stage_out(const float* v, uint32_t base, uint32_
     for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
     const uint32_t addr = base + swz(row_off + c * 16, swz_mask);
     sts128(addr, make_uint4(h[0], h[1], h[2], h[3]));
-    if (n_parts == 2) {
+    if (n_parts >= 2) {
       uint32_t l[4];
+      float r0[4], r1[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float r0 = v[8 * c + 2 * i] - __uint_as_float(h[i] << 16);
-        const float r1 = v[8 * c + 2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
-        l[i] = pack_bf16x2(r0, r1);
+        r0[i] = v[8 * c + 2 * i] - __uint_as_float(h[i] << 16);
+        r1[i] = v[8 * c + 2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
+        l[i] = pack_bf16x2(r0[i], r1[i]);
       }
       sts128(addr + part_bytes, make_uint4(l[0], l[1], l[2], l[3]));
+      if (n_parts == 3) {   // third plane: what the first two leave of the 24-bit mantissa (exact)
+        uint32_t m[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          m[i] = pack_bf16x2(r0[i] - __uint_as_float(l[i] << 16), r1[i] - __uint_as_float(l[i] & 0xFFFF0000u));
+        sts128(addr + 2u * part_bytes, make_uint4(m[0], m[1], m[2], m[3]));
+      }
     }
   }
 }
@@ -392,7 +402,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const int part_coff = p.part_coff;
   const uint32_t e_buf_bytes = p.e_buf_bytes, swz_in = p.e_swz_mask, swz_out = p.e_out_swz_mask;
   const uint32_t part_bytes = p.e_part_bytes;     // one bf16 plane (hi or lo) of a staging buffer
-  constexpr bool kGen = SIG == EPI_SIG_GENERIC;
+  constexpr bool kGen = SIG == EPI_SIG_GENERIC || SIG == EPI_SIG_X6;
   static_assert(kGen || (MODE == EPI_TC_LINEAR && NP == 1), "specialised signatures are plain-bf16 linear epilogues");
   constexpr bool kRt = kGen || SIG == EPI_SIG_LINEAR;      // adds / outputs / scale decided at run time
   const bool has_add0 = kRt ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT);
@@ -535,11 +545,16 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
                 u.z = bf16x2_scale_min(u.z, inv_slope); u.w = bf16x2_scale_min(u.w, inv_slope);
               }
               unpack_bf16x8(u, f);
-              if (n_parts == 2) {
+              if (n_parts >= 2) {
                 float g2[8];
                 unpack_bf16x8(lds128(base + part_bytes + swz(row_off_in + c * 16, swz_in)), g2);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += g2[i];
+                if (n_parts == 3) {
+                  unpack_bf16x8(lds128(base + 2u * part_bytes + swz(row_off_in + c * 16, swz_in)), g2);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] += g2[i];
+                }
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -554,11 +569,16 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
             for (int c = 0; c < CW / 8; ++c) {
               float f[8];
               unpack_bf16x8(lds128(base + swz(row_off_in + c * 16, swz_in)), f);
-              if (n_parts == 2) {
+              if (n_parts >= 2) {
                 float g2[8];
                 unpack_bf16x8(lds128(base + part_bytes + swz(row_off_in + c * 16, swz_in)), g2);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += g2[i];
+                if (n_parts == 3) {
+                  unpack_bf16x8(lds128(base + 2u * part_bytes + swz(row_off_in + c * 16, swz_in)), g2);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] += g2[i];
+                }
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[8 * c + i] += f[i];
@@ -578,9 +598,13 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
         if (MODE == EPI_TC_GATE) {
 #pragma unroll
           for (int c = 0; c < CW / 2; ++c) {
-            const float t = tanh_fast(v[2 * c]);
-            const float sg = 0.5f * tanh_fast(0.5f * v[2 * c + 1]) + 0.5f;   // sigmoid(x) = (1 + tanh(x/2)) / 2
-            v[c] = t * sg;
+            if (NP == 1) {
+              const float t = tanh_fast(v[2 * c]);
+              const float sg = 0.5f * tanh_fast(0.5f * v[2 * c + 1]) + 0.5f;   // sigmoid(x) = (1 + tanh(x/2)) / 2
+              v[c] = t * sg;
+            } else {   // fp32-tolerance modes: the libm-grade functions of the fp32 kernels (kernels_f32.cuh)
+              v[c] = tanhf(v[2 * c]) * (1.0f / (1.0f + expf(-v[2 * c + 1])));
+            }
           }
         }
         if (out_f32) {   // debug / parity hook only: plain per-thread stores
@@ -855,6 +879,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!SMALL && p.cw == 64) VSG_EPI(64);
       else if (p.cw == 32) VSG_EPI(32);
       else VSG_EPI(16);
+    } else if constexpr (SIG == EPI_SIG_X6) {   // three planes per tensor: chunks of 32 / 16 channels (staging = 3 x the plain size)
+#define VSG_EPI6(CWV)                                                                                             \
+  do {                                                                                                            \
+    if (p.mode == EPI_TC_LINEAR)                                                                                  \
+      conv_tc_epilogue<CWV, EPI_TC_LINEAR, 3, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp); \
+    else if (p.mode == EPI_TC_GATE)                                                                               \
+      conv_tc_epilogue<CWV, EPI_TC_GATE, 3, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);   \
+    else                                                                                                          \
+      conv_tc_epilogue<CWV, EPI_TC_COUPLE, 3, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp); \
+  } while (0)
+      if (p.cw == 32) VSG_EPI6(32);
+      else VSG_EPI6(16);
+#undef VSG_EPI6
     } else {   // specialised signature: plain-bf16 linear epilogue with compile-time feature flags
       if (!SMALL && p.cw == 64)
         conv_tc_epilogue<64, EPI_TC_LINEAR, 1, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
@@ -877,10 +914,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ---- glue kernels of the bf16 path --------------------------------------------------------------
 
-// [B, C, T] fp32 (reference layout) -> [B, T, C] bf16 (channels-last).  32x32 smem tile.
-// split != 0: rows are [hi (C) | lo (C)] with hi = bf16(x), lo = bf16(x - hi)  (split-bf16 mode).
+// [B, C, T] fp32 (reference layout) -> [B, T, planes * C] bf16 (channels-last).  32x32 smem tile.
+// planes = 2: rows are [hi (C) | lo (C)] with hi = bf16(x), lo = bf16(x - hi)  (split-bf16 mode);
+// planes = 3: [hi | mid | lo], the fp32 value exactly (the flow at the fp32 tolerance).
 __global__ void transpose_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int T,
-                                         int split) {
+                                         int planes) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
@@ -889,14 +927,16 @@ __global__ void transpose_to_bf16_kernel(const float* __restrict__ x, __nv_bfloa
     tile[i][tx] = (c < C && t < T) ? x[((long long)b * C + c) * T + t] : 0.f;
   }
   __syncthreads();
-  const int W = split ? 2 * C : C;
+  const int W = planes * C;
   for (int i = ty; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + tx;
     if (t < T && c < C) {
-      const float v = tile[tx][i];
-      const __nv_bfloat16 hi = __float2bfloat16(v);
-      y[((long long)b * T + t) * W + c] = hi;
-      if (split) y[((long long)b * T + t) * W + C + c] = __float2bfloat16(v - __bfloat162float(hi));
+      float v = tile[tx][i];
+      for (int pl = 0; pl < planes; ++pl) {
+        const __nv_bfloat16 h = __float2bfloat16(v);
+        y[((long long)b * T + t) * W + pl * C + c] = h;
+        v -= __bfloat162float(h);
+      }
     }
   }
 }
@@ -929,15 +969,19 @@ __global__ void posterior_sample_from_stats_kernel(const float* __restrict__ sta
   z[i] = (stats[b * 2 * CT + r] + noise[i] * expf(stats[b * 2 * CT + CT + r])) * mask[b * T + t];
 }
 
-// [B, T, C] bf16 -> [B, C, T] fp32; flip != 0 reverses the channel order (an odd number of Flips).
+// [B, T, planes * C] bf16 -> [B, C, T] fp32 (the planes of a value are summed); flip != 0 reverses the channel order
+// (an odd number of Flips).
 __global__ void transpose_from_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int T,
-                                           int flip) {
+                                           int flip, int planes) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + tx;
-    tile[i][tx] = (c < C && t < T) ? __bfloat162float(x[((long long)b * T + t) * C + c]) : 0.f;
+    float v = 0.f;
+    if (c < C && t < T)
+      for (int pl = 0; pl < planes; ++pl) v += __bfloat162float(x[((long long)b * T + t) * planes * C + pl * C + c]);
+    tile[i][tx] = v;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {

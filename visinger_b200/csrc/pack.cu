@@ -124,18 +124,21 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
     VSG_TRY(L.bias(p + "pre", H, b, true));
     VSG_TRY(pack_conv_f32(L, W, b, H, half, 1, Identity{}, &fl.pre[0]));
     VSG_TRY(pack_conv_tc(P, W, b, H, half, 1, &fl.pre_tc[0]));
+    VSG_TRY(pack_conv_tc(P, W, b, H, half, 1, &fl.pre_x6[0], 3));
     {
       std::vector<float> Wf(W.size());
       for (int co = 0; co < H; ++co)
         for (int ci = 0; ci < half; ++ci) Wf[(size_t)co * half + ci] = W[(size_t)co * half + (half - 1 - ci)];
       VSG_TRY(pack_conv_f32(L, Wf, b, H, half, 1, Identity{}, &fl.pre[1]));
       VSG_TRY(pack_conv_tc(P, Wf, b, H, half, 1, &fl.pre_tc[1]));
+      VSG_TRY(pack_conv_tc(P, Wf, b, H, half, 1, &fl.pre_x6[1], 3));
     }
     // post: Conv1d(H -> half, 1)      flow.py:62 (mean_only)
     VSG_TRY(L.eff_weight(p + "post", half, H, 1, W));
     VSG_TRY(L.bias(p + "post", half, b, true));
     VSG_TRY(pack_conv_f32(L, W, b, half, H, 1, Identity{}, &fl.post[0]));
     VSG_TRY(pack_conv_tc(P, W, b, half, H, 1, &fl.post_tc[0]));
+    VSG_TRY(pack_conv_tc(P, W, b, half, H, 1, &fl.post_x6[0], 3));
     {
       std::vector<float> Wf(W.size()), bf(b.size());
       for (int co = 0; co < half; ++co) {
@@ -144,6 +147,7 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
       }
       VSG_TRY(pack_conv_f32(L, Wf, bf, half, H, 1, Identity{}, &fl.post[1]));
       VSG_TRY(pack_conv_tc(P, Wf, bf, half, H, 1, &fl.post_tc[1]));
+      VSG_TRY(pack_conv_tc(P, Wf, bf, half, H, 1, &fl.post_x6[1], 3));
     }
     // WaveNet                        encoder.py:131-165
     fl.in_layers.resize(NL);
@@ -151,6 +155,7 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
     fl.in_tc.resize(NL);
     fl.res_tc.resize(NL);
     fl.skip_tc.resize(NL);
+    fl.in_x6.resize(NL); fl.res_x6.resize(NL); fl.skip_x6.resize(NL);
     for (int i = 0; i < NL; ++i) {
       const std::string pi = p + "enc.in_layers." + std::to_string(i);
       VSG_TRY(L.eff_weight(pi, 2 * H, H, K, W));
@@ -164,6 +169,7 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
           memcpy(&Wg[(size_t)gi(co) * H * K], &W[(size_t)co * H * K], (size_t)H * K * sizeof(float));
         }
         VSG_TRY(pack_conv_tc(P, Wg, bg, 2 * H, H, K, &fl.in_tc[i]));
+        VSG_TRY(pack_conv_tc(P, Wg, bg, 2 * H, H, K, &fl.in_x6[i], 3));
       }
       const int rs = (i < NL - 1) ? 2 * H : H;
       const std::string pr = p + "enc.res_skip_layers." + std::to_string(i);
@@ -174,9 +180,12 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
         std::vector<float> Wr(W.begin(), W.begin() + (size_t)H * H), br(b.begin(), b.begin() + H);
         std::vector<float> Ws(W.begin() + (size_t)H * H, W.end()), bs(b.begin() + H, b.end());
         VSG_TRY(pack_conv_tc(P, Wr, br, H, H, 1, &fl.res_tc[i]));
+        VSG_TRY(pack_conv_tc(P, Wr, br, H, H, 1, &fl.res_x6[i], 3));
         VSG_TRY(pack_conv_tc(P, Ws, bs, H, H, 1, &fl.skip_tc[i]));
+        VSG_TRY(pack_conv_tc(P, Ws, bs, H, H, 1, &fl.skip_x6[i], 3));
       } else {
         VSG_TRY(pack_conv_tc(P, W, b, H, H, 1, &fl.skip_tc[i]));
+        VSG_TRY(pack_conv_tc(P, W, b, H, H, 1, &fl.skip_x6[i], 3));
       }
     }
     if (c.flow_gin > 0) {
@@ -356,7 +365,7 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
   VSG_TRY(L.bias(pre + "conv_pre", UIC, b, true));
   VSG_TRY(pack_conv_f32(L, W, b, UIC, C0, 7, Identity{}, &P->conv_pre));
   VSG_TRY(pack_conv_tc(P, W, b, UIC, C0, 7, &P->conv_pre_tc));
-  VSG_TRY(pack_conv_tc(P, W, b, UIC, C0, 7, &P->conv_pre_x3, true));
+  VSG_TRY(pack_conv_tc(P, W, b, UIC, C0, 7, &P->conv_pre_x3, 2));
   if (c.dec_gin > 0) {   // cond: Conv1d(gin -> UIC, 1)            decoder.py:37-38
     VSG_TRY(L.eff_weight(pre + "cond", UIC, c.dec_gin, 1, W));
     VSG_TRY(L.bias(pre + "cond", UIC, b, true));
@@ -398,7 +407,7 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
             Wc[((size_t)co * st.Cin + ci) * nr + jj] = W[((size_t)ci * st.Cout + co) * k + j0 + s * (nr - 1 - jj)];
       VSG_TRY(pack_conv_f32(L, Wc, b, st.Cout, st.Cin, nr, Identity{}, &ph.f32));
       VSG_TRY(pack_conv_tc(P, Wc, b, st.Cout, st.Cin, nr, &ph.tc));
-      VSG_TRY(pack_conv_tc(P, Wc, b, st.Cout, st.Cin, nr, &ph.x3, true));
+      VSG_TRY(pack_conv_tc(P, Wc, b, st.Cout, st.Cin, nr, &ph.x3, 2));
     }
     {   // merged polyphase convolution for the tensor-core path (one launch, contiguous stores)
       int off_min = 1 << 30, off_max = -(1 << 30);
@@ -443,7 +452,7 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
         VSG_TRY(L.bias(n1, ch, b, true));
         VSG_TRY(pack_conv_f32(L, W, b, ch, ch, rb.kernel, Identity{}, &rb.c1[q]));
         VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_tc[q]));
-        VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_x3[q], true));
+        VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_x3[q], 2));
         if (c.dec_resblock == 1 && rb.dilations[q] == 1) VSG_TRY(pack_conv_rowpacked(P, W, ch, rb.kernel, &rb.c1_rp[q]));
         if (c.dec_resblock == 1) {
           const std::string n2 = pb + "convs2." + std::to_string(q);
@@ -451,7 +460,7 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
           VSG_TRY(L.bias(n2, ch, b, true));
           VSG_TRY(pack_conv_f32(L, W, b, ch, ch, rb.kernel, Identity{}, &rb.c2[q]));
           VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_tc[q]));
-          VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_x3[q], true));
+          VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_x3[q], 2));
           VSG_TRY(pack_conv_rowpacked(P, W, ch, rb.kernel, &rb.c2_rp[q]));
           b2s.push_back(b);
         }

@@ -4,9 +4,9 @@
 
 namespace vsg {
 // Conv1d-style weight W[co][ci][j] (+ bias[co]) -> bf16 K-major pack and its TMA tensor map.
-// x3: split-bf16 pack [W_hi | W_lo] for the fp32-tolerance tensor-core mode.
+// planes = 2: split-bf16 pack [W_hi | W_lo] (decoder at the fp32 tolerance); planes = 3: [W_hi | W_mid | W_lo] (flow).
 int pack_conv_tc(VsgPack* P, const std::vector<float>& W, const std::vector<float>& b, int Cout, int Cin, int k,
-                 ConvWTC* out, bool x3 = false);
+                 ConvWTC* out, int planes = 1);
 // Dilation-1 Conv1d(C -> C, k), C in {16, 32}, as Conv1d(64 -> 64) over rows of 64 / C time steps with block-Toeplitz
 // weights (rp_tc.cuh); leaves out->has_tmap false for shapes the row-packed kernel does not take.
 int pack_conv_rowpacked(VsgPack* P, const std::vector<float>& W, int C, int k, ConvWTC* out);

@@ -95,6 +95,7 @@ struct EpiTC {
   const float* mask = nullptr;      // [B][Lout]
   int couple_sign = -1;
   int ld = 0;                       // leading dimension (channels per row) of the add / out tensors; 0 = their own width
+  int part_stride = 0;              // channels between the bf16 planes of the add / out tensors; 0 = their own width
   int add0_is_act = 0;              // add0 holds leaky_relu(residual): invert it in the epilogue
   const float* bias = nullptr;
   const float* bcond = nullptr; int bcond_bs = 0;
@@ -143,9 +144,10 @@ static const TunedPlan kTunedPlans[] = {
 // One convolution launch.  x: [B, Lin, Cin] bf16 channels-last; add/out tensors: [B, Lout, Cout].
 int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, int B, int Lin, int in_off0, int dil,
                    int Lq, int out_stride, int out_phase, int Lout, const EpiTC& e, const TCOptions& opt, int* error_flag,
-                   cudaStream_t st, int x_ld = 0) {
+                   cudaStream_t st, int x_ld = 0, int x_part_stride = 0) {
   if (x_ld == 0) x_ld = w.CinT;
-  if (w.x3 && e.mode != EPI_TC_LINEAR) return fail(VSG_EUNSUPPORTED, "split-bf16 supports the linear epilogue only");
+  if (x_part_stride == 0) x_part_stride = w.Cin;          // channels between the bf16 planes of an input row
+  if (w.planes == 2 && e.mode != EPI_TC_LINEAR) return fail(VSG_EUNSUPPORTED, "split-bf16 supports the linear epilogue only");
   if (!w.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 16 "
                                                  "(conv %d -> %d)", w.Cin, w.Cout);
   if (Lq <= 0 || B <= 0) return VSG_OK;
@@ -159,8 +161,10 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   // low-channel convolutions run the SMALL kernel instantiation (<= 32-channel epilogue chunks, 2 CTAs / SM)
   bool small = NT <= 64 && (NT <= 32 || NT % 32 == 0);
   int cw_max = small ? std::min(NT, 32) : pick_cw(NT);
+  if (w.planes == 3) cw_max = std::min(cw_max, 32);       // the three-plane epilogue is instantiated for 32 / 16 channels
   const int cout_eff = e.mode == EPI_TC_GATE ? w.Cout / 2 : w.Cout;  // channels of the add / out tensors
-  const int n_parts = w.x3 ? 2 : 1;                                    // bf16 planes of every epilogue tensor
+  const int n_parts = w.planes;                                        // bf16 planes of every epilogue tensor
+  const int part_stride = e.part_stride ? e.part_stride : cout_eff;
   const int ld = e.ld ? e.ld : n_parts * cout_eff;
   const int n_adds = (e.add0 ? 1 : 0) + (e.add1 ? 1 : 0), n_outs = (e.out_raw ? 1 : 0) + (e.out_act ? 1 : 0);
   const size_t half_budget = 110 * 1024;
@@ -178,18 +182,36 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     q.mb = mb;
     q.KC = KC; q.ktaps = w.ktaps; q.dil = dil; q.in_off0 = in_off0;
     const int nc = w.Cin / KC;
-    if ((w.x3 ? 2 : 1) * nc > kMaxAChunks) return false;
     q.n_achunks = 0; q.n_wtiles = 0;
-    for (int part = 0; part < (w.x3 ? 2 : 1); ++part)       // x3: hi chunks meet W_hi and W_lo, lo chunks meet W_hi
-      for (int c = 0; c < nc; ++c) {
-        const int i = q.n_achunks++;
-        q.a_coff[i] = part * w.Cin + c * KC;
-        q.n_wpass[i] = (w.x3 && part == 0) ? 2 : 1;
-        q.w_coff[i][0] = c * KC;
-        q.w_coff[i][1] = w.Cin + c * KC;
-        q.n_wtiles += q.n_wpass[i] * w.ktaps;
-      }
-    q.n_parts = n_parts; q.part_coff = cout_eff;
+    if (w.planes == 3) {
+      // Three planes per operand (24 mantissa bits), six of the nine plane products (the rest are below 2^-24).  The
+      // tensor pipe's fp32 accumulation TRUNCATES once per instruction (tools/acc_probe.py), at the magnitude of the
+      // running sum: the small products go first, onto a small accumulator, and hi x hi comes last in a sweep of its own
+      // (tests/emulate_tc_accumulate.py: z error 1.1e-6 in this order, 1.6e-5 with hi x hi first).
+      static const int sweeps[4][3] = {{2, 0, -1}, {1, 1, 0}, {0, 2, 1}, {0, 0, -1}};   // {A plane, W plane, W plane | -1}
+      if (4 * nc > kMaxAChunks) return false;
+      for (int sIdx = 0; sIdx < 4; ++sIdx)
+        for (int c = 0; c < nc; ++c) {
+          const int i = q.n_achunks++;
+          q.a_coff[i] = sweeps[sIdx][0] * x_part_stride + c * KC;
+          q.n_wpass[i] = sweeps[sIdx][2] >= 0 ? 2 : 1;
+          q.w_coff[i][0] = sweeps[sIdx][1] * w.Cin + c * KC;
+          q.w_coff[i][1] = (sweeps[sIdx][2] >= 0 ? sweeps[sIdx][2] : 0) * w.Cin + c * KC;
+          q.n_wtiles += q.n_wpass[i] * w.ktaps;
+        }
+    } else {
+      if (w.planes * nc > kMaxAChunks) return false;
+      for (int part = 0; part < w.planes; ++part)       // x3: hi chunks meet W_hi and W_lo, lo chunks meet W_hi
+        for (int c = 0; c < nc; ++c) {
+          const int i = q.n_achunks++;
+          q.a_coff[i] = part * x_part_stride + c * KC;
+          q.n_wpass[i] = (w.x3 && part == 0) ? 2 : 1;
+          q.w_coff[i][0] = c * KC;
+          q.w_coff[i][1] = w.Cin + c * KC;
+          q.n_wtiles += q.n_wpass[i] * w.ktaps;
+        }
+    }
+    q.n_parts = n_parts; q.part_coff = part_stride;
     q.Cout = w.Cout; q.n_tile = NT; q.n_ntiles = w.Cout / NT; q.CoutT = w.CoutT;
     q.halo_mode = (halo_ok && (w.ktaps > 1 || mb > 1)) ? 1 : 0;
     const int rows = q.halo_mode ? 128 * mb + halo : 128;
@@ -221,7 +243,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
       // One A stage feeds (passes x taps x mb x KC/16) MMAs; a TMA round trip is ~3000 cycles, so a short-kernel conv
       // (k = 3: ~1500 cycles of MMA per stage at C = 256) needs 3-4 stages in flight where k = 11 is fine with 2.
       const double mma_cyc = std::max(40.0, NT / 2.0);
-      const double stage_cyc = (double)(w.x3 ? 1.5 : 1.0) * w.ktaps * mb * (KC / 16) * mma_cyc;
+      const double stage_cyc = (double)(w.planes > 1 ? 1.5 : 1.0) * w.ktaps * mb * (KC / 16) * mma_cyc;
       int want_a = std::min(4, std::max(2, (int)(3000.0 / stage_cyc) + 2));
       if (2 * (size_t)q.a_stage_bytes + e_bytes + 2 * (size_t)q.w_stage_bytes > budget) return false;
       while (want_a > 2 && (size_t)want_a * q.a_stage_bytes + e_bytes + 3 * (size_t)q.w_stage_bytes > budget) --want_a;
@@ -259,13 +281,13 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     // measured best plans (tools/tune_plans.py on a B200) take precedence over the model
     for (const TunedPlan& t : kTunedPlans)
       if (t.cin == w.Cin && t.cout == w.Cout && t.k == w.ktaps && t.n_adds == n_adds && t.n_outs == n_outs &&
-          t.x3 == (w.x3 ? 1 : 0) && (Lq >= 128 * t.mb)) {
+          w.planes <= 2 && t.x3 == (w.x3 ? 1 : 0) && (Lq >= 128 * t.mb)) {
         topt.force_mb = t.mb; topt.force_cw = t.cw; topt.force_two = t.two; topt.force_resident = t.resident;
         break;
       }
   }
   const int mb_max = opt.max_mb;
-  const double n_mma = (double)(w.x3 ? 3 : 1) * (w.Cin / 16) * w.ktaps;
+  const double n_mma = (double)(w.planes == 3 ? 6 : w.x3 ? 3 : 1) * (w.Cin / 16) * w.ktaps;
   // N = 256 streams 32 KB of weights per (chunk, tap) for only 4 MMAs: with short kernels (k = 3) the L2 -> SM weight
   // traffic, not the tensor pipe, is the limit (ncu: 4.8 TB/s of L2 reads at C = 256, k = 3).  Splitting N into
   // 2 x 128 lets a tile take two 128-row blocks (TMEM: 2 x 2 x 128 columns), which quarters the weight bytes per row.
@@ -277,6 +299,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     NT = nt_cand[ci];
     small = NT <= 64 && (NT <= 32 || NT % 32 == 0);
     cw_max = small ? std::min(NT, 32) : pick_cw(NT);
+    if (w.planes == 3) cw_max = std::min(cw_max, 32);
   for (int two = small ? 1 : 0; two >= 0; --two)
     for (int mb = std::min(NT <= 128 ? (small ? 4 : 2) : 1, mb_max); mb >= 1; mb >>= 1)
       for (int cw = cw_max; cw >= 16; cw >>= 1) {
@@ -302,6 +325,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   NT = planned ? p.n_tile : nt_final_default;
   small = NT <= 64 && (NT <= 32 || NT % 32 == 0);
   cw_max = small ? std::min(NT, 32) : pick_cw(NT);
+  if (w.planes == 3) cw_max = std::min(cw_max, 32);
   if (!planned && (topt.force_mb || topt.force_cw)) {   // a tuned entry that does not fit this launch: use the model
     topt = TCOptions();
     topt.halo_mode = opt.halo_mode; topt.w_resident = opt.w_resident; topt.max_mb = opt.max_mb;
@@ -348,8 +372,8 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (opt.plan_only) return VSG_OK;
 
   CUtensorMap tmA, tmAdd0, tmAdd1, tmRaw, tmAct;
-  VSG_TRY(encode_3d(&tmA, x, (uint64_t)w.CinT, (uint64_t)Lin, (uint64_t)B, (uint64_t)x_ld, (uint64_t)Lin * x_ld,
-                    (uint32_t)KC, (uint32_t)p.a_box_rows, KC));
+  VSG_TRY(encode_3d(&tmA, x, (uint64_t)((w.planes - 1) * x_part_stride + w.Cin), (uint64_t)Lin, (uint64_t)B, (uint64_t)x_ld,
+                    (uint64_t)Lin * x_ld, (uint32_t)KC, (uint32_t)p.a_box_rows, KC));
   // epilogue tensors: rows are the q positions of this (poly)phase: row stride out_stride*ld, base shifted by phase
   auto emap = [&](CUtensorMap* m, const __nv_bfloat16* base, int width, int box_c) -> int {
     return encode_3d(m, base + (size_t)out_phase * ld, (uint64_t)width, (uint64_t)Lq, (uint64_t)B,
@@ -359,28 +383,29 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (p.n_tile != pick_ntile(w.Cout))    // the packed map's box is pick_ntile rows: rebuild it for the chosen N tile
     VSG_TRY(encode_2d(&tmW, w.w, (uint64_t)w.CinT, (uint64_t)w.ktaps * w.Cout, (uint32_t)KC, (uint32_t)p.n_tile, KC));
   tmAdd0 = tmAdd1 = tmRaw = tmAct = tmA;
-  if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0, n_parts * w.Cout, p.cw));
-  if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1, n_parts * w.Cout, p.cw));
-  if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw, n_parts * cout_eff, ow));
-  if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act, n_parts * cout_eff, ow));
+  const int add_w = (n_parts - 1) * part_stride + w.Cout, out_w = (n_parts - 1) * part_stride + cout_eff;
+  if (e.add0) VSG_TRY(emap(&tmAdd0, e.add0, add_w, p.cw));
+  if (e.add1) VSG_TRY(emap(&tmAdd1, e.add1, add_w, p.cw));
+  if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw, out_w, ow));
+  if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act, out_w, ow));
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvTC);
-  static const KernelFn kernels[2][4] = {
+  static const KernelFn kernels[2][5] = {
       {conv_tc_kernel<false, EPI_SIG_GENERIC>, conv_tc_kernel<false, EPI_SIG_ACT>, conv_tc_kernel<false, EPI_SIG_RES_ACT>,
-       conv_tc_kernel<false, EPI_SIG_LINEAR>},
+       conv_tc_kernel<false, EPI_SIG_LINEAR>, conv_tc_kernel<false, EPI_SIG_X6>},
       {conv_tc_kernel<true, EPI_SIG_GENERIC>, conv_tc_kernel<true, EPI_SIG_ACT>, conv_tc_kernel<true, EPI_SIG_RES_ACT>,
-       conv_tc_kernel<true, EPI_SIG_LINEAR>}};
+       conv_tc_kernel<true, EPI_SIG_LINEAR>, conv_tc_kernel<true, EPI_SIG_X6>}};
   // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[P->device & 63];
   if (!attr_set) {
     for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 4; ++b)
+      for (int b = 0; b < 5; ++b)
         VSG_CUDA_TRY(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
   // the decoder's two dominant epilogues run kernels specialised on their feature flags (conv_tc.cuh, EPI_SIG_*)
-  int sig = EPI_SIG_GENERIC;
-  if (opt.epi_sigs && e.mode == EPI_TC_LINEAR && !w.x3 && e.bias && !e.bcond && !e.mask && !e.out_f32) {
+  int sig = w.planes == 3 ? EPI_SIG_X6 : EPI_SIG_GENERIC;
+  if (opt.epi_sigs && e.mode == EPI_TC_LINEAR && w.planes == 1 && e.bias && !e.bcond && !e.mask && !e.out_f32) {
     sig = EPI_SIG_LINEAR;
     if (!e.out_raw && e.out_act && !e.add1 && e.scale == 1.0f) {
       if (!e.add0) sig = EPI_SIG_ACT;
@@ -822,22 +847,25 @@ size_t dec_max_elems(const VsgPack* P, int B, int T) {
 }  // namespace
 
 // Conv1d-style weight W[co][ci][j] -> bf16 [j][co][ci] (K-major rows) + its 2-D TMA map.
-// x3: every row is [W_hi (Cin) | W_lo (Cin)] with W_hi = bf16(W), W_lo = bf16(W - W_hi).
+// planes = 2 ("x3"): every row is [W_hi (Cin) | W_lo (Cin)] with W_hi = bf16(W), W_lo = bf16(W - W_hi);
+// planes = 3: [W_hi | W_mid | W_lo], the fp32 weight exactly.
 int pack_conv_tc(VsgPack* P, const std::vector<float>& W, const std::vector<float>& b, int Cout, int Cin, int k,
-                 ConvWTC* out, bool x3) {
-  const int CinT = x3 ? 2 * Cin : Cin;
+                 ConvWTC* out, int planes) {
+  const int CinT = planes * Cin;
   out->Cin = Cin; out->Cout = Cout; out->CinT = CinT; out->CoutT = Cout; out->ktaps = k;
-  out->has_tmap = false; out->x3 = x3;
+  out->has_tmap = false; out->x3 = planes == 2; out->planes = planes;
   const int KC = pick_kc(Cin), NT = pick_ntile(Cout);
   if (KC == 0 || NT == 0 || k < 1) return VSG_OK;   // not representable on the tensor-core path; fp32 mode still works
   std::vector<__nv_bfloat16> wp((size_t)k * Cout * CinT);
   for (int j = 0; j < k; ++j)
     for (int co = 0; co < Cout; ++co)
       for (int ci = 0; ci < Cin; ++ci) {
-        const float v = W[((size_t)co * Cin + ci) * k + j];
-        const __nv_bfloat16 hi = __float2bfloat16(v);
-        wp[((size_t)j * Cout + co) * CinT + ci] = hi;
-        if (x3) wp[((size_t)j * Cout + co) * CinT + Cin + ci] = __float2bfloat16(v - __bfloat162float(hi));
+        float v = W[((size_t)co * Cin + ci) * k + j];
+        for (int pl = 0; pl < planes; ++pl) {
+          const __nv_bfloat16 h = __float2bfloat16(v);
+          wp[((size_t)j * Cout + co) * CinT + (size_t)pl * Cin + ci] = h;
+          v -= __bfloat162float(h);
+        }
       }
   void* dw = nullptr;
   VSG_CUDA_TRY(cudaMalloc(&dw, wp.size() * sizeof(__nv_bfloat16) + 256));
@@ -892,32 +920,42 @@ int pack_resblock_bias_sums(VsgPack* P, const std::vector<std::vector<float>>& b
   return VSG_OK;
 }
 
-size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T) {
+bool x3_flow_on_tensor_cores() {
+  static const bool ffma = getenv("VSG_X3_FLOW_FFMA") != nullptr && getenv("VSG_X3_FLOW_FFMA")[0] == '1';
+  return !ffma;
+}
+
+size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T, int planes) {
   const VsgConfig& c = P->cfg;
   size_t n = 0;
   n += align256((size_t)B * c.flow_n_flows * 2 * c.flow_hidden * c.flow_n_layers * sizeof(float));   // cond
-  n += align256((size_t)B * T * c.flow_channels * 2);                                               // state, channels-last
-  n += 3 * align256((size_t)B * T * c.flow_hidden * 2);                                             // h, acts, out
+  n += align256((size_t)B * T * c.flow_channels * 2 * planes);                                      // state, channels-last
+  n += 3 * align256((size_t)B * T * c.flow_hidden * 2 * planes);                                    // h, acts, out
   return n + 512;
 }
 
 // ResidualCouplingBlock.forward (modules/visinger/flow.py:33-40) on the tensor-core kernels.  The coupling state,
 // WaveNet state, gate output and skip sum all live channels-last in bf16; every elementwise op of the reference
 // (mask multiplies, gate, residual / skip routing, coupling) is an epilogue of the convolution that produces it.
+// planes = 1: plain bf16 (throughput mode).  planes = 3: every tensor and weight is three bf16 planes (hi, mid, lo =
+// the fp32 value exactly) and every product runs as six plane products, small ones first (launch_conv_tc): the flow at
+// north_star's fp32 tolerance (z <= 1e-5) on tcgen05 -- the bf16x3 precision mode.
 int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, float* y, int B, int T,
-                    int reverse, Workspace& ws, cudaStream_t st) {
+                    int reverse, Workspace& ws, cudaStream_t st, int planes) {
   const VsgConfig& c = P->cfg;
   const int C = c.flow_channels, H = c.flow_hidden, NL = c.flow_n_layers, NF = c.flow_n_flows, half = C / 2;
   const int K = c.flow_kernel_size;
+  const bool x6 = planes == 3;
+  if (planes != 1 && planes != 3) return fail(VSG_EINVAL, "flow_forward_tc: planes must be 1 or 3");
   if (!P->flow_layers.empty() && !P->flow_layers[0].pre_tc[0].has_tmap)
     return fail(VSG_EUNSUPPORTED, "bf16 flow needs channels/2 and hidden_channels to be multiples of 16");
   const int condO = 2 * H * NL;
   typedef __nv_bfloat16 bf;
   float* cond = ws.take<float>((size_t)B * NF * condO);
-  bf* u = ws.take<bf>((size_t)B * T * C);
-  bf* h = ws.take<bf>((size_t)B * T * H);
-  bf* acts = ws.take<bf>((size_t)B * T * H);
-  bf* out = ws.take<bf>((size_t)B * T * H);
+  bf* u = ws.take<bf>((size_t)B * T * C * planes);        // rows [hi (C) | mid (C) | lo (C)]
+  bf* h = ws.take<bf>((size_t)B * T * H * planes);
+  bf* acts = ws.take<bf>((size_t)B * T * H * planes);
+  bf* out = ws.take<bf>((size_t)B * T * H * planes);
   int* err = ws.take<int>(1);
   if (ws.overflow) return fail(VSG_ENOMEM, "flow workspace too small: need %zu bytes", ws.off);
   VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
@@ -930,7 +968,7 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
   }
   {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(x, u, C, T, 0);
+    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(x, u, C, T, planes);
     VSG_LAUNCH_CHECK("transpose_to_bf16_kernel");
   }
   for (int step = 0; step < NF; ++step) {
@@ -940,41 +978,46 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
     const bf* x0 = u + (flipped ? half : 0);
     bf* x1 = u + (flipped ? 0 : half);
     {  // h = pre(x0) * mask
+      const ConvWTC& w = x6 ? fl.pre_x6[flipped] : fl.pre_tc[flipped];
       EpiTC e;
-      e.bias = fl.pre_tc[flipped].bias; e.mask = mask; e.out_raw = h;
-      VSG_TRY(launch_conv_tc(P, fl.pre_tc[flipped], x0, B, T, 0, 1, T, 1, 0, T, e, opt, err, st, C));
+      e.bias = w.bias; e.mask = mask; e.out_raw = h;
+      VSG_TRY(launch_conv_tc(P, w, x0, B, T, 0, 1, T, 1, 0, T, e, opt, err, st, planes * C, C));
     }
     int dil = 1;
     for (int i = 0; i < NL; ++i) {
       const bool last = (i == NL - 1);
       {  // acts = tanh(.) * sigmoid(.) of in_layer(h) + cond
+        const ConvWTC& w = x6 ? fl.in_x6[i] : fl.in_tc[i];
         EpiTC e;
-        e.mode = EPI_TC_GATE; e.bias = fl.in_tc[i].bias; e.out_raw = acts;
+        e.mode = EPI_TC_GATE; e.bias = w.bias; e.out_raw = acts;
         if (c.flow_gin > 0) { e.bcond = cond + (size_t)f * condO * B + (size_t)i * 2 * H; e.bcond_bs = condO; }
-        VSG_TRY(launch_conv_tc(P, fl.in_tc[i], h, B, T, -((K * dil - dil) / 2), dil, T, 1, 0, T, e, opt, err, st));
+        VSG_TRY(launch_conv_tc(P, w, h, B, T, -((K * dil - dil) / 2), dil, T, 1, 0, T, e, opt, err, st));
       }
       if (!last) {  // h = (h + res(acts)) * mask
+        const ConvWTC& w = x6 ? fl.res_x6[i] : fl.res_tc[i];
         EpiTC e;
-        e.bias = fl.res_tc[i].bias; e.add0 = h; e.mask = mask; e.out_raw = h;
-        VSG_TRY(launch_conv_tc(P, fl.res_tc[i], acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+        e.bias = w.bias; e.add0 = h; e.mask = mask; e.out_raw = h;
+        VSG_TRY(launch_conv_tc(P, w, acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
       }
       {  // out (+)= skip(acts); masked after the last layer
+        const ConvWTC& w = x6 ? fl.skip_x6[i] : fl.skip_tc[i];
         EpiTC e;
-        e.bias = fl.skip_tc[i].bias; e.add0 = (i > 0) ? out : nullptr; e.mask = last ? mask : nullptr; e.out_raw = out;
-        VSG_TRY(launch_conv_tc(P, fl.skip_tc[i], acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+        e.bias = w.bias; e.add0 = (i > 0) ? out : nullptr; e.mask = last ? mask : nullptr; e.out_raw = out;
+        VSG_TRY(launch_conv_tc(P, w, acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
       }
       dil *= c.flow_dilation_rate;
     }
     {  // m = post(out) * mask ; x1 = (x1 - m) * mask | m + x1 * mask
+      const ConvWTC& w = x6 ? fl.post_x6[flipped] : fl.post_tc[flipped];
       EpiTC e;
       e.mode = EPI_TC_COUPLE; e.couple_sign = reverse ? -1 : 1;
-      e.bias = fl.post_tc[flipped].bias; e.mask = mask; e.add0 = x1; e.out_raw = x1; e.ld = C;
-      VSG_TRY(launch_conv_tc(P, fl.post_tc[flipped], out, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+      e.bias = w.bias; e.mask = mask; e.add0 = x1; e.out_raw = x1; e.ld = planes * C; e.part_stride = C;
+      VSG_TRY(launch_conv_tc(P, w, out, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
     }
   }
   {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(u, y, C, T, (NF & 1) ? 1 : 0);
+    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(u, y, C, T, (NF & 1) ? 1 : 0, planes);
     VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
   }
   return VSG_OK;
@@ -1057,7 +1100,7 @@ int posterior_forward_tc(const VsgPack* P, const float* x, const float* mask, co
   }
   {
     dim3 grid((T + 31) / 32, (2 * Co + 31) / 32, B), block(32, 8);
-    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(sb, stats, 2 * Co, T, 0);
+    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(sb, stats, 2 * Co, T, 0, 1);
     VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
   }
   const long long n = (long long)B * Co * T;
@@ -1187,7 +1230,7 @@ int relenc_forward_tc(const VsgPack* P, const float* x, const float* mask, const
   VSG_TRY(relenc_core_tc(P, x, mask, g, g_t, B, T, ws, st, &xb, &err));
   const int H = P->relenc.hidden;
   dim3 grid((T + 31) / 32, (H + 31) / 32, B), block(32, 8);
-  transpose_from_bf16_kernel<<<grid, block, 0, st>>>(xb, y, H, T, 0);
+  transpose_from_bf16_kernel<<<grid, block, 0, st>>>(xb, y, H, T, 0, 1);
   VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
   return VSG_OK;
 }
@@ -1219,7 +1262,7 @@ int frame_prior_forward_tc(const VsgPack* P, const float* x, const float* mask, 
   }
   {
     dim3 grid((T + 31) / 32, (2 * H + 31) / 32, B), block(32, 8);
-    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(sb, st32, 2 * H, T, 0);
+    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(sb, st32, 2 * H, T, 0, 1);
     VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
   }
   const long long n = (long long)B * H * T;
@@ -1374,7 +1417,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
   }
   {  // boundary: [B, C, T] fp32 -> [B, T, C] bf16, once
     dim3 grid((T + 31) / 32, (C0 + 31) / 32, B), block(32, 8);
-    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(z, zt, C0, T, x3 ? 1 : 0);
+    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(z, zt, C0, T, x3 ? 2 : 1);
     VSG_LAUNCH_CHECK("transpose_to_bf16_kernel");
   }
   int cur_io = 0;
@@ -1588,7 +1631,7 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
   std::vector<float> W(w, w + (size_t)Cout * Cin * k), bz(Cout, 0.f);
   if (bias) bz.assign(bias, bias + Cout);
   ConvWTC wt;
-  int rc = pack_conv_tc(&tmp, W, bz, Cout, Cin, k, &wt, (flags & 4) != 0);
+  int rc = pack_conv_tc(&tmp, W, bz, Cout, Cin, k, &wt, (flags & 256) ? 3 : (flags & 4) ? 2 : 1);   // bit 8: three planes
   int* err = nullptr;
   if (rc == VSG_OK && cudaMalloc(&err, sizeof(int)) != cudaSuccess) rc = fail(VSG_ECUDA, "cudaMalloc failed");
   if (rc == VSG_OK) {
@@ -1605,7 +1648,7 @@ extern "C" int vsg_debug_conv1d_bf16(const void* x_bf16, const float* w, const f
     TCOptions opt;
     opt.halo_mode = flags & 1;
     opt.w_resident = (flags >> 1) & 1;
-    opt.max_mb = (flags >> 4) ? (flags >> 4) : 4;
+    opt.max_mb = ((flags >> 4) & 15) ? ((flags >> 4) & 15) : 4;
     opt.force_mb = g_debug_force.force_mb; opt.force_cw = g_debug_force.force_cw;
     opt.force_two = g_debug_force.force_two; opt.force_resident = g_debug_force.force_resident;
     cudaEvent_t e0, e1;

@@ -65,6 +65,7 @@ struct ConvWTC {
   CUtensorMap tmap;     // 2-D map over [ktaps*CoutT rows][CinT]
   bool has_tmap = false;
   bool x3 = false;      // split-bf16 pack: rows are [W_hi (Cin) | W_lo (Cin)], CinT = 2*Cin
+  int planes = 1;       // bf16 planes per weight: 1 plain, 2 = x3, 3 = [W_hi | W_mid | W_lo] (the fp32 weight exactly)
 };
 
 struct UpsPhase {
@@ -84,6 +85,9 @@ struct FlowLayer {
   std::vector<ConvWTC> in_tc;       // gate-interleaved
   std::vector<ConvWTC> res_tc;      // res_skip rows [0, H): the residual half (absent for the last layer)
   std::vector<ConvWTC> skip_tc;     // res_skip rows [H, 2H) (all H rows for the last layer)
+  // the same packs on three bf16 planes per weight: the flow at the fp32 tolerance on the tensor cores (flow only)
+  ConvWTC pre_x6[2], post_x6[2];
+  std::vector<ConvWTC> in_x6, res_x6, skip_x6;
 };
 
 // PosteriorEncoder (modules/visinger/encoder.py:76-101): pre (1x1) -> WaveNet -> proj (1x1) -> reparameterised sample.
