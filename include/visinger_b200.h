@@ -336,9 +336,10 @@ int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32
  *   bit 0 HALO activation tiles | bits 4-7 cap on 128-row blocks per tile | bit 8 no programmatic dependent launch |
  *   bit 9 no fused resblock pairs | bit 10 one launch per upsampler polyphase | bit 11 never split N = 256 tiles |
  *   bit 12 store raw AND activated resblock streams | bit 13 generic epilogue images only |
- *   bit 14 resblock chains of a stage on one stream | bit 15 no whole-resblock kernel (C <= 64 stages fall back to the
- *   fused pairs / per-conv kernels) | bits 16-20 cap on 128-row blocks per resblock tile | bits 21-23 resblock epilogue
- *   warp sets (0 = 4). */
+ *   bit 14 resblock chains of a stage on one stream | bit 15 whole-resblock kernel rb_tc (opt-in) | bits 16-20 cap on
+ *   128-row blocks per resblock tile | bits 21-23 resblock epilogue warp sets (0 = 4) | bit 24 no row-packed resblock
+ *   kernel | bit 25 row-packed kernel at C = 64 too | bit 26 no block-Toeplitz form | bit 27 no specialised images for
+ *   the last conv2 of a resblock (running-sum epilogues). */
 int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t l2_tensor_mb, int32_t min_tiles);
 
 #ifdef __cplusplus

@@ -68,3 +68,38 @@ def synth_utterances(seed, n, min_frames=120, max_frames=1280, n_spk=1, lengths=
                 note_dur=torch.from_numpy(np.stack([pad(u[2], Tph) for u in utts])).long(),
                 mel2ph=torch.from_numpy(np.stack([pad(u[3], T) for u in utts])).long(),
                 spk_ids=torch.from_numpy(rng.integers(0, n_spk, n)).long())
+
+
+def config4_lengths(n, seed=1234):
+    """BASELINE.json configs[3] / SURVEY.md 8d "Config 4": T_i = clip(round(80 * LogNormal(ln 5.6, 0.45)), 120, 1280)."""
+    rng = np.random.default_rng(seed)
+    return np.clip(np.round(80.0 * rng.lognormal(np.log(5.6), 0.45, n)), 120, 1280).astype(np.int64)
+
+
+def full_model_mirror(seed=4321, precision="fp32"):
+    """The full-hparams mirror model with seeded weights: constructor init under `seed`, flow `post` layers
+    re-randomised (zero-initialised in the reference).  tests/golden/make_golden_model_full.py loads
+    exactly this state dict into the unmodified reference model, so the fixture holds outputs only."""
+    from visinger_b200.models.visinger import VISinger
+    torch.manual_seed(seed)
+    m = VISinger(73, 117, 132, full_hparams(), precision=precision).eval()
+    gen = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for f in range(4):
+            post = m.flow.flows[2 * f].post
+            post.weight.copy_(0.05 * torch.randn(post.weight.shape, generator=gen))
+            post.bias.copy_(0.05 * torch.randn(post.bias.shape, generator=gen))
+    return m
+
+
+FULL_GOLDEN_B = 8
+FULL_GOLDEN_WAV_STRIDE = 53
+FULL_GOLDEN_T_STRIDE = 7
+
+
+def full_model_batch():
+    lengths = config4_lengths(64)[:FULL_GOLDEN_B]
+    batch = synth_utterances(seed=1234, n=FULL_GOLDEN_B, lengths=lengths)
+    T = batch["mel2ph"].shape[1]
+    noise = torch.randn(FULL_GOLDEN_B, 192, T, generator=torch.Generator().manual_seed(11))
+    return batch, noise, lengths

@@ -104,3 +104,40 @@ def test_forward_graphed_equals_eager_forward(cuda_device):
     got2 = m.forward_graphed(*args, spk_id=d["spk_ids"], noise=noise2)          # replay, new contents
     assert torch.equal(got2["wav_out"], eager2["wav_out"])
     assert maxabs(got2["wav_out"].cpu(), torch.from_numpy(z["wav_out"])) > 1e-3     # and it really is a different waveform
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_config4_full_hparams_mixed_length_batch_vs_reference_golden(cuda_device, precision):
+    """BASELINE.json configs[3] at the full config/models/visinger.yaml sizes: 8 mixed-length utterances (218 .. 1280
+    frames) right-padded to 1280, through the whole forward(infer=True), against the unmodified reference on the
+    IDENTICAL padded batch, weights and noise (tests/golden/make_golden_model_full.py) -- strided over the whole waveform,
+    the last 20 frames of every utterance in full, and the padded region after each utterance in full (the decoder is
+    unmasked, models/visinger.py:111: the reference's output is NOT zero there)."""
+    from model_inputs import (full_model_mirror, full_model_batch, FULL_GOLDEN_WAV_STRIDE as WS,
+                              FULL_GOLDEN_T_STRIDE as TS)
+    z = load_npz("full_model")
+    batch, noise, lengths = full_model_batch()
+    assert lengths.tolist() == z["lengths"].tolist() and batch["mel2ph"].shape[1] == int(z["T"])
+    m = full_model_mirror(precision=precision).to(cuda_device)
+    d = {k: v.to(cuda_device) for k, v in batch.items()}
+    ret = {}
+    out = m(d["text_tokens"], d["note_pitch"], d["note_dur"], d["mel2ph"], spk_id=d["spk_ids"], infer=True,
+            noise=noise.to(cuda_device))
+    wav = out["wav_out"].cpu()
+    hop, T = 300, int(z["T"])
+    ref_s = torch.from_numpy(z["wav_strided"])
+    e_strided = maxabs(wav[:, ::WS], ref_s)
+    e_tail = e_pad = 0.0
+    for b, n in enumerate(lengths.tolist()):
+        e_tail = max(e_tail, maxabs(wav[b, (n - 20) * hop: n * hop], torch.from_numpy(z["wav_tails"][b])))
+        seg = wav[b, n * hop: min(T, n + 10) * hop]
+        e_pad = max(e_pad, maxabs(seg, torch.from_numpy(z["wav_pads"][b][:seg.numel()])))
+    rel = float((wav[:, ::WS] - ref_s).norm() / ref_s.norm())
+    e_f0 = maxabs(out["f0_pred"].cpu(), torch.from_numpy(z["f0_pred"]))
+    print(f"config 4, full hparams, B=8 mixed lengths, {precision}: waveform max-abs strided {e_strided:.3e}, last 20 frames "
+          f"{e_tail:.3e}, padded region {e_pad:.3e} (|ref|max {float(ref_s.abs().max()):.3e}), rel-L2 {rel:.3e}, f0 {e_f0:.3e}")
+    if precision == "bf16":
+        assert rel <= 3e-2 and max(e_strided, e_tail, e_pad) <= 5e-3
+    else:
+        assert max(e_strided, e_tail, e_pad) <= 1e-4 and e_f0 <= 5e-5

@@ -112,7 +112,11 @@ enum : int { EPI_TC_LINEAR = 0, EPI_TC_GATE = 1, EPI_TC_COUPLE = 2 };
 // image -- splitting the generic kernel per mode made the step slower.)
 //   EPI_SIG_X6       the generic epilogue on THREE bf16 planes per tensor (hi, mid, lo = 24 mantissa bits: every fp32 value
 //                    exactly), linear / gate / coupling with full-precision tanh / sigmoid: the flow at the fp32 tolerance
-enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2, EPI_SIG_LINEAR = 3, EPI_SIG_X6 = 4 };
+//   EPI_SIG_SUM0 / SUM1 / FINAL   the last conv2 of the stage's first / middle / last resblock: residual recovered from the
+//                    activated stream, [+ running resblock sum,] -> raw running sum | x scale -> leaky_relu'd stage output
+//                    (decoder.py:47-54).  On the run-time-flag image these launches cost 25 % more than a plain conv2.
+enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2, EPI_SIG_LINEAR = 3, EPI_SIG_X6 = 4,
+             EPI_SIG_SUM0 = 5, EPI_SIG_SUM1 = 6, EPI_SIG_FINAL = 7, EPI_SIG_COUNT = 8 };
 
 namespace tc {
 
@@ -405,11 +409,12 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   constexpr bool kGen = SIG == EPI_SIG_GENERIC || SIG == EPI_SIG_X6;
   static_assert(kGen || (MODE == EPI_TC_LINEAR && NP == 1), "specialised signatures are plain-bf16 linear epilogues");
   constexpr bool kRt = kGen || SIG == EPI_SIG_LINEAR;      // adds / outputs / scale decided at run time
-  const bool has_add0 = kRt ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT);
-  const bool has_add1 = kRt ? (p.has_add1 && MODE == EPI_TC_LINEAR) : false;
-  const bool has_raw = kRt ? (p.has_raw != 0) : false;
-  const bool has_act = kRt ? (p.has_act && MODE == EPI_TC_LINEAR) : true;
-  const float scale = kRt ? p.scale : 1.0f, slope = p.slope;
+  constexpr bool kSum = SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_FINAL;
+  const bool has_add0 = kRt ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT || kSum);
+  const bool has_add1 = kRt ? (p.has_add1 && MODE == EPI_TC_LINEAR) : (SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_FINAL);
+  const bool has_raw = kRt ? (p.has_raw != 0) : (SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1);
+  const bool has_act = kRt ? (p.has_act && MODE == EPI_TC_LINEAR) : !(SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1);
+  const float scale = (kRt || SIG == EPI_SIG_FINAL) ? p.scale : 1.0f, slope = p.slope;
   const bool add0_is_act = kRt ? (p.add0_is_act != 0) : true;
   const float inv_slope = 1.0f / p.slope;
   const float* const bias = p.bias;
@@ -420,7 +425,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   // staging carve-up: [add0 x n_add_bufs][add1 x n_add_bufs][raw x 2][act x 2], each e_buf_bytes
   const uint32_t add0_b = smem_base + p.e_off;
   const uint32_t add1_b = add0_b + (has_add0 ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
-  const uint32_t raw_b = add1_b + ((kRt && p.has_add1) ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
+  const uint32_t raw_b = add1_b + ((kRt ? p.has_add1 != 0 : has_add1) ? (uint32_t)n_add_bufs * e_buf_bytes : 0u);
   const uint32_t act_b = raw_b + (has_raw ? 2u * e_buf_bytes : 0u);
   const bool has_add = has_add0 || has_add1;
   const bool has_out = has_raw || has_act;

@@ -119,7 +119,7 @@ struct TCOptions {
   int split_n = 1;
   int single_stream = 1;
   int chain_streams = 1;
-  int epi_sigs = 1;
+  int epi_sigs = 2;         // 0: one generic image; 1: ACT / RES_ACT / LINEAR images; 2: + SUM0 / SUM1 / FINAL
   int epi_sets = 2;
   int fuse_rb = 0;          // whole-ResBlock1 kernel (rb_tc.cuh) for the C <= 64 stages (opt-in: bit 15)
   int rb_max_mb = 0;        // cap on 128-row blocks per resblock tile (0 = as many as fit)
@@ -389,17 +389,19 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (e.out_raw) VSG_TRY(emap(&tmRaw, e.out_raw, out_w, ow));
   if (e.out_act) VSG_TRY(emap(&tmAct, e.out_act, out_w, ow));
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvTC);
-  static const KernelFn kernels[2][5] = {
+  static const KernelFn kernels[2][EPI_SIG_COUNT] = {
       {conv_tc_kernel<false, EPI_SIG_GENERIC>, conv_tc_kernel<false, EPI_SIG_ACT>, conv_tc_kernel<false, EPI_SIG_RES_ACT>,
-       conv_tc_kernel<false, EPI_SIG_LINEAR>, conv_tc_kernel<false, EPI_SIG_X6>},
+       conv_tc_kernel<false, EPI_SIG_LINEAR>, conv_tc_kernel<false, EPI_SIG_X6>, conv_tc_kernel<false, EPI_SIG_SUM0>,
+       conv_tc_kernel<false, EPI_SIG_SUM1>, conv_tc_kernel<false, EPI_SIG_FINAL>},
       {conv_tc_kernel<true, EPI_SIG_GENERIC>, conv_tc_kernel<true, EPI_SIG_ACT>, conv_tc_kernel<true, EPI_SIG_RES_ACT>,
-       conv_tc_kernel<true, EPI_SIG_LINEAR>, conv_tc_kernel<true, EPI_SIG_X6>}};
+       conv_tc_kernel<true, EPI_SIG_LINEAR>, conv_tc_kernel<true, EPI_SIG_X6>, conv_tc_kernel<true, EPI_SIG_SUM0>,
+       conv_tc_kernel<true, EPI_SIG_SUM1>, conv_tc_kernel<true, EPI_SIG_FINAL>}};
   // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[P->device & 63];
   if (!attr_set) {
     for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 5; ++b)
+      for (int b = 0; b < EPI_SIG_COUNT; ++b)
         VSG_CUDA_TRY(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
@@ -410,6 +412,9 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     if (!e.out_raw && e.out_act && !e.add1 && e.scale == 1.0f) {
       if (!e.add0) sig = EPI_SIG_ACT;
       else if (e.add0_is_act) sig = EPI_SIG_RES_ACT;
+    } else if (opt.epi_sigs >= 2 && e.add0 && e.add0_is_act) {     // last conv2 of a resblock (single activated stream)
+      if (e.out_raw && !e.out_act && e.scale == 1.0f) sig = e.add1 ? EPI_SIG_SUM1 : EPI_SIG_SUM0;
+      else if (!e.out_raw && e.out_act && e.add1) sig = EPI_SIG_FINAL;
     }
   }
   // Programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, resident-weight fetch) may
@@ -1840,7 +1845,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.merge_ups = (halo_mode & 1024) ? 0 : 1;                            // bit 10: one launch per polyphase
   g_default_opts.split_n = (halo_mode & 2048) ? 0 : 1;                              // bit 11: never split N = 256 tiles
   g_default_opts.single_stream = (halo_mode & 4096) ? 0 : 1;                        // bit 12: store raw + activated copies
-  g_default_opts.epi_sigs = (halo_mode & 8192) ? 0 : 1;                             // bit 13: generic epilogue kernels only
+  g_default_opts.epi_sigs = (halo_mode & 8192) ? 0 : (halo_mode & (1 << 27)) ? 1 : 2; // bit 13: generic epilogue kernels only; bit 27: no SUM / FINAL images
   g_default_opts.chain_streams = (halo_mode & 16384) ? 0 : 1;                       // bit 14: resblock chains on one stream
   g_default_opts.epi_sets = (halo_mode & 8192) ? 1 : 2;                             // bit 13: one set of epilogue warps
   g_default_opts.fuse_rb = (halo_mode & 32768) ? 1 : 0;                             // bit 15: whole-resblock kernel
