@@ -339,7 +339,8 @@ int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32
  *   bit 14 resblock chains of a stage on one stream | bit 15 whole-resblock kernel rb_tc (opt-in) | bits 16-20 cap on
  *   128-row blocks per resblock tile | bits 21-23 resblock epilogue warp sets (0 = 4) | bit 24 no row-packed resblock
  *   kernel | bit 25 row-packed kernel at C = 64 too | bit 26 no block-Toeplitz form | bit 27 no specialised images for
- *   the last conv2 of a resblock (running-sum epilogues). */
+ *   the last conv2 of a resblock (running-sum epilogues) | bits 28-29 conv_post on the CUDA-core kernels (1 register
+ *   window, 2 shared-memory window) instead of tcgen05. */
 int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t l2_tensor_mb, int32_t min_tiles);
 
 #ifdef __cplusplus

@@ -282,3 +282,27 @@ def test_rowpacked_resblock_kernel(cuda_device, C, k, dils, B, L, max_mb, varian
     """Row-packed whole ResBlock1 (rp_tc.cuh), with the dilation-1 convolutions in the block-Toeplitz form (256) and with
     every convolution tap by tap (256 | 512): same checks as the per-row kernel."""
     _run_resblock_case(cuda_device, C, k, dils, B, L, max_mb, variant)
+
+
+@pytest.mark.parametrize("B,T", [(2, 40), (3, 333), (1, 1000)])
+def test_conv_post_tensor_core_equals_cuda_core(cuda_device, B, T):
+    """conv_post (decoder.py:55-57) on tcgen05 -- rows of 4 samples x 16 channels, Conv1d(64 -> 16, 3 row taps) with
+    block-Toeplitz [W_hi | W_lo] weights, tanh epilogue -- against the CUDA-core window kernels on the same stage output
+    (option bits 28-29): the same waveform up to fp32 summation order."""
+    from visinger_b200 import _lib
+    sd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
+    m = build_gen(GEN_FULL, sd, cuda_device, precision="bf16")
+    x, _, g = make_inputs(3 + T, B, 192, T, 256)
+    xd, gd = x.to(cuda_device), g.to(cuda_device)
+    try:
+        tc = m(xd, g=gd).clone()
+        _lib.set_tc_options(1 | (1 << 28))
+        win = m(xd, g=gd).clone()
+        _lib.set_tc_options(1 | (2 << 28))
+        sm = m(xd, g=gd).clone()
+    finally:
+        _lib.set_tc_options(1)
+    assert torch.equal(win, sm)
+    err = maxabs(tc, win)
+    print(f"conv_post tcgen05 vs CUDA cores B={B} T={T}: max-abs {err:.3e} (|wav|max {float(win.abs().max()):.3e})")
+    assert err <= 2e-6

@@ -93,11 +93,12 @@ struct ConvTC {
   const float* mask;            // [B][Lout] row mask or null (LINEAR: v *= mask; COUPLE: see below)
   int couple_sign;              // COUPLE: -1 reverse  x1 = (x1 - m) * mask,  +1 forward  x1 = m + x1 * mask
   uint32_t e_out_swz_mask;      // swizzle of the output staging rows (GATE halves the row width)
-  float* out_f32;               // optional fp32 copy of the raw value [B, Lout, Cout] (debug / parity hook)
+  float* out_f32;               // optional fp32 copy of the raw value [B, Lout, Cout] (debug / parity hook); EPI_TC_TANH: the output
+  int tanh_cols;                // EPI_TC_TANH: out_f32[(b * Lq + q) * tanh_cols + i] = tanh(acc[i]), i < tanh_cols (<= 4)
   int* error_flag;              // set to 1 if a barrier wait times out
 };
 
-enum : int { EPI_TC_LINEAR = 0, EPI_TC_GATE = 1, EPI_TC_COUPLE = 2 };
+enum : int { EPI_TC_LINEAR = 0, EPI_TC_GATE = 1, EPI_TC_COUPLE = 2, EPI_TC_TANH = 3 };
 
 // Epilogue signatures: the decoder's two dominant epilogues get their own kernel instantiations in which every feature
 // flag is a compile-time constant.  The generic kernel carries 12 epilogue variants (3 chunk widths x 4 modes; ~15 k SASS
@@ -116,7 +117,9 @@ enum : int { EPI_TC_LINEAR = 0, EPI_TC_GATE = 1, EPI_TC_COUPLE = 2 };
 //                    activated stream, [+ running resblock sum,] -> raw running sum | x scale -> leaky_relu'd stage output
 //                    (decoder.py:47-54).  On the run-time-flag image these launches cost 25 % more than a plain conv2.
 enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2, EPI_SIG_LINEAR = 3, EPI_SIG_X6 = 4,
-             EPI_SIG_SUM0 = 5, EPI_SIG_SUM1 = 6, EPI_SIG_FINAL = 7, EPI_SIG_COUNT = 8 };
+             EPI_SIG_SUM0 = 5, EPI_SIG_SUM1 = 6, EPI_SIG_FINAL = 7,
+             EPI_SIG_POST = 8,     // conv_post on the row-packed stage output: tanh of <= 4 accumulator columns -> fp32 waveform
+             EPI_SIG_COUNT = 9 };
 
 namespace tc {
 
@@ -385,6 +388,7 @@ __device__ __forceinline__ void stage_out(const float* v, uint32_t base, uint32_
 //                      out[c] = tanh(a) * sigmoid(s)  -- fused_add_tanh_sigmoid_multiply, encoder.py:206-213;
 //                      the output tensor has Cout / 2 channels
 //       EPI_TC_COUPLE  m = (acc + bias) * mask; out = (add0 - m) * mask | m + add0 * mask  (flow.py:78,83)
+//       EPI_TC_TANH    wav = tanh(acc) of the first tanh_cols columns, fp32, straight to global memory (decoder.py:56-57)
 template <int CW, int MODE, int NP, int SIG = EPI_SIG_GENERIC>
 __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, const CUtensorMap& tmAdd1,
                                                  const CUtensorMap& tmRaw, const CUtensorMap& tmAct, const ConvTC& p,
@@ -407,13 +411,14 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const uint32_t e_buf_bytes = p.e_buf_bytes, swz_in = p.e_swz_mask, swz_out = p.e_out_swz_mask;
   const uint32_t part_bytes = p.e_part_bytes;     // one bf16 plane (hi or lo) of a staging buffer
   constexpr bool kGen = SIG == EPI_SIG_GENERIC || SIG == EPI_SIG_X6;
-  static_assert(kGen || (MODE == EPI_TC_LINEAR && NP == 1), "specialised signatures are plain-bf16 linear epilogues");
+  static_assert(kGen || ((MODE == EPI_TC_LINEAR || (MODE == EPI_TC_TANH && SIG == EPI_SIG_POST)) && NP == 1),
+                "specialised signatures are plain-bf16 linear epilogues");
   constexpr bool kRt = kGen || SIG == EPI_SIG_LINEAR;      // adds / outputs / scale decided at run time
   constexpr bool kSum = SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_FINAL;
   const bool has_add0 = kRt ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT || kSum);
   const bool has_add1 = kRt ? (p.has_add1 && MODE == EPI_TC_LINEAR) : (SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_FINAL);
   const bool has_raw = kRt ? (p.has_raw != 0) : (SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1);
-  const bool has_act = kRt ? (p.has_act && MODE == EPI_TC_LINEAR) : !(SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1);
+  const bool has_act = kRt ? (p.has_act && MODE == EPI_TC_LINEAR) : !(SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_POST);
   const float scale = (kRt || SIG == EPI_SIG_FINAL) ? p.scale : 1.0f, slope = p.slope;
   const bool add0_is_act = kRt ? (p.add0_is_act != 0) : true;
   const float inv_slope = 1.0f / p.slope;
@@ -609,6 +614,16 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
               v[c] = t * sg;
             } else {   // fp32-tolerance modes: the libm-grade functions of the fp32 kernels (kernels_f32.cuh)
               v[c] = tanhf(v[2 * c]) * (1.0f / (1.0f + expf(-v[2 * c + 1])));
+            }
+          }
+        }
+        if (MODE == EPI_TC_TANH) {   // one 16-byte store per row; the lanes of a warp cover 512 contiguous bytes
+          if (srow < tile_stride && q < p.Lq) {
+            float* dst = p.out_f32 + ((long long)b * p.Lq + q) * p.tanh_cols;
+            if (p.tanh_cols == 4) {
+              *reinterpret_cast<float4*>(dst) = make_float4(tanhf(v[0]), tanhf(v[1]), tanhf(v[2]), tanhf(v[3]));
+            } else {
+              for (int i = 0; i < p.tanh_cols; ++i) dst[i] = tanhf(v[i]);
             }
           }
         }
@@ -897,6 +912,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.cw == 32) VSG_EPI6(32);
       else VSG_EPI6(16);
 #undef VSG_EPI6
+    } else if constexpr (SIG == EPI_SIG_POST) {
+      conv_tc_epilogue<16, EPI_TC_TANH, 1, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
     } else {   // specialised signature: plain-bf16 linear epilogue with compile-time feature flags
       if (!SMALL && p.cw == 64)
         conv_tc_epilogue<64, EPI_TC_LINEAR, 1, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
@@ -1075,6 +1092,69 @@ __global__ void __launch_bounds__(128) conv_post_bf16_win_kernel(const __nv_bflo
 #pragma unroll
     for (int i = 0; i < S; ++i)
       if (n0 + i < L) out[i] = tanhf(acc[i]);
+  }
+}
+
+// The same computation with the input staged through shared memory: a CTA of 128 threads produces 128 * S consecutive
+// samples of one utterance; the 128 * S + K - 1 input rows (C bf16 each) are fetched with fully coalesced 16-byte loads
+// (the window kernel above has every lane 8 rows = 256 B apart: 32 sectors per load instruction, and the L1 pipe, not
+// HBM, set its pace: 93 us for 173 MB) and every thread then slides its window over shared memory.  Rows are padded by
+// 16 bytes per S rows so that the lanes' 16-byte reads fall into distinct banks.
+template <int C, int K, int S>
+__global__ void __launch_bounds__(128) conv_post_bf16_smem_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[C][K]*/,
+                                                                  float* __restrict__ wav, int L, int tiles_per_b, int total_tiles) {
+  static_assert(C == 16 && S == 8, "layout below assumes 32-byte rows and 8 samples per thread");
+  constexpr int TS = 128 * S;                    // samples per tile
+  constexpr int ROWS = TS + K - 1;
+  constexpr int pad = (K - 1) / 2;
+  constexpr int V = C / 8;                       // 16-byte vectors per row
+  __shared__ uint4 tile[ROWS * V + ROWS / S + 2];   // + one pad vector per S rows
+  float wr[K][C];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int j = 0; j < K; ++j) wr[j][c] = __ldg(w + c * K + j);
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int b = t / tiles_per_b, n_tile0 = (t - b * tiles_per_b) * TS;
+    const uint4* xb = reinterpret_cast<const uint4*>(x + (long long)b * L * C);
+    __syncthreads();                             // the previous tile is fully consumed
+    for (int i = threadIdx.x; i < ROWS * V; i += 128) {
+      const int r = i / V, pos = n_tile0 - pad + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (pos >= 0 && pos < L) v = __ldg(xb + (long long)pos * V + (i - r * V));
+      tile[i + r / S] = v;
+    }
+    __syncthreads();
+    const int r0 = threadIdx.x * S;              // my first row inside the tile
+    float acc[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < S + K - 1; ++r) {
+      float f[C];
+      const int rr = r0 + r;
+      const uint4* row = tile + rr * V + rr / S;
+#pragma unroll
+      for (int c8 = 0; c8 < V; ++c8) tc::unpack_bf16x8(row[c8], f + 8 * c8);
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        const int j = r - i;
+        if (j >= 0 && j < K) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[i] = fmaf(wr[j][c], f[c], acc[i]);
+        }
+      }
+    }
+    const int n0 = n_tile0 + r0;
+    float* out = wav + (long long)b * L + n0;
+    if (n0 + S <= L && (((long long)b * L + n0) & 3) == 0) {
+      reinterpret_cast<float4*>(out)[0] = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+      reinterpret_cast<float4*>(out)[1] = make_float4(tanhf(acc[4]), tanhf(acc[5]), tanhf(acc[6]), tanhf(acc[7]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < S; ++i)
+        if (n0 + i < L) out[i] = tanhf(acc[i]);
+    }
   }
 }
 

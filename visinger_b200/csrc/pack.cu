@@ -472,6 +472,23 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
   VSG_TRY(L.eff_weight(pre + "conv_post", 1, ch, 7, W));
   VSG_TRY(L.upload(W, &P->conv_post_w));
   P->conv_post_k = 7;
+  // Tensor-core form (plain bf16 mode): S = 64 / ch consecutive samples are one 128-byte row of the channels-last stage
+  // output, and conv_post becomes Conv1d(64 -> 16, 3 row taps) with block-Toeplitz weights whose output column s' < S is
+  // sample S r + s' of row r:   W'[s'][s ch + c][m] = w[c][S (m - 1) + s - s' + 3]   (zero outside the 7 taps).
+  if ((ch == 16 || ch == 32) && 64 / ch >= 3) {
+    const int S = 64 / ch;
+    std::vector<float> Wt((size_t)16 * 64 * 3, 0.f), bz(16, 0.f);
+    for (int sp = 0; sp < S; ++sp)
+      for (int m = 0; m < 3; ++m)
+        for (int s2 = 0; s2 < S; ++s2) {
+          const int j = S * (m - 1) + s2 - sp + 3;
+          if (j < 0 || j >= 7) continue;
+          for (int cc = 0; cc < ch; ++cc) Wt[((size_t)sp * 64 + s2 * ch + cc) * 3 + m] = W[(size_t)cc * 7 + j];
+        }
+    VSG_TRY(pack_conv_tc(P, Wt, bz, 16, 64, 3, &P->conv_post_rp, 2));   // [W_hi | W_lo]: no weight rounding in the last layer
+    P->conv_post_rp.wsplit = true;
+    if (P->conv_post_rp.has_tmap) P->conv_post_S = S;
+  }
   P->has_dec = true;
   return VSG_OK;
 }

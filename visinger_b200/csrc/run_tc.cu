@@ -106,6 +106,7 @@ struct EpiTC {
   __nv_bfloat16* out_raw = nullptr;
   __nv_bfloat16* out_act = nullptr;
   float* out_f32 = nullptr;
+  int tanh_cols = 0;                // EPI_TC_TANH: samples per row written to out_f32
 };
 
 // HALO mode verified on B200 (tools/tc_probe.py): the UMMA unit applies the swizzle XOR to absolute
@@ -129,6 +130,7 @@ struct TCOptions {
   int rp_max_c = 32;        // widest stage the row-packed kernel takes
   int rp_packed = 1;        // dilation-1 convolutions in the block-Toeplitz form (0: every conv tap by tap)
   int rp_max_mb = 0;        // cap on 128-row blocks per row-packed tile (0 = as many as fit)
+  int conv_post = 0;        // conv_post kernel: 0 tcgen05 (row-packed, tanh epilogue), 1 register window, 2 shared-memory window
   uint32_t* rp_trace = nullptr;   // tuning aid (vsg_debug_resblock_bf16 with VSG_RP_TRACE set): pipeline event clocks of CTA 0
 };
 
@@ -145,9 +147,10 @@ static const TunedPlan kTunedPlans[] = {
 int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, int B, int Lin, int in_off0, int dil,
                    int Lq, int out_stride, int out_phase, int Lout, const EpiTC& e, const TCOptions& opt, int* error_flag,
                    cudaStream_t st, int x_ld = 0, int x_part_stride = 0) {
-  if (x_ld == 0) x_ld = w.CinT;
+  const int a_planes = w.wsplit ? 1 : w.planes;           // bf16 planes of the activations and of every epilogue tensor
+  if (x_ld == 0) x_ld = a_planes * w.Cin;
   if (x_part_stride == 0) x_part_stride = w.Cin;          // channels between the bf16 planes of an input row
-  if (w.planes == 2 && e.mode != EPI_TC_LINEAR) return fail(VSG_EUNSUPPORTED, "split-bf16 supports the linear epilogue only");
+  if (w.planes == 2 && !w.wsplit && e.mode != EPI_TC_LINEAR) return fail(VSG_EUNSUPPORTED, "split-bf16 supports the linear epilogue only");
   if (!w.has_tmap) return fail(VSG_EUNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 16 "
                                                  "(conv %d -> %d)", w.Cin, w.Cout);
   if (Lq <= 0 || B <= 0) return VSG_OK;
@@ -163,7 +166,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   int cw_max = small ? std::min(NT, 32) : pick_cw(NT);
   if (w.planes == 3) cw_max = std::min(cw_max, 32);       // the three-plane epilogue is instantiated for 32 / 16 channels
   const int cout_eff = e.mode == EPI_TC_GATE ? w.Cout / 2 : w.Cout;  // channels of the add / out tensors
-  const int n_parts = w.planes;                                        // bf16 planes of every epilogue tensor
+  const int n_parts = a_planes;
   const int part_stride = e.part_stride ? e.part_stride : cout_eff;
   const int ld = e.ld ? e.ld : n_parts * cout_eff;
   const int n_adds = (e.add0 ? 1 : 0) + (e.add1 ? 1 : 0), n_outs = (e.out_raw ? 1 : 0) + (e.out_act ? 1 : 0);
@@ -200,12 +203,12 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
           q.n_wtiles += q.n_wpass[i] * w.ktaps;
         }
     } else {
-      if (w.planes * nc > kMaxAChunks) return false;
-      for (int part = 0; part < w.planes; ++part)       // x3: hi chunks meet W_hi and W_lo, lo chunks meet W_hi
+      if (a_planes * nc > kMaxAChunks) return false;
+      for (int part = 0; part < a_planes; ++part)       // x3: hi chunks meet W_hi and W_lo, lo chunks meet W_hi
         for (int c = 0; c < nc; ++c) {
           const int i = q.n_achunks++;
           q.a_coff[i] = part * x_part_stride + c * KC;
-          q.n_wpass[i] = (w.x3 && part == 0) ? 2 : 1;
+          q.n_wpass[i] = (w.x3 && part == 0) ? 2 : 1;       // (wsplit: the single activation plane meets W_hi and W_lo)
           q.w_coff[i][0] = c * KC;
           q.w_coff[i][1] = w.Cin + c * KC;
           q.n_wtiles += q.n_wpass[i] * w.ktaps;
@@ -359,6 +362,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.bias = e.bias; p.bcond = e.bcond; p.bcond_bs = e.bcond_bs;
   p.scale = e.scale; p.slope = e.slope;
   p.out_f32 = e.out_f32;
+  p.tanh_cols = e.tanh_cols;
   p.error_flag = error_flag;
 
   static const bool debug_plan = getenv("VSG_DEBUG_PLAN") != nullptr;
@@ -372,7 +376,7 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   if (opt.plan_only) return VSG_OK;
 
   CUtensorMap tmA, tmAdd0, tmAdd1, tmRaw, tmAct;
-  VSG_TRY(encode_3d(&tmA, x, (uint64_t)((w.planes - 1) * x_part_stride + w.Cin), (uint64_t)Lin, (uint64_t)B, (uint64_t)x_ld,
+  VSG_TRY(encode_3d(&tmA, x, (uint64_t)((a_planes - 1) * x_part_stride + w.Cin), (uint64_t)Lin, (uint64_t)B, (uint64_t)x_ld,
                     (uint64_t)Lin * x_ld, (uint32_t)KC, (uint32_t)p.a_box_rows, KC));
   // epilogue tensors: rows are the q positions of this (poly)phase: row stride out_stride*ld, base shifted by phase
   auto emap = [&](CUtensorMap* m, const __nv_bfloat16* base, int width, int box_c) -> int {
@@ -392,10 +396,10 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   static const KernelFn kernels[2][EPI_SIG_COUNT] = {
       {conv_tc_kernel<false, EPI_SIG_GENERIC>, conv_tc_kernel<false, EPI_SIG_ACT>, conv_tc_kernel<false, EPI_SIG_RES_ACT>,
        conv_tc_kernel<false, EPI_SIG_LINEAR>, conv_tc_kernel<false, EPI_SIG_X6>, conv_tc_kernel<false, EPI_SIG_SUM0>,
-       conv_tc_kernel<false, EPI_SIG_SUM1>, conv_tc_kernel<false, EPI_SIG_FINAL>},
+       conv_tc_kernel<false, EPI_SIG_SUM1>, conv_tc_kernel<false, EPI_SIG_FINAL>, conv_tc_kernel<false, EPI_SIG_POST>},
       {conv_tc_kernel<true, EPI_SIG_GENERIC>, conv_tc_kernel<true, EPI_SIG_ACT>, conv_tc_kernel<true, EPI_SIG_RES_ACT>,
        conv_tc_kernel<true, EPI_SIG_LINEAR>, conv_tc_kernel<true, EPI_SIG_X6>, conv_tc_kernel<true, EPI_SIG_SUM0>,
-       conv_tc_kernel<true, EPI_SIG_SUM1>, conv_tc_kernel<true, EPI_SIG_FINAL>}};
+       conv_tc_kernel<true, EPI_SIG_SUM1>, conv_tc_kernel<true, EPI_SIG_FINAL>, conv_tc_kernel<true, EPI_SIG_POST>}};
   // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[P->device & 63];
@@ -407,7 +411,12 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   }
   // the decoder's two dominant epilogues run kernels specialised on their feature flags (conv_tc.cuh, EPI_SIG_*)
   int sig = w.planes == 3 ? EPI_SIG_X6 : EPI_SIG_GENERIC;
-  if (opt.epi_sigs && e.mode == EPI_TC_LINEAR && w.planes == 1 && e.bias && !e.bcond && !e.mask && !e.out_f32) {
+  if (e.mode == EPI_TC_TANH) {
+    if (a_planes != 1 || p.cw != 16 || e.tanh_cols < 1 || e.tanh_cols > 4 || !e.out_f32 || out_stride != 1 || Lq != Lout)
+      return fail(VSG_EINVAL, "tanh epilogue: needs a plain-bf16 N = 16 convolution and an fp32 output");
+    sig = EPI_SIG_POST;
+  }
+  if (opt.epi_sigs && e.mode == EPI_TC_LINEAR && a_planes == 1 && e.bias && !e.bcond && !e.mask && !e.out_f32) {
     sig = EPI_SIG_LINEAR;
     if (!e.out_raw && e.out_act && !e.add1 && e.scale == 1.0f) {
       if (!e.add0) sig = EPI_SIG_ACT;
@@ -1589,10 +1598,23 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
   {  // wav = tanh(conv_post(leaky_relu(x)))   (decoder.py:55-57); the stage output already holds leaky_relu(x)
     if (!x3 && ch == 16 && P->conv_post_k == 7) {   // the model's shape: sliding-window kernel
       constexpr int S = 8;
-      const int gpb = (L + S - 1) / S, total = gpb * B;
-      const int blocks = std::min((total + 127) / 128, 8 * P->sm_count);
-      conv_post_bf16_win_kernel<16, 7, S><<<blocks, 128, 0, st>>>(io[cur_io], P->conv_post_w, wav, L, gpb, total);
-      VSG_LAUNCH_CHECK("conv_post_bf16_win_kernel");
+      const int post_mode = opt.conv_post;        // 0 tensor cores, 1 register-window kernel, 2 shared-memory kernel (A/B)
+      if (post_mode == 0 && P->conv_post_S == 4 && L % 4 == 0) {
+        // conv_post on the tensor cores: rows of 4 samples x 16 channels, Conv1d(64 -> 16, 3 row taps), tanh epilogue
+        EpiTC e;
+        e.mode = EPI_TC_TANH; e.out_f32 = wav; e.tanh_cols = 4;
+        VSG_TRY(launch_conv_tc(P, P->conv_post_rp, io[cur_io], B, L / 4, -1, 1, L / 4, 1, 0, L / 4, e, opt, err, st));
+      } else if (post_mode == 1) {
+        const int gpb = (L + S - 1) / S, total = gpb * B;
+        const int blocks = std::min((total + 127) / 128, 8 * P->sm_count);
+        conv_post_bf16_win_kernel<16, 7, S><<<blocks, 128, 0, st>>>(io[cur_io], P->conv_post_w, wav, L, gpb, total);
+        VSG_LAUNCH_CHECK("conv_post_bf16_win_kernel");
+      } else {
+        const int tpb = (L + 128 * S - 1) / (128 * S), total = tpb * B;
+        const int blocks = std::min(total, 6 * P->sm_count);
+        conv_post_bf16_smem_kernel<16, 7, S><<<blocks, 128, 0, st>>>(io[cur_io], P->conv_post_w, wav, L, tpb, total);
+        VSG_LAUNCH_CHECK("conv_post_bf16_smem_kernel");
+      }
     } else {
       dim3 grid((L + 255) / 256, B);
       conv_post_bf16_kernel<<<grid, 256, (size_t)ch * P->conv_post_k * sizeof(float), st>>>(io[cur_io], P->conv_post_w, wav,
@@ -1854,6 +1876,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.fuse_rp = (halo_mode & (1 << 24)) ? 0 : 1;                         // bit 24: no row-packed resblock kernel
   g_default_opts.rp_max_c = (halo_mode & (1 << 25)) ? 64 : 32;                      // bit 25: row-packed kernel at C = 64 too
   g_default_opts.rp_packed = (halo_mode & (1 << 26)) ? 0 : 1;                       // bit 26: no block-Toeplitz form
+  g_default_opts.conv_post = (halo_mode >> 28) & 3;                                 // bits 28-29: conv_post on CUDA cores (1 / 2)
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;
   return VSG_OK;

@@ -66,6 +66,7 @@ struct ConvWTC {
   bool has_tmap = false;
   bool x3 = false;      // split-bf16 pack: rows are [W_hi (Cin) | W_lo (Cin)], CinT = 2*Cin
   int planes = 1;       // bf16 planes per weight: 1 plain, 2 = x3, 3 = [W_hi | W_mid | W_lo] (the fp32 weight exactly)
+  bool wsplit = false;  // planes == 2 pack used with ONE-plane activations: x * W_hi + x * W_lo (weights at ~16 mantissa bits)
 };
 
 struct UpsPhase {
@@ -159,6 +160,8 @@ struct VsgPack {
   float* dec_cond_b = nullptr;
   std::vector<vsg::UpStage> ups;
   float* conv_post_w = nullptr;  // [C_last][k]
+  vsg::ConvWTC conv_post_rp;        // conv_post as a row-packed tensor-core conv: Conv1d(64 -> 16, 3 row taps) over rows of 64 / C_last samples
+  int conv_post_S = 0;           // samples per packed row (0: shape not taken; CUDA-core kernel)
   int conv_post_k = 7;
 };
 
