@@ -52,10 +52,11 @@ enum {
                              (waveform max-abs <= 1e-4, flow z <= 1e-5 vs the reference) */
   VSG_PRECISION_BF16 = 1, /* bf16 operands + storage, fp32 accumulate on tcgen05 tensor
                              cores (TMEM accumulators, TMA-fed): the throughput mode     */
-  VSG_PRECISION_BF16X3 = 2 /* split-bf16 on the same tensor-core kernels: every activation and weight is a
-                             (hi, lo) bf16 pair (~16 mantissa bits), every product three MMAs
-                             (hi*hi + hi*lo + lo*hi), fp32 accumulate.  Decoder within the fp32-mode
-                             waveform tolerance; the flow (z <= 1e-5) keeps the fp32 FFMA kernels    */
+  VSG_PRECISION_BF16X3 = 2 /* split-bf16 on the same tensor-core kernels, fp32-mode tolerances on tcgen05.  Decoder:
+                             every activation and weight is a (hi, lo) bf16 pair (~16 mantissa bits), every
+                             product three MMAs (hi*hi + hi*lo + lo*hi).  Flow (z <= 1e-5 on a state of magnitude ~5):
+                             three planes (hi, mid, lo = the fp32 value exactly), six plane products per MMA product,
+                             issued small-first because the tensor pipe's fp32 accumulation truncates            */
 };
 
 #define VSG_MAX_UPS 8

@@ -59,6 +59,7 @@ struct RpTC {
   int n_k, packed_stages;         // 16-wide K slices of the row-packed form ((k + S - 1) * C / 16), ring stages they fill (4 each)
   int tps, direct_stages;         // compact taps per ring stage, ring stages of one direct convolution
   int mb;                         // 128-row blocks per tile
+  int spb;                        // epilogue warp sets per block (1, 2 or 4): 4 / spb blocks are drained concurrently
   int H, V;                       // halo time steps per side, valid time steps per tile (both multiples of S)
   int m_tiles_per_b, total_tiles;
   int n_wst;                      // weight ring stages
@@ -117,7 +118,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     if (p.add1) prefetch_tmap(&wm.add1);
     for (int b = 0; b < kRpMaxBlocks; ++b) {
       mbar_init(bar(kRpBarAccFull + b), 1);
-      const uint32_t warps_per_block = mb >= 3 ? 4u : 16u / (uint32_t)mb;     // epilogue warps that drain one block
+      const uint32_t warps_per_block = 4u * (uint32_t)p.spb;                  // epilogue warps that drain one block
       mbar_init(bar(kRpBarReady + b), warps_per_block);
       mbar_init(bar(kRpBarReady + kRpMaxBlocks + b), warps_per_block);
     }
@@ -334,26 +335,26 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     }
   } else if (warp >= 4) {
     // ===================== epilogue: 4 sets of 4 warps (warp % 4 = TMEM lane quarter) =====================
-    // The sets split the tile's blocks: with 4 blocks set s owns block s and drains all 64 columns of its rows (four
-    // tcgen05.ld in two waves, ONE fence / arrive per block and convolution); with 2 blocks two sets share a block
-    // (32 columns each), with 1 block all four do (16 columns each).  A thread always owns the same rows, so its
-    // shared-memory, tensor-memory and barrier addresses are loop constants.
+    // `spb` sets share a block (each drains 64 / spb of its columns) and the 4 / spb groups of sets take the tile's blocks
+    // round-robin: spb = 1 -> set s owns block s and drains all 64 columns of its rows (four tcgen05.ld in two waves, ONE
+    // fence / arrive per block and convolution); spb = 2 on a 4-block tile -> sets {0, 1} drain blocks 0 and 2, sets
+    // {2, 3} blocks 1 and 3, 32 columns per thread: a block's hand-over chain (accumulator full -> A tile of the next
+    // convolution ready) is half as long, which is what bounds the kernel -- the issuer waits for block b + 1 of the
+    // previous convolution before it may start block b.
     const int set = (warp - 4) >> 2, quarter = warp & 3;
-    const int spb = mb >= 3 ? 1 : 4 / mb;                        // sets per block
-    const int blk = set / spb;                                   // my block
+    const int spb = p.spb;                                       // sets per block
+    const int n_slots = 4 / spb;                                 // blocks drained concurrently
+    const int slot = set / spb;                                  // my blocks: slot, slot + n_slots, ...
     const int nch = 4 / spb;                                     // my 16-column chunks: chunk0 .. chunk0 + nch - 1
     const int chunk0 = (set % spb) * nch;
-    if (blk < mb) {
+    if (slot < mb) {
     constexpr int NB = C == 16 ? 1 : C == 32 ? 2 : 0;            // bias register sets (C = 64: loaded per chunk)
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t x_col0 = (uint32_t)(mb * 64);                 // residual stream x (fp32) lives after the c1 accumulators
     const float slope = p.slope, inv_slope = 1.0f / p.slope, scale = p.scale;
-    const int L = p.L, H = p.H, V = p.V, R = 128 * S * mb;
-    const int row = blk * 128 + quarter * 32 + lane;             // my row of the tile
-    const uint32_t row_off = tile_off + (uint32_t)row * 128u;
-    const uint32_t swz_row = (uint32_t)(row & 7) << 4;           // 16-byte chunk index of a row is XORed with (row & 7)
-    const uint32_t taddr0 = tmem_base + lane_addr + (uint32_t)(blk * 64 + chunk0 * 16);
-    const uint32_t bar_acc = bar(kRpBarAccFull + blk), bar_ready = bar(kRpBarReady + blk);
+    const int L = p.L, H = p.H, V = p.V;
+    const int row_in_blk = quarter * 32 + lane;
+    const uint32_t swz_row = (uint32_t)(row_in_blk & 7) << 4;    // 16-byte chunk index of a row is XORed with (row & 7)
     const float* const bias_s = reinterpret_cast<const float*>(smem_gen + p.bias_off);
     asm volatile("griddepcontrol.wait;" ::: "memory");          // add1 / outputs belong to the stream's previous kernels
     TileIter it;
@@ -363,24 +364,25 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     uint32_t ntr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next(), ++n_tile) {
       const int t_tile0 = it.mt * V - H;                         // time step of tile row 0, sub-step 0
-      const int t_row = row * S;                                 // my row's first time step inside the tile
-      // rows (partly) outside the utterance: the next convolution must see zeros there
-      const bool row_out = (t_tile0 + t_row < 0) || (t_tile0 + t_row + S > L);
       // ---- x0 = inverse leaky_relu of the input tile (bf16 in P) -> fp32 in tensor memory
       mbar_wait(bar(kRpBarAFull), n_tile & 1u, error_flag);
+      for (int blk = slot; blk < mb; blk += n_slots) {
+        const uint32_t row_off = tile_off + (uint32_t)(blk * 128 + row_in_blk) * 128u;
+        const uint32_t taddr0 = tmem_base + lane_addr + (uint32_t)(blk * 64 + chunk0 * 16);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < nch) {
-          const uint32_t cb = (uint32_t)((chunk0 + j) * 32);
-          uint32_t r[16];
+        for (int j = 0; j < 4; ++j) {
+          if (j < nch) {
+            const uint32_t cb = (uint32_t)((chunk0 + j) * 32);
+            uint32_t r[16];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float f[8];
-            unpack_bf16x8(lds128(p_base + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row)), f);
+            for (int h = 0; h < 2; ++h) {
+              float f[8];
+              unpack_bf16x8(lds128(p_base + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row)), f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r[8 * h + i] = __float_as_uint(fminf(f[i], f[i] * inv_slope));
+              for (int i = 0; i < 8; ++i) r[8 * h + i] = __float_as_uint(fminf(f[i], f[i] * inv_slope));
+            }
+            tmem_st16(taddr0 + x_col0 + (uint32_t)(j * 16), r);
           }
-          tmem_st16(taddr0 + x_col0 + (uint32_t)(j * 16), r);
         }
       }
       for (int c = 0; c < n_convs; ++c, ++n) {
@@ -395,6 +397,14 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
             bias_r[jb][4 * i] = bv.x; bias_r[jb][4 * i + 1] = bv.y; bias_r[jb][4 * i + 2] = bv.z; bias_r[jb][4 * i + 3] = bv.w;
           }
         }
+        for (int blk = slot; blk < mb; blk += n_slots) {
+        const int row = blk * 128 + row_in_blk;                    // my row of the tile
+        const int t_row = row * S;                                 // its first time step inside the tile
+        // rows (partly) outside the utterance: the next convolution must see zeros there
+        const bool row_out = (t_tile0 + t_row < 0) || (t_tile0 + t_row + S > L);
+        const uint32_t row_off = tile_off + (uint32_t)row * 128u;
+        const uint32_t taddr0 = tmem_base + lane_addr + (uint32_t)(blk * 64 + chunk0 * 16);
+        const uint32_t bar_acc = bar(kRpBarAccFull + blk), bar_ready = bar(kRpBarReady + blk);
         // conv c reads P (c even) / Q (c odd) and writes the other; its accumulator is T (c even) / X (c odd)
         const uint32_t dst = ((c & 1) ? p_base : q_base) + row_off;
         const uint32_t taddr = taddr0 + ((c & 1) ? x_col0 : 0u);
@@ -506,6 +516,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
           if (lane == 0) mbar_arrive(bar_rdy);
         }
         if (trace && ntr < 1021) trace[ntr++] = (uint32_t)clock();
+        }
       }
     }
     }

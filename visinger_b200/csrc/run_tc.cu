@@ -130,6 +130,9 @@ struct TCOptions {
   int rp_max_c = 32;        // widest stage the row-packed kernel takes
   int rp_packed = 1;        // dilation-1 convolutions in the block-Toeplitz form (0: every conv tap by tap)
   int rp_max_mb = 0;        // cap on 128-row blocks per row-packed tile (0 = as many as fit)
+  int rp_spb2 = 0;          // row-packed kernel, 3- / 4-block tiles: two epilogue warp sets per block, two blocks per set
+                            // (measured slower: 314 / 415 / 513 us vs 289 / 386 / 491 at C = 32 -- the per-block hand-over, not the
+                            // drain itself, is what a set spends its time on)
   int conv_post = 0;        // conv_post kernel: 0 tcgen05 (row-packed, tanh epilogue), 1 register window, 2 shared-memory window
   uint32_t* rp_trace = nullptr;   // tuning aid (vsg_debug_resblock_bf16 with VSG_RP_TRACE set): pipeline event clocks of CTA 0
 };
@@ -797,6 +800,7 @@ int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   p.packed_mask = pl.packed_mask; p.n_k = pl.n_k; p.packed_stages = pl.packed_stages;
   p.tps = pl.tps; p.direct_stages = pl.direct_stages;
   p.mb = pl.mb; p.H = pl.H; p.V = pl.V;
+  p.spb = pl.mb >= 3 ? (opt.rp_spb2 ? 2 : 1) : 4 / pl.mb;   // epilogue warp sets per block
   p.m_tiles_per_b = (L + pl.V - 1) / pl.V;
   p.total_tiles = p.m_tiles_per_b * B;
   p.n_wst = pl.n_wst;
@@ -1796,6 +1800,7 @@ extern "C" int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, cons
     opt.rb_issuers = (sets >> 4) & 15;
     opt.rp_max_mb = max_mb;
     opt.rp_packed = (sets & 512) ? 0 : 1;
+    opt.rp_spb2 = (sets & 1024) ? 1 : 0;              // bit 10: two epilogue warp sets per block, two blocks per set
     uint32_t* d_trace = nullptr;
     if (row_packed && getenv("VSG_RP_TRACE")) {
       cudaMalloc(&d_trace, 5 * 1024 * sizeof(uint32_t));
@@ -1876,6 +1881,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.fuse_rp = (halo_mode & (1 << 24)) ? 0 : 1;                         // bit 24: no row-packed resblock kernel
   g_default_opts.rp_max_c = (halo_mode & (1 << 25)) ? 64 : 32;                      // bit 25: row-packed kernel at C = 64 too
   g_default_opts.rp_packed = (halo_mode & (1 << 26)) ? 0 : 1;                       // bit 26: no block-Toeplitz form
+  g_default_opts.rp_spb2 = (halo_mode & (1 << 30)) ? 1 : 0;                         // bit 30: row-packed kernel, two epilogue sets per block
   g_default_opts.conv_post = (halo_mode >> 28) & 3;                                 // bits 28-29: conv_post on CUDA cores (1 / 2)
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;

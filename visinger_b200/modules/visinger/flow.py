@@ -95,8 +95,8 @@ class Flip(nn.Module):
 class ResidualCouplingBlock(PackedModuleMixin, nn.Module):
     """Reference `ResidualCouplingBlock` (modules/visinger/flow.py:15-44) on B200 CUDA kernels.
 
-    `precision`: "fp32" (parity mode: fp32 FFMA kernels; z within 1e-5 of the reference) or "bf16"
-    (tcgen05 tensor-core mode).
+    `precision`: "fp32" (parity mode: fp32 FFMA kernels; z within 1e-5 of the reference), "bf16x3" (the same tolerance
+    on the tcgen05 kernels: three bf16 planes per value) or "bf16" (tcgen05 throughput mode).
     """
 
     def __init__(self, channels, hidden_channels, kernel_size, dilation_rate, n_layers, n_flows=4, gin_channels=0,
