@@ -14,8 +14,9 @@ the metric's roofline is quoted on), random weights of config/models/visinger.ya
   roofline  decoder convolutions (the dominant kernels): algorithmic FLOPs (SURVEY.md 8d:
             333 911 680 FLOP per latent frame) / CUDA-event time of the generator region
   cpu_baseline  the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1 only)
-  parity_mode   (N=1) the same workload in bf16x3 -- the tensor-core mode that meets the fp32 tolerances -- with its
-            measured distance to the CPU oracle on a full-length utterance
+  parity_mode   (N=1) the same workload in bf16x3 -- the tensor-core mode that meets the fp32 tolerances (decoder on two
+            bf16 planes per value, flow on three; no CUDA-core convolution) -- with its measured distance to the CPU
+            oracle on a full-length utterance
   bf16      (N=1) the headline mode's distance to the CPU oracle on the same full-length utterance: relative L2,
             max-abs and the reference's own log-mel L1 (MelSpectrogramFixed, utils/audio/mel_processing.py:28-38)
   full_model  (N=1) BASELINE.json configs[3]: the whole VISinger.forward(infer=True) -- native transformer stacks of the prior
@@ -503,6 +504,8 @@ def main():
             parity = {"precision": "bf16x3", "value": audio_per_step * k3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / k3,
                       "wav_max_abs_err": err3, "z_max_abs_err": errz, "mel_l1": mel3,
                       "meets_fp32_tolerance": bool(err3 <= 1e-4 and errz <= 1e-5),
+                      "arithmetic": "tcgen05 throughout: decoder on two bf16 planes per value (3 MMAs per product), flow on "
+                                    "three (6 plane products, small-first: the tensor pipe's fp32 accumulation truncates)",
                       "vs": f"CPU {cpu.kind} (fp32) on utterance 0 of the batch, T={T}"}
             del hp3
             torch.cuda.empty_cache()
