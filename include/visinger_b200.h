@@ -341,7 +341,8 @@ int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32
  *   128-row blocks per resblock tile | bits 21-23 resblock epilogue warp sets (0 = 4) | bit 24 no row-packed resblock
  *   kernel | bit 25 row-packed kernel at C = 64 too | bit 26 no block-Toeplitz form | bit 27 no specialised images for
  *   the last conv2 of a resblock (running-sum epilogues) | bits 28-29 conv_post on the CUDA-core kernels (1 register
- *   window, 2 shared-memory window) instead of tcgen05. */
+ *   window, 2 shared-memory window) instead of tcgen05 | bit 30 row-packed kernel with two epilogue warp sets per block |
+ *   bit 31 flow with separate res / skip launches and one cond_layer GEMV per flow. */
 int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t l2_tensor_mb, int32_t min_tiles);
 
 #ifdef __cplusplus

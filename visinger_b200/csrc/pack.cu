@@ -115,7 +115,7 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
   if (C % 2 || C <= 0 || H <= 0 || NL <= 0 || K % 2 == 0 || c.flow_dilation_rate < 1)
     return fail(VSG_EINVAL, "bad flow config (channels %d hidden %d kernel %d layers %d)", C, H, K, NL);
   P->flow_layers.resize(c.flow_n_flows);
-  std::vector<float> W, b;
+  std::vector<float> W, b, cond_w_all, cond_b_all;
   for (int f = 0; f < c.flow_n_flows; ++f) {
     FlowLayer& fl = P->flow_layers[f];
     const std::string p = pre + "flows." + std::to_string(2 * f) + ".";
@@ -125,6 +125,15 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
     VSG_TRY(pack_conv_f32(L, W, b, H, half, 1, Identity{}, &fl.pre[0]));
     VSG_TRY(pack_conv_tc(P, W, b, H, half, 1, &fl.pre_tc[0]));
     VSG_TRY(pack_conv_tc(P, W, b, H, half, 1, &fl.pre_x6[0], 3));
+    auto zero_extend = [&](const std::vector<float>& Wi, const std::vector<float>& bi, int flipped) -> int {
+      std::vector<float> W2((size_t)2 * H * half, 0.f), b2((size_t)2 * H, 0.f);
+      std::copy(Wi.begin(), Wi.end(), W2.begin());
+      std::copy(bi.begin(), bi.end(), b2.begin());
+      VSG_TRY(pack_conv_tc(P, W2, b2, 2 * H, half, 1, &fl.pre2_tc[flipped][0]));
+      VSG_TRY(pack_conv_tc(P, W2, b2, 2 * H, half, 1, &fl.pre2_tc[flipped][1], 3));
+      return VSG_OK;
+    };
+    VSG_TRY(zero_extend(W, b, 0));
     {
       std::vector<float> Wf(W.size());
       for (int co = 0; co < H; ++co)
@@ -132,6 +141,7 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
       VSG_TRY(pack_conv_f32(L, Wf, b, H, half, 1, Identity{}, &fl.pre[1]));
       VSG_TRY(pack_conv_tc(P, Wf, b, H, half, 1, &fl.pre_tc[1]));
       VSG_TRY(pack_conv_tc(P, Wf, b, H, half, 1, &fl.pre_x6[1], 3));
+      VSG_TRY(zero_extend(Wf, b, 1));
     }
     // post: Conv1d(H -> half, 1)      flow.py:62 (mean_only)
     VSG_TRY(L.eff_weight(p + "post", half, H, 1, W));
@@ -156,6 +166,7 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
     fl.res_tc.resize(NL);
     fl.skip_tc.resize(NL);
     fl.in_x6.resize(NL); fl.res_x6.resize(NL); fl.skip_x6.resize(NL);
+    fl.rs_tc[0].resize(NL); fl.rs_tc[1].resize(NL);
     for (int i = 0; i < NL; ++i) {
       const std::string pi = p + "enc.in_layers." + std::to_string(i);
       VSG_TRY(L.eff_weight(pi, 2 * H, H, K, W));
@@ -177,6 +188,8 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
       VSG_TRY(L.bias(pr, rs, b, true));
       VSG_TRY(pack_conv_f32(L, W, b, rs, H, 1, Identity{}, &fl.res_skip[i]));
       if (i < NL - 1) {
+        VSG_TRY(pack_conv_tc(P, W, b, 2 * H, H, 1, &fl.rs_tc[0][i]));
+        VSG_TRY(pack_conv_tc(P, W, b, 2 * H, H, 1, &fl.rs_tc[1][i], 3));
         std::vector<float> Wr(W.begin(), W.begin() + (size_t)H * H), br(b.begin(), b.begin() + H);
         std::vector<float> Ws(W.begin() + (size_t)H * H, W.end()), bs(b.begin() + H, b.end());
         VSG_TRY(pack_conv_tc(P, Wr, br, H, H, 1, &fl.res_tc[i]));
@@ -202,7 +215,13 @@ int pack_flow(const Loader& L, const std::string& pre, VsgPack* P) {
         }
       VSG_TRY(L.upload(Wp, &fl.cond_w));
       VSG_TRY(L.upload(bp, &fl.cond_b));
+      cond_w_all.insert(cond_w_all.end(), Wp.begin(), Wp.end());
+      cond_b_all.insert(cond_b_all.end(), bp.begin(), bp.end());
     }
+  }
+  if (c.flow_gin > 0) {
+    VSG_TRY(L.upload(cond_w_all, &P->flow_cond_w));
+    VSG_TRY(L.upload(cond_b_all, &P->flow_cond_b));
   }
   P->has_flow = true;
   return VSG_OK;

@@ -133,6 +133,7 @@ struct TCOptions {
   int rp_spb2 = 0;          // row-packed kernel, 3- / 4-block tiles: two epilogue warp sets per block, two blocks per set
                             // (measured slower: 314 / 415 / 513 us vs 289 / 386 / 491 at C = 32 -- the per-block hand-over, not the
                             // drain itself, is what a set spends its time on)
+  int flow_merge = 1;       // flow: res_skip as one launch on the [h | out] tensor, every flow's cond_layer in one GEMV
   int conv_post = 0;        // conv_post kernel: 0 tcgen05 (row-packed, tanh epilogue), 1 register window, 2 shared-memory window
   uint32_t* rp_trace = nullptr;   // tuning aid (vsg_debug_resblock_bf16 with VSG_RP_TRACE set): pipeline event clocks of CTA 0
 };
@@ -971,18 +972,28 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
   typedef __nv_bfloat16 bf;
   float* cond = ws.take<float>((size_t)B * NF * condO);
   bf* u = ws.take<bf>((size_t)B * T * C * planes);        // rows [hi (C) | mid (C) | lo (C)]
-  bf* h = ws.take<bf>((size_t)B * T * H * planes);
+  // WaveNet state h and skip sum `out` side by side: rows [h (H) | out (H)] per plane, so that res_skip_layers[i] is one
+  // launch (the Conv1d(H -> 2H) it is in the reference) and `pre`, zero-extended to 2H channels, also clears the skip sum
+  bf* hs = ws.take<bf>((size_t)B * T * 2 * H * planes);
   bf* acts = ws.take<bf>((size_t)B * T * H * planes);
-  bf* out = ws.take<bf>((size_t)B * T * H * planes);
   int* err = ws.take<int>(1);
   if (ws.overflow) return fail(VSG_ENOMEM, "flow workspace too small: need %zu bytes", ws.off);
   VSG_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
   const TCOptions opt = g_default_opts;
+  const bool merged = opt.flow_merge != 0;
+  bf* const h = hs;
+  bf* const out = hs + H;
+  const int hs_ld = planes * 2 * H;                       // row width of hs; its planes are 2H channels apart
+  const int cond_bs = merged ? NF * condO : condO;        // floats between the utterances of the condition table
   if (c.flow_gin > 0) {
     if (!g) return fail(VSG_EINVAL, "flow was built with gin_channels=%d but g is NULL", c.flow_gin);
-    for (int f = 0; f < NF; ++f)
-      VSG_TRY(launch_cond(P->flow_layers[f].cond_w, P->flow_layers[f].cond_b, g, cond + (size_t)f * condO * B, condO,
-                          c.flow_gin, B, st));
+    if (merged) {   // every flow's cond_layer in one GEMV launch: cond[b][f * condO + o]
+      VSG_TRY(launch_cond(P->flow_cond_w, P->flow_cond_b, g, cond, NF * condO, c.flow_gin, B, st));
+    } else {
+      for (int f = 0; f < NF; ++f)
+        VSG_TRY(launch_cond(P->flow_layers[f].cond_w, P->flow_layers[f].cond_b, g, cond + (size_t)f * condO * B, condO,
+                            c.flow_gin, B, st));
+    }
   }
   {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
@@ -995,10 +1006,11 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
     const FlowLayer& fl = P->flow_layers[f];
     const bf* x0 = u + (flipped ? half : 0);
     bf* x1 = u + (flipped ? 0 : half);
-    {  // h = pre(x0) * mask
-      const ConvWTC& w = x6 ? fl.pre_x6[flipped] : fl.pre_tc[flipped];
+    {  // h = pre(x0) * mask  (merged: and out = 0)
+      const ConvWTC& w = merged ? fl.pre2_tc[flipped][x6 ? 1 : 0] : x6 ? fl.pre_x6[flipped] : fl.pre_tc[flipped];
       EpiTC e;
-      e.bias = w.bias; e.mask = mask; e.out_raw = h;
+      e.bias = w.bias; e.mask = mask; e.out_raw = hs;
+      if (!merged) { e.ld = hs_ld; e.part_stride = 2 * H; }
       VSG_TRY(launch_conv_tc(P, w, x0, B, T, 0, 1, T, 1, 0, T, e, opt, err, st, planes * C, C));
     }
     int dil = 1;
@@ -1008,20 +1020,32 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
         const ConvWTC& w = x6 ? fl.in_x6[i] : fl.in_tc[i];
         EpiTC e;
         e.mode = EPI_TC_GATE; e.bias = w.bias; e.out_raw = acts;
-        if (c.flow_gin > 0) { e.bcond = cond + (size_t)f * condO * B + (size_t)i * 2 * H; e.bcond_bs = condO; }
-        VSG_TRY(launch_conv_tc(P, w, h, B, T, -((K * dil - dil) / 2), dil, T, 1, 0, T, e, opt, err, st));
+        if (c.flow_gin > 0) {
+          e.bcond = merged ? cond + (size_t)f * condO + (size_t)i * 2 * H : cond + (size_t)f * condO * B + (size_t)i * 2 * H;
+          e.bcond_bs = cond_bs;
+        }
+        VSG_TRY(launch_conv_tc(P, w, h, B, T, -((K * dil - dil) / 2), dil, T, 1, 0, T, e, opt, err, st, hs_ld, 2 * H));
       }
-      if (!last) {  // h = (h + res(acts)) * mask
-        const ConvWTC& w = x6 ? fl.res_x6[i] : fl.res_tc[i];
+      if (merged && !last) {  // [h | out] = ([h | out] + res_skip(acts)) * mask   (masking the running skip sum is a no-op
+                              //  on the valid frames and the sum is masked after the last layer anyway, encoder.py:195)
+        const ConvWTC& w = fl.rs_tc[x6 ? 1 : 0][i];
         EpiTC e;
-        e.bias = w.bias; e.add0 = h; e.mask = mask; e.out_raw = h;
+        e.bias = w.bias; e.add0 = hs; e.mask = mask; e.out_raw = hs;
         VSG_TRY(launch_conv_tc(P, w, acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
-      }
-      {  // out (+)= skip(acts); masked after the last layer
-        const ConvWTC& w = x6 ? fl.skip_x6[i] : fl.skip_tc[i];
-        EpiTC e;
-        e.bias = w.bias; e.add0 = (i > 0) ? out : nullptr; e.mask = last ? mask : nullptr; e.out_raw = out;
-        VSG_TRY(launch_conv_tc(P, w, acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+      } else {
+        if (!last) {  // h = (h + res(acts)) * mask
+          const ConvWTC& w = x6 ? fl.res_x6[i] : fl.res_tc[i];
+          EpiTC e;
+          e.bias = w.bias; e.add0 = h; e.mask = mask; e.out_raw = h; e.ld = hs_ld; e.part_stride = 2 * H;
+          VSG_TRY(launch_conv_tc(P, w, acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+        }
+        {  // out (+)= skip(acts); masked after the last layer
+          const ConvWTC& w = x6 ? fl.skip_x6[i] : fl.skip_tc[i];
+          EpiTC e;
+          e.bias = w.bias; e.add0 = (i > 0 || merged) ? out : nullptr; e.mask = last ? mask : nullptr; e.out_raw = out;
+          e.ld = hs_ld; e.part_stride = 2 * H;
+          VSG_TRY(launch_conv_tc(P, w, acts, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+        }
       }
       dil *= c.flow_dilation_rate;
     }
@@ -1030,7 +1054,7 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
       EpiTC e;
       e.mode = EPI_TC_COUPLE; e.couple_sign = reverse ? -1 : 1;
       e.bias = w.bias; e.mask = mask; e.add0 = x1; e.out_raw = x1; e.ld = planes * C; e.part_stride = C;
-      VSG_TRY(launch_conv_tc(P, w, out, B, T, 0, 1, T, 1, 0, T, e, opt, err, st));
+      VSG_TRY(launch_conv_tc(P, w, out, B, T, 0, 1, T, 1, 0, T, e, opt, err, st, hs_ld, 2 * H));
     }
   }
   {
@@ -1882,6 +1906,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.rp_max_c = (halo_mode & (1 << 25)) ? 64 : 32;                      // bit 25: row-packed kernel at C = 64 too
   g_default_opts.rp_packed = (halo_mode & (1 << 26)) ? 0 : 1;                       // bit 26: no block-Toeplitz form
   g_default_opts.rp_spb2 = (halo_mode & (1 << 30)) ? 1 : 0;                         // bit 30: row-packed kernel, two epilogue sets per block
+  g_default_opts.flow_merge = ((uint32_t)halo_mode & (1u << 31)) ? 0 : 1;           // bit 31: flow with separate res / skip / cond launches
   g_default_opts.conv_post = (halo_mode >> 28) & 3;                                 // bits 28-29: conv_post on CUDA cores (1 / 2)
   if (l2_tensor_mb >= 0) g_l2_tensor_mb = l2_tensor_mb;
   if (min_tiles > 0) g_min_tiles = min_tiles;

@@ -89,6 +89,11 @@ struct FlowLayer {
   // the same packs on three bf16 planes per weight: the flow at the fp32 tolerance on the tensor cores (flow only)
   ConvWTC pre_x6[2], post_x6[2];
   std::vector<ConvWTC> in_x6, res_x6, skip_x6;
+  // merged launches (flow only): the WaveNet state h and the skip sum live side by side in one tensor [.., h (H) | out (H)],
+  // so res_skip_layers[i] (encoder.py:160-164) runs as the ONE Conv1d(H -> 2H) it is in the reference, and `pre` is
+  // zero-extended to 2H output channels so that it also clears the skip sum.  [0] plain bf16, [1] three planes.
+  ConvWTC pre2_tc[2][2];            // [flipped][planes == 3]
+  std::vector<ConvWTC> rs_tc[2];    // layers 0 .. n_layers - 2
 };
 
 // PosteriorEncoder (modules/visinger/encoder.py:76-101): pre (1x1) -> WaveNet -> proj (1x1) -> reparameterised sample.
@@ -153,6 +158,8 @@ struct VsgPack {
   std::vector<void*> allocs;
   // flow
   std::vector<vsg::FlowLayer> flow_layers;
+  float* flow_cond_w = nullptr;  // cond_layer of every flow stacked: [n_flows * 2H * n_layers][gin] (one GEMV launch)
+  float* flow_cond_b = nullptr;
   // decoder
   vsg::ConvW32 conv_pre;
   vsg::ConvWTC conv_pre_tc, conv_pre_x3;
