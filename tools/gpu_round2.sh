@@ -16,9 +16,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 echo "== ncu: bench step launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2_launches_bench_step.csv \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-parity-mode --no-sharded --no-full-model > gpurun_out/ncu_b.log 2>&1; tail -2 gpurun_out/ncu_b.log
-echo "== ncu: bf16x3 hot path launch list (three-plane flow on tcgen05)"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_flow_x6.csv \
-    python tools/time_flow.py > gpurun_out/ncu_f.log 2>&1; tail -2 gpurun_out/ncu_f.log
 echo "== ncu --set full: row-packed resblock kernel (C=32, k=11), the last conv2 of a C=64 resblock and conv_post on tcgen05"
 timeout 400 ncu --set full --import-source on --clock-control none -k regex:rp_tc -c 1 -o gpurun_out/r2_rp32k11 -f \
     python tools/time_rb.py --rp 1 --only 32,11 --reps 2 > gpurun_out/ncu_c.log 2>&1; tail -2 gpurun_out/ncu_c.log
