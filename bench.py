@@ -447,8 +447,21 @@ def main():
             wav, _ = hp.infer(*[t.to(dev, non_blocking=True) for t in host])
             wav_host.copy_(wav.view(B, -1), non_blocking=True)
 
+    # the decoder region on its own (roofline): one CUDA graph, like the step it is a part of
+    dec_graph = None
+    if graph is not None:
+        for _ in range(2):
+            hp.decode(devin[0], devin[4])
+        torch.cuda.synchronize()
+        dec_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(dec_graph):
+            dec_keep = hp.decode(devin[0], devin[4])     # noqa: F841  (keeps the captured output alive)
+
     def step_decoder():
-        hp.decode(devin[0], devin[4])
+        if dec_graph is not None:
+            dec_graph.replay()
+        else:
+            hp.decode(devin[0], devin[4])
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -551,7 +564,7 @@ def main():
                          "frac": dec_tflops / peak, "frac_of_burst_peak": dec_tflops / pk["bf16_burst"], "traffic": traffic,
                          "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum over the {traffic_launches} conv_tc / rp_tc / "
                                          "conv_post launches of one decoder pass (profiles/r2_decoder_traffic.json)",
-                         "kernel": "decoder convolutions (vsg_generator_forward region)",
+                         "kernel": "decoder convolutions (vsg_generator_forward region, replayed as one CUDA graph like the step)",
                          "algorithmic": f"{DEC_FLOP_PER_FRAME} FLOP/frame x {B * T} frames",
                          "ms": ms_dec / args.steps, "peak_source": pk["src"] + ", sustained bf16"},
         }
