@@ -119,7 +119,8 @@ enum : int { EPI_TC_LINEAR = 0, EPI_TC_GATE = 1, EPI_TC_COUPLE = 2, EPI_TC_TANH 
 enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2, EPI_SIG_LINEAR = 3, EPI_SIG_X6 = 4,
              EPI_SIG_SUM0 = 5, EPI_SIG_SUM1 = 6, EPI_SIG_FINAL = 7,
              EPI_SIG_POST = 8,     // conv_post on the row-packed stage output: tanh of <= 4 accumulator columns -> fp32 waveform
-             EPI_SIG_COUNT = 9 };
+             EPI_SIG_ACT_X3 = 9, EPI_SIG_RES_ACT_X3 = 10,   // ACT / RES_ACT on two bf16 planes per tensor (the bf16x3 decoder)
+             EPI_SIG_COUNT = 11 };
 
 namespace tc {
 
@@ -411,11 +412,12 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const uint32_t e_buf_bytes = p.e_buf_bytes, swz_in = p.e_swz_mask, swz_out = p.e_out_swz_mask;
   const uint32_t part_bytes = p.e_part_bytes;     // one bf16 plane (hi or lo) of a staging buffer
   constexpr bool kGen = SIG == EPI_SIG_GENERIC || SIG == EPI_SIG_X6;
-  static_assert(kGen || ((MODE == EPI_TC_LINEAR || (MODE == EPI_TC_TANH && SIG == EPI_SIG_POST)) && NP == 1),
-                "specialised signatures are plain-bf16 linear epilogues");
+  constexpr bool kX3Sig = SIG == EPI_SIG_ACT_X3 || SIG == EPI_SIG_RES_ACT_X3;
+  static_assert(kGen || ((MODE == EPI_TC_LINEAR || (MODE == EPI_TC_TANH && SIG == EPI_SIG_POST)) && NP == (kX3Sig ? 2 : 1)),
+                "specialised signatures are linear epilogues on one bf16 plane (two for the _X3 images)");
   constexpr bool kRt = kGen || SIG == EPI_SIG_LINEAR;      // adds / outputs / scale decided at run time
   constexpr bool kSum = SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_FINAL;
-  const bool has_add0 = kRt ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT || kSum);
+  const bool has_add0 = kRt ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT || SIG == EPI_SIG_RES_ACT_X3 || kSum);
   const bool has_add1 = kRt ? (p.has_add1 && MODE == EPI_TC_LINEAR) : (SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_FINAL);
   const bool has_raw = kRt ? (p.has_raw != 0) : (SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1);
   const bool has_act = kRt ? (p.has_act && MODE == EPI_TC_LINEAR) : !(SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_POST);
@@ -550,7 +552,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
             for (int c = 0; c < CW / 8; ++c) {
               float f[8];
               uint4 u = lds128(base + swz(row_off_in + c * 16, swz_in));
-              if (add0_is_act) {   // plain bf16 only: residual = a > 0 ? a : a / slope = min(a, a / slope)
+              if (add0_is_act && n_parts == 1) {   // residual = a > 0 ? a : a / slope = min(a, a / slope), on packed pairs
                 u.x = bf16x2_scale_min(u.x, inv_slope); u.y = bf16x2_scale_min(u.y, inv_slope);
                 u.z = bf16x2_scale_min(u.z, inv_slope); u.w = bf16x2_scale_min(u.w, inv_slope);
               }
@@ -564,6 +566,10 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
                   unpack_bf16x8(lds128(base + 2u * part_bytes + swz(row_off_in + c * 16, swz_in)), g2);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[i] += g2[i];
+                }
+                if (add0_is_act) {   // split planes: the same recovery on the fp32 sum of the planes
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] = fminf(f[i], f[i] * inv_slope);
                 }
               }
 #pragma unroll
@@ -912,6 +918,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.cw == 32) VSG_EPI6(32);
       else VSG_EPI6(16);
 #undef VSG_EPI6
+    } else if constexpr (SIG == EPI_SIG_ACT_X3 || SIG == EPI_SIG_RES_ACT_X3) {
+      if (!SMALL && p.cw == 64)
+        conv_tc_epilogue<64, EPI_TC_LINEAR, 2, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
+      else if (p.cw == 32)
+        conv_tc_epilogue<32, EPI_TC_LINEAR, 2, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
+      else
+        conv_tc_epilogue<16, EPI_TC_LINEAR, 2, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
     } else if constexpr (SIG == EPI_SIG_POST) {
       conv_tc_epilogue<16, EPI_TC_TANH, 1, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
     } else {   // specialised signature: plain-bf16 linear epilogue with compile-time feature flags

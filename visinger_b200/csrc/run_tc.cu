@@ -400,10 +400,12 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   static const KernelFn kernels[2][EPI_SIG_COUNT] = {
       {conv_tc_kernel<false, EPI_SIG_GENERIC>, conv_tc_kernel<false, EPI_SIG_ACT>, conv_tc_kernel<false, EPI_SIG_RES_ACT>,
        conv_tc_kernel<false, EPI_SIG_LINEAR>, conv_tc_kernel<false, EPI_SIG_X6>, conv_tc_kernel<false, EPI_SIG_SUM0>,
-       conv_tc_kernel<false, EPI_SIG_SUM1>, conv_tc_kernel<false, EPI_SIG_FINAL>, conv_tc_kernel<false, EPI_SIG_POST>},
+       conv_tc_kernel<false, EPI_SIG_SUM1>, conv_tc_kernel<false, EPI_SIG_FINAL>, conv_tc_kernel<false, EPI_SIG_POST>,
+       conv_tc_kernel<false, EPI_SIG_ACT_X3>, conv_tc_kernel<false, EPI_SIG_RES_ACT_X3>},
       {conv_tc_kernel<true, EPI_SIG_GENERIC>, conv_tc_kernel<true, EPI_SIG_ACT>, conv_tc_kernel<true, EPI_SIG_RES_ACT>,
        conv_tc_kernel<true, EPI_SIG_LINEAR>, conv_tc_kernel<true, EPI_SIG_X6>, conv_tc_kernel<true, EPI_SIG_SUM0>,
-       conv_tc_kernel<true, EPI_SIG_SUM1>, conv_tc_kernel<true, EPI_SIG_FINAL>, conv_tc_kernel<true, EPI_SIG_POST>}};
+       conv_tc_kernel<true, EPI_SIG_SUM1>, conv_tc_kernel<true, EPI_SIG_FINAL>, conv_tc_kernel<true, EPI_SIG_POST>,
+       conv_tc_kernel<true, EPI_SIG_ACT_X3>, conv_tc_kernel<true, EPI_SIG_RES_ACT_X3>}};
   // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[P->device & 63];
@@ -419,6 +421,11 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
     if (a_planes != 1 || p.cw != 16 || e.tanh_cols < 1 || e.tanh_cols > 4 || !e.out_f32 || out_stride != 1 || Lq != Lout)
       return fail(VSG_EINVAL, "tanh epilogue: needs a plain-bf16 N = 16 convolution and an fp32 output");
     sig = EPI_SIG_POST;
+  }
+  if (opt.epi_sigs >= 2 && e.mode == EPI_TC_LINEAR && a_planes == 2 && e.bias && !e.bcond && !e.mask && !e.out_f32 &&
+      !e.out_raw && e.out_act && !e.add1 && e.scale == 1.0f) {     // the bf16x3 decoder's two dominant epilogues
+    if (!e.add0) sig = EPI_SIG_ACT_X3;
+    else if (e.add0_is_act) sig = EPI_SIG_RES_ACT_X3;
   }
   if (opt.epi_sigs && e.mode == EPI_TC_LINEAR && a_planes == 1 && e.bias && !e.bcond && !e.mask && !e.out_f32) {
     sig = EPI_SIG_LINEAR;
@@ -1470,6 +1477,10 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
     e.out_act = io[cur_io];
     VSG_TRY(launch_conv_tc(P, W(P->conv_pre_tc, P->conv_pre_x3), zt, B, T, -3, 1, T, 1, 0, T, e, opt, err, st));
   }
+  // Only leaky_relu(x) is stored for the running stream (see below); split-bf16 recovers the residual from the two
+  // planes in fp32 (x = a >= 0 ? a : a / slope: as exact as a raw copy at ~16 mantissa bits) unless VSG_X3_TWO_STREAMS=1
+  static const bool x3_two_streams = getenv("VSG_X3_TWO_STREAMS") != nullptr && getenv("VSG_X3_TWO_STREAMS")[0] == '1';
+  const bool one_stream_all = opt.single_stream && !(x3 && x3_two_streams);
   int L = T, ch = UIC;
   for (int i = 0; i < c.dec_n_ups; ++i) {
     const UpStage& us = P->ups[i];
@@ -1487,7 +1498,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
         EpiTC e;
         e.bias = us.merged_tc.bias;
         e.out_act = bUA;
-        if (x3 || !opt.single_stream) e.out_raw = bU;
+        if (!one_stream_all) e.out_raw = bU;
         VSG_TRY(launch_conv_tc(P, W(us.merged_tc, us.merged_x3), xin, nb, Lin, us.merged_in_off0, 1, Lin, 1, 0, Lin, e, opt,
                                err, st));
       } else {
@@ -1495,16 +1506,16 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
           EpiTC e;
           e.bias = us.phases[r].tc.bias;
           e.out_act = bUA;
-          if (x3 || !opt.single_stream) e.out_raw = bU;
+          if (!one_stream_all) e.out_raw = bU;
           const int Lq = (Lout - r + us.rate - 1) / us.rate;
           VSG_TRY(launch_conv_tc(P, W(us.phases[r].tc, us.phases[r].x3), xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r,
                                  Lout, e, opt, err, st));
         }
       }
-      // Plain bf16: only leaky_relu(x) is stored for the running stream; the residual x is recovered from it in the
-      // consumer's epilogue (a > 0 ? a : a / slope -- as exact in bf16 as a second, raw copy), so the upsampler and every
-      // non-final conv2 write one tensor instead of two.  Split-bf16 keeps the raw copy (exactness of the lo plane).
-      const bool one_stream = !x3 && opt.single_stream;
+      // Only leaky_relu(x) is stored for the running stream; the residual x is recovered from it in the consumer's
+      // epilogue (a > 0 ? a : a / slope -- as exact as a second, raw copy at the stream's precision), so the upsampler and
+      // every non-final conv2 write one tensor instead of two.
+      const bool one_stream = one_stream_all;
       const cudaStream_t st_main = st;
       // C <= 64 stages: every ResBlock1 is ONE kernel (rb_tc.cuh); the three launches of a stage are chained through the
       // running sum, so they stay on the caller's stream (their CTAs own all of tensor memory and cannot co-reside anyway)
