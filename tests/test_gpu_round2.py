@@ -285,14 +285,16 @@ def test_rowpacked_resblock_kernel(cuda_device, C, k, dils, B, L, max_mb, varian
     _run_resblock_case(cuda_device, C, k, dils, B, L, max_mb, variant)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
 @pytest.mark.parametrize("B,T", [(2, 40), (3, 333), (1, 1000)])
-def test_conv_post_tensor_core_equals_cuda_core(cuda_device, B, T):
+def test_conv_post_tensor_core_equals_cuda_core(cuda_device, B, T, precision):
     """conv_post (decoder.py:55-57) on tcgen05 -- rows of 4 samples x 16 channels, Conv1d(64 -> 16, 3 row taps) with
-    block-Toeplitz [W_hi | W_lo] weights, tanh epilogue -- against the CUDA-core window kernels on the same stage output
-    (option bits 28-29): the same waveform up to fp32 summation order."""
+    block-Toeplitz [W_hi | W_lo] weights, tanh epilogue (bf16x3: rows of 2 samples x 2 planes x 16 channels, 5 row taps) --
+    against the CUDA-core kernels on the same stage output (option bits 28-29): the same waveform up to fp32 summation
+    order."""
     from visinger_b200 import _lib
     sd = O.synth_state_dict(gen_shapes(GEN_FULL), 1234)
-    m = build_gen(GEN_FULL, sd, cuda_device, precision="bf16")
+    m = build_gen(GEN_FULL, sd, cuda_device, precision=precision)
     x, _, g = make_inputs(3 + T, B, 192, T, 256)
     xd, gd = x.to(cuda_device), g.to(cuda_device)
     try:
@@ -305,5 +307,5 @@ def test_conv_post_tensor_core_equals_cuda_core(cuda_device, B, T):
         _lib.set_tc_options(1)
     assert torch.equal(win, sm)
     err = maxabs(tc, win)
-    print(f"conv_post tcgen05 vs CUDA cores B={B} T={T}: max-abs {err:.3e} (|wav|max {float(win.abs().max()):.3e})")
-    assert err <= 2e-6
+    print(f"conv_post tcgen05 vs CUDA cores {precision} B={B} T={T}: max-abs {err:.3e} (|wav|max {float(win.abs().max()):.3e})")
+    assert 0.0 < err <= 2e-6 or (err == 0.0 and T < 0)      # different summation order, same waveform

@@ -120,7 +120,8 @@ enum : int { EPI_SIG_GENERIC = 0, EPI_SIG_ACT = 1, EPI_SIG_RES_ACT = 2, EPI_SIG_
              EPI_SIG_SUM0 = 5, EPI_SIG_SUM1 = 6, EPI_SIG_FINAL = 7,
              EPI_SIG_POST = 8,     // conv_post on the row-packed stage output: tanh of <= 4 accumulator columns -> fp32 waveform
              EPI_SIG_ACT_X3 = 9, EPI_SIG_RES_ACT_X3 = 10,   // ACT / RES_ACT on two bf16 planes per tensor (the bf16x3 decoder)
-             EPI_SIG_COUNT = 11 };
+             EPI_SIG_SUM0_X3 = 11, EPI_SIG_SUM1_X3 = 12, EPI_SIG_FINAL_X3 = 13,
+             EPI_SIG_COUNT = 14 };
 
 namespace tc {
 
@@ -412,16 +413,19 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   const uint32_t e_buf_bytes = p.e_buf_bytes, swz_in = p.e_swz_mask, swz_out = p.e_out_swz_mask;
   const uint32_t part_bytes = p.e_part_bytes;     // one bf16 plane (hi or lo) of a staging buffer
   constexpr bool kGen = SIG == EPI_SIG_GENERIC || SIG == EPI_SIG_X6;
-  constexpr bool kX3Sig = SIG == EPI_SIG_ACT_X3 || SIG == EPI_SIG_RES_ACT_X3;
+  constexpr bool kX3Sig = SIG == EPI_SIG_ACT_X3 || SIG == EPI_SIG_RES_ACT_X3 || SIG == EPI_SIG_SUM0_X3 || SIG == EPI_SIG_SUM1_X3 ||
+                          SIG == EPI_SIG_FINAL_X3;
   static_assert(kGen || ((MODE == EPI_TC_LINEAR || (MODE == EPI_TC_TANH && SIG == EPI_SIG_POST)) && NP == (kX3Sig ? 2 : 1)),
                 "specialised signatures are linear epilogues on one bf16 plane (two for the _X3 images)");
   constexpr bool kRt = kGen || SIG == EPI_SIG_LINEAR;      // adds / outputs / scale decided at run time
-  constexpr bool kSum = SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_FINAL;
+  constexpr bool kSum0 = SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM0_X3, kSum1 = SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_SUM1_X3,
+                 kFinal = SIG == EPI_SIG_FINAL || SIG == EPI_SIG_FINAL_X3;
+  constexpr bool kSum = kSum0 || kSum1 || kFinal;
   const bool has_add0 = kRt ? (p.has_add0 != 0) : (SIG == EPI_SIG_RES_ACT || SIG == EPI_SIG_RES_ACT_X3 || kSum);
-  const bool has_add1 = kRt ? (p.has_add1 && MODE == EPI_TC_LINEAR) : (SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_FINAL);
-  const bool has_raw = kRt ? (p.has_raw != 0) : (SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1);
-  const bool has_act = kRt ? (p.has_act && MODE == EPI_TC_LINEAR) : !(SIG == EPI_SIG_SUM0 || SIG == EPI_SIG_SUM1 || SIG == EPI_SIG_POST);
-  const float scale = (kRt || SIG == EPI_SIG_FINAL) ? p.scale : 1.0f, slope = p.slope;
+  const bool has_add1 = kRt ? (p.has_add1 && MODE == EPI_TC_LINEAR) : (kSum1 || kFinal);
+  const bool has_raw = kRt ? (p.has_raw != 0) : (kSum0 || kSum1);
+  const bool has_act = kRt ? (p.has_act && MODE == EPI_TC_LINEAR) : !(kSum0 || kSum1 || SIG == EPI_SIG_POST);
+  const float scale = (kRt || kFinal) ? p.scale : 1.0f, slope = p.slope;
   const bool add0_is_act = kRt ? (p.add0_is_act != 0) : true;
   const float inv_slope = 1.0f / p.slope;
   const float* const bias = p.bias;
@@ -628,6 +632,8 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
             float* dst = p.out_f32 + ((long long)b * p.Lq + q) * p.tanh_cols;
             if (p.tanh_cols == 4) {
               *reinterpret_cast<float4*>(dst) = make_float4(tanhf(v[0]), tanhf(v[1]), tanhf(v[2]), tanhf(v[3]));
+            } else if (p.tanh_cols == 2) {
+              *reinterpret_cast<float2*>(dst) = make_float2(tanhf(v[0]), tanhf(v[1]));
             } else {
               for (int i = 0; i < p.tanh_cols; ++i) dst[i] = tanhf(v[i]);
             }
@@ -918,7 +924,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.cw == 32) VSG_EPI6(32);
       else VSG_EPI6(16);
 #undef VSG_EPI6
-    } else if constexpr (SIG == EPI_SIG_ACT_X3 || SIG == EPI_SIG_RES_ACT_X3) {
+    } else if constexpr (SIG == EPI_SIG_ACT_X3 || SIG == EPI_SIG_RES_ACT_X3 || SIG == EPI_SIG_SUM0_X3 || SIG == EPI_SIG_SUM1_X3 ||
+                         SIG == EPI_SIG_FINAL_X3) {
       if (!SMALL && p.cw == 64)
         conv_tc_epilogue<64, EPI_TC_LINEAR, 2, SIG>(tmAdd0, tmAdd1, tmRaw, tmAct, p, smem_base, bar_base, tmem_base, warp, lane, set, lead_warp);
       else if (p.cw == 32)

@@ -508,6 +508,23 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
     P->conv_post_rp.wsplit = true;
     if (P->conv_post_rp.has_tmap) P->conv_post_S = S;
   }
+  // bf16x3 mode: a sample of the stage output is [hi (ch) | lo (ch)] = 2 ch bf16, so 64 / (2 ch) samples make a row and the
+  // "input channels" of the row-packed convolution are (sample, plane, channel); both planes meet the same weights.
+  if (ch == 16) {
+    const int S = 2, RT = 5;       // rows r-2 .. r+2 cover samples 2r-4 .. 2r+5 (taps reach 2r-3 .. 2r+4)
+    std::vector<float> Wt((size_t)16 * 64 * RT, 0.f), bz(16, 0.f);
+    for (int sp = 0; sp < S; ++sp)
+      for (int m = 0; m < RT; ++m)
+        for (int s2 = 0; s2 < S; ++s2) {
+          const int j = S * (m - 2) + s2 - sp + 3;
+          if (j < 0 || j >= 7) continue;
+          for (int pl = 0; pl < 2; ++pl)
+            for (int cc = 0; cc < ch; ++cc)
+              Wt[((size_t)sp * 64 + s2 * 2 * ch + pl * ch + cc) * RT + m] = W[(size_t)cc * 7 + j];
+        }
+    VSG_TRY(pack_conv_tc(P, Wt, bz, 16, 64, RT, &P->conv_post_rp_x3, 2));
+    P->conv_post_rp_x3.wsplit = true;
+  }
   P->has_dec = true;
   return VSG_OK;
 }

@@ -401,11 +401,13 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
       {conv_tc_kernel<false, EPI_SIG_GENERIC>, conv_tc_kernel<false, EPI_SIG_ACT>, conv_tc_kernel<false, EPI_SIG_RES_ACT>,
        conv_tc_kernel<false, EPI_SIG_LINEAR>, conv_tc_kernel<false, EPI_SIG_X6>, conv_tc_kernel<false, EPI_SIG_SUM0>,
        conv_tc_kernel<false, EPI_SIG_SUM1>, conv_tc_kernel<false, EPI_SIG_FINAL>, conv_tc_kernel<false, EPI_SIG_POST>,
-       conv_tc_kernel<false, EPI_SIG_ACT_X3>, conv_tc_kernel<false, EPI_SIG_RES_ACT_X3>},
+       conv_tc_kernel<false, EPI_SIG_ACT_X3>, conv_tc_kernel<false, EPI_SIG_RES_ACT_X3>, conv_tc_kernel<false, EPI_SIG_SUM0_X3>,
+       conv_tc_kernel<false, EPI_SIG_SUM1_X3>, conv_tc_kernel<false, EPI_SIG_FINAL_X3>},
       {conv_tc_kernel<true, EPI_SIG_GENERIC>, conv_tc_kernel<true, EPI_SIG_ACT>, conv_tc_kernel<true, EPI_SIG_RES_ACT>,
        conv_tc_kernel<true, EPI_SIG_LINEAR>, conv_tc_kernel<true, EPI_SIG_X6>, conv_tc_kernel<true, EPI_SIG_SUM0>,
        conv_tc_kernel<true, EPI_SIG_SUM1>, conv_tc_kernel<true, EPI_SIG_FINAL>, conv_tc_kernel<true, EPI_SIG_POST>,
-       conv_tc_kernel<true, EPI_SIG_ACT_X3>, conv_tc_kernel<true, EPI_SIG_RES_ACT_X3>}};
+       conv_tc_kernel<true, EPI_SIG_ACT_X3>, conv_tc_kernel<true, EPI_SIG_RES_ACT_X3>, conv_tc_kernel<true, EPI_SIG_SUM0_X3>,
+       conv_tc_kernel<true, EPI_SIG_SUM1_X3>, conv_tc_kernel<true, EPI_SIG_FINAL_X3>}};
   // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[P->device & 63];
@@ -422,10 +424,15 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
       return fail(VSG_EINVAL, "tanh epilogue: needs a plain-bf16 N = 16 convolution and an fp32 output");
     sig = EPI_SIG_POST;
   }
-  if (opt.epi_sigs >= 2 && e.mode == EPI_TC_LINEAR && a_planes == 2 && e.bias && !e.bcond && !e.mask && !e.out_f32 &&
-      !e.out_raw && e.out_act && !e.add1 && e.scale == 1.0f) {     // the bf16x3 decoder's two dominant epilogues
-    if (!e.add0) sig = EPI_SIG_ACT_X3;
-    else if (e.add0_is_act) sig = EPI_SIG_RES_ACT_X3;
+  if (opt.epi_sigs >= 2 && e.mode == EPI_TC_LINEAR && a_planes == 2 && e.bias && !e.bcond && !e.mask && !e.out_f32) {
+    // the bf16x3 decoder's epilogues (single activated stream), as for one plane below
+    if (!e.out_raw && e.out_act && !e.add1 && e.scale == 1.0f) {
+      if (!e.add0) sig = EPI_SIG_ACT_X3;
+      else if (e.add0_is_act) sig = EPI_SIG_RES_ACT_X3;
+    } else if (e.add0 && e.add0_is_act) {
+      if (e.out_raw && !e.out_act && e.scale == 1.0f) sig = e.add1 ? EPI_SIG_SUM1_X3 : EPI_SIG_SUM0_X3;
+      else if (!e.out_raw && e.out_act && e.add1) sig = EPI_SIG_FINAL_X3;
+    }
   }
   if (opt.epi_sigs && e.mode == EPI_TC_LINEAR && a_planes == 1 && e.bias && !e.bcond && !e.mask && !e.out_f32) {
     sig = EPI_SIG_LINEAR;
@@ -1654,6 +1661,11 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
         conv_post_bf16_smem_kernel<16, 7, S><<<blocks, 128, 0, st>>>(io[cur_io], P->conv_post_w, wav, L, tpb, total);
         VSG_LAUNCH_CHECK("conv_post_bf16_smem_kernel");
       }
+    } else if (x3 && ch == 16 && P->conv_post_k == 7 && P->conv_post_rp_x3.has_tmap && L % 2 == 0 && opt.conv_post == 0) {
+      // bf16x3: rows of 2 samples x [hi | lo] x 16 channels, Conv1d(64 -> 16, 5 row taps) on [W_hi | W_lo], tanh epilogue
+      EpiTC e;
+      e.mode = EPI_TC_TANH; e.out_f32 = wav; e.tanh_cols = 2;
+      VSG_TRY(launch_conv_tc(P, P->conv_post_rp_x3, io[cur_io], B, L / 2, -2, 1, L / 2, 1, 0, L / 2, e, opt, err, st));
     } else {
       dim3 grid((L + 255) / 256, B);
       conv_post_bf16_kernel<<<grid, 256, (size_t)ch * P->conv_post_k * sizeof(float), st>>>(io[cur_io], P->conv_post_w, wav,

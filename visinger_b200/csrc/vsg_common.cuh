@@ -168,6 +168,7 @@ struct VsgPack {
   std::vector<vsg::UpStage> ups;
   float* conv_post_w = nullptr;  // [C_last][k]
   vsg::ConvWTC conv_post_rp;        // conv_post as a row-packed tensor-core conv: Conv1d(64 -> 16, 3 row taps) over rows of 64 / C_last samples
+  vsg::ConvWTC conv_post_rp_x3;  // the same for the bf16x3 stage output (rows of 2 samples x 2 planes x 16 channels, 5 row taps)
   int conv_post_S = 0;           // samples per packed row (0: shape not taken; CUDA-core kernel)
   int conv_post_k = 7;
 };
