@@ -326,7 +326,8 @@ int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, const float* b,
 int vsg_debug_set_plan(int32_t mb, int32_t cw, int32_t two_ctas, int32_t resident, int32_t reps);
 float vsg_debug_last_ms(void);
 
-/* Host-only tuning aid: print (stderr) the tile plan the launcher would choose for one convolution. */
+/* Host-only tuning aid: print (stderr) the tile plan the launcher would choose for one convolution.
+ * x3: 0 plain bf16, 1 two bf16 planes per value (split-bf16), 2 three planes (the flow at the fp32 tolerance). */
 int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t B, int32_t L, int32_t n_adds,
                    int32_t n_outs, int32_t x3);
 

@@ -79,3 +79,21 @@ def test_random_init_matches_reference_parameter_layout():
     assert all(float(sd[k].abs().max()) > 0 for k in sd if ".post.weight" in k)
     again = HotPath.random_init(F, G, "cpu", precision="bf16", seed=7).state_dict()
     assert all(torch.equal(sd[k], again[k]) for k in sd)
+
+
+def test_three_plane_plans_exist_for_every_flow_convolution():
+    """Host-only planner (no GPU): the chunk table of a three-plane convolution has four sweeps over the channel chunks
+    (csrc/run_tc.cu::launch_conv_tc), which must fit the kernel's table and shared memory for every convolution of the
+    flow at config/models/visinger.yaml sizes (pre 96 -> 192 / 384, in_layer 192 -> 384 k5, res_skip 192 -> 384 / 192,
+    post 192 -> 96) in both split modes, with and without residual operands."""
+    import ctypes
+    from visinger_b200 import _lib
+    L = _lib.lib()
+    L.vsg_debug_plan.argtypes = [ctypes.c_int32] * 9
+    L.vsg_debug_plan.restype = ctypes.c_int
+    for planes_code in (0, 2):
+        for cin, cout, k, n_adds in ((96, 192, 1, 0), (96, 384, 1, 0), (192, 384, 5, 0), (192, 384, 1, 1), (192, 192, 1, 1),
+                                    (192, 96, 1, 1)):
+            for B, T in ((16, 1000), (1, 1), (3, 130)):
+                rc = L.vsg_debug_plan(cin, cout, k, 1, B, T, n_adds, 1, planes_code)
+                assert rc == 0, (planes_code, cin, cout, k, _lib.last_error_message() if hasattr(_lib, "last_error_message") else rc)

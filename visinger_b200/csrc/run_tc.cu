@@ -1897,8 +1897,10 @@ extern "C" int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dila
                               int32_t n_outs, int32_t x3) {
   VsgPack tmp;
   ConvWTC wt;
-  wt.Cin = Cin; wt.Cout = Cout; wt.CinT = x3 ? 2 * Cin : Cin; wt.CoutT = Cout; wt.ktaps = k; wt.has_tmap = true; wt.x3 = x3 != 0;
-  static __nv_bfloat16 dummy;
+  const int planes = x3 == 2 ? 3 : x3 ? 2 : 1;            // x3: 0 plain bf16, 1 two planes (split-bf16), 2 three planes (flow, fp32 tolerance)
+  wt.Cin = Cin; wt.Cout = Cout; wt.CinT = planes * Cin; wt.CoutT = Cout; wt.ktaps = k; wt.has_tmap = true;
+  wt.x3 = planes == 2; wt.planes = planes;
+  static __nv_bfloat16 dummy, dummy_in;                    // (a k > 1 convolution must not alias its input)
   EpiTC e;
   if (n_adds > 0) e.add0 = &dummy;
   if (n_adds > 1) e.add1 = &dummy;
@@ -1906,7 +1908,7 @@ extern "C" int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dila
   if (n_outs > 1) e.out_raw = &dummy;
   TCOptions opt = g_default_opts;
   opt.plan_only = 1;
-  return launch_conv_tc(&tmp, wt, &dummy, B, L, -((k - 1) * dilation / 2), dilation, L, 1, 0, L, e, opt, nullptr, 0);
+  return launch_conv_tc(&tmp, wt, &dummy_in, B, L, -((k - 1) * dilation / 2), dilation, L, 1, 0, L, e, opt, nullptr, 0);
 }
 
 // Select the default A-operand feeding mode of the tensor-core convolutions (process-wide; tests and tuning).
