@@ -22,9 +22,9 @@ the metric's roofline is quoted on), random weights of config/models/visinger.ya
   full_model  (N=1) BASELINE.json configs[3]: the whole VISinger.forward(infer=True) -- native transformer stacks of the prior
             network, length regulator, fused frame-prior head, flow, decoder -- on 64 mixed-length utterances, host
             tokens -> host waveforms, with the bf16 mode's distance to the fp32 mode on the same padded batch
-  sharded   BASELINE.json configs[4]: 512 mixed-length utterances (log-normal lengths, seed 1234) -> LPT shard by
-            utterance -> length buckets -> per-rank serving loop -> pinned host results; strong scaling (fixed total
-            work), with padding overhead and per-rank imbalance
+  sharded   BASELINE.json configs[4]: 512 mixed-length utterances (log-normal lengths, seed 1234) -> length buckets over
+            the whole list -> LPT assignment of the batches to ranks -> per-rank serving loop -> pinned host results;
+            strong scaling (fixed total work), with padding overhead and per-rank imbalance
 
 Multi-GPU: utterances are independent, so ranks shard by utterance with no collective on the data path
 (weak scaling: every rank runs the same per-GPU batch); torch.distributed is used only for the barrier
@@ -227,18 +227,17 @@ def run_reference(args, rank):
 
 def sharded_leg(hp, dev, rank, world, barrier, max_over_ranks, n_utt=512, frames_per_batch=16000):
     """BASELINE.json configs[4] through the hot path: 512 synthetic utterances with the CSD-like length distribution of
-    SURVEY.md 8(d) (seed 1234) are sharded by utterance over the ranks (LPT on frame count, reference analogue: the rank
-    slicing of tasks/base.py:130-133), length-bucketed within each shard (utils/commons/dataset_utils.py:69-118) and run
-    through the per-rank serving loop.  Timed from "padded batches in pinned host memory" (what the reference's collater
+    SURVEY.md 8(d) (seed 1234) are length-bucketed over the whole list (utils/commons/dataset_utils.py:69-118) and the
+    batches assigned to the ranks longest-first on their padded size (reference analogue: the rank slicing of
+    tasks/base.py:130-133; visinger_b200.sharding.plan_sharded_batches), then run through the per-rank serving loop.  Timed from "padded batches in pinned host memory" (what the reference's collater
     hands over) to "all int16 / fp32 results in pinned host memory"; device time, max over ranks."""
     import numpy as np
     import torch
-    from visinger_b200.sharding import HostBatchRunner, bucket_by_length, shard_utterances
+    from visinger_b200.sharding import HostBatchRunner, plan_sharded_batches
     rng = np.random.default_rng(1234)
     lengths = np.clip(np.round(80 * rng.lognormal(np.log(5.6), 0.45, n_utt)), 120, 1280).astype(int).tolist()
-    shards = shard_utterances(lengths, world)
-    plans = [bucket_by_length(sh, lengths, frames_per_batch, 64) for sh in shards]
-    loads = [sum(lengths[i] for i in sh) for sh in shards]
+    plans = plan_sharded_batches(lengths, world, frames_per_batch, 64)      # length buckets first, then LPT of the batches
+    loads = [sum(lengths[i] for b in pl for i in b) for pl in plans]
     padded = [sum(len(b) * max(lengths[i] for i in b) for b in pl) for pl in plans]
     gen = torch.Generator().manual_seed(4000 + rank)
     pool = torch.randn(3, 192 * 1280 * 64 // 8, generator=gen)       # one pool of random values, sliced per batch (host time)
@@ -274,14 +273,16 @@ def sharded_leg(hp, dev, rank, world, barrier, max_over_ranks, n_utt=512, frames
     ms, d2h = res["fp32"]
     ms16, d2h16 = res["int16"]
     return {"workload": f"{n_utt} utterances, T_i = clip(round(80 * LogNormal(ln 5.6, 0.45)), 120, 1280) frames (seed 1234), "
-                        f"{audio:.0f} s audio in total; LPT shard by utterance -> buckets of <= {frames_per_batch} padded frames "
-                        "-> HotPath.infer per batch on 2 streams -> pinned host results",
+                        f"{audio:.0f} s audio in total; length-sorted buckets of <= {frames_per_batch} padded frames (smaller with more "
+                        "ranks: ~6 batches per rank) -> LPT assignment of the batches to ranks -> HotPath.infer per batch on 2 "
+                        "streams -> pinned host results",
             "scaling": "strong", "value": audio / (ms * 1e-3), "unit": UNIT, "ms": ms,
             "value_int16_output": audio / (ms16 * 1e-3), "ms_int16_output": ms16,
             "d2h_bytes_rank0": d2h, "d2h_bytes_rank0_int16": d2h16,
             "batches_per_rank": [len(pl) for pl in plans],
-            "padding_overhead": max(p / l for p, l in zip(padded, loads)),
-            "imbalance_max_over_mean": max(loads) / (sum(loads) / len(loads)),
+            "padding_overhead": sum(padded) / sum(loads),
+            "imbalance_max_over_mean": max(padded) / (sum(padded) / len(padded)),
+            "efficiency_bound": sum(loads) / (len(padded) * max(padded)),
             "timed": "padded batches in pinned host memory -> results in pinned host memory, CUDA events, max over ranks"}
 
 
