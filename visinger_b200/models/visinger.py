@@ -331,9 +331,12 @@ class VISinger(nn.Module):
     `forward(text_tokens, pitch_tokens, dur_tokens, mel2ph, spk_embed=None, spk_id=None, f0=None, uv=None, mel=None,
     infer=False, **kwargs) -> dict` with keys `wav_out` [B, T*hop] and `f0_pred`.
 
-    The prior network (text encoder, pitch predictor, frame prior) runs in PyTorch on the GPU; from `z_p` on --
-    prior sampling, flow reverse, HiFi-GAN decoder (models/visinger.py:107-111) -- one `vsg_infer` call runs the
-    hand-written CUDA path.  `infer=False` (training) is out of scope and raises.
+    The prior network runs on the native kernels too: the `RelativeEncoder` stacks of the text encoder, pitch predictor
+    and frame prior (`vsg_relenc_forward`), the length regulator with its data-dependent frame positions
+    (`vsg_length_regulate`) and the fused frame-prior head (`vsg_frame_prior_forward`: encoder -> proj -> prior sampling);
+    from `z_p` on -- flow reverse, HiFi-GAN decoder (models/visinger.py:107-111) -- one `vsg_infer_zp` call.  What stays in
+    PyTorch is token-rate glue: three embedding lookups, one Linear(576 -> 192), the speaker embedding and the 1x1 head of
+    the pitch predictor.  `infer=False` (training) is out of scope and raises.
 
     Extra keyword arguments (not in the reference): `noise` injects the prior noise instead of
     `torch.randn_like(mu_p)` (CPU and CUDA generators differ, so parity tests need it); `precision` selects
