@@ -285,6 +285,59 @@ def test_rowpacked_resblock_kernel(cuda_device, C, k, dils, B, L, max_mb, varian
     _run_resblock_case(cuda_device, C, k, dils, B, L, max_mb, variant)
 
 
+# split-bf16 instantiation (bf16x3 mode): tiles of 1 .. 2 blocks, ragged tiles, utterances shorter than the halo
+RP_X3_CASES = [
+    (16, 3, (1, 3, 5), 2, 5000, 0), (16, 7, (1, 3, 5), 3, 700, 0), (16, 11, (1, 3, 5), 1, 6148, 0), (16, 5, (1, 2), 1, 600, 1),
+    (16, 7, (1, 3, 5), 2, 40, 0), (32, 3, (1, 3, 5), 2, 3000, 0), (32, 7, (1, 3, 5), 2, 1024, 1), (32, 11, (1, 3, 5), 1, 2502, 0),
+    (32, 9, (2, 1), 1, 1200, 0)]
+
+
+def _two_planes(v):
+    """Value carried by the two bf16 planes [hi | lo] of v (about 16 mantissa bits)."""
+    hi = v.float().to(torch.bfloat16)
+    lo = (v.float() - hi.float()).to(torch.bfloat16)
+    return hi.double() + lo.double()
+
+
+@pytest.mark.parametrize("C,k,dils,B,L,max_mb", RP_X3_CASES)
+@pytest.mark.parametrize("variant", [256 | 2048, 256 | 512 | 2048])
+def test_rowpacked_resblock_kernel_split_bf16(cuda_device, C, k, dils, B, L, max_mb, variant):
+    """Row-packed whole ResBlock1 in the split-bf16 arithmetic of the bf16x3 mode (rp_tc.cuh, X3): two-plane activations
+    and weights, three MMAs per product, fp32 residual stream in tensor memory -- against ResBlock1.forward
+    (decoder.py:91-104) in float64 at the fp32 tolerance; block-Toeplitz form and tap by tap."""
+    from visinger_b200 import _lib
+    gen = torch.Generator().manual_seed(C * 17 + k + L)
+    x = torch.randn(B, L, C, generator=gen)
+    xa2 = _lib.split_bf16(F.leaky_relu(x, 0.1))
+    ws = [torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5 for _ in range(2 * len(dils))]   # full fp32 weights: W_lo is live
+    bs = [torch.randn(C, generator=gen) * 0.1 for _ in range(2 * len(dils))]
+    add2 = _lib.split_bf16(torch.randn(B, L, C, generator=gen))
+    d = cuda_device
+    a = xa2[..., :C].double() + xa2[..., C:].double()
+    xr = torch.minimum(a, a * 10.0)
+    for q, dl in enumerate(dils):
+        t = F.conv1d(a.transpose(1, 2), _two_planes(ws[2 * q]), bs[2 * q].double(), dilation=dl, padding=(k - 1) * dl // 2)
+        ta = _two_planes(F.leaky_relu(t, 0.1))
+        xr = xr + F.conv1d(ta, _two_planes(ws[2 * q + 1]), bs[2 * q + 1].double(), padding=(k - 1) // 2).transpose(1, 2)
+        a = _two_planes(F.leaky_relu(xr, 0.1))
+    for use_add, scale in ((True, 1.0 / 3.0), (False, 1.0)):
+        want = (xr + (add2[..., :C].double() + add2[..., C:].double() if use_add else 0.0)) * scale
+        out, raw, act = _lib.debug_resblock_bf16(xa2.to(d), ws, bs, dils, add1=add2.to(d) if use_add else None, scale=scale,
+                                                 max_mb=max_mb, sets=variant)
+        err = (out.cpu().double() - want).abs()
+        rel = float((out.cpu().double() - want).norm() / want.norm())
+        print(f"resblock x3[{variant}] C={C} k={k} L={L}: max err {float(err.max()):.3e} rel-L2 {rel:.3e} (|want| <= {float(want.abs().max()):.2f})")
+        # two-plane roundings of the intermediates may fall the other way than the float64 reference's (2^-17 of an O(1)
+        # value) and the tensor pipe accumulates C k products in truncating fp32
+        assert float(err.max()) <= 2e-5 * float(want.abs().max()) and rel <= 1e-5
+        raw, act = raw.cpu(), act.cpu()
+        assert maxabs(raw[..., :C].double() + raw[..., C:].double(), out.cpu().double()) <= 2e-5 * float(want.abs().max())
+        assert maxabs(act[..., :C].double() + act[..., C:].double(), F.leaky_relu(out.cpu().double(), 0.1)) <= 2e-5 * float(want.abs().max())
+        assert torch.equal(raw[..., :C], out.cpu().to(torch.bfloat16))
+    out2, _, _ = _lib.debug_resblock_bf16(xa2.to(d), ws, bs, dils, scale=1.0, max_mb=max_mb, sets=variant)
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
 @pytest.mark.parametrize("B,T", [(2, 40), (3, 333), (1, 1000)])
 def test_conv_post_tensor_core_equals_cuda_core(cuda_device, B, T, precision):

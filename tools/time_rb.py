@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--rp", type=int, default=0, help="1: row-packed kernel (rp_tc.cuh); 2: row-packed, no Toeplitz form")
     ap.add_argument("--max-mb", type=int, default=0)
     ap.add_argument("--spb2", type=int, default=0, help="1: row-packed kernel with two epilogue warp sets per block (two blocks per set)")
+    ap.add_argument("--x3", type=int, default=0, help="1: the row-packed kernel's split-bf16 instantiation (bf16x3 mode; needs --rp 1)")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--frames", type=int, default=1000)
     args = ap.parse_args()
@@ -37,13 +38,15 @@ def main():
                 continue
             L = rate * args.frames
             gen = torch.Generator().manual_seed(C + k)
-            xa = F.leaky_relu(torch.randn(args.batch, L, C, generator=gen), 0.1).to(torch.bfloat16).to(dev).contiguous()
+            xa = F.leaky_relu(torch.randn(args.batch, L, C, generator=gen), 0.1)
+            xa = (_lib.split_bf16(xa) if args.x3 else xa.to(torch.bfloat16)).to(dev).contiguous()
             ws = [torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5 for _ in range(6)]
             bs = [torch.randn(C, generator=gen) * 0.1 for _ in range(6)]
-            add1 = torch.randn(args.batch, L, C, generator=gen).to(torch.bfloat16).to(dev).contiguous()
+            add1 = torch.randn(args.batch, L, C, generator=gen)
+            add1 = (_lib.split_bf16(add1) if args.x3 else add1.to(torch.bfloat16)).to(dev).contiguous()
             out, raw, act, ms = _lib.debug_resblock_bf16(xa, ws, bs, dils, add1=add1, scale=1 / 3, max_mb=args.max_mb,
-                                                         sets=args.sets | (args.issuers << 4) | (256 if args.rp else 0) | (512 if args.rp == 2 else 0) | (1024 if args.spb2 else 0), want_raw=False, want_f32=False, reps=args.reps)
-            mb = args.max_mb or 512 // (2 * C)
+                                                         sets=args.sets | (args.issuers << 4) | (256 if args.rp else 0) | (512 if args.rp == 2 else 0) | (1024 if args.spb2 else 0) | (2048 if args.x3 else 0), want_raw=False, want_f32=False, reps=args.reps)
+            mb = args.max_mb or (2 if args.x3 else 512 // (2 * C))
             H = (k - 1) // 2 * 12
             V = 128 * mb - 2 * H
             tiles = -(-L // V) * args.batch

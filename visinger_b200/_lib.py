@@ -472,10 +472,16 @@ def debug_pair_bf16(xa_bld: torch.Tensor, w1, b1, w2, b2, d1: int, add0=None, ad
 def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scale: float = 1.0, max_mb: int = 0, sets: int = 0,
                         want_raw: bool = True, want_act: bool = True, reps: int = 1, want_f32: bool = True):
     """Per-layer parity hook of the whole-ResBlock1 kernel (csrc/rb_tc.cuh).  xa_bld / add1: CUDA bf16 [B, L, C];
-    ws / bs: lists [c1_0, c2_0, c1_1, c2_1, ...] of fp32 [C, C, k] / [C].  Returns (out_f32, out_raw_bf16, out_act_bf16[, ms])."""
+    ws / bs: lists [c1_0, c2_0, c1_1, c2_1, ...] of fp32 [C, C, k] / [C].  Returns (out_f32, out_raw_bf16, out_act_bf16[, ms]).
+    sets bit 11 (with bit 8): the row-packed kernel's split-bf16 instantiation -- xa / add1 / raw / act are two-plane
+    tensors [B, L, 2 C] (`split_bf16`), out_f32 stays [B, L, C]."""
     require_cuda(xa_bld, "xa")
     assert xa_bld.dtype == torch.bfloat16 and xa_bld.is_contiguous()
     B, Lx, C = xa_bld.shape
+    x3 = bool(sets & 2048)
+    if x3:
+        assert C % 2 == 0
+        C //= 2
     k = ws[0].shape[2]
     n_pairs = len(dilations)
     assert len(ws) == 2 * n_pairs and len(bs) == 2 * n_pairs
@@ -484,8 +490,8 @@ def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scal
     dl = (ctypes.c_int32 * n_pairs)(*[int(d) for d in dilations])
     dev = xa_bld.device
     out = torch.zeros(B, Lx, C, dtype=torch.float32, device=dev) if want_f32 else None
-    raw = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev) if want_raw else None
-    act = torch.zeros(B, Lx, C, dtype=torch.bfloat16, device=dev) if want_act else None
+    raw = torch.zeros(B, Lx, (2 if x3 else 1) * C, dtype=torch.bfloat16, device=dev) if want_raw else None
+    act = torch.zeros(B, Lx, (2 if x3 else 1) * C, dtype=torch.bfloat16, device=dev) if want_act else None
     assert add1 is None or (add1.is_cuda and add1.dtype == torch.bfloat16 and add1.is_contiguous())
     torch.cuda.synchronize(dev)
     if reps > 1:

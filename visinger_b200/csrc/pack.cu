@@ -463,7 +463,8 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
       rb.dilations.assign(c.dec_resblock_dilations[j], c.dec_resblock_dilations[j] + nd);
       const std::string pb = pre + "resblocks." + std::to_string(i * c.dec_n_kernels + j) + ".";
       rb.c1.resize(nd); rb.c1_tc.resize(nd); rb.c1_x3.resize(nd);
-      if (c.dec_resblock == 1) { rb.c2.resize(nd); rb.c2_tc.resize(nd); rb.c2_x3.resize(nd); rb.c1_rp.resize(nd); rb.c2_rp.resize(nd); }
+      if (c.dec_resblock == 1) { rb.c2.resize(nd); rb.c2_tc.resize(nd); rb.c2_x3.resize(nd); rb.c1_rp.resize(nd); rb.c2_rp.resize(nd);
+                                   rb.c1_rp_x3.resize(nd); rb.c2_rp_x3.resize(nd); }
       std::vector<std::vector<float>> b2s;
       for (int q = 0; q < nd; ++q) {
         const std::string n1 = pb + (c.dec_resblock == 1 ? "convs1." : "convs.") + std::to_string(q);
@@ -472,7 +473,10 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
         VSG_TRY(pack_conv_f32(L, W, b, ch, ch, rb.kernel, Identity{}, &rb.c1[q]));
         VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_tc[q]));
         VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c1_x3[q], 2));
-        if (c.dec_resblock == 1 && rb.dilations[q] == 1) VSG_TRY(pack_conv_rowpacked(P, W, ch, rb.kernel, &rb.c1_rp[q]));
+        if (c.dec_resblock == 1 && rb.dilations[q] == 1) {
+          VSG_TRY(pack_conv_rowpacked(P, W, ch, rb.kernel, &rb.c1_rp[q]));
+          VSG_TRY(pack_conv_rowpacked(P, W, ch, rb.kernel, &rb.c1_rp_x3[q], 2));
+        }
         if (c.dec_resblock == 1) {
           const std::string n2 = pb + "convs2." + std::to_string(q);
           VSG_TRY(L.eff_weight(n2, ch, ch, rb.kernel, W));
@@ -481,6 +485,7 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
           VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_tc[q]));
           VSG_TRY(pack_conv_tc(P, W, b, ch, ch, rb.kernel, &rb.c2_x3[q], 2));
           VSG_TRY(pack_conv_rowpacked(P, W, ch, rb.kernel, &rb.c2_rp[q]));
+          VSG_TRY(pack_conv_rowpacked(P, W, ch, rb.kernel, &rb.c2_rp_x3[q], 2));
           b2s.push_back(b);
         }
       }

@@ -9,7 +9,7 @@ int pack_conv_tc(VsgPack* P, const std::vector<float>& W, const std::vector<floa
                  ConvWTC* out, int planes = 1);
 // Dilation-1 Conv1d(C -> C, k), C in {16, 32}, as Conv1d(64 -> 64) over rows of 64 / C time steps with block-Toeplitz
 // weights (rp_tc.cuh); leaves out->has_tmap false for shapes the row-packed kernel does not take.
-int pack_conv_rowpacked(VsgPack* P, const std::vector<float>& W, int C, int k, ConvWTC* out);
+int pack_conv_rowpacked(VsgPack* P, const std::vector<float>& W, int C, int k, ConvWTC* out, int planes = 1);
 // rb->c2_bsum[q] = b2[0] + ... + b2[q] on the device (the row-packed kernel keeps the c2 biases out of tensor memory).
 int pack_resblock_bias_sums(VsgPack* P, const std::vector<std::vector<float>>& b2, ResBlockPack* rb);
 }  // namespace vsg

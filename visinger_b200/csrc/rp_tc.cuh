@@ -39,6 +39,17 @@
 // warp, elect_one per instruction), 2..3 idle, 4..19 epilogue: warp % 4 = TMEM lane quarter, set (warp - 4) / 4 owns
 // block `set` of a 4-block tile (all 64 columns of its rows; the four blocks are in flight together, staggered by the
 // MMA order), or shares a block with other sets when the tile has fewer blocks.
+//
+// X3 = true is the same kernel in the split-bf16 arithmetic of the bf16x3 mode (fp32-tolerance results on tcgen05): every
+// activation is two bf16 planes (hi = bf16(v), lo = bf16(v - hi); global rows [hi (C) | lo (C)] per time step), every
+// weight tile comes as W_hi and W_lo, and every product is three MMAs issued small-first (lo * W_hi, hi * W_lo,
+// hi * W_hi).  The input's planes are interleaved per time step, which no tensor map can turn into two 128-byte-row
+// SWIZZLE_128B tiles (a box narrower than the swizzle span is padded to it), so the input tile is staged unswizzled in
+// the -- still unused -- Q buffers and the epilogue warps, which read every input value anyway to seed the residual
+// stream, write the two P planes themselves.  The residual stream is still the fp32 accumulator in
+// tensor memory -- more exact than the two-plane stream of the per-convolution kernels.  Four activation tiles (P / Q x
+// hi / lo) leave room for 2-block tiles only and not for a whole convolution's weights, so the weight ring (16 KB
+// stages: [W_hi | W_lo]) is streamed per BLOCK instead of per convolution (L2 -> shared memory twice per tile).
 #pragma once
 #include "conv_tc.cuh"
 #include "rb_tc.cuh"
@@ -64,11 +75,12 @@ struct RpTC {
   int m_tiles_per_b, total_tiles;
   int n_wst;                      // weight ring stages
   uint32_t margin_bytes;          // zero margin before / after the tile inside P and Q (>= the largest tap reach)
-  uint32_t buf_bytes;             // margin + 128 * 128 * mb + margin
+  uint32_t buf_bytes;             // margin + 128 * 128 * mb + margin (X3: the lo plane of P / Q follows its hi plane at + buf_bytes)
   uint32_t p_off, q_off, w_off, bar_off, bias_off;   // shared-memory carve-up relative to the 1024-aligned base
   uint32_t tmem_cols;
   const float* bias[kRpMaxConvs];  // even c: bias of c1_q; odd c: b2_0 + ... + b2_q (the residual stream's running bias)
   const __nv_bfloat16* add1;      // running resblock sum [B, L, C] or null (read for the tile's valid steps only)
+                                  // (X3: add1 / out_raw / out_act are two-plane tensors [B, L, 2 C], rows [hi | lo])
   __nv_bfloat16* out_raw;         // (x_out + add1) * scale as bf16, or null
   __nv_bfloat16* out_act;         // leaky_relu of the same, or null
   float* out_f32;                 // fp32 copy (parity hook), or null
@@ -87,13 +99,14 @@ constexpr int kRpBarWFull = 3 * kRpMaxBlocks;                     // [kRpMaxWSta
 constexpr int kRpBarWEmpty = kRpBarWFull + kRpMaxWStages;         // [kRpMaxWStages]
 constexpr int kRpBarAFull = kRpBarWEmpty + kRpMaxWStages;
 constexpr int kRpBarPFree = kRpBarAFull + 1;
-constexpr int kRpNumBars = kRpBarPFree + 1;
+constexpr int kRpBarX0 = kRpBarPFree + 1;                         // [kRpMaxBlocks] X3: P planes + residual stream of a block written
+constexpr int kRpNumBars = kRpBarX0 + kRpMaxBlocks;
 constexpr int kRpEpiWarps = 16;
 constexpr int kRpThreads = (4 + kRpEpiWarps) * 32;                // 640
 
 }  // namespace tc
 
-template <int C>
+template <int C, bool X3 = false>
 __global__ void __launch_bounds__(tc::kRpThreads, 1)
 rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ RpMaps wm, const RpTC p) {
   using namespace tc;
@@ -101,6 +114,9 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
   constexpr int KK = C / 16;                     // 16-wide K slices per time step
   constexpr uint32_t kStep16 = (uint32_t)(C * 2) / 16u;     // 16-byte units per time step
   constexpr uint32_t kSlotBytes = C * C * 2 > 1024 ? C * C * 2 : 1024;   // one compact tap tile inside a ring stage
+  constexpr uint32_t kTapBytes = X3 ? 2 * kSlotBytes : kSlotBytes;      // X3: [W_hi tile | W_lo tile] per tap
+  constexpr uint32_t kStageBytes = X3 ? 2 * kRpStageBytes : kRpStageBytes;   // X3: [W_hi 8 KB | W_lo 8 KB]
+  constexpr int NPL = X3 ? 2 : 1;                // bf16 planes per activation tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -121,6 +137,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
       const uint32_t warps_per_block = 4u * (uint32_t)p.spb;                  // epilogue warps that drain one block
       mbar_init(bar(kRpBarReady + b), warps_per_block);
       mbar_init(bar(kRpBarReady + kRpMaxBlocks + b), warps_per_block);
+      mbar_init(bar(kRpBarX0 + b), warps_per_block);
     }
     for (int s = 0; s < kRpMaxWStages; ++s) { mbar_init(bar(kRpBarWFull + s), 1); mbar_init(bar(kRpBarWEmpty + s), 1); }
     mbar_init(bar(kRpBarAFull), 1);
@@ -131,12 +148,14 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
   {  // zero margins of P and Q: rows the taps reach beyond the tile; never written afterwards
     const uint32_t margin16 = p.margin_bytes / 16u;
     const uint32_t tail16 = (p.margin_bytes + 16384u * (uint32_t)mb) / 16u;
-    uint4* pg = reinterpret_cast<uint4*>(smem_gen + p.p_off);
-    uint4* qg = reinterpret_cast<uint4*>(smem_gen + p.q_off);
-    for (uint32_t i = threadIdx.x; i < margin16; i += blockDim.x) {
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      pg[i] = z; qg[i] = z;
-      pg[tail16 + i] = z; qg[tail16 + i] = z;
+    for (int pl = 0; pl < NPL; ++pl) {
+      uint4* pg = reinterpret_cast<uint4*>(smem_gen + p.p_off + (uint32_t)pl * p.buf_bytes);
+      uint4* qg = reinterpret_cast<uint4*>(smem_gen + p.q_off + (uint32_t)pl * p.buf_bytes);
+      for (uint32_t i = threadIdx.x; i < margin16; i += blockDim.x) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        pg[i] = z; qg[i] = z;
+        pg[tail16 + i] = z; qg[tail16 + i] = z;
+      }
     }
     fence_async_smem();
     // biases -> shared memory [n_convs][C] (the epilogue re-reads them every convolution step)
@@ -151,6 +170,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
 
   const uint32_t p_base = smem_base + p.p_off, q_base = smem_base + p.q_off, w_base = smem_base + p.w_off;
   const uint32_t tile_off = p.margin_bytes;                      // byte offset of tile row 0 inside P / Q
+  const uint32_t lo_delta = p.buf_bytes;                         // X3: the lo plane of a tile, relative to its hi plane
 
   if (warp == 0) {
     // ===================== TMA producer: input tiles -> P, weight ring in the order the issuers consume it =====================
@@ -161,44 +181,70 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     uint32_t st = 0, eph = 0;                                     // eph bit s: parity of stage s's next "empty" completion
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next(), ++n_tile) {
       // (the previous tile's weight loads were all issued above, so waiting for P here cannot starve the issuers)
-      if (n_tile > 0) mbar_wait(bar(kRpBarPFree), (n_tile - 1) & 1u, error_flag);   // P no longer read by the previous tile
+      // P (X3: Q, where the input is staged) no longer read by the previous tile
+      if (n_tile > 0) mbar_wait(bar(kRpBarPFree), (n_tile - 1) & 1u, error_flag);
       const int row0 = (it.mt * p.V - p.H) / S;                  // exact: V and H are multiples of S
       if (elect_one()) {
-        mbar_expect_tx(bar(kRpBarAFull), 16384u * (uint32_t)mb);
-        for (int bx = 0; bx < mb; ++bx)
-          tma_load_3d(p_base + tile_off + 16384u * (uint32_t)bx, &tmA, bar(kRpBarAFull), 0, row0 + 128 * bx, it.b);
+        mbar_expect_tx(bar(kRpBarAFull), 16384u * (uint32_t)(mb * NPL));
+        for (int bx = 0; bx < mb; ++bx) {
+          if (X3) {   // staged unswizzled, 256-byte rows [S][hi C | lo C]: rows 0 .. 63 of a block in Q_hi's tile, 64 .. 127 in Q_lo's
+            tma_load_3d(q_base + tile_off + 16384u * (uint32_t)bx, &tmA, bar(kRpBarAFull), 0, row0 + 128 * bx, it.b);
+            tma_load_3d(q_base + lo_delta + tile_off + 16384u * (uint32_t)bx, &tmA, bar(kRpBarAFull), 0, row0 + 128 * bx + 64, it.b);
+          } else {
+            tma_load_3d(p_base + tile_off + 16384u * (uint32_t)bx, &tmA, bar(kRpBarAFull), 0, row0 + 128 * bx, it.b);
+          }
+        }
       }
       // L2 prefetch: the running sum this tile's last convolution will add, and the NEXT tile's input (its TMA load can
       // only be issued once P is free; from L2 it lands in a quarter of the HBM latency)
       if (p.add1) {
         if (elect_one())
-          for (int bx = 0; bx < mb; ++bx) tma_prefetch_3d(&wm.add1, 0, row0 + 128 * bx, it.b);
+          for (int bx = 0; bx < mb; ++bx) {
+            if (X3) {
+              tma_prefetch_3d(&wm.add1, 0, row0 + 128 * bx, it.b);
+              tma_prefetch_3d(&wm.add1, 0, row0 + 128 * bx + 64, it.b);
+            } else {
+              tma_prefetch_3d(&wm.add1, 0, row0 + 128 * bx, it.b);
+            }
+          }
       }
       if (tile + (int)gridDim.x < total_tiles) {
         TileIter nx = it;
         nx.next();
         const int nrow0 = (nx.mt * p.V - p.H) / S;
         if (elect_one())
-          for (int bx = 0; bx < mb; ++bx) tma_prefetch_3d(&tmA, 0, nrow0 + 128 * bx, nx.b);
+          for (int bx = 0; bx < mb; ++bx) {
+            if (X3) {
+              tma_prefetch_3d(&tmA, 0, nrow0 + 128 * bx, nx.b);
+              tma_prefetch_3d(&tmA, 0, nrow0 + 128 * bx + 64, nx.b);
+            } else {
+              tma_prefetch_3d(&tmA, 0, nrow0 + 128 * bx, nx.b);
+            }
+          }
       }
       for (int c = 0; c < n_convs; ++c) {
         const bool packed = (p.packed_mask >> c) & 1u;
         const int ns = packed ? p.packed_stages : p.direct_stages;
-        for (int i = 0; i < ns; ++i) {
+        const int n_pass = X3 ? mb : 1;                            // X3: the ring is streamed once per block
+        for (int ii = 0; ii < ns * n_pass; ++ii) {
+          const int i = X3 ? ii % ns : ii;
           mbar_wait(bar(kRpBarWEmpty + (int)st), ((eph >> st) & 1u) ^ 1u, error_flag);
           eph ^= 1u << st;
-          const uint32_t dst = w_base + st * kRpStageBytes;
+          const uint32_t dst = w_base + st * kStageBytes;
           if (packed) {
             if (elect_one()) {
-              mbar_expect_tx(bar(kRpBarWFull + (int)st), kRpStageBytes);
+              mbar_expect_tx(bar(kRpBarWFull + (int)st), kStageBytes);
               tma_load_2d(dst, &wm.w[c], bar(kRpBarWFull + (int)st), 0, i * 64);
+              if (X3) tma_load_2d(dst + kRpStageBytes, &wm.w[c], bar(kRpBarWFull + (int)st), 64, i * 64);
             }
           } else {
             const int j0 = i * p.tps, j1 = min(k, j0 + p.tps);
             if (elect_one()) {
-              mbar_expect_tx(bar(kRpBarWFull + (int)st), (uint32_t)(j1 - j0) * (uint32_t)(C * C * 2));
-              for (int j = j0; j < j1; ++j)
-                tma_load_2d(dst + (uint32_t)(j - j0) * kSlotBytes, &wm.w[c], bar(kRpBarWFull + (int)st), 0, j * C);
+              mbar_expect_tx(bar(kRpBarWFull + (int)st), (uint32_t)(j1 - j0) * (uint32_t)(C * C * 2 * NPL));
+              for (int j = j0; j < j1; ++j) {
+                tma_load_2d(dst + (uint32_t)(j - j0) * kTapBytes, &wm.w[c], bar(kRpBarWFull + (int)st), 0, j * C);
+                if (X3) tma_load_2d(dst + (uint32_t)(j - j0) * kTapBytes + kSlotBytes, &wm.w[c], bar(kRpBarWFull + (int)st), C, j * C);
+              }
             }
           }
           st = (st + 1 == (uint32_t)n_wst) ? 0u : st + 1;
@@ -216,15 +262,36 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     constexpr uint32_t hi_dir = (((8u * C * 2u) >> 4) & 0x3FFFu) | (1u << 14) | (kDirCode << 29);
     auto mk_row = [&](uint32_t lo) { return ((uint64_t)hi_row << 32) | (uint64_t)lo; };
     auto mk_dir = [&](uint32_t lo) { return ((uint64_t)hi_dir << 32) | (uint64_t)lo; };
-    constexpr uint32_t lo_flag = 1u << 16, blk16 = 16384u >> 4, stage16 = kRpStageBytes >> 4, slot16 = kSlotBytes >> 4;
+    constexpr uint32_t lo_flag = 1u << 16, blk16 = 16384u >> 4, stage16 = kStageBytes >> 4, slot16 = kSlotBytes >> 4;
+    constexpr uint32_t tap16 = kTapBytes >> 4, wlo16 = kRpStageBytes >> 4;   // X3: W_lo follows W_hi inside a tap slot / a packed stage
+    const uint32_t alo16 = lo_delta >> 4;                                    // X3: lo plane of the A tile
     const uint32_t p16 = (p_base + tile_off) >> 4, q16 = (q_base + tile_off) >> 4, w16_0 = w_base >> 4;
     const int n_k = p.n_k, packed_stages = p.packed_stages, tps = p.tps, direct_stages = p.direct_stages, cen = (k - 1) / 2;
     const int full_groups = n_k >> 2, tail = n_k & 3;             // packed form: K slices in groups of 4 = one ring stage
     const uint32_t packed_mask = p.packed_mask;
     const int d0 = p.dil[0], d1 = p.dil[2], d2 = p.dil[4], d3 = p.dil[6];
     const uint32_t bar_acc = bar(kRpBarAccFull), bar_ready = bar(kRpBarReady), bar_wfull = bar(kRpBarWFull),
-                   bar_wempty = bar(kRpBarWEmpty), bar_afull = bar(kRpBarAFull), bar_pfree = bar(kRpBarPFree);
+                   bar_wempty = bar(kRpBarWEmpty), bar_afull = bar(kRpBarAFull), bar_pfree = bar(kRpBarPFree), bar_x0 = bar(kRpBarX0);
     uint32_t ws0 = 0, wph = 0, n = 0, n_tile = 0;                 // wph bit s: parity of stage s's next "full" completion
+    // one product of the GEMM: a single MMA, or (X3) the three plane products, smallest first
+    auto mma_row = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
+      if (X3) {
+        if (elect_one()) umma_bf16(d, mk_row(a + alo16), mk_row(b), idesc_row, acc);
+        if (elect_one()) umma_bf16(d, mk_row(a), mk_row(b + wlo16), idesc_row, 1u);
+        if (elect_one()) umma_bf16(d, mk_row(a), mk_row(b), idesc_row, 1u);
+      } else {
+        if (elect_one()) umma_bf16(d, mk_row(a), mk_row(b), idesc_row, acc);
+      }
+    };
+    auto mma_dir = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
+      if (X3) {
+        if (elect_one()) umma_bf16(d, mk_row(a + alo16), mk_dir(b), idesc_dir, acc);
+        if (elect_one()) umma_bf16(d, mk_row(a), mk_dir(b + slot16), idesc_dir, 1u);
+        if (elect_one()) umma_bf16(d, mk_row(a), mk_dir(b), idesc_dir, 1u);
+      } else {
+        if (elect_one()) umma_bf16(d, mk_row(a), mk_dir(b), idesc_dir, acc);
+      }
+    };
     uint32_t* const trace = (p.trace && blockIdx.x == 0 && lane == 0) ? p.trace : nullptr;
     uint32_t ntr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n_tile) {
@@ -241,78 +308,79 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
         uint32_t blk_lo = (lo_flag | ((c & 1) ? q16 : p16)) - (packed ? (uint32_t)(cen * KK * 2) : 0u);
         uint32_t d_tmem = tmem_base + ((c & 1) ? (uint32_t)(64 * mb) : 0u);
         if (trace && ntr < 1022) trace[ntr++] = (uint32_t)clock();
+        uint32_t st = ws0;
         for (int b = 0; b < mb; ++b) {
           // block b reads blocks b-1 .. b+1 of the previous convolution's output and overwrites accumulator b: all
           // released through `ready` of the previous step (b-1 and b were waited for by the previous iterations)
           if (c == 0) {
-            if (b == 0) mbar_wait(bar_afull, n_tile & 1u, error_flag);
+            if (X3) {   // P is written by the epilogue warps (see the x0 phase), block by block
+              if (b == 0) mbar_wait(bar_x0, n_tile & 1u, error_flag);
+              if (b + 1 < mb) mbar_wait(bar_x0 + 8u * (b + 1), n_tile & 1u, error_flag);
+            } else if (b == 0) {
+              mbar_wait(bar_afull, n_tile & 1u, error_flag);
+            }
             if (n > 0) mbar_wait(bar_prev + 8u * b, prev_par, error_flag);
           } else {
             if (b == 0) mbar_wait(bar_prev, prev_par, error_flag);
             if (b + 1 < mb) mbar_wait(bar_prev + 8u * (b + 1), prev_par, error_flag);
           }
           fence_after_sync();
-          uint32_t st = ws0;
+          if (!X3) st = ws0;                                       // (X3: the ring is streamed per block and just runs on)
           if (packed) {
             // K slice m = 0 .. n_k - 1: input sub-step -cen + m / KK, channels 16 (m % KK) ..; consecutive slices are
             // consecutive 32-byte pieces of the row-packed tile and of the stage's [64 x 64] SWIZZLE_128B weight tile
             uint32_t a_lo = blk_lo;
             uint32_t accumulate = acc0;
             for (int g = 0; g < full_groups; ++g) {
-              if (b == 0) {
+              if (X3 || b == 0) {
                 mbar_wait(bar_wfull + 8u * st, (wph >> st) & 1u, error_flag);
                 wph ^= 1u << st;
                 fence_after_sync();
               }
               const uint32_t b_lo = lo_flag | (w16_0 + st * stage16);
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (elect_one()) umma_bf16(d_tmem, mk_row(a_lo + 2u * u), mk_row(b_lo + 2u * u), idesc_row, u > 0 ? 1u : accumulate);
+              for (int u = 0; u < 4; ++u) mma_row(d_tmem, a_lo + 2u * u, b_lo + 2u * u, u > 0 ? 1u : accumulate);
               accumulate = 1u;
               a_lo += 8u;
-              if (b == mb - 1) {
+              if (X3 || b == mb - 1) {
                 if (elect_one()) umma_commit(bar_wempty + 8u * st);
               }
               st = (st + 1 == (uint32_t)n_wst) ? 0u : st + 1;
             }
             if (tail) {
-              if (b == 0) {
+              if (X3 || b == 0) {
                 mbar_wait(bar_wfull + 8u * st, (wph >> st) & 1u, error_flag);
                 wph ^= 1u << st;
                 fence_after_sync();
               }
               const uint32_t b_lo = lo_flag | (w16_0 + st * stage16);
-              if (elect_one()) umma_bf16(d_tmem, mk_row(a_lo), mk_row(b_lo), idesc_row, accumulate);
-              if (tail > 1) {
-                if (elect_one()) umma_bf16(d_tmem, mk_row(a_lo + 2u), mk_row(b_lo + 2u), idesc_row, 1u);
-              }
-              if (tail > 2) {
-                if (elect_one()) umma_bf16(d_tmem, mk_row(a_lo + 4u), mk_row(b_lo + 4u), idesc_row, 1u);
-              }
-              if (b == mb - 1) {
+              mma_row(d_tmem, a_lo, b_lo, accumulate);
+              if (tail > 1) mma_row(d_tmem, a_lo + 2u, b_lo + 2u, 1u);
+              if (tail > 2) mma_row(d_tmem, a_lo + 4u, b_lo + 4u, 1u);
+              if (X3 || b == mb - 1) {
                 if (elect_one()) umma_commit(bar_wempty + 8u * st);
               }
+              if (X3) st = (st + 1 == (uint32_t)n_wst) ? 0u : st + 1;
             }
           } else {
             int slot = 0;
             for (int j = 0; j < k; ++j) {
-              if (b == 0 && slot == 0) {
+              if ((X3 || b == 0) && slot == 0) {
                 mbar_wait(bar_wfull + 8u * st, (wph >> st) & 1u, error_flag);
                 wph ^= 1u << st;
                 fence_after_sync();
               }
-              const uint32_t b_lo = lo_flag | (w16_0 + st * stage16 + (uint32_t)slot * slot16);
+              const uint32_t b_lo = lo_flag | (w16_0 + st * stage16 + (uint32_t)slot * tap16);
               const uint32_t a_lo0 = blk_lo + (uint32_t)((j - cen) * d * (int)kStep16);
 #pragma unroll
               for (int sp = 0; sp < S; ++sp) {
 #pragma unroll
                 for (int kk = 0; kk < KK; ++kk)
-                  if (elect_one())
-                    umma_bf16(d_tmem + (uint32_t)(sp * C), mk_row(a_lo0 + (uint32_t)sp * kStep16 + 2u * kk), mk_dir(b_lo + 2u * kk),
-                              idesc_dir, (j > 0 || kk > 0) ? 1u : acc0);
+                  mma_dir(d_tmem + (uint32_t)(sp * C), a_lo0 + (uint32_t)sp * kStep16 + 2u * kk, b_lo + 2u * kk,
+                          (j > 0 || kk > 0) ? 1u : acc0);
               }
               if (slot == tps - 1 || j == k - 1) {
-                if (b == mb - 1) {
+                if (X3 || b == mb - 1) {
                   if (elect_one()) umma_commit(bar_wempty + 8u * st);
                 }
                 st = (st + 1 == (uint32_t)n_wst) ? 0u : st + 1;
@@ -326,10 +394,14 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
           blk_lo += blk16;
           d_tmem += 64u;
         }
-        ws0 += ns;
-        if (ws0 >= (uint32_t)n_wst) ws0 -= (uint32_t)n_wst;
-        if (c == n_convs - 2) {
-          if (elect_one()) umma_commit(bar_pfree);               // last reader of P (c even) is done
+        if (X3) {
+          ws0 = st;
+        } else {
+          ws0 += ns;
+          if (ws0 >= (uint32_t)n_wst) ws0 -= (uint32_t)n_wst;
+        }
+        if (c == n_convs - (X3 ? 1 : 2)) {
+          if (elect_one()) umma_commit(bar_pfree);               // last reader of P (c even; X3: of Q, c odd) is done
         }
       }
     }
@@ -348,7 +420,8 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     const int nch = 4 / spb;                                     // my 16-column chunks: chunk0 .. chunk0 + nch - 1
     const int chunk0 = (set % spb) * nch;
     if (slot < mb) {
-    constexpr int NB = C == 16 ? 1 : C == 32 ? 2 : 0;            // bias register sets (C = 64: loaded per chunk)
+    constexpr int NB = C == 16 ? 1 : (C == 32 && !X3) ? 2 : 0;   // bias register sets (C = 64, X3 at C = 32: loaded per chunk)
+    constexpr int MAXCH = X3 ? 2 : 4;                            // 16-column chunks per thread (X3 tiles have <= 2 blocks: spb >= 2)
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t x_col0 = (uint32_t)(mb * 64);                 // residual stream x (fp32) lives after the c1 accumulators
     const float slope = p.slope, inv_slope = 1.0f / p.slope, scale = p.scale;
@@ -369,20 +442,41 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
       for (int blk = slot; blk < mb; blk += n_slots) {
         const uint32_t row_off = tile_off + (uint32_t)(blk * 128 + row_in_blk) * 128u;
         const uint32_t taddr0 = tmem_base + lane_addr + (uint32_t)(blk * 64 + chunk0 * 16);
+        // X3: my row of the staged input, 256 bytes [S][hi C | lo C]
+        const uint32_t stg_row = q_base + (row_in_blk >= 64 ? lo_delta : 0u) + tile_off + (uint32_t)(blk * 16384 + (row_in_blk & 63) * 256);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < MAXCH; ++j) {
           if (j < nch) {
             const uint32_t cb = (uint32_t)((chunk0 + j) * 32);
             uint32_t r[16];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               float f[8];
-              unpack_bf16x8(lds128(p_base + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row)), f);
+              if (X3) {
+                const uint32_t so = (uint32_t)(((((chunk0 + j) * 16) / C) * 2 * C + ((chunk0 + j) * 16) % C) * 2 + h * 16);
+                const uint4 vh = lds128(stg_row + so), vl = lds128(stg_row + so + (uint32_t)(C * 2));
+                sts128(p_base + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row), vh);
+                sts128(p_base + lo_delta + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row), vl);
+                float fl[8];
+                unpack_bf16x8(vh, f);
+                unpack_bf16x8(vl, fl);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += fl[i];
+              } else {
+                unpack_bf16x8(lds128(p_base + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row)), f);
+              }
 #pragma unroll
               for (int i = 0; i < 8; ++i) r[8 * h + i] = __float_as_uint(fminf(f[i], f[i] * inv_slope));
             }
             tmem_st16(taddr0 + x_col0 + (uint32_t)(j * 16), r);
           }
+        }
+        if (X3) {   // the block's P planes (generic -> async proxy) and residual stream are in place: conv 0 may read them
+          tmem_wait_st();
+          fence_async_smem();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(kRpBarX0 + blk));
         }
       }
       for (int c = 0; c < n_convs; ++c, ++n) {
@@ -410,19 +504,29 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
         const uint32_t taddr = taddr0 + ((c & 1) ? x_col0 : 0u);
         const uint32_t bar_rdy = bar_ready + ((n & 1u) ? 8u * kRpMaxBlocks : 0u);
         // ---- last convolution: the running sum of my rows is fetched before the accumulator is waited for
-        uint4 a0[4], a1[4];
-        bool valid[4];
+        uint4 a0[MAXCH], a1[MAXCH], l0[X3 ? MAXCH : 1], l1[X3 ? MAXCH : 1];
+        bool valid[MAXCH];
         long long g_row = 0;
+        // X3: the two-plane tensors have rows [hi (C) | lo (C)] per time step: chunk ch of my row starts at
+        // g_row * 2 + x3_off(ch) (hi plane; the lo plane C elements further)
+        auto x3_off = [&](int ch) { return (long long)(((ch * 16) / C) * 2 * C + (ch * 16) % C); };
         if (is_last) {
           g_row = ((long long)it.b * L + t_tile0 + t_row) * C;   // my row's 64 values are contiguous in the output
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < MAXCH; ++j) {
             const int t = t_row + ((chunk0 + j) * 16) / C;
             valid[j] = j < nch && t >= H && t < H + V && t_tile0 + t < L;
             a0[j] = make_uint4(0u, 0u, 0u, 0u); a1[j] = a0[j];
+            if (X3) { l0[j] = a0[j]; l1[j] = a0[j]; }
             if (valid[j] && p.add1) {
-              a0[j] = ldg128(p.add1 + g_row + (chunk0 + j) * 16);
-              a1[j] = ldg128(p.add1 + g_row + (chunk0 + j) * 16 + 8);
+              if (X3) {
+                const __nv_bfloat16* ap = p.add1 + 2 * g_row + x3_off(chunk0 + j);
+                a0[j] = ldg128(ap); a1[j] = ldg128(ap + 8);
+                l0[j] = ldg128(ap + C); l1[j] = ldg128(ap + C + 8);
+              } else {
+                a0[j] = ldg128(p.add1 + g_row + (chunk0 + j) * 16);
+                a1[j] = ldg128(p.add1 + g_row + (chunk0 + j) * 16 + 8);
+              }
             }
           }
         }
@@ -431,7 +535,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
         fence_after_sync();
         if (trace && ntr < 1021) trace[ntr++] = (uint32_t)clock();
 #pragma unroll
-        for (int j2 = 0; j2 < 4; j2 += 2) {
+        for (int j2 = 0; j2 < MAXCH; j2 += 2) {
           if (j2 < nch) {
             uint32_t ra[2][16];
             tmem_ld16_nowait(taddr + (uint32_t)(j2 * 16), ra[0]);
@@ -463,24 +567,48 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
                 }
                 const uint32_t cb = (uint32_t)((chunk0 + j) * 32);
                 if (!is_last) {
-                  uint32_t h[8];
+                  uint32_t h[8], hl[X3 ? 8 : 1];
+                  if (X3) {   // leaky_relu in fp32, then the two planes: hi = bf16(a), lo = bf16(a - hi)
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) h[i] = bf16x2_scale_max(pack_bf16x2(v[2 * i], v[2 * i + 1]), slope);
+                    for (int i = 0; i < 8; ++i) {
+                      const float e0 = fmaxf(v[2 * i], v[2 * i] * slope), e1 = fmaxf(v[2 * i + 1], v[2 * i + 1] * slope);
+                      h[i] = pack_bf16x2(e0, e1);
+                      hl[i] = pack_bf16x2(e0 - __uint_as_float(h[i] << 16), e1 - __uint_as_float(h[i] & 0xffff0000u));
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) h[i] = bf16x2_scale_max(pack_bf16x2(v[2 * i], v[2 * i + 1]), slope);
+                  }
                   if (row_out) {
                     const int tg = t_tile0 + t_row + ((chunk0 + j) * 16) / C;
                     if (tg < 0 || tg >= L) {
 #pragma unroll
                       for (int i = 0; i < 8; ++i) h[i] = 0u;
+                      if (X3) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) hl[i] = 0u;
+                      }
                     }
                   }
                   sts128(dst + (cb ^ swz_row), make_uint4(h[0], h[1], h[2], h[3]));
                   sts128(dst + ((cb + 16u) ^ swz_row), make_uint4(h[4], h[5], h[6], h[7]));
+                  if (X3) {
+                    sts128(dst + lo_delta + (cb ^ swz_row), make_uint4(hl[0], hl[1], hl[2], hl[3]));
+                    sts128(dst + lo_delta + ((cb + 16u) ^ swz_row), make_uint4(hl[4], hl[5], hl[6], hl[7]));
+                  }
                 } else if (valid[j]) {
                   // ---- block output: (x_out [+ running sum]) * scale -> bf16 raw / leaky_relu'd, valid steps only
                   const long long g_off = g_row + (chunk0 + j) * 16;
                   float f[16];
                   unpack_bf16x8(a0[j], f);
                   unpack_bf16x8(a1[j], f + 8);
+                  if (X3) {
+                    float fl[16];
+                    unpack_bf16x8(l0[j], fl);
+                    unpack_bf16x8(l1[j], fl + 8);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] += fl[i];
+                  }
 #pragma unroll
                   for (int i = 0; i < 16; ++i) v[i] = (v[i] + f[i]) * scale;
                   if (p.out_f32) {
@@ -489,6 +617,33 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
                     for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                   }
                   uint32_t h[8];
+                  if (X3) {
+                    const long long g2 = 2 * g_row + x3_off(chunk0 + j);
+                    uint32_t hl[8];
+                    if (p.out_raw) {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) {
+                        h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                        hl[i] = pack_bf16x2(v[2 * i] - __uint_as_float(h[i] << 16), v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u));
+                      }
+                      stg128(p.out_raw + g2, make_uint4(h[0], h[1], h[2], h[3]));
+                      stg128(p.out_raw + g2 + 8, make_uint4(h[4], h[5], h[6], h[7]));
+                      stg128(p.out_raw + g2 + C, make_uint4(hl[0], hl[1], hl[2], hl[3]));
+                      stg128(p.out_raw + g2 + C + 8, make_uint4(hl[4], hl[5], hl[6], hl[7]));
+                    }
+                    if (p.out_act) {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) {
+                        const float e0 = fmaxf(v[2 * i], v[2 * i] * slope), e1 = fmaxf(v[2 * i + 1], v[2 * i + 1] * slope);
+                        h[i] = pack_bf16x2(e0, e1);
+                        hl[i] = pack_bf16x2(e0 - __uint_as_float(h[i] << 16), e1 - __uint_as_float(h[i] & 0xffff0000u));
+                      }
+                      stg128(p.out_act + g2, make_uint4(h[0], h[1], h[2], h[3]));
+                      stg128(p.out_act + g2 + 8, make_uint4(h[4], h[5], h[6], h[7]));
+                      stg128(p.out_act + g2 + C, make_uint4(hl[0], hl[1], hl[2], hl[3]));
+                      stg128(p.out_act + g2 + C + 8, make_uint4(hl[4], hl[5], hl[6], hl[7]));
+                    }
+                  } else {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
                   if (p.out_raw) {
@@ -500,6 +655,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
                     for (int i = 0; i < 8; ++i) h[i] = bf16x2_scale_max(h[i], slope);
                     stg128(p.out_act + g_off, make_uint4(h[0], h[1], h[2], h[3]));
                     stg128(p.out_act + g_off + 8, make_uint4(h[4], h[5], h[6], h[7]));
+                  }
                   }
                 }
               }

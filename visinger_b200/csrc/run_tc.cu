@@ -130,6 +130,7 @@ struct TCOptions {
   int rp_max_c = 32;        // widest stage the row-packed kernel takes
   int rp_packed = 1;        // dilation-1 convolutions in the block-Toeplitz form (0: every conv tap by tap)
   int rp_max_mb = 0;        // cap on 128-row blocks per row-packed tile (0 = as many as fit)
+  int rp_x3 = 1;            // bf16x3 mode: the row-packed kernel's split-bf16 instantiation for the C <= 32 stages (bit 1: off)
   int rp_spb2 = 0;          // row-packed kernel, 3- / 4-block tiles: two epilogue warp sets per block, two blocks per set
                             // (measured slower: 314 / 415 / 513 us vs 289 / 386 / 491 at C = 32 -- the per-block hand-over, not the
                             // drain itself, is what a set spends its time on)
@@ -742,10 +743,14 @@ struct RpPlan {
   size_t smem;
 };
 
-bool rp_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RpPlan* out) {
+// x3: the split-bf16 instantiation (two planes per activation tile, [W_hi | W_lo] ring stages streamed per block)
+bool rp_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RpPlan* out, bool x3 = false) {
   const int k = rb.kernel, nd = (int)rb.dilations.size();
   if ((C != 16 && C != 32 && C != 64) || k % 2 == 0 || nd < 1 || 2 * nd > kRpMaxConvs) return false;
   if ((int)rb.c1_tc.size() != nd || (int)rb.c2_tc.size() != nd || (int)rb.c2_bsum.size() != nd) return false;
+  if (x3 && (C == 64 || (int)rb.c1_x3.size() != nd || (int)rb.c2_x3.size() != nd)) return false;
+  const std::vector<ConvWTC>&c1v = x3 ? rb.c1_x3 : rb.c1_tc, &c2v = x3 ? rb.c2_x3 : rb.c2_tc;
+  const std::vector<ConvWTC>&c1p = x3 ? rb.c1_rp_x3 : rb.c1_rp, &c2p = x3 ? rb.c2_rp_x3 : rb.c2_rp;
   RpPlan p;
   p.S = 64 / C;
   if (L % p.S) return false;
@@ -753,14 +758,14 @@ bool rp_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RpPlan*
   int H = 0, dmax = 1;
   p.packed_mask = 0;
   for (int q = 0; q < nd; ++q) {
-    const ConvWTC &w1 = rb.c1_tc[q], &w2 = rb.c2_tc[q];
-    if (!w1.has_tmap || !w2.has_tmap || w1.x3 || w2.x3 || w1.Cin != C || w1.Cout != C || w2.Cin != C || w2.Cout != C ||
+    const ConvWTC &w1 = c1v[q], &w2 = c2v[q];
+    if (!w1.has_tmap || !w2.has_tmap || w1.x3 != x3 || w2.x3 != x3 || w1.Cin != C || w1.Cout != C || w2.Cin != C || w2.Cout != C ||
         w1.ktaps != k || w2.ktaps != k || rb.dilations[q] < 1) return false;
     H += cen * (rb.dilations[q] + 1);
     dmax = std::max(dmax, rb.dilations[q]);
     if (opt.rp_packed && p.S > 1) {
-      if (rb.dilations[q] == 1 && (int)rb.c1_rp.size() == nd && rb.c1_rp[q].has_tmap) p.packed_mask |= 1u << (2 * q);
-      if ((int)rb.c2_rp.size() == nd && rb.c2_rp[q].has_tmap) p.packed_mask |= 1u << (2 * q + 1);
+      if (rb.dilations[q] == 1 && (int)c1p.size() == nd && c1p[q].has_tmap) p.packed_mask |= 1u << (2 * q);
+      if ((int)c2p.size() == nd && c2p[q].has_tmap) p.packed_mask |= 1u << (2 * q + 1);
     }
   }
   p.H = (H + p.S - 1) / p.S * p.S;
@@ -773,17 +778,21 @@ bool rp_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RpPlan*
   p.margin_bytes = (uint32_t)((reach_bytes + 1023) & ~1023);
   int need = 0;
   for (int c = 0; c < 2 * nd; ++c) need = std::max(need, ((p.packed_mask >> c) & 1u) ? p.packed_stages : p.direct_stages);
-  const int mb_max = opt.rp_max_mb > 0 ? std::min(opt.rp_max_mb, kRpMaxBlocks) : kRpMaxBlocks;
+  // (x3: the epilogue's register budget is sized for <= 2 column chunks per thread, i.e. tiles of <= 2 blocks)
+  const int mb_cap = x3 ? 2 : kRpMaxBlocks;
+  const int mb_max = opt.rp_max_mb > 0 ? std::min(opt.rp_max_mb, mb_cap) : mb_cap;
+  const size_t stage_bytes = x3 ? 2 * kRpStageBytes : kRpStageBytes;
   for (int mb = mb_max; mb >= 1; --mb) {
     const int V = 128 * p.S * mb - 2 * p.H;
     if (V < 32 * p.S) return false;
     p.mb = mb; p.V = V;
     p.buf_bytes = 2 * p.margin_bytes + 16384u * (uint32_t)mb;
-    const size_t fixed = 2 * (size_t)p.buf_bytes + 8 * tc::kRpNumBars + 64 + kRpMaxConvs * 64 * sizeof(float) + 1024;
-    if (fixed + (size_t)need * kRpStageBytes > kSmemMax) continue;
+    const size_t fixed = (x3 ? 4 : 2) * (size_t)p.buf_bytes + 8 * tc::kRpNumBars + 64 + kRpMaxConvs * 64 * sizeof(float) + 1024;
+    // x3 streams the ring once per block (two stages are enough to run; more is prefetch depth)
+    if (fixed + (size_t)(x3 ? std::min(need, 2) : need) * stage_bytes > kSmemMax) continue;
     // a convolution's stages are released by its last block: twice the largest need keeps a whole convolution of prefetch
-    p.n_wst = (int)std::min<size_t>({(size_t)kRpMaxWStages, (size_t)2 * need, (kSmemMax - fixed) / kRpStageBytes});
-    p.smem = fixed + (size_t)p.n_wst * kRpStageBytes;
+    p.n_wst = (int)std::min<size_t>({(size_t)kRpMaxWStages, (size_t)2 * need, (kSmemMax - fixed) / stage_bytes});
+    p.smem = fixed + (size_t)p.n_wst * stage_bytes;
     if (mb > 1 && 128 * p.S * (mb - 1) - 2 * p.H >= L) continue;   // a smaller tile covers the utterance
     *out = p;
     return true;
@@ -795,9 +804,10 @@ bool rp_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RpPlan*
 //   out = (resblock(x) [+ add1]) * scale  ->  out_raw (bf16) and / or out_act = leaky_relu(out) (bf16) [, out_f32]
 int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfloat16* xa, int B, int L,
                  const __nv_bfloat16* add1, __nv_bfloat16* out_raw, __nv_bfloat16* out_act, float* out_f32, float scale,
-                 const TCOptions& opt, int* error_flag, cudaStream_t st) {
+                 const TCOptions& opt, int* error_flag, cudaStream_t st, bool x3 = false) {
+  // x3: xa / add1 / out_raw / out_act are two-plane tensors [B, L, 2 C] (rows [hi | lo]); out_f32 stays [B, L, C]
   RpPlan pl;
-  if (!rp_plan(rb, C, L, opt, &pl)) return fail(VSG_EUNSUPPORTED, "resblock shape not supported by the row-packed kernel");
+  if (!rp_plan(rb, C, L, opt, &pl, x3)) return fail(VSG_EUNSUPPORTED, "resblock shape not supported by the row-packed kernel");
   if ((const void*)xa == (const void*)out_raw || (const void*)xa == (const void*)out_act)
     return fail(VSG_EINVAL, "fused resblock must not run in place (tiles read halo rows of their neighbours)");
   const int nd = (int)rb.dilations.size();
@@ -809,8 +819,13 @@ int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   for (int q = 0; q < nd; ++q) {
     p.dil[2 * q] = rb.dilations[q]; p.dil[2 * q + 1] = 1;
     p.bias[2 * q] = rb.c1_tc[q].bias; p.bias[2 * q + 1] = rb.c2_bsum[q];
-    maps.w[2 * q] = ((pl.packed_mask >> (2 * q)) & 1u) ? rb.c1_rp[q].tmap : rb.c1_tc[q].tmap;
-    maps.w[2 * q + 1] = ((pl.packed_mask >> (2 * q + 1)) & 1u) ? rb.c2_rp[q].tmap : rb.c2_tc[q].tmap;
+    if (x3) {
+      maps.w[2 * q] = ((pl.packed_mask >> (2 * q)) & 1u) ? rb.c1_rp_x3[q].tmap : rb.c1_x3[q].tmap;
+      maps.w[2 * q + 1] = ((pl.packed_mask >> (2 * q + 1)) & 1u) ? rb.c2_rp_x3[q].tmap : rb.c2_x3[q].tmap;
+    } else {
+      maps.w[2 * q] = ((pl.packed_mask >> (2 * q)) & 1u) ? rb.c1_rp[q].tmap : rb.c1_tc[q].tmap;
+      maps.w[2 * q + 1] = ((pl.packed_mask >> (2 * q + 1)) & 1u) ? rb.c2_rp[q].tmap : rb.c2_tc[q].tmap;
+    }
   }
   p.packed_mask = pl.packed_mask; p.n_k = pl.n_k; p.packed_stages = pl.packed_stages;
   p.tps = pl.tps; p.direct_stages = pl.direct_stages;
@@ -820,8 +835,8 @@ int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   p.total_tiles = p.m_tiles_per_b * B;
   p.n_wst = pl.n_wst;
   p.margin_bytes = pl.margin_bytes; p.buf_bytes = pl.buf_bytes;
-  p.p_off = 0; p.q_off = pl.buf_bytes; p.w_off = 2 * pl.buf_bytes;
-  p.bar_off = p.w_off + (uint32_t)pl.n_wst * kRpStageBytes;
+  p.p_off = 0; p.q_off = (x3 ? 2 : 1) * pl.buf_bytes; p.w_off = (x3 ? 4 : 2) * pl.buf_bytes;
+  p.bar_off = p.w_off + (uint32_t)pl.n_wst * (x3 ? 2 : 1) * kRpStageBytes;
   p.bias_off = p.bar_off + 8 * tc::kRpNumBars + 64;
   p.tmem_cols = 32;
   while (p.tmem_cols < (uint32_t)(2 * pl.mb * 64)) p.tmem_cols <<= 1;
@@ -831,22 +846,32 @@ int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   p.trace = opt.rp_trace;
   static const bool debug_plan = getenv("VSG_DEBUG_PLAN") != nullptr;
   if (debug_plan || opt.plan_only)
-    fprintf(stderr, "[vsg plan] ROWPACKED RESBLOCK C%d k%d pairs%d B%d L%d | S%d mb%d H%d V%d packed 0x%x K slices %d (stages %d) "
-                    "direct stages %d ring %d margin %u smem %zu KB tmem %u tiles %d\n", C, rb.kernel, nd, B, L, pl.S, pl.mb,
+    fprintf(stderr, "[vsg plan] ROWPACKED RESBLOCK%s C%d k%d pairs%d B%d L%d | S%d mb%d H%d V%d packed 0x%x K slices %d (stages %d) "
+                    "direct stages %d ring %d margin %u smem %zu KB tmem %u tiles %d\n", x3 ? " x3" : "", C, rb.kernel, nd, B, L, pl.S, pl.mb,
             pl.H, pl.V, pl.packed_mask, pl.n_k, pl.packed_stages, pl.direct_stages, pl.n_wst,
             pl.margin_bytes, pl.smem / 1024, p.tmem_cols, p.total_tiles);
   if (opt.plan_only) return VSG_OK;
   // the input as rows of 64 channels = S time steps: [B, L, C] == [B, L / S, 64]
   CUtensorMap tmA;
-  VSG_TRY(encode_3d(&tmA, xa, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
-  maps.add1 = tmA;
-  if (add1) VSG_TRY(encode_3d(&maps.add1, add1, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
+  if (x3) {
+    // two-plane rows [hi (C) | lo (C)] per time step: S time steps = 128 elements per packed row, staged unswizzled in
+    // boxes of 64 rows (the kernel's epilogue warps write the swizzled plane tiles)
+    VSG_TRY(encode_3d(&tmA, xa, 128, (uint64_t)(L / pl.S), (uint64_t)B, 128, (uint64_t)L * 2 * C, 128, 64, 0));
+    maps.add1 = tmA;
+    if (add1) VSG_TRY(encode_3d(&maps.add1, add1, 128, (uint64_t)(L / pl.S), (uint64_t)B, 128, (uint64_t)L * 2 * C, 128, 64, 0));
+  } else {
+    VSG_TRY(encode_3d(&tmA, xa, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
+    maps.add1 = tmA;
+    if (add1) VSG_TRY(encode_3d(&maps.add1, add1, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
+  }
   using RpFn = void (*)(CUtensorMap, RpMaps, RpTC);
-  RpFn fn = C == 16 ? rp_tc_kernel<16> : C == 32 ? rp_tc_kernel<32> : rp_tc_kernel<64>;
+  RpFn fn = x3 ? (C == 16 ? (RpFn)rp_tc_kernel<16, true> : (RpFn)rp_tc_kernel<32, true>)
+               : (C == 16 ? (RpFn)rp_tc_kernel<16> : C == 32 ? (RpFn)rp_tc_kernel<32> : (RpFn)rp_tc_kernel<64>);
   static bool rp_attr_set_dev[64] = {false};
   bool& attr_set = rp_attr_set_dev[P->device & 63];
   if (!attr_set) {
-    for (RpFn f : {(RpFn)rp_tc_kernel<16>, (RpFn)rp_tc_kernel<32>, (RpFn)rp_tc_kernel<64>})
+    for (RpFn f : {(RpFn)rp_tc_kernel<16>, (RpFn)rp_tc_kernel<32>, (RpFn)rp_tc_kernel<64>, (RpFn)rp_tc_kernel<16, true>,
+                   (RpFn)rp_tc_kernel<32, true>})
       VSG_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
@@ -920,7 +945,7 @@ int pack_conv_tc(VsgPack* P, const std::vector<float>& W, const std::vector<floa
 // input, slice m = channels 16 (m % KK) .. of input sub-step sigma = m / KK - (k-1)/2 (KK = C / 16), through tap
 // j = sigma - s' + (k-1)/2:   W'[m][n][ci'] = W[co][16 (m % KK) + ci'][j]   (zero outside the k taps).
 // Four slices share one [64 x 64] SWIZZLE_128B tile (K index = 16 (m % 4) + ci'): packed as Conv1d(64 -> 64, ceil(n_k / 4) taps).
-int pack_conv_rowpacked(VsgPack* P, const std::vector<float>& W, int C, int k, ConvWTC* out) {
+int pack_conv_rowpacked(VsgPack* P, const std::vector<float>& W, int C, int k, ConvWTC* out, int planes) {
   out->has_tmap = false;
   if ((C != 16 && C != 32) || k % 2 == 0) return VSG_OK;
   const int S = 64 / C, KK = C / 16, cen = (k - 1) / 2, n_k = (k + S - 1) * KK, n_g = (n_k + 3) / 4;
@@ -935,7 +960,7 @@ int pack_conv_rowpacked(VsgPack* P, const std::vector<float>& W, int C, int k, C
           Wp[((size_t)(sp * C + co) * 64 + 16 * (m % 4) + ci) * n_g + m / 4] = W[((size_t)co * C + c_lo + ci) * k + j];
     }
   }
-  return pack_conv_tc(P, Wp, bz, 64, 64, n_g, out);
+  return pack_conv_tc(P, Wp, bz, 64, 64, n_g, out, planes);   // planes = 2: rows [W_hi (64) | W_lo (64)]
 }
 
 int pack_resblock_bias_sums(VsgPack* P, const std::vector<std::vector<float>>& b2, ResBlockPack* rb) {
@@ -1533,17 +1558,18 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       }
       static const int rp_max_c_env = getenv("VSG_RP_MAX_C") ? atoi(getenv("VSG_RP_MAX_C")) : -1;   // A/B aid
       const int rp_max_c = rp_max_c_env >= 0 ? rp_max_c_env : opt.rp_max_c;
-      bool rp_stage = c.dec_resblock == 1 && !x3 && opt.fuse_rp && ch <= rp_max_c;
+      // (bf16x3: the kernel's split-bf16 instantiation; it reads the single activated stream)
+      bool rp_stage = c.dec_resblock == 1 && (x3 ? (opt.rp_x3 && one_stream_all) : true) && opt.fuse_rp && ch <= rp_max_c;
       for (int j = 0; j < NK && rp_stage; ++j) {
         RpPlan rp;
-        rp_stage = rp_plan(us.blocks[j], ch, L, opt, &rp) && L >= 256;
+        rp_stage = rp_plan(us.blocks[j], ch, L, opt, &rp, x3) && L >= 256;
       }
       if (rb_stage || rp_stage) {
         for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
           const bool lastj = (j == NK - 1);
           if (rp_stage)
             VSG_TRY(launch_rp_tc(P, us.blocks[j], ch, bUA, nb, L, j > 0 ? bS : nullptr, lastj ? nullptr : bS, lastj ? xout : nullptr,
-                                 nullptr, lastj ? 1.0f / (float)NK : 1.0f, opt, err, st));
+                                 nullptr, lastj ? 1.0f / (float)NK : 1.0f, opt, err, st, x3));
           else
             VSG_TRY(launch_rb_tc(P, us.blocks[j], ch, bUA, nb, L, j > 0 ? bS : nullptr, lastj ? nullptr : bS, lastj ? xout : nullptr,
                                  nullptr, lastj ? 1.0f / (float)NK : 1.0f, opt, err, st));
@@ -1823,7 +1849,9 @@ extern "C" int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, cons
   rb.dilations.assign(dilations, dilations + n_pairs);
   rb.c1_tc.resize(n_pairs); rb.c2_tc.resize(n_pairs);
   rb.c1_rp.resize(n_pairs); rb.c2_rp.resize(n_pairs);
+  rb.c1_x3.resize(n_pairs); rb.c2_x3.resize(n_pairs); rb.c1_rp_x3.resize(n_pairs); rb.c2_rp_x3.resize(n_pairs);
   const bool row_packed = (sets & 256) != 0;              // bit 8: the row-packed kernel (rp_tc.cuh); bit 9: no Toeplitz form
+  const bool x3 = row_packed && (sets & 2048) != 0;       // bit 11: split-bf16 instantiation (two-plane tensors [B, L, 2 C])
   int rc = VSG_OK;
   const size_t wn = (size_t)C * C * k;
   std::vector<std::vector<float>> b2s;
@@ -1836,6 +1864,12 @@ extern "C" int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, cons
     if (rc == VSG_OK) rc = pack_conv_tc(&tmp, W2, B2, C, C, k, &rb.c2_tc[q]);
     if (rc == VSG_OK && row_packed && dilations[q] == 1) rc = pack_conv_rowpacked(&tmp, W1, C, k, &rb.c1_rp[q]);
     if (rc == VSG_OK && row_packed) rc = pack_conv_rowpacked(&tmp, W2, C, k, &rb.c2_rp[q]);
+    if (x3) {
+      if (rc == VSG_OK) rc = pack_conv_tc(&tmp, W1, B1, C, C, k, &rb.c1_x3[q], 2);
+      if (rc == VSG_OK) rc = pack_conv_tc(&tmp, W2, B2, C, C, k, &rb.c2_x3[q], 2);
+      if (rc == VSG_OK && dilations[q] == 1) rc = pack_conv_rowpacked(&tmp, W1, C, k, &rb.c1_rp_x3[q], 2);
+      if (rc == VSG_OK) rc = pack_conv_rowpacked(&tmp, W2, C, k, &rb.c2_rp_x3[q], 2);
+    }
   }
   int* err = nullptr;
   if (rc == VSG_OK && cudaMalloc(&err, sizeof(int)) != cudaSuccess) rc = fail(VSG_ECUDA, "cudaMalloc failed");
@@ -1859,7 +1893,7 @@ extern "C" int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, cons
     auto run = [&]() {
       if (row_packed)
         return launch_rp_tc(&tmp, rb, C, (const __nv_bfloat16*)xa_bf16, B, L, (const __nv_bfloat16*)add1_bf16,
-                            (__nv_bfloat16*)out_raw_bf16, (__nv_bfloat16*)out_act_bf16, out_f32, scale, opt, err, 0);
+                            (__nv_bfloat16*)out_raw_bf16, (__nv_bfloat16*)out_act_bf16, out_f32, scale, opt, err, 0, x3);
       return launch_rb_tc(&tmp, rb, C, (const __nv_bfloat16*)xa_bf16, B, L, (const __nv_bfloat16*)add1_bf16,
                           (__nv_bfloat16*)out_raw_bf16, (__nv_bfloat16*)out_act_bf16, out_f32, scale, opt, err, 0);
     };
@@ -1930,6 +1964,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.fuse_rp = (halo_mode & (1 << 24)) ? 0 : 1;                         // bit 24: no row-packed resblock kernel
   g_default_opts.rp_max_c = (halo_mode & (1 << 25)) ? 64 : 32;                      // bit 25: row-packed kernel at C = 64 too
   g_default_opts.rp_packed = (halo_mode & (1 << 26)) ? 0 : 1;                       // bit 26: no block-Toeplitz form
+  g_default_opts.rp_x3 = (halo_mode & 2) ? 0 : 1;                                   // bit 1: bf16x3 mode without the row-packed resblock kernel
   g_default_opts.rp_spb2 = (halo_mode & (1 << 30)) ? 1 : 0;                         // bit 30: row-packed kernel, two epilogue sets per block
   g_default_opts.flow_merge = ((uint32_t)halo_mode & (1u << 31)) ? 0 : 1;           // bit 31: flow with separate res / skip / cond launches
   g_default_opts.conv_post = (halo_mode >> 28) & 3;                                 // bits 28-29: conv_post on CUDA cores (1 / 2)

@@ -132,6 +132,7 @@ struct ResBlockPack {
   std::vector<ConvWTC> c1_tc, c2_tc;
   std::vector<ConvWTC> c1_x3, c2_x3;   // split-bf16 packs
   std::vector<ConvWTC> c1_rp, c2_rp;   // row-packed block-Toeplitz packs of the dilation-1 convolutions (C <= 32; rp_tc.cuh)
+  std::vector<ConvWTC> c1_rp_x3, c2_rp_x3;   // the same as split-bf16 packs [W_hi | W_lo] (bf16x3 mode)
   std::vector<float*> c2_bsum;         // running bias of the residual stream: b2_0 + ... + b2_q, fp32 [C] each (rp_tc.cuh)
 };
 
