@@ -474,7 +474,8 @@ def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scal
     """Per-layer parity hook of the whole-ResBlock1 kernel (csrc/rb_tc.cuh).  xa_bld / add1: CUDA bf16 [B, L, C];
     ws / bs: lists [c1_0, c2_0, c1_1, c2_1, ...] of fp32 [C, C, k] / [C].  Returns (out_f32, out_raw_bf16, out_act_bf16[, ms]).
     sets bit 11 (with bit 8): the row-packed kernel's split-bf16 instantiation -- xa / add1 / raw / act are two-plane
-    tensors [B, L, 2 C] (`split_bf16`), out_f32 stays [B, L, C]."""
+    tensors [B, L, 2 C] (`split_bf16`), out_f32 stays [B, L, C].  (The kernel takes xa / add1 and writes raw as planar
+    tensors [2][B, L, C]; the conversion from / to the decoder's rows [hi | lo] happens here.)"""
     require_cuda(xa_bld, "xa")
     assert xa_bld.dtype == torch.bfloat16 and xa_bld.is_contiguous()
     B, Lx, C = xa_bld.shape
@@ -482,6 +483,9 @@ def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scal
     if x3:
         assert C % 2 == 0
         C //= 2
+        xa_bld = torch.stack([xa_bld[..., :C], xa_bld[..., C:]]).contiguous()
+        if add1 is not None:
+            add1 = torch.stack([add1[..., :C], add1[..., C:]]).contiguous()
     k = ws[0].shape[2]
     n_pairs = len(dilations)
     assert len(ws) == 2 * n_pairs and len(bs) == 2 * n_pairs
@@ -490,7 +494,7 @@ def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scal
     dl = (ctypes.c_int32 * n_pairs)(*[int(d) for d in dilations])
     dev = xa_bld.device
     out = torch.zeros(B, Lx, C, dtype=torch.float32, device=dev) if want_f32 else None
-    raw = torch.zeros(B, Lx, (2 if x3 else 1) * C, dtype=torch.bfloat16, device=dev) if want_raw else None
+    raw = torch.zeros((2, B, Lx, C) if x3 else (B, Lx, C), dtype=torch.bfloat16, device=dev) if want_raw else None
     act = torch.zeros(B, Lx, (2 if x3 else 1) * C, dtype=torch.bfloat16, device=dev) if want_act else None
     assert add1 is None or (add1.is_cuda and add1.dtype == torch.bfloat16 and add1.is_contiguous())
     torch.cuda.synchronize(dev)
@@ -507,6 +511,8 @@ def debug_resblock_bf16(xa_bld: torch.Tensor, ws, bs, dilations, add1=None, scal
         if reps > 1:
             lib().vsg_debug_set_plan(0, 0, -1, -1, 1)
     check(rc, "vsg_debug_resblock_bf16")
+    if x3 and raw is not None:
+        raw = torch.cat([raw[0], raw[1]], dim=-1)
     return (out, raw, act, ms) if reps > 1 else (out, raw, act)
 
 

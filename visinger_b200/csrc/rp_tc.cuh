@@ -41,12 +41,12 @@
 // MMA order), or shares a block with other sets when the tile has fewer blocks.
 //
 // X3 = true is the same kernel in the split-bf16 arithmetic of the bf16x3 mode (fp32-tolerance results on tcgen05): every
-// activation is two bf16 planes (hi = bf16(v), lo = bf16(v - hi); global rows [hi (C) | lo (C)] per time step), every
-// weight tile comes as W_hi and W_lo, and every product is three MMAs issued small-first (lo * W_hi, hi * W_lo,
-// hi * W_hi).  The input's planes are interleaved per time step, which no tensor map can turn into two 128-byte-row
-// SWIZZLE_128B tiles (a box narrower than the swizzle span is padded to it), so the input tile is staged unswizzled in
-// the -- still unused -- Q buffers and the epilogue warps, which read every input value anyway to seed the residual
-// stream, write the two P planes themselves.  The residual stream is still the fp32 accumulator in
+// activation is two bf16 planes (hi = bf16(v), lo = bf16(v - hi)), every weight tile comes as W_hi and W_lo, and every
+// product is three MMAs issued small-first (lo * W_hi, hi * W_lo, hi * W_hi).  The input and the running resblock sum
+// are PLANAR two-plane tensors ([2][B, L, C]: each plane loads through the one-plane row-packed tensor map; planes
+// interleaved per time step cannot -- a box narrower than the swizzle span is padded to it in shared memory -- and a
+// first version that staged such rows unswizzled and re-laid them in the epilogue lost 10 k cycles per tile to the
+// serialised load -> re-lay -> first MMA chain); the stage output keeps the decoder's rows [hi (C) | lo (C)].  The residual stream is still the fp32 accumulator in
 // tensor memory -- more exact than the two-plane stream of the per-convolution kernels.  Four activation tiles (P / Q x
 // hi / lo) leave room for 2-block tiles only and not for a whole convolution's weights, so the weight ring (16 KB
 // stages: [W_hi | W_lo]) is streamed per BLOCK instead of per convolution (L2 -> shared memory twice per tile).
@@ -80,7 +80,9 @@ struct RpTC {
   uint32_t tmem_cols;
   const float* bias[kRpMaxConvs];  // even c: bias of c1_q; odd c: b2_0 + ... + b2_q (the residual stream's running bias)
   const __nv_bfloat16* add1;      // running resblock sum [B, L, C] or null (read for the tile's valid steps only)
-                                  // (X3: add1 / out_raw / out_act are two-plane tensors [B, L, 2 C], rows [hi | lo])
+                                  // (X3: the input, add1 and out_raw are planar two-plane tensors, the lo plane
+                                  // plane_stride elements after the hi plane; out_act has rows [hi (C) | lo (C)])
+  long long plane_stride;
   __nv_bfloat16* out_raw;         // (x_out + add1) * scale as bf16, or null
   __nv_bfloat16* out_act;         // leaky_relu of the same, or null
   float* out_f32;                 // fp32 copy (parity hook), or null
@@ -89,7 +91,7 @@ struct RpTC {
   uint32_t* trace;                // tuning aid: CTA 0 logs clock() at its pipeline events ([5 roles][1024] words), or null
 };
 
-struct RpMaps { CUtensorMap w[kRpMaxConvs]; CUtensorMap add1; };
+struct RpMaps { CUtensorMap w[kRpMaxConvs]; CUtensorMap add1; CUtensorMap a_lo, add1_lo; };   // (*_lo: X3, the lo planes)
 
 namespace tc {
 
@@ -99,8 +101,7 @@ constexpr int kRpBarWFull = 3 * kRpMaxBlocks;                     // [kRpMaxWSta
 constexpr int kRpBarWEmpty = kRpBarWFull + kRpMaxWStages;         // [kRpMaxWStages]
 constexpr int kRpBarAFull = kRpBarWEmpty + kRpMaxWStages;
 constexpr int kRpBarPFree = kRpBarAFull + 1;
-constexpr int kRpBarX0 = kRpBarPFree + 1;                         // [kRpMaxBlocks] X3: P planes + residual stream of a block written
-constexpr int kRpNumBars = kRpBarX0 + kRpMaxBlocks;
+constexpr int kRpNumBars = kRpBarPFree + 1;
 constexpr int kRpEpiWarps = 16;
 constexpr int kRpThreads = (4 + kRpEpiWarps) * 32;                // 640
 
@@ -132,12 +133,12 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     prefetch_tmap(&tmA);
     for (int c = 0; c < n_convs; ++c) prefetch_tmap(&wm.w[c]);
     if (p.add1) prefetch_tmap(&wm.add1);
+    if (X3) { prefetch_tmap(&wm.a_lo); if (p.add1) prefetch_tmap(&wm.add1_lo); }
     for (int b = 0; b < kRpMaxBlocks; ++b) {
       mbar_init(bar(kRpBarAccFull + b), 1);
       const uint32_t warps_per_block = 4u * (uint32_t)p.spb;                  // epilogue warps that drain one block
       mbar_init(bar(kRpBarReady + b), warps_per_block);
       mbar_init(bar(kRpBarReady + kRpMaxBlocks + b), warps_per_block);
-      mbar_init(bar(kRpBarX0 + b), warps_per_block);
     }
     for (int s = 0; s < kRpMaxWStages; ++s) { mbar_init(bar(kRpBarWFull + s), 1); mbar_init(bar(kRpBarWEmpty + s), 1); }
     mbar_init(bar(kRpBarAFull), 1);
@@ -181,18 +182,13 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     uint32_t st = 0, eph = 0;                                     // eph bit s: parity of stage s's next "empty" completion
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next(), ++n_tile) {
       // (the previous tile's weight loads were all issued above, so waiting for P here cannot starve the issuers)
-      // P (X3: Q, where the input is staged) no longer read by the previous tile
-      if (n_tile > 0) mbar_wait(bar(kRpBarPFree), (n_tile - 1) & 1u, error_flag);
+      if (n_tile > 0) mbar_wait(bar(kRpBarPFree), (n_tile - 1) & 1u, error_flag);   // P no longer read by the previous tile
       const int row0 = (it.mt * p.V - p.H) / S;                  // exact: V and H are multiples of S
       if (elect_one()) {
         mbar_expect_tx(bar(kRpBarAFull), 16384u * (uint32_t)(mb * NPL));
         for (int bx = 0; bx < mb; ++bx) {
-          if (X3) {   // staged unswizzled, 256-byte rows [S][hi C | lo C]: rows 0 .. 63 of a block in Q_hi's tile, 64 .. 127 in Q_lo's
-            tma_load_3d(q_base + tile_off + 16384u * (uint32_t)bx, &tmA, bar(kRpBarAFull), 0, row0 + 128 * bx, it.b);
-            tma_load_3d(q_base + lo_delta + tile_off + 16384u * (uint32_t)bx, &tmA, bar(kRpBarAFull), 0, row0 + 128 * bx + 64, it.b);
-          } else {
-            tma_load_3d(p_base + tile_off + 16384u * (uint32_t)bx, &tmA, bar(kRpBarAFull), 0, row0 + 128 * bx, it.b);
-          }
+          tma_load_3d(p_base + tile_off + 16384u * (uint32_t)bx, &tmA, bar(kRpBarAFull), 0, row0 + 128 * bx, it.b);
+          if (X3) tma_load_3d(p_base + lo_delta + tile_off + 16384u * (uint32_t)bx, &wm.a_lo, bar(kRpBarAFull), 0, row0 + 128 * bx, it.b);
         }
       }
       // L2 prefetch: the running sum this tile's last convolution will add, and the NEXT tile's input (its TMA load can
@@ -200,12 +196,8 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
       if (p.add1) {
         if (elect_one())
           for (int bx = 0; bx < mb; ++bx) {
-            if (X3) {
-              tma_prefetch_3d(&wm.add1, 0, row0 + 128 * bx, it.b);
-              tma_prefetch_3d(&wm.add1, 0, row0 + 128 * bx + 64, it.b);
-            } else {
-              tma_prefetch_3d(&wm.add1, 0, row0 + 128 * bx, it.b);
-            }
+            tma_prefetch_3d(&wm.add1, 0, row0 + 128 * bx, it.b);
+            if (X3) tma_prefetch_3d(&wm.add1_lo, 0, row0 + 128 * bx, it.b);
           }
       }
       if (tile + (int)gridDim.x < total_tiles) {
@@ -214,12 +206,8 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
         const int nrow0 = (nx.mt * p.V - p.H) / S;
         if (elect_one())
           for (int bx = 0; bx < mb; ++bx) {
-            if (X3) {
-              tma_prefetch_3d(&tmA, 0, nrow0 + 128 * bx, nx.b);
-              tma_prefetch_3d(&tmA, 0, nrow0 + 128 * bx + 64, nx.b);
-            } else {
-              tma_prefetch_3d(&tmA, 0, nrow0 + 128 * bx, nx.b);
-            }
+            tma_prefetch_3d(&tmA, 0, nrow0 + 128 * bx, nx.b);
+            if (X3) tma_prefetch_3d(&wm.a_lo, 0, nrow0 + 128 * bx, nx.b);
           }
       }
       for (int c = 0; c < n_convs; ++c) {
@@ -271,7 +259,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     const uint32_t packed_mask = p.packed_mask;
     const int d0 = p.dil[0], d1 = p.dil[2], d2 = p.dil[4], d3 = p.dil[6];
     const uint32_t bar_acc = bar(kRpBarAccFull), bar_ready = bar(kRpBarReady), bar_wfull = bar(kRpBarWFull),
-                   bar_wempty = bar(kRpBarWEmpty), bar_afull = bar(kRpBarAFull), bar_pfree = bar(kRpBarPFree), bar_x0 = bar(kRpBarX0);
+                   bar_wempty = bar(kRpBarWEmpty), bar_afull = bar(kRpBarAFull), bar_pfree = bar(kRpBarPFree);
     uint32_t ws0 = 0, wph = 0, n = 0, n_tile = 0;                 // wph bit s: parity of stage s's next "full" completion
     // one product of the GEMM: a single MMA, or (X3) the three plane products, smallest first
     auto mma_row = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
@@ -313,12 +301,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
           // block b reads blocks b-1 .. b+1 of the previous convolution's output and overwrites accumulator b: all
           // released through `ready` of the previous step (b-1 and b were waited for by the previous iterations)
           if (c == 0) {
-            if (X3) {   // P is written by the epilogue warps (see the x0 phase), block by block
-              if (b == 0) mbar_wait(bar_x0, n_tile & 1u, error_flag);
-              if (b + 1 < mb) mbar_wait(bar_x0 + 8u * (b + 1), n_tile & 1u, error_flag);
-            } else if (b == 0) {
-              mbar_wait(bar_afull, n_tile & 1u, error_flag);
-            }
+            if (b == 0) mbar_wait(bar_afull, n_tile & 1u, error_flag);
             if (n > 0) mbar_wait(bar_prev + 8u * b, prev_par, error_flag);
           } else {
             if (b == 0) mbar_wait(bar_prev, prev_par, error_flag);
@@ -400,8 +383,8 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
           ws0 += ns;
           if (ws0 >= (uint32_t)n_wst) ws0 -= (uint32_t)n_wst;
         }
-        if (c == n_convs - (X3 ? 1 : 2)) {
-          if (elect_one()) umma_commit(bar_pfree);               // last reader of P (c even; X3: of Q, c odd) is done
+        if (c == n_convs - 2) {
+          if (elect_one()) umma_commit(bar_pfree);               // last reader of P (c even) is done
         }
       }
     }
@@ -442,8 +425,6 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
       for (int blk = slot; blk < mb; blk += n_slots) {
         const uint32_t row_off = tile_off + (uint32_t)(blk * 128 + row_in_blk) * 128u;
         const uint32_t taddr0 = tmem_base + lane_addr + (uint32_t)(blk * 64 + chunk0 * 16);
-        // X3: my row of the staged input, 256 bytes [S][hi C | lo C]
-        const uint32_t stg_row = q_base + (row_in_blk >= 64 ? lo_delta : 0u) + tile_off + (uint32_t)(blk * 16384 + (row_in_blk & 63) * 256);
 #pragma unroll
         for (int j = 0; j < MAXCH; ++j) {
           if (j < nch) {
@@ -452,31 +433,18 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               float f[8];
+              unpack_bf16x8(lds128(p_base + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row)), f);
               if (X3) {
-                const uint32_t so = (uint32_t)(((((chunk0 + j) * 16) / C) * 2 * C + ((chunk0 + j) * 16) % C) * 2 + h * 16);
-                const uint4 vh = lds128(stg_row + so), vl = lds128(stg_row + so + (uint32_t)(C * 2));
-                sts128(p_base + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row), vh);
-                sts128(p_base + lo_delta + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row), vl);
                 float fl[8];
-                unpack_bf16x8(vh, f);
-                unpack_bf16x8(vl, fl);
+                unpack_bf16x8(lds128(p_base + lo_delta + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row)), fl);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += fl[i];
-              } else {
-                unpack_bf16x8(lds128(p_base + row_off + ((cb + (uint32_t)(h * 16)) ^ swz_row)), f);
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) r[8 * h + i] = __float_as_uint(fminf(f[i], f[i] * inv_slope));
             }
             tmem_st16(taddr0 + x_col0 + (uint32_t)(j * 16), r);
           }
-        }
-        if (X3) {   // the block's P planes (generic -> async proxy) and residual stream are in place: conv 0 may read them
-          tmem_wait_st();
-          fence_async_smem();
-          fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(kRpBarX0 + blk));
         }
       }
       for (int c = 0; c < n_convs; ++c, ++n) {
@@ -507,8 +475,8 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
         uint4 a0[MAXCH], a1[MAXCH], l0[X3 ? MAXCH : 1], l1[X3 ? MAXCH : 1];
         bool valid[MAXCH];
         long long g_row = 0;
-        // X3: the two-plane tensors have rows [hi (C) | lo (C)] per time step: chunk ch of my row starts at
-        // g_row * 2 + x3_off(ch) (hi plane; the lo plane C elements further)
+        // X3: out_act has rows [hi (C) | lo (C)] per time step: chunk ch of my row starts at g_row * 2 + x3_off(ch)
+        // (hi plane; the lo plane C elements further); add1 / out_raw are planar
         auto x3_off = [&](int ch) { return (long long)(((ch * 16) / C) * 2 * C + (ch * 16) % C); };
         if (is_last) {
           g_row = ((long long)it.b * L + t_tile0 + t_row) * C;   // my row's 64 values are contiguous in the output
@@ -519,13 +487,11 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
             a0[j] = make_uint4(0u, 0u, 0u, 0u); a1[j] = a0[j];
             if (X3) { l0[j] = a0[j]; l1[j] = a0[j]; }
             if (valid[j] && p.add1) {
+              a0[j] = ldg128(p.add1 + g_row + (chunk0 + j) * 16);
+              a1[j] = ldg128(p.add1 + g_row + (chunk0 + j) * 16 + 8);
               if (X3) {
-                const __nv_bfloat16* ap = p.add1 + 2 * g_row + x3_off(chunk0 + j);
-                a0[j] = ldg128(ap); a1[j] = ldg128(ap + 8);
-                l0[j] = ldg128(ap + C); l1[j] = ldg128(ap + C + 8);
-              } else {
-                a0[j] = ldg128(p.add1 + g_row + (chunk0 + j) * 16);
-                a1[j] = ldg128(p.add1 + g_row + (chunk0 + j) * 16 + 8);
+                l0[j] = ldg128(p.add1 + p.plane_stride + g_row + (chunk0 + j) * 16);
+                l1[j] = ldg128(p.add1 + p.plane_stride + g_row + (chunk0 + j) * 16 + 8);
               }
             }
           }
@@ -626,10 +592,10 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
                         h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
                         hl[i] = pack_bf16x2(v[2 * i] - __uint_as_float(h[i] << 16), v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u));
                       }
-                      stg128(p.out_raw + g2, make_uint4(h[0], h[1], h[2], h[3]));
-                      stg128(p.out_raw + g2 + 8, make_uint4(h[4], h[5], h[6], h[7]));
-                      stg128(p.out_raw + g2 + C, make_uint4(hl[0], hl[1], hl[2], hl[3]));
-                      stg128(p.out_raw + g2 + C + 8, make_uint4(hl[4], hl[5], hl[6], hl[7]));
+                      stg128(p.out_raw + g_off, make_uint4(h[0], h[1], h[2], h[3]));
+                      stg128(p.out_raw + g_off + 8, make_uint4(h[4], h[5], h[6], h[7]));
+                      stg128(p.out_raw + p.plane_stride + g_off, make_uint4(hl[0], hl[1], hl[2], hl[3]));
+                      stg128(p.out_raw + p.plane_stride + g_off + 8, make_uint4(hl[4], hl[5], hl[6], hl[7]));
                     }
                     if (p.out_act) {
 #pragma unroll

@@ -805,7 +805,8 @@ bool rp_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RpPlan*
 int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfloat16* xa, int B, int L,
                  const __nv_bfloat16* add1, __nv_bfloat16* out_raw, __nv_bfloat16* out_act, float* out_f32, float scale,
                  const TCOptions& opt, int* error_flag, cudaStream_t st, bool x3 = false) {
-  // x3: xa / add1 / out_raw / out_act are two-plane tensors [B, L, 2 C] (rows [hi | lo]); out_f32 stays [B, L, C]
+  // x3: xa / add1 / out_raw are PLANAR two-plane tensors [2][B, L, C] (hi plane, then lo plane); out_act has the decoder's
+  // rows [B, L, 2 C] = [hi (C) | lo (C)] per time step; out_f32 stays [B, L, C]
   RpPlan pl;
   if (!rp_plan(rb, C, L, opt, &pl, x3)) return fail(VSG_EUNSUPPORTED, "resblock shape not supported by the row-packed kernel");
   if ((const void*)xa == (const void*)out_raw || (const void*)xa == (const void*)out_act)
@@ -831,6 +832,10 @@ int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   p.tps = pl.tps; p.direct_stages = pl.direct_stages;
   p.mb = pl.mb; p.H = pl.H; p.V = pl.V;
   p.spb = pl.mb >= 3 ? (opt.rp_spb2 ? 2 : 1) : 4 / pl.mb;   // epilogue warp sets per block
+  // x3, two blocks: block 1's drain is exposed (nothing left to issue behind it), so all four sets drain every block
+  static const bool x3_spb2 = getenv("VSG_RP_X3_SPB2") != nullptr;   // A/B aid
+  if (x3 && !x3_spb2) p.spb = 4;
+  p.plane_stride = (long long)B * L * C;
   p.m_tiles_per_b = (L + pl.V - 1) / pl.V;
   p.total_tiles = p.m_tiles_per_b * B;
   p.n_wst = pl.n_wst;
@@ -853,16 +858,14 @@ int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   if (opt.plan_only) return VSG_OK;
   // the input as rows of 64 channels = S time steps: [B, L, C] == [B, L / S, 64]
   CUtensorMap tmA;
-  if (x3) {
-    // two-plane rows [hi (C) | lo (C)] per time step: S time steps = 128 elements per packed row, staged unswizzled in
-    // boxes of 64 rows (the kernel's epilogue warps write the swizzled plane tiles)
-    VSG_TRY(encode_3d(&tmA, xa, 128, (uint64_t)(L / pl.S), (uint64_t)B, 128, (uint64_t)L * 2 * C, 128, 64, 0));
-    maps.add1 = tmA;
-    if (add1) VSG_TRY(encode_3d(&maps.add1, add1, 128, (uint64_t)(L / pl.S), (uint64_t)B, 128, (uint64_t)L * 2 * C, 128, 64, 0));
-  } else {
-    VSG_TRY(encode_3d(&tmA, xa, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
-    maps.add1 = tmA;
-    if (add1) VSG_TRY(encode_3d(&maps.add1, add1, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
+  VSG_TRY(encode_3d(&tmA, xa, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
+  maps.add1 = tmA; maps.a_lo = tmA; maps.add1_lo = tmA;
+  if (add1) VSG_TRY(encode_3d(&maps.add1, add1, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
+  if (x3) {   // the lo planes
+    VSG_TRY(encode_3d(&maps.a_lo, xa + p.plane_stride, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
+    maps.add1_lo = maps.a_lo;
+    if (add1)
+      VSG_TRY(encode_3d(&maps.add1_lo, add1 + p.plane_stride, 64, (uint64_t)(L / pl.S), (uint64_t)B, 64, (uint64_t)L * C, 64, 128, 64));
   }
   using RpFn = void (*)(CUtensorMap, RpMaps, RpTC);
   RpFn fn = x3 ? (C == 16 ? (RpFn)rp_tc_kernel<16, true> : (RpFn)rp_tc_kernel<32, true>)
@@ -1524,31 +1527,6 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       const int nb = std::min(pl.sub[i], B - b0);
       const bf* xin = stage_in + (size_t)b0 * Lin * Cin * np;
       bf* xout = stage_out + (size_t)b0 * L * ch * np;
-      if (opt.merge_ups && !x3 && us.merged_tc.has_tmap && Lout == Lin * us.rate) {   // (split-bf16 planes would interleave wrongly)
-        // ConvTranspose1d (decoder.py:46) as ONE convolution Cin -> rate*Cout over the input rate: its channels-last
-        // output [nb, Lin, rate*Cout] is, byte for byte, the upsampled [nb, Lin*rate, Cout] tensor
-        EpiTC e;
-        e.bias = us.merged_tc.bias;
-        e.out_act = bUA;
-        if (!one_stream_all) e.out_raw = bU;
-        VSG_TRY(launch_conv_tc(P, W(us.merged_tc, us.merged_x3), xin, nb, Lin, us.merged_in_off0, 1, Lin, 1, 0, Lin, e, opt,
-                               err, st));
-      } else {
-        for (int r = 0; r < us.rate; ++r) {   // one strided launch per polyphase
-          EpiTC e;
-          e.bias = us.phases[r].tc.bias;
-          e.out_act = bUA;
-          if (!one_stream_all) e.out_raw = bU;
-          const int Lq = (Lout - r + us.rate - 1) / us.rate;
-          VSG_TRY(launch_conv_tc(P, W(us.phases[r].tc, us.phases[r].x3), xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r,
-                                 Lout, e, opt, err, st));
-        }
-      }
-      // Only leaky_relu(x) is stored for the running stream; the residual x is recovered from it in the consumer's
-      // epilogue (a > 0 ? a : a / slope -- as exact as a second, raw copy at the stream's precision), so the upsampler and
-      // every non-final conv2 write one tensor instead of two.
-      const bool one_stream = one_stream_all;
-      const cudaStream_t st_main = st;
       // C <= 64 stages: every ResBlock1 is ONE kernel (rb_tc.cuh); the three launches of a stage are chained through the
       // running sum, so they stay on the caller's stream (their CTAs own all of tensor memory and cannot co-reside anyway)
       bool rb_stage = c.dec_resblock == 1 && !x3 && opt.fuse_rb && ch <= 64;
@@ -1564,6 +1542,36 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
         RpPlan rp;
         rp_stage = rp_plan(us.blocks[j], ch, L, opt, &rp, x3) && L >= 256;
       }
+      // bf16x3 row-packed stages: the upsampler writes its two planes PLANAR ([2][nb, L, ch]: each plane is then an
+      // ordinary one-plane tensor for the resblock kernel's row-packed tensor map), as is the running resblock sum
+      const bool planar = x3 && rp_stage;
+      const int up_ld = planar ? ch : 0, up_part = planar ? (int)((size_t)nb * L * ch) : 0;
+      if (opt.merge_ups && !x3 && us.merged_tc.has_tmap && Lout == Lin * us.rate) {   // (split-bf16 planes would interleave wrongly)
+        // ConvTranspose1d (decoder.py:46) as ONE convolution Cin -> rate*Cout over the input rate: its channels-last
+        // output [nb, Lin, rate*Cout] is, byte for byte, the upsampled [nb, Lin*rate, Cout] tensor
+        EpiTC e;
+        e.bias = us.merged_tc.bias;
+        e.out_act = bUA;
+        if (!one_stream_all) e.out_raw = bU;
+        VSG_TRY(launch_conv_tc(P, W(us.merged_tc, us.merged_x3), xin, nb, Lin, us.merged_in_off0, 1, Lin, 1, 0, Lin, e, opt,
+                               err, st));
+      } else {
+        for (int r = 0; r < us.rate; ++r) {   // one strided launch per polyphase
+          EpiTC e;
+          e.bias = us.phases[r].tc.bias;
+          e.out_act = bUA;
+          e.ld = up_ld; e.part_stride = up_part;
+          if (!one_stream_all) e.out_raw = bU;
+          const int Lq = (Lout - r + us.rate - 1) / us.rate;
+          VSG_TRY(launch_conv_tc(P, W(us.phases[r].tc, us.phases[r].x3), xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r,
+                                 Lout, e, opt, err, st));
+        }
+      }
+      // Only leaky_relu(x) is stored for the running stream; the residual x is recovered from it in the consumer's
+      // epilogue (a > 0 ? a : a / slope -- as exact as a second, raw copy at the stream's precision), so the upsampler and
+      // every non-final conv2 write one tensor instead of two.
+      const bool one_stream = one_stream_all;
+      const cudaStream_t st_main = st;
       if (rb_stage || rp_stage) {
         for (int j = 0; j < NK; ++j) {        // xs = sum_j resblock_j(x); x = xs / NK (decoder.py:47-54)
           const bool lastj = (j == NK - 1);
