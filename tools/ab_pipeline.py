@@ -1,0 +1,44 @@
+"""A/B the serving loop (HotPath.pipeline) at bench size: one run stream vs two (consecutive requests in flight together).
+    python tools/ab_pipeline.py [--precision bf16]
+Host inputs -> host waveforms, CUDA events around `steps` submissions + flush."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from visinger_b200.configs import VISINGER_FLOW, VISINGER_GENERATOR
+from visinger_b200.models.visinger import HotPath
+
+prec = sys.argv[2] if len(sys.argv) > 2 and sys.argv[1] == "--precision" else "bf16"
+B, T, steps, rounds = 16, 1000, 20, 3
+dev = torch.device("cuda:0")
+hp = HotPath.random_init(VISINGER_FLOW, VISINGER_GENERATOR, dev, precision=prec, seed=0)
+gen = torch.Generator().manual_seed(1)
+mu = torch.randn(B, 192, T, generator=gen).pin_memory()
+logs = (0.3 * torch.randn(B, 192, T, generator=gen) - 1.0).pin_memory()
+noise = torch.randn(B, 192, T, generator=gen).pin_memory()
+mask = torch.ones(B, 1, T).pin_memory()
+g = (0.1 * torch.randn(B, 256, 1, generator=gen)).pin_memory()
+ref = None
+for depth, rs in ((2, 1), (4, 1), (4, 2), (6, 3), (2, 1), (4, 2)):
+    pipe = hp.pipeline(B, T, dev, depth=depth, run_streams=rs)
+    for _ in range(depth + 2):
+        t = pipe.submit(mu, logs, noise, mask, g)
+    w = pipe.result(t).clone()
+    torch.cuda.synchronize()
+    if ref is None:
+        ref = w
+    best = 1e9
+    for r in range(rounds):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            pipe.submit(mu, logs, noise, mask, g)
+        pipe.flush()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / steps)
+    print(f"depth {depth} run_streams {rs}: {best:.3f} ms / step = {B * T * 0.0125 / best * 1e3:.0f} audio-s/s, "
+          f"identical to the first configuration: {bool(torch.equal(w, ref))}", flush=True)
+    del pipe
+    torch.cuda.empty_cache()

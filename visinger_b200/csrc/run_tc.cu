@@ -1380,6 +1380,8 @@ SubBatchPlan plan_sub_batches(const VsgPack* P, int B, int T) {
     long long sub = std::max<long long>(1, ((long long)g_l2_tensor_mb << 20) / (long long)(per_utt * 2));
     if (sub * tiles_per_utt < g_min_tiles) sub = (g_min_tiles + tiles_per_utt - 1) / tiles_per_utt;
     if (g_l2_tensor_mb <= 0 || sub * 2 > B) sub = B;               // not worth splitting
+    static const int only_c = getenv("VSG_L2_ONLY_C") ? atoi(getenv("VSG_L2_ONLY_C")) : 0;   // A/B aid: sub-batch one stage width only
+    if (only_c > 0 && us.Cout != only_c) sub = B;
     pl.sub[i] = (int)std::min<long long>(sub, B);
     pl.inter_elems = std::max(pl.inter_elems, per_utt * (size_t)pl.sub[i]);
     pl.io_elems = std::max(pl.io_elems, per_utt * (size_t)B);

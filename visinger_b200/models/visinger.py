@@ -171,10 +171,10 @@ class HotPath(PackedModuleMixin, nn.Module):
         return cache[key]
 
     @torch.no_grad()
-    def pipeline(self, B: int, T: int, device=None, depth: int = 2) -> "HotPathPipeline":
+    def pipeline(self, B: int, T: int, device=None, depth: int = 2, run_streams: int = 1) -> "HotPathPipeline":
         """Double-buffered serving loop for host-resident requests (see HotPathPipeline)."""
         dev = torch.device(device) if device is not None else next(self.parameters()).device
-        return HotPathPipeline(self, B, T, dev, depth)
+        return HotPathPipeline(self, B, T, dev, depth, run_streams)
 
     def decode(self, z, g):
         """Generator only, through the shared pack (used by bench.py for the decoder roofline)."""
@@ -265,7 +265,10 @@ class HotPathPipeline:
     request's waveform is in its pinned host buffer.  Nothing here is specific to a benchmark: it is the loop a
     synthesis server would run."""
 
-    def __init__(self, hp: "HotPath", B: int, T: int, device: torch.device, depth: int = 2):
+    def __init__(self, hp: "HotPath", B: int, T: int, device: torch.device, depth: int = 2, run_streams: int = 1):
+        # run_streams > 1: consecutive requests replay on alternating streams, so the kernels of two requests are in
+        # flight together (the latency-bound flow launches and the tails of one request's persistent decoder kernels
+        # are filled by the other's CTAs); use depth >= 2 * run_streams so the copies still overlap
         self.device = torch.device(device)
         self.B, self.T, self.depth = B, T, depth
         self.slots = [HotPathGraph(hp, B, T, self.device) for _ in range(depth)]
@@ -273,6 +276,7 @@ class HotPathPipeline:
         self.wav_host = [torch.empty(B, T * hop, dtype=torch.float32).pin_memory() for _ in range(depth)]
         with torch.cuda.device(self.device):
             self.s_up, self.s_run, self.s_down = (torch.cuda.Stream(self.device) for _ in range(3))
+            self.s_runs = [self.s_run] + [torch.cuda.Stream(self.device) for _ in range(max(1, run_streams) - 1)]
         self._ran = [None] * depth       # event: graph of this slot finished
         self._down = [None] * depth      # event: waveform of this slot is in host memory
         self._n = 0
@@ -294,12 +298,13 @@ class HotPathPipeline:
             if g is not None:
                 slot.g.copy_(g, non_blocking=True)
             up = self.s_up.record_event()
-        with torch.cuda.stream(self.s_run):
-            self.s_run.wait_event(up)
+        s_run = self.s_runs[self._n % len(self.s_runs)]
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(up)
             if self._down[s] is not None:
-                self.s_run.wait_event(self._down[s])
+                s_run.wait_event(self._down[s])
             slot.replay()
-            self._ran[s] = self.s_run.record_event()
+            self._ran[s] = s_run.record_event()
         with torch.cuda.stream(self.s_down):
             self.s_down.wait_event(self._ran[s])
             self.wav_host[s].copy_(slot.wav.view(self.B, -1), non_blocking=True)
