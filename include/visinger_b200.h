@@ -335,8 +335,8 @@ int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32
  * L2-resident batch tiling of the decoder (target MB of one intermediate tensor per sub-batch, 0 = no tiling, <0 =
  * keep; minimum tiles per launch, <=0 = keep).
  * halo_mode is a bit field (A/B switches for bench.py and the tests; all off = the shipped configuration, halo_mode = 1):
- *   bit 0 HALO activation tiles | bit 1 bf16x3 mode without the row-packed resblock kernel | bits 4-7 cap on 128-row
- *   blocks per tile | bit 8 no programmatic dependent launch |
+ *   bit 0 HALO activation tiles | bit 1 bf16x3 mode without the row-packed resblock kernel | bit 2 row-packed kernel as
+ *   two CTAs per SM (opt-in, measured equal) | bits 4-7 cap on 128-row blocks per tile | bit 8 no programmatic dependent launch |
  *   bit 9 no fused resblock pairs | bit 10 one launch per upsampler polyphase | bit 11 never split N = 256 tiles |
  *   bit 12 store raw AND activated resblock streams | bit 13 generic epilogue images only |
  *   bit 14 resblock chains of a stage on one stream | bit 15 whole-resblock kernel rb_tc (opt-in) | bits 16-20 cap on

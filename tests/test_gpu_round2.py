@@ -277,11 +277,12 @@ def test_fused_resblock_kernel(cuda_device, C, k, dils, B, L, max_mb):
 
 
 @pytest.mark.parametrize("C,k,dils,B,L,max_mb", RP_CASES)
-@pytest.mark.parametrize("variant", [256, 256 | 512, 256 | 1024])
+@pytest.mark.parametrize("variant", [256, 256 | 512, 256 | 1024, 256 | 4096])
 def test_rowpacked_resblock_kernel(cuda_device, C, k, dils, B, L, max_mb, variant):
     """Row-packed whole ResBlock1 (rp_tc.cuh), with the dilation-1 convolutions in the block-Toeplitz form (256) and with
     every convolution tap by tap (256 | 512), and with two epilogue warp sets sharing a block, each set
-    draining two blocks (256 | 1024; opt-in, measured slower): same checks as the per-row kernel."""
+    draining two blocks (256 | 1024; opt-in, measured slower), and as two CTAs per SM with 8 epilogue warps, 2-block tiles
+    and the weight ring streamed per block (256 | 4096): same checks as the per-row kernel."""
     _run_resblock_case(cuda_device, C, k, dils, B, L, max_mb, variant)
 
 

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--max-mb", type=int, default=0)
     ap.add_argument("--spb2", type=int, default=0, help="1: row-packed kernel with two epilogue warp sets per block (two blocks per set)")
     ap.add_argument("--x3", type=int, default=0, help="1: the row-packed kernel's split-bf16 instantiation (bf16x3 mode; needs --rp 1)")
+    ap.add_argument("--two-cta", type=int, default=0, help="1: row-packed kernel as two CTAs per SM (8 epilogue warps, 2-block tiles)")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--frames", type=int, default=1000)
     args = ap.parse_args()
@@ -45,7 +46,7 @@ def main():
             add1 = torch.randn(args.batch, L, C, generator=gen)
             add1 = (_lib.split_bf16(add1) if args.x3 else add1.to(torch.bfloat16)).to(dev).contiguous()
             out, raw, act, ms = _lib.debug_resblock_bf16(xa, ws, bs, dils, add1=add1, scale=1 / 3, max_mb=args.max_mb,
-                                                         sets=args.sets | (args.issuers << 4) | (256 if args.rp else 0) | (512 if args.rp == 2 else 0) | (1024 if args.spb2 else 0) | (2048 if args.x3 else 0), want_raw=False, want_f32=False, reps=args.reps)
+                                                         sets=args.sets | (args.issuers << 4) | (256 if args.rp else 0) | (512 if args.rp == 2 else 0) | (1024 if args.spb2 else 0) | (2048 if args.x3 else 0) | (4096 if args.two_cta else 0), want_raw=False, want_f32=False, reps=args.reps)
             mb = args.max_mb or (2 if args.x3 else 512 // (2 * C))
             H = (k - 1) // 2 * 12
             V = 128 * mb - 2 * H

@@ -107,8 +107,10 @@ constexpr int kRpThreads = (4 + kRpEpiWarps) * 32;                // 640
 
 }  // namespace tc
 
-template <int C, bool X3 = false>
-__global__ void __launch_bounds__(tc::kRpThreads, 1)
+// NSETS = 2: the two-CTAs-per-SM form -- 8 epilogue warps, tiles of <= 2 blocks (256 accumulator columns), weights
+// streamed per block like X3: two independent hand-over chains share an SM's tensor pipe and fill each other's bubbles.
+template <int C, bool X3 = false, int NSETS = 4>
+__global__ void __launch_bounds__((4 + 4 * NSETS) * 32, NSETS == 2 ? 2 : 1)
 rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ RpMaps wm, const RpTC p) {
   using namespace tc;
   constexpr int S = 64 / C;                      // time steps per 128-byte row
@@ -118,6 +120,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
   constexpr uint32_t kTapBytes = X3 ? 2 * kSlotBytes : kSlotBytes;      // X3: [W_hi tile | W_lo tile] per tap
   constexpr uint32_t kStageBytes = X3 ? 2 * kRpStageBytes : kRpStageBytes;   // X3: [W_hi 8 KB | W_lo 8 KB]
   constexpr int NPL = X3 ? 2 : 1;                // bf16 planes per activation tile
+  constexpr bool STREAM = X3 || NSETS == 2;      // the weight ring is streamed per block (not held for a whole convolution)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -213,9 +216,9 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
       for (int c = 0; c < n_convs; ++c) {
         const bool packed = (p.packed_mask >> c) & 1u;
         const int ns = packed ? p.packed_stages : p.direct_stages;
-        const int n_pass = X3 ? mb : 1;                            // X3: the ring is streamed once per block
+        const int n_pass = STREAM ? mb : 1;                        // STREAM: the ring is streamed once per block
         for (int ii = 0; ii < ns * n_pass; ++ii) {
-          const int i = X3 ? ii % ns : ii;
+          const int i = STREAM ? ii % ns : ii;
           mbar_wait(bar(kRpBarWEmpty + (int)st), ((eph >> st) & 1u) ^ 1u, error_flag);
           eph ^= 1u << st;
           const uint32_t dst = w_base + st * kStageBytes;
@@ -308,14 +311,14 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
             if (b + 1 < mb) mbar_wait(bar_prev + 8u * (b + 1), prev_par, error_flag);
           }
           fence_after_sync();
-          if (!X3) st = ws0;                                       // (X3: the ring is streamed per block and just runs on)
+          if (!STREAM) st = ws0;                                   // (STREAM: the ring is streamed per block and just runs on)
           if (packed) {
             // K slice m = 0 .. n_k - 1: input sub-step -cen + m / KK, channels 16 (m % KK) ..; consecutive slices are
             // consecutive 32-byte pieces of the row-packed tile and of the stage's [64 x 64] SWIZZLE_128B weight tile
             uint32_t a_lo = blk_lo;
             uint32_t accumulate = acc0;
             for (int g = 0; g < full_groups; ++g) {
-              if (X3 || b == 0) {
+              if (STREAM || b == 0) {
                 mbar_wait(bar_wfull + 8u * st, (wph >> st) & 1u, error_flag);
                 wph ^= 1u << st;
                 fence_after_sync();
@@ -325,13 +328,13 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
               for (int u = 0; u < 4; ++u) mma_row(d_tmem, a_lo + 2u * u, b_lo + 2u * u, u > 0 ? 1u : accumulate);
               accumulate = 1u;
               a_lo += 8u;
-              if (X3 || b == mb - 1) {
+              if (STREAM || b == mb - 1) {
                 if (elect_one()) umma_commit(bar_wempty + 8u * st);
               }
               st = (st + 1 == (uint32_t)n_wst) ? 0u : st + 1;
             }
             if (tail) {
-              if (X3 || b == 0) {
+              if (STREAM || b == 0) {
                 mbar_wait(bar_wfull + 8u * st, (wph >> st) & 1u, error_flag);
                 wph ^= 1u << st;
                 fence_after_sync();
@@ -340,15 +343,15 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
               mma_row(d_tmem, a_lo, b_lo, accumulate);
               if (tail > 1) mma_row(d_tmem, a_lo + 2u, b_lo + 2u, 1u);
               if (tail > 2) mma_row(d_tmem, a_lo + 4u, b_lo + 4u, 1u);
-              if (X3 || b == mb - 1) {
+              if (STREAM || b == mb - 1) {
                 if (elect_one()) umma_commit(bar_wempty + 8u * st);
               }
-              if (X3) st = (st + 1 == (uint32_t)n_wst) ? 0u : st + 1;
+              if (STREAM) st = (st + 1 == (uint32_t)n_wst) ? 0u : st + 1;
             }
           } else {
             int slot = 0;
             for (int j = 0; j < k; ++j) {
-              if ((X3 || b == 0) && slot == 0) {
+              if ((STREAM || b == 0) && slot == 0) {
                 mbar_wait(bar_wfull + 8u * st, (wph >> st) & 1u, error_flag);
                 wph ^= 1u << st;
                 fence_after_sync();
@@ -363,7 +366,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
                           (j > 0 || kk > 0) ? 1u : acc0);
               }
               if (slot == tps - 1 || j == k - 1) {
-                if (X3 || b == mb - 1) {
+                if (STREAM || b == mb - 1) {
                   if (elect_one()) umma_commit(bar_wempty + 8u * st);
                 }
                 st = (st + 1 == (uint32_t)n_wst) ? 0u : st + 1;
@@ -377,7 +380,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
           blk_lo += blk16;
           d_tmem += 64u;
         }
-        if (X3) {
+        if (STREAM) {
           ws0 = st;
         } else {
           ws0 += ns;
@@ -398,7 +401,7 @@ rp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Rp
     // previous convolution before it may start block b.
     const int set = (warp - 4) >> 2, quarter = warp & 3;
     const int spb = p.spb;                                       // sets per block
-    const int n_slots = 4 / spb;                                 // blocks drained concurrently
+    const int n_slots = NSETS / spb;                             // blocks drained concurrently
     const int slot = set / spb;                                  // my blocks: slot, slot + n_slots, ...
     const int nch = 4 / spb;                                     // my 16-column chunks: chunk0 .. chunk0 + nch - 1
     const int chunk0 = (set % spb) * nch;

@@ -130,6 +130,7 @@ struct TCOptions {
   int rp_max_c = 32;        // widest stage the row-packed kernel takes
   int rp_packed = 1;        // dilation-1 convolutions in the block-Toeplitz form (0: every conv tap by tap)
   int rp_max_mb = 0;        // cap on 128-row blocks per row-packed tile (0 = as many as fit)
+  int rp_two_cta = 0;       // row-packed kernel, plain bf16: two CTAs per SM (8 epilogue warps, 2-block tiles, streamed ring); bit 2
   int rp_x3 = 1;            // bf16x3 mode: the row-packed kernel's split-bf16 instantiation for the C <= 32 stages (bit 1: off)
   int rp_spb2 = 0;          // row-packed kernel, 3- / 4-block tiles: two epilogue warp sets per block, two blocks per set
                             // (measured slower: 314 / 415 / 513 us vs 289 / 386 / 491 at C = 32 -- the per-block hand-over, not the
@@ -738,6 +739,7 @@ int launch_rb_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
 
 // ---- row-packed whole ResBlock1 (rp_tc.cuh) ------------------------------------------------------------------------
 struct RpPlan {
+  bool two_cta;
   int S, mb, H, V, n_k, packed_stages, tps, direct_stages, n_wst;
   uint32_t packed_mask, margin_bytes, buf_bytes;
   size_t smem;
@@ -779,7 +781,10 @@ bool rp_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RpPlan*
   int need = 0;
   for (int c = 0; c < 2 * nd; ++c) need = std::max(need, ((p.packed_mask >> c) & 1u) ? p.packed_stages : p.direct_stages);
   // (x3: the epilogue's register budget is sized for <= 2 column chunks per thread, i.e. tiles of <= 2 blocks)
-  const int mb_cap = x3 ? 2 : kRpMaxBlocks;
+  const bool two_cta = opt.rp_two_cta && !x3 && C <= 32;
+  const bool stream = x3 || two_cta;
+  const size_t smem_max = two_cta ? (kSmemMax - 2048) / 2 : kSmemMax;
+  const int mb_cap = stream ? 2 : kRpMaxBlocks;
   const int mb_max = opt.rp_max_mb > 0 ? std::min(opt.rp_max_mb, mb_cap) : mb_cap;
   const size_t stage_bytes = x3 ? 2 * kRpStageBytes : kRpStageBytes;
   for (int mb = mb_max; mb >= 1; --mb) {
@@ -788,12 +793,13 @@ bool rp_plan(const ResBlockPack& rb, int C, int L, const TCOptions& opt, RpPlan*
     p.mb = mb; p.V = V;
     p.buf_bytes = 2 * p.margin_bytes + 16384u * (uint32_t)mb;
     const size_t fixed = (x3 ? 4 : 2) * (size_t)p.buf_bytes + 8 * tc::kRpNumBars + 64 + kRpMaxConvs * 64 * sizeof(float) + 1024;
-    // x3 streams the ring once per block (two stages are enough to run; more is prefetch depth)
-    if (fixed + (size_t)(x3 ? std::min(need, 2) : need) * stage_bytes > kSmemMax) continue;
+    // x3 / two CTAs stream the ring once per block (two stages are enough to run; more is prefetch depth)
+    if (fixed + (size_t)(stream ? std::min(need, 2) : need) * stage_bytes > smem_max) continue;
     // a convolution's stages are released by its last block: twice the largest need keeps a whole convolution of prefetch
-    p.n_wst = (int)std::min<size_t>({(size_t)kRpMaxWStages, (size_t)2 * need, (kSmemMax - fixed) / stage_bytes});
+    p.n_wst = (int)std::min<size_t>({(size_t)kRpMaxWStages, (size_t)2 * need, (smem_max - fixed) / stage_bytes});
     p.smem = fixed + (size_t)p.n_wst * stage_bytes;
     if (mb > 1 && 128 * p.S * (mb - 1) - 2 * p.H >= L) continue;   // a smaller tile covers the utterance
+    p.two_cta = two_cta;
     *out = p;
     return true;
   }
@@ -832,6 +838,7 @@ int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   p.tps = pl.tps; p.direct_stages = pl.direct_stages;
   p.mb = pl.mb; p.H = pl.H; p.V = pl.V;
   p.spb = pl.mb >= 3 ? (opt.rp_spb2 ? 2 : 1) : 4 / pl.mb;   // epilogue warp sets per block
+  if (pl.two_cta) p.spb = 2 / pl.mb;                        // (two epilogue sets per CTA)
   // x3, two blocks: block 1's drain is exposed (nothing left to issue behind it), so all four sets drain every block
   static const bool x3_spb2 = getenv("VSG_RP_X3_SPB2") != nullptr;   // A/B aid
   if (x3 && !x3_spb2) p.spb = 4;
@@ -869,12 +876,13 @@ int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   }
   using RpFn = void (*)(CUtensorMap, RpMaps, RpTC);
   RpFn fn = x3 ? (C == 16 ? (RpFn)rp_tc_kernel<16, true> : (RpFn)rp_tc_kernel<32, true>)
+               : pl.two_cta ? (C == 16 ? (RpFn)rp_tc_kernel<16, false, 2> : (RpFn)rp_tc_kernel<32, false, 2>)
                : (C == 16 ? (RpFn)rp_tc_kernel<16> : C == 32 ? (RpFn)rp_tc_kernel<32> : (RpFn)rp_tc_kernel<64>);
   static bool rp_attr_set_dev[64] = {false};
   bool& attr_set = rp_attr_set_dev[P->device & 63];
   if (!attr_set) {
     for (RpFn f : {(RpFn)rp_tc_kernel<16>, (RpFn)rp_tc_kernel<32>, (RpFn)rp_tc_kernel<64>, (RpFn)rp_tc_kernel<16, true>,
-                   (RpFn)rp_tc_kernel<32, true>})
+                   (RpFn)rp_tc_kernel<32, true>, (RpFn)rp_tc_kernel<16, false, 2>, (RpFn)rp_tc_kernel<32, false, 2>})
       VSG_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     attr_set = true;
   }
@@ -883,8 +891,8 @@ int launch_rp_tc(const VsgPack* P, const ResBlockPack& rb, int C, const __nv_bfl
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.gridDim = dim3(std::min(p.total_tiles, P->sm_count));
-  cfg.blockDim = dim3(tc::kRpThreads);
+  cfg.gridDim = dim3(std::min(p.total_tiles, (pl.two_cta ? 2 : 1) * P->sm_count));
+  cfg.blockDim = dim3(pl.two_cta ? (4 + 4 * 2) * 32 : tc::kRpThreads);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = st;
   cfg.attrs = attr;
@@ -1539,7 +1547,9 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       static const int rp_max_c_env = getenv("VSG_RP_MAX_C") ? atoi(getenv("VSG_RP_MAX_C")) : -1;   // A/B aid
       const int rp_max_c = rp_max_c_env >= 0 ? rp_max_c_env : opt.rp_max_c;
       // (bf16x3: the kernel's split-bf16 instantiation; it reads the single activated stream)
-      bool rp_stage = c.dec_resblock == 1 && (x3 ? (opt.rp_x3 && one_stream_all) : true) && opt.fuse_rp && ch <= rp_max_c;
+      // (its planar planes are addressed through the conv kernel's int part_stride: nb * L * ch must fit)
+      bool rp_stage = c.dec_resblock == 1 && (x3 ? (opt.rp_x3 && one_stream_all && (size_t)nb * L * ch < ((size_t)1 << 31)) : true) &&
+                      opt.fuse_rp && ch <= rp_max_c;
       for (int j = 0; j < NK && rp_stage; ++j) {
         RpPlan rp;
         rp_stage = rp_plan(us.blocks[j], ch, L, opt, &rp, x3) && L >= 256;
@@ -1892,6 +1902,7 @@ extern "C" int vsg_debug_resblock_bf16(const void* xa_bf16, const float* w, cons
     opt.rp_max_mb = max_mb;
     opt.rp_packed = (sets & 512) ? 0 : 1;
     opt.rp_spb2 = (sets & 1024) ? 1 : 0;              // bit 10: two epilogue warp sets per block, two blocks per set
+    opt.rp_two_cta = (sets & 4096) ? 1 : 0;           // bit 12: the two-CTAs-per-SM form (8 epilogue warps, 2-block tiles)
     uint32_t* d_trace = nullptr;
     if (row_packed && getenv("VSG_RP_TRACE")) {
       cudaMalloc(&d_trace, 5 * 1024 * sizeof(uint32_t));
@@ -1974,6 +1985,7 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.fuse_rp = (halo_mode & (1 << 24)) ? 0 : 1;                         // bit 24: no row-packed resblock kernel
   g_default_opts.rp_max_c = (halo_mode & (1 << 25)) ? 64 : 32;                      // bit 25: row-packed kernel at C = 64 too
   g_default_opts.rp_packed = (halo_mode & (1 << 26)) ? 0 : 1;                       // bit 26: no block-Toeplitz form
+  g_default_opts.rp_two_cta = (halo_mode & 4) ? 1 : 0;                              // bit 2: row-packed kernel as two CTAs per SM
   g_default_opts.rp_x3 = (halo_mode & 2) ? 0 : 1;                                   // bit 1: bf16x3 mode without the row-packed resblock kernel
   g_default_opts.rp_spb2 = (halo_mode & (1 << 30)) ? 1 : 0;                         // bit 30: row-packed kernel, two epilogue sets per block
   g_default_opts.flow_merge = ((uint32_t)halo_mode & (1u << 31)) ? 0 : 1;           // bit 31: flow with separate res / skip / cond launches
