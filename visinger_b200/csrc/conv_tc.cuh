@@ -59,7 +59,6 @@ struct ConvTC {
   int mb;                       // 128-row blocks per tile
   int tile_stride;              // rows between consecutive tiles (128*mb, or less when a fused pair discards its halo rows)
   int m_tiles_per_b, total_tiles;
-  int rev_B;                    // > 0 (= B): walk the tiles backwards (TileIter)
   int bar_slot0, tmem_col0;     // barrier bank / TMEM column offset of this half (fused pair: second conv uses bank 1)
   uint32_t a_off;               // start of the A ring inside shared memory (0 for the plain kernel)
   int t_row_off;                // fused pair: time of row 0 of the intermediate tile relative to the tile's first output row
@@ -293,25 +292,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // per-tile integer divisions: the stride is decomposed once, then advanced with carries.
 struct TileIter {
   int nt, mt, b, s_nt, s_mt, s_b, n_ntiles, m_tiles;
-  int wmt, wb, fm, fb;   // walking state; fm / fb >= 0: reversed order (mt = fm - wmt, b = fb - wb)
-  // rev_B > 0: walk the tiles from the LAST utterance's last m-tile backwards (launches that read what the previous
-  // launch wrote last find it in L2: see the serpentine order of generator_forward_tc)
-  __device__ __forceinline__ void init(int tile0, int step, int n_ntiles_, int m_tiles_, int rev_B = 0) {
+  __device__ __forceinline__ void init(int tile0, int step, int n_ntiles_, int m_tiles_) {
     n_ntiles = n_ntiles_; m_tiles = m_tiles_;
-    nt = tile0 % n_ntiles; wmt = (tile0 / n_ntiles) % m_tiles; wb = tile0 / (n_ntiles * m_tiles);
+    nt = tile0 % n_ntiles; mt = (tile0 / n_ntiles) % m_tiles; b = tile0 / (n_ntiles * m_tiles);
     s_nt = step % n_ntiles; s_mt = (step / n_ntiles) % m_tiles; s_b = step / (n_ntiles * m_tiles);
-    fm = rev_B > 0 ? m_tiles - 1 : -1; fb = rev_B > 0 ? rev_B - 1 : -1;
-    mt = fm >= 0 ? fm - wmt : wmt; b = fb >= 0 ? fb - wb : wb;
   }
   __device__ __forceinline__ void next() {
     nt += s_nt;
     int c = nt >= n_ntiles ? 1 : 0;
     nt -= c ? n_ntiles : 0;
-    wmt += s_mt + c;
-    c = wmt >= m_tiles ? 1 : 0;
-    wmt -= c ? m_tiles : 0;
-    wb += s_b + c;
-    mt = fm >= 0 ? fm - wmt : wmt; b = fb >= 0 ? fb - wb : wb;
+    mt += s_mt + c;
+    c = mt >= m_tiles ? 1 : 0;
+    mt -= c ? m_tiles : 0;
+    b += s_b + c;
   }
 };
 
@@ -456,7 +449,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
 
   // add-operand prefetch cursor (leader only): walks (tile, chunk) units n_add_bufs-1 ahead of the consumers
   TileIter pf;
-  pf.init((int)blockIdx.x, (int)gridDim.x, n_ntiles, m_tiles_per_b, p.rev_B);
+  pf.init((int)blockIdx.x, (int)gridDim.x, n_ntiles, m_tiles_per_b);
   int pf_cc = 0, pf_buf = 0, pf_left = my_tiles * n_echunks;
   auto issue_next_add = [&]() {
     if (pf_left <= 0) return;
@@ -495,7 +488,7 @@ __device__ __forceinline__ void conv_tc_epilogue(const CUtensorMap& tmAdd0, cons
   int as = 0, add_buf = 0;
   uint32_t pacc = 0, add_phase = 0, out_count = 0;
   TileIter it;
-  it.init((int)blockIdx.x, (int)gridDim.x, n_ntiles, m_tiles_per_b, p.rev_B);
+  it.init((int)blockIdx.x, (int)gridDim.x, n_ntiles, m_tiles_per_b);
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next()) {
     const int nt = it.nt, b = it.b;
     const int tile_row0 = it.mt * tile_stride;
@@ -843,7 +836,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int sa = 0, sw = 0;
       uint32_t pa = 0, pw = 0;
       TileIter it;
-      it.init((int)blockIdx.x, (int)gridDim.x, p.n_ntiles, p.m_tiles_per_b, p.rev_B);
+      it.init((int)blockIdx.x, (int)gridDim.x, p.n_ntiles, p.m_tiles_per_b);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it.next()) {
         const int nt = it.nt, mt = it.mt, b = it.b;
         const int row0 = mt * p.tile_stride + p.in_off0;

@@ -107,7 +107,6 @@ struct EpiTC {
   __nv_bfloat16* out_act = nullptr;
   float* out_f32 = nullptr;
   int tanh_cols = 0;                // EPI_TC_TANH: samples per row written to out_f32
-  int reverse = 0;                  // walk the tiles from the end of the batch backwards (serpentine launch order)
 };
 
 // HALO mode verified on B200 (tools/tc_probe.py): the UMMA unit applies the swizzle XOR to absolute
@@ -131,7 +130,6 @@ struct TCOptions {
   int rp_max_c = 32;        // widest stage the row-packed kernel takes
   int rp_packed = 1;        // dilation-1 convolutions in the block-Toeplitz form (0: every conv tap by tap)
   int rp_max_mb = 0;        // cap on 128-row blocks per row-packed tile (0 = as many as fit)
-  int serpentine = 0;       // decoder, per-convolution ResBlock1 stages: every conv2 walks its tiles backwards (bit 3)
   int rp_two_cta = 0;       // row-packed kernel, plain bf16: two CTAs per SM (8 epilogue warps, 2-block tiles, streamed ring); bit 2
   int rp_x3 = 1;            // bf16x3 mode: the row-packed kernel's split-bf16 instantiation for the C <= 32 stages (bit 1: off)
   int rp_spb2 = 0;          // row-packed kernel, 3- / 4-block tiles: two epilogue warp sets per block, two blocks per set
@@ -355,7 +353,6 @@ int launch_conv_tc(const VsgPack* P, const ConvWTC& w, const __nv_bfloat16* x, i
   p.tile_stride = 128 * p.mb;
   p.m_tiles_per_b = (Lq + p.tile_stride - 1) / p.tile_stride;
   p.total_tiles = p.m_tiles_per_b * p.n_ntiles * B;
-  p.rev_B = e.reverse ? B : 0;
   p.e_swz_mask = cw >= 64 ? 7u : cw >= 32 ? 3u : 1u;
   p.e_out_swz_mask = ow >= 64 ? 7u : ow >= 32 ? 3u : ow >= 16 ? 1u : 0u;
   p.mode = e.mode; p.mask = e.mask; p.couple_sign = e.couple_sign;
@@ -1656,10 +1653,6 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
             e1.bias = rb.c1_tc[q].bias; e1.out_act = tmp;
             VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
             e2.bias = rb.c2_tc[q].bias;
-            // serpentine order: conv1 wrote the END of its output last, so conv2 starts there (L2 hits instead of the
-            // LRU thrash of two forward sweeps over a tensor larger than L2); the next conv1 then finds conv2's last-written
-            // tiles -- the beginning -- in L2 too
-            e2.reverse = opt.serpentine;
             if (!last) { e2.out_act = nra; if (!one_stream) e2.out_raw = nr; }
             if (sum_wait) VSG_CUDA_TRY(cudaStreamWaitEvent(st, cs->sum_done[j - 1], 0));
             VSG_TRY(launch_conv_tc(P, W(rb.c2_tc[q], rb.c2_x3[q]), tmp, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
@@ -1992,7 +1985,6 @@ extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t
   g_default_opts.fuse_rp = (halo_mode & (1 << 24)) ? 0 : 1;                         // bit 24: no row-packed resblock kernel
   g_default_opts.rp_max_c = (halo_mode & (1 << 25)) ? 64 : 32;                      // bit 25: row-packed kernel at C = 64 too
   g_default_opts.rp_packed = (halo_mode & (1 << 26)) ? 0 : 1;                       // bit 26: no block-Toeplitz form
-  g_default_opts.serpentine = (halo_mode & 8) ? 1 : 0;                              // bit 3: serpentine tile order (conv2 launches run backwards)
   g_default_opts.rp_two_cta = (halo_mode & 4) ? 1 : 0;                              // bit 2: row-packed kernel as two CTAs per SM
   g_default_opts.rp_x3 = (halo_mode & 2) ? 0 : 1;                                   // bit 1: bf16x3 mode without the row-packed resblock kernel
   g_default_opts.rp_spb2 = (halo_mode & (1 << 30)) ? 1 : 0;                         // bit 30: row-packed kernel, two epilogue sets per block
