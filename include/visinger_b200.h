@@ -331,6 +331,14 @@ float vsg_debug_last_ms(void);
 int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t B, int32_t L, int32_t n_adds,
                    int32_t n_outs, int32_t x3);
 
+/* Host-only (no GPU): the tile plan of the row-packed whole-ResBlock1 kernel for one resblock shape -- C channels, k taps,
+ * n_pairs (conv1, conv2) pairs with the given dilations, L time steps per utterance.  variant: 0 plain bf16, 1 split-bf16
+ * (bf16x3 mode), 2 plain bf16 as two CTAs per SM.  out[8] = { 128-row blocks per tile, halo time steps per side, valid
+ * time steps per tile, weight-ring stages, dynamic shared memory in bytes, mask of the convolutions in the block-Toeplitz
+ * form, tiles per utterance, tensor-memory columns }.  VSG_EUNSUPPORTED: the shape runs on the per-convolution kernels. */
+int vsg_debug_rp_plan(int32_t C, int32_t k, int32_t n_pairs, const int32_t* dilations, int32_t L, int32_t variant,
+                      int32_t* out);
+
 /* Process-wide tuning defaults of the tensor-core path: activation-operand feeding mode, resident weights, and the
  * L2-resident batch tiling of the decoder (target MB of one intermediate tensor per sub-batch, 0 = no tiling, <0 =
  * keep; minimum tiles per launch, <=0 = keep).

@@ -97,3 +97,39 @@ def test_three_plane_plans_exist_for_every_flow_convolution():
             for B, T in ((16, 1000), (1, 1), (3, 130)):
                 rc = L.vsg_debug_plan(cin, cout, k, 1, B, T, n_adds, 1, planes_code)
                 assert rc == 0, (planes_code, cin, cout, k, _lib.last_error_message() if hasattr(_lib, "last_error_message") else rc)
+
+
+def test_rowpacked_resblock_plans():
+    """Host-only planner of the row-packed whole-ResBlock1 kernel (csrc/run_tc.cu::rp_plan): at the model's C = 32 / C = 16
+    stages (decoder.py:91-104 with kernel sizes 3 / 7 / 11, dilations 1 / 3 / 5) every variant must fit its shared-memory
+    and tensor-memory budget, cover an utterance with whole tiles, and recompute exactly the halo the six convolutions reach;
+    shapes the kernel does not take must be refused, not mis-planned."""
+    import ctypes
+    from visinger_b200 import _lib
+    L = _lib.lib()
+    L.vsg_debug_rp_plan.argtypes = [ctypes.c_int32] * 3 + [ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int32,
+                                                            ctypes.POINTER(ctypes.c_int32)]
+    L.vsg_debug_rp_plan.restype = ctypes.c_int
+    dil = (ctypes.c_int32 * 3)(1, 3, 5)
+    out = (ctypes.c_int32 * 8)()
+    smem_max = 227 * 1024
+    for C, rate in ((32, 150), (16, 300)):
+        S = 64 // C
+        for k in (3, 7, 11):
+            for T in (1000, 37, 2):
+                Lx = rate * T
+                for variant in (0, 1, 2):
+                    rc = L.vsg_debug_rp_plan(C, k, 3, dil, Lx, variant, out)
+                    assert rc == 0, (C, k, T, variant)
+                    mb, H, V, ring, smem, packed, tiles, tmem = list(out)
+                    halo = (k - 1) // 2 * (1 + 1 + 3 + 1 + 5 + 1)
+                    assert H == (halo + S - 1) // S * S and V == 128 * S * mb - 2 * H and V > 0
+                    assert tiles * V >= Lx and (tiles - 1) * V < Lx
+                    assert 1 <= mb <= (4 if variant == 0 else 2) and ring >= 2
+                    assert smem <= (smem_max if variant < 2 else (smem_max - 2048) // 2)
+                    assert tmem >= 2 * 64 * mb and tmem <= (512 if variant < 2 else 256)
+                    assert packed == 0b101011          # conv1 of the dilation-1 pair and every conv2 in the Toeplitz form
+    # refused: an odd number of time steps at C = 32 (rows hold two), even kernel sizes, C = 64 in the split-bf16 form
+    assert L.vsg_debug_rp_plan(32, 3, 3, dil, 301, 0, out) != 0
+    assert L.vsg_debug_rp_plan(16, 4, 3, dil, 3000, 0, out) != 0
+    assert L.vsg_debug_rp_plan(64, 3, 3, dil, 3000, 1, out) != 0

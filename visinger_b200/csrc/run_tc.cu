@@ -1966,6 +1966,38 @@ extern "C" int vsg_debug_plan(int32_t Cin, int32_t Cout, int32_t k, int32_t dila
   return launch_conv_tc(&tmp, wt, &dummy_in, B, L, -((k - 1) * dilation / 2), dilation, L, 1, 0, L, e, opt, nullptr, 0);
 }
 
+// Host-only: the tile plan of the row-packed whole-ResBlock1 kernel (rp_tc.cuh) for one resblock shape; no GPU needed.
+//   variant: 0 plain bf16, 1 split-bf16 (bf16x3 mode), 2 plain bf16 as two CTAs per SM
+//   out[8]: mb, H, V, ring stages, dynamic shared memory (bytes), packed mask, tiles per utterance, accumulator columns
+// Returns VSG_EUNSUPPORTED when the kernel does not take the shape (the caller then runs the per-convolution kernels).
+extern "C" int vsg_debug_rp_plan(int32_t C, int32_t k, int32_t n_pairs, const int32_t* dilations, int32_t L, int32_t variant,
+                                 int32_t* out) {
+  if (!dilations || !out || n_pairs < 1 || n_pairs > VSG_MAX_RESBLOCK_DILATIONS) return fail(VSG_EINVAL, "bad argument");
+  const bool x3 = variant == 1;
+  ResBlockPack rb;
+  rb.kernel = k;
+  rb.dilations.assign(dilations, dilations + n_pairs);
+  ConvWTC w;                                  // what pack_conv_tc / pack_conv_rowpacked would record for this shape
+  w.Cin = C; w.Cout = C; w.CinT = (x3 ? 2 : 1) * C; w.CoutT = C; w.ktaps = k; w.has_tmap = true; w.x3 = x3; w.planes = x3 ? 2 : 1;
+  ConvWTC wp = w;
+  wp.has_tmap = (C == 16 || C == 32) && (k % 2 == 1);
+  rb.c1_tc.assign(n_pairs, w); rb.c2_tc.assign(n_pairs, w);
+  rb.c1_x3.assign(n_pairs, w); rb.c2_x3.assign(n_pairs, w);
+  rb.c1_rp.assign(n_pairs, wp); rb.c2_rp.assign(n_pairs, wp);
+  rb.c1_rp_x3.assign(n_pairs, wp); rb.c2_rp_x3.assign(n_pairs, wp);
+  if (x3) for (auto* v : {&rb.c1_tc, &rb.c2_tc}) for (auto& e : *v) { e.x3 = false; e.planes = 1; e.CinT = C; }
+  rb.c2_bsum.assign(n_pairs, nullptr);
+  TCOptions opt = g_default_opts;
+  opt.rp_two_cta = variant == 2 ? 1 : 0;
+  RpPlan pl;
+  if (!rp_plan(rb, C, L, opt, &pl, x3)) return fail(VSG_EUNSUPPORTED, "resblock shape not supported by the row-packed kernel");
+  uint32_t tmem = 32;
+  while (tmem < (uint32_t)(2 * pl.mb * 64)) tmem <<= 1;
+  out[0] = pl.mb; out[1] = pl.H; out[2] = pl.V; out[3] = pl.n_wst; out[4] = (int32_t)pl.smem; out[5] = (int32_t)pl.packed_mask;
+  out[6] = (L + pl.V - 1) / pl.V; out[7] = (int32_t)tmem;
+  return VSG_OK;
+}
+
 // Select the default A-operand feeding mode of the tensor-core convolutions (process-wide; tests and tuning).
 extern "C" int vsg_set_tc_options(int32_t halo_mode, int32_t w_resident, int32_t l2_tensor_mb, int32_t min_tiles) {
   g_default_opts.halo_mode = halo_mode & 1;
