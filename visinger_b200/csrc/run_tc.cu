@@ -1596,7 +1596,10 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
         }
         continue;
       }
-      if (chains) {   // fork: the other chains start once the upsampled input is complete
+      // A/B aid: VSG_CHAIN_MIN_C = narrowest stage whose resblock chains run on separate streams (read per call)
+      const char* cmc = getenv("VSG_CHAIN_MIN_C");
+      const bool chains_st = chains && (!cmc || ch >= atoi(cmc));
+      if (chains_st) {   // fork: the other chains start once the upsampled input is complete
         VSG_CUDA_TRY(cudaEventRecord(cs->fork, st_main));
         for (int j = 1; j < NK; ++j) VSG_CUDA_TRY(cudaStreamWaitEvent(cs->s[j - 1], cs->fork, 0));
       }
@@ -1607,14 +1610,14 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
         const ResBlockPack& rb = us.blocks[j];
         const int nd = (int)rb.dilations.size(), k = rb.kernel;
         const bf* cur = one_stream ? bUA : bU; const bf* curA = bUA;
-        const int cj = chains ? j : 0;
+        const int cj = chains_st ? j : 0;
         bf *bR = cR[cj], *bRA = cRA[cj], *bT = cT[cj], *bTA = cTA[cj];
-        if (chains) st = j == 0 ? st_main : cs->s[j - 1];
+        if (chains_st) st = j == 0 ? st_main : cs->s[j - 1];
         for (int q = 0; q < nd; ++q) {
           const bool last = (q == nd - 1);
           const int d = rb.dilations[q];
           // the running sum is read-modify-written by the last conv of every chain, in chain order
-          const bool sum_wait = chains && last && j > 0;
+          const bool sum_wait = chains_st && last && j > 0;
           EpiTC e2;
           e2.add0 = cur;
           e2.add0_is_act = one_stream ? 1 : 0;
@@ -1667,12 +1670,12 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
             cur = one_stream ? nra : nr; curA = nra;
           }
         }
-        if (chains && j < NK - 1) VSG_CUDA_TRY(cudaEventRecord(cs->sum_done[j], st));
+        if (chains_st && j < NK - 1) VSG_CUDA_TRY(cudaEventRecord(cs->sum_done[j], st));
       }
       return VSG_OK;
       };
       const int rc_chains = run_resblocks();
-      if (chains) {   // join: the stage output (written by the last chain) and every scratch buffer are settled
+      if (chains_st) {   // join: the stage output (written by the last chain) and every scratch buffer are settled
         st = st_main;
         cudaError_t je = cudaSuccess;
         for (int j = 1; j < NK; ++j) {
