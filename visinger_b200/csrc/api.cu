@@ -33,12 +33,19 @@ size_t flow_ws(const VsgPack* p, int B, int T, int prec) {
 }
 // fp32: CUDA-core FFMA kernels.  bf16: tcgen05, one bf16 plane.  bf16x3: tcgen05 on three bf16 planes per value (the
 // flow's z <= 1e-5 needs all 24 mantissa bits of its state; the decoder's 1e-4 is met by two planes).
+// *masked (optional): in = the caller wants y * mask; out = true if the flow's last kernel applied it (tensor-core modes:
+// the mask rides on the final layout change), false if the caller still has to
 int run_flow(const VsgPack* pack, const float* x, const float* mask, const float* g, float* y, int B, int T, int reverse,
-             int precision, Workspace& ws, cudaStream_t st) {
-  if (precision == VSG_PRECISION_BF16) return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, st, 1);
-  if (precision == VSG_PRECISION_BF16X3 && x3_flow_on_tensor_cores() && !pack->flow_layers.empty() &&
-      pack->flow_layers[0].pre_x6[0].has_tmap)
-    return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, st, 3);
+             int precision, Workspace& ws, cudaStream_t st, bool* masked = nullptr) {
+  const bool want = masked && *masked;
+  if (masked) *masked = false;
+  const bool tc1 = precision == VSG_PRECISION_BF16;
+  const bool tc3 = precision == VSG_PRECISION_BF16X3 && x3_flow_on_tensor_cores() && !pack->flow_layers.empty() &&
+                   pack->flow_layers[0].pre_x6[0].has_tmap;
+  if (tc1 || tc3) {
+    if (masked) *masked = want;
+    return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, st, tc1 ? 1 : 3, want ? mask : nullptr);
+  }
   return flow_forward_f32(pack, x, mask, g, y, B, T, reverse, ws, st);
 }
 size_t dec_ws(const VsgPack* p, int B, int T, int prec) {
@@ -121,14 +128,19 @@ extern "C" int vsg_infer(const VsgPack* pack, const float* mu_p, const float* lo
   // z_p = (mu_p + noise * exp(logs_p)) * mask                       models/visinger.py:107
   VSG_TRY(prior_sample(mu_p, logs_p, noise, mask, z, B, C, T, st));
   // z_q = flow(z_p, mask, g, reverse=True) * mask                    models/visinger.py:109
-  VSG_TRY(run_flow(pack, z, mask, g, z, B, T, 1, precision, ws, st));
-  VSG_TRY(mask_mul(z, mask, z, B, C, T, st));
-  if (z_q_out)
-    VSG_CUDA_TRY(cudaMemcpyAsync(z_q_out, z, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // (tensor-core modes: the flow's last kernel writes z * mask straight into the caller's z_q buffer, which the decoder
+  // then reads -- no separate mask pass, no copy)
+  float* zq = z;
+  bool masked = true;
+  if (precision != VSG_PRECISION_FP32 && z_q_out) zq = z_q_out;
+  VSG_TRY(run_flow(pack, z, mask, g, zq, B, T, 1, precision, ws, st, &masked));
+  if (!masked) VSG_TRY(mask_mul(zq, mask, zq, B, C, T, st));
+  if (z_q_out && zq != z_q_out)
+    VSG_CUDA_TRY(cudaMemcpyAsync(z_q_out, zq, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // wav = decoder(z_q * mask, g)                                      models/visinger.py:111
   ws.off = mark;   // the flow scratch is dead; the decoder reuses it
-  if (precision == VSG_PRECISION_FP32) VSG_TRY(generator_forward_f32(pack, z, g, wav, B, T, ws, st));
-  else VSG_TRY(generator_forward_tc(pack, z, g, wav, B, T, ws, st, precision == VSG_PRECISION_BF16X3));
+  if (precision == VSG_PRECISION_FP32) VSG_TRY(generator_forward_f32(pack, zq, g, wav, B, T, ws, st));
+  else VSG_TRY(generator_forward_tc(pack, zq, g, wav, B, T, ws, st, precision == VSG_PRECISION_BF16X3));
   (void)launches;
   return VSG_OK;
 }
@@ -229,12 +241,15 @@ extern "C" int vsg_infer_zp(const VsgPack* pack, const float* z_p, const float* 
   float* z = ws.take<float>((size_t)B * C * T);
   if (ws.overflow) return fail(VSG_ENOMEM, "workspace too small");
   const size_t mark = ws.off;
-  VSG_TRY(run_flow(pack, z_p, mask, g, z, B, T, 1, precision, ws, st));
-  VSG_TRY(mask_mul(z, mask, z, B, C, T, st));
-  if (z_q_out)
-    VSG_CUDA_TRY(cudaMemcpyAsync(z_q_out, z, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  float* zq = z;                // (as in vsg_infer: the tensor-core flow writes z * mask straight into the caller's buffer)
+  bool masked = true;
+  if (precision != VSG_PRECISION_FP32 && z_q_out) zq = z_q_out;
+  VSG_TRY(run_flow(pack, z_p, mask, g, zq, B, T, 1, precision, ws, st, &masked));
+  if (!masked) VSG_TRY(mask_mul(zq, mask, zq, B, C, T, st));
+  if (z_q_out && zq != z_q_out)
+    VSG_CUDA_TRY(cudaMemcpyAsync(z_q_out, zq, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
   ws.off = mark;
-  if (precision == VSG_PRECISION_FP32) VSG_TRY(generator_forward_f32(pack, z, g, wav, B, T, ws, st));
-  else VSG_TRY(generator_forward_tc(pack, z, g, wav, B, T, ws, st, precision == VSG_PRECISION_BF16X3));
+  if (precision == VSG_PRECISION_FP32) VSG_TRY(generator_forward_f32(pack, zq, g, wav, B, T, ws, st));
+  else VSG_TRY(generator_forward_tc(pack, zq, g, wav, B, T, ws, st, precision == VSG_PRECISION_BF16X3));
   return VSG_OK;
 }

@@ -1012,9 +1012,9 @@ __global__ void posterior_sample_from_stats_kernel(const float* __restrict__ sta
 }
 
 // [B, T, planes * C] bf16 -> [B, C, T] fp32 (the planes of a value are summed); flip != 0 reverses the channel order
-// (an odd number of Flips).
+// (an odd number of Flips); mask != null: the output is multiplied by mask[b][t] (`z * mask`, models/visinger.py:109-111).
 __global__ void transpose_from_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int T,
-                                           int flip, int planes) {
+                                           int flip, int planes, const float* __restrict__ mask = nullptr) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
@@ -1028,7 +1028,8 @@ __global__ void transpose_from_bf16_kernel(const __nv_bfloat16* __restrict__ x, 
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, t = t0 + tx;
-    if (c < C && t < T) y[((long long)b * C + (flip ? C - 1 - c : c)) * T + t] = tile[tx][i];
+    if (c < C && t < T)
+      y[((long long)b * C + (flip ? C - 1 - c : c)) * T + t] = mask ? tile[tx][i] * mask[(long long)b * T + t] : tile[tx][i];
   }
 }
 

@@ -1010,7 +1010,7 @@ size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T, int planes) {
 // the fp32 value exactly) and every product runs as six plane products, small ones first (launch_conv_tc): the flow at
 // north_star's fp32 tolerance (z <= 1e-5) on tcgen05 -- the bf16x3 precision mode.
 int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, float* y, int B, int T,
-                    int reverse, Workspace& ws, cudaStream_t st, int planes) {
+                    int reverse, Workspace& ws, cudaStream_t st, int planes, const float* out_mask) {
   const VsgConfig& c = P->cfg;
   const int C = c.flow_channels, H = c.flow_hidden, NL = c.flow_n_layers, NF = c.flow_n_flows, half = C / 2;
   const int K = c.flow_kernel_size;
@@ -1109,7 +1109,7 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
   }
   {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(u, y, C, T, (NF & 1) ? 1 : 0, planes);
+    transpose_from_bf16_kernel<<<grid, block, 0, st>>>(u, y, C, T, (NF & 1) ? 1 : 0, planes, out_mask);   // (out_mask: y * mask)
     VSG_LAUNCH_CHECK("transpose_from_bf16_kernel");
   }
   return VSG_OK;
