@@ -36,7 +36,10 @@ size_t flow_ws(const VsgPack* p, int B, int T, int prec) {
 // *masked (optional): in = the caller wants y * mask; out = true if the flow's last kernel applied it (tensor-core modes:
 // the mask rides on the final layout change), false if the caller still has to
 int run_flow(const VsgPack* pack, const float* x, const float* mask, const float* g, float* y, int B, int T, int reverse,
-             int precision, Workspace& ws, cudaStream_t st, bool* masked = nullptr) {
+             int precision, Workspace& ws, cudaStream_t st, bool* masked = nullptr, const float* ps_logs = nullptr,
+             const float* ps_noise = nullptr, bool* sampled = nullptr) {
+  // ps_logs / ps_noise (with `sampled`): x is mu_p; *sampled = true if the flow's first kernel drew the prior sample itself
+  if (sampled) *sampled = false;
   const bool want = masked && *masked;
   if (masked) *masked = false;
   const bool tc1 = precision == VSG_PRECISION_BF16;
@@ -44,7 +47,9 @@ int run_flow(const VsgPack* pack, const float* x, const float* mask, const float
                    pack->flow_layers[0].pre_x6[0].has_tmap;
   if (tc1 || tc3) {
     if (masked) *masked = want;
-    return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, st, tc1 ? 1 : 3, want ? mask : nullptr);
+    if (sampled && ps_logs && ps_noise) *sampled = true;
+    return flow_forward_tc(pack, x, mask, g, y, B, T, reverse, ws, st, tc1 ? 1 : 3, want ? mask : nullptr,
+                           sampled ? ps_logs : nullptr, sampled ? ps_noise : nullptr);
   }
   return flow_forward_f32(pack, x, mask, g, y, B, T, reverse, ws, st);
 }
@@ -126,14 +131,21 @@ extern "C" int vsg_infer(const VsgPack* pack, const float* mu_p, const float* lo
   const size_t mark = ws.off;
   int launches = 0;
   // z_p = (mu_p + noise * exp(logs_p)) * mask                       models/visinger.py:107
-  VSG_TRY(prior_sample(mu_p, logs_p, noise, mask, z, B, C, T, st));
+  // (tensor-core modes: drawn by the flow's first kernel while it lays the state out channels-last)
+  const bool fuse_ps = precision != VSG_PRECISION_FP32 &&
+                       (precision == VSG_PRECISION_BF16 || (x3_flow_on_tensor_cores() && !pack->flow_layers.empty() &&
+                                                            pack->flow_layers[0].pre_x6[0].has_tmap));
+  if (!fuse_ps) VSG_TRY(prior_sample(mu_p, logs_p, noise, mask, z, B, C, T, st));
   // z_q = flow(z_p, mask, g, reverse=True) * mask                    models/visinger.py:109
   // (tensor-core modes: the flow's last kernel writes z * mask straight into the caller's z_q buffer, which the decoder
   // then reads -- no separate mask pass, no copy)
   float* zq = z;
   bool masked = true;
   if (precision != VSG_PRECISION_FP32 && z_q_out) zq = z_q_out;
-  VSG_TRY(run_flow(pack, z, mask, g, zq, B, T, 1, precision, ws, st, &masked));
+  bool sampled = false;
+  VSG_TRY(run_flow(pack, fuse_ps ? mu_p : z, mask, g, zq, B, T, 1, precision, ws, st, &masked, fuse_ps ? logs_p : nullptr,
+                   fuse_ps ? noise : nullptr, fuse_ps ? &sampled : nullptr));
+  if (fuse_ps && !sampled) return fail(VSG_EINVAL, "internal: the flow did not draw the prior sample");
   if (!masked) VSG_TRY(mask_mul(zq, mask, zq, B, C, T, st));
   if (z_q_out && zq != z_q_out)
     VSG_CUDA_TRY(cudaMemcpyAsync(z_q_out, zq, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -959,14 +959,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // [B, C, T] fp32 (reference layout) -> [B, T, planes * C] bf16 (channels-last).  32x32 smem tile.
 // planes = 2: rows are [hi (C) | lo (C)] with hi = bf16(x), lo = bf16(x - hi)  (split-bf16 mode);
 // planes = 3: [hi | mid | lo], the fp32 value exactly (the flow at the fp32 tolerance).
+// ps_logs != null: x is mu_p and the value laid out is the prior sample z_p = (mu_p + noise * exp(logs_p)) * mask
+// (models/visinger.py:107; the arithmetic of prior_sample_kernel), so the hot path needs no fp32 z_p tensor at all.
 __global__ void transpose_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int T,
-                                         int planes) {
+                                         int planes, const float* __restrict__ ps_logs = nullptr,
+                                         const float* __restrict__ ps_noise = nullptr, const float* __restrict__ ps_mask = nullptr) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, t = t0 + tx;
-    tile[i][tx] = (c < C && t < T) ? x[((long long)b * C + c) * T + t] : 0.f;
+    float v = 0.f;
+    if (c < C && t < T) {
+      const long long idx = ((long long)b * C + c) * T + t;
+      v = x[idx];
+      if (ps_logs) v = (v + ps_noise[idx] * expf(ps_logs[idx])) * ps_mask[(long long)b * T + t];
+    }
+    tile[i][tx] = v;
   }
   __syncthreads();
   const int W = planes * C;

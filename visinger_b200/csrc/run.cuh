@@ -24,7 +24,8 @@ int generator_forward_f32(const VsgPack* P, const float* z, const float* g, floa
 size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T, int planes = 1);
 size_t dec_ws_bytes_tc(const VsgPack* P, int B, int T, bool x3);
 int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, float* y, int B, int T,
-                    int reverse, Workspace& ws, cudaStream_t st, int planes = 1, const float* out_mask = nullptr);   // out_mask: y * mask   // planes = 3: fp32 tolerance (bf16x3 mode)
+                    int reverse, Workspace& ws, cudaStream_t st, int planes = 1, const float* out_mask = nullptr,   // out_mask: y * mask
+                    const float* ps_logs = nullptr, const float* ps_noise = nullptr);   // x = mu_p: prior sampling at the entry   // planes = 3: fp32 tolerance (bf16x3 mode)
 // VSG_X3_FLOW_FFMA=1 in the environment: the bf16x3 mode runs the flow on the fp32 CUDA-core kernels (A/B measurements)
 bool x3_flow_on_tensor_cores();
 int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float* wav, int B, int T, Workspace& ws,

@@ -1010,7 +1010,7 @@ size_t flow_ws_bytes_tc(const VsgPack* P, int B, int T, int planes) {
 // the fp32 value exactly) and every product runs as six plane products, small ones first (launch_conv_tc): the flow at
 // north_star's fp32 tolerance (z <= 1e-5) on tcgen05 -- the bf16x3 precision mode.
 int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const float* g, float* y, int B, int T,
-                    int reverse, Workspace& ws, cudaStream_t st, int planes, const float* out_mask) {
+                    int reverse, Workspace& ws, cudaStream_t st, int planes, const float* out_mask, const float* ps_logs, const float* ps_noise) {
   const VsgConfig& c = P->cfg;
   const int C = c.flow_channels, H = c.flow_hidden, NL = c.flow_n_layers, NF = c.flow_n_flows, half = C / 2;
   const int K = c.flow_kernel_size;
@@ -1047,7 +1047,7 @@ int flow_forward_tc(const VsgPack* P, const float* x, const float* mask, const f
   }
   {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(x, u, C, T, planes);
+    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(x, u, C, T, planes, ps_logs, ps_noise, mask);   // (ps_*: x = mu_p, prior sampling fused)
     VSG_LAUNCH_CHECK("transpose_to_bf16_kernel");
   }
   for (int step = 0; step < NF; ++step) {
