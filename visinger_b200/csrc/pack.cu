@@ -451,6 +451,7 @@ int pack_decoder(const Loader& L, const std::string& pre, VsgPack* P) {
       }
       st.merged_in_off0 = off_min;
       VSG_TRY(pack_conv_tc(P, Wm, bm, s * st.Cout, st.Cin, kt, &st.merged_tc));
+      VSG_TRY(pack_conv_tc(P, Wm, bm, s * st.Cout, st.Cin, kt, &st.merged_x3, 2));   // (bf16x3: used where the output is planar)
     }
     // resblocks                                                            decoder.py:28-32
     st.blocks.resize(c.dec_n_kernels);

@@ -1559,12 +1559,17 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       // ordinary one-plane tensor for the resblock kernel's row-packed tensor map), as is the running resblock sum
       const bool planar = x3 && rp_stage;
       const int up_ld = planar ? ch : 0, up_part = planar ? (int)((size_t)nb * L * ch) : 0;
-      if (opt.merge_ups && !x3 && us.merged_tc.has_tmap && Lout == Lin * us.rate) {   // (split-bf16 planes would interleave wrongly)
+      // (split-bf16 planes interleaved per row would come out wrong; PLANAR planes are one-plane tensors each, so the
+      // bf16x3 row-packed stages take the merged form too)
+      static const bool x3_merge_off = getenv("VSG_X3_NO_MERGED_UPS") != nullptr;   // A/B aid
+      if (opt.merge_ups && (!x3 || (planar && us.merged_x3.has_tmap && !x3_merge_off)) && us.merged_tc.has_tmap &&
+          Lout == Lin * us.rate) {
         // ConvTranspose1d (decoder.py:46) as ONE convolution Cin -> rate*Cout over the input rate: its channels-last
         // output [nb, Lin, rate*Cout] is, byte for byte, the upsampled [nb, Lin*rate, Cout] tensor
         EpiTC e;
         e.bias = us.merged_tc.bias;
         e.out_act = bUA;
+        if (planar) { e.ld = us.rate * ch; e.part_stride = up_part; }
         if (!one_stream_all) e.out_raw = bU;
         VSG_TRY(launch_conv_tc(P, W(us.merged_tc, us.merged_x3), xin, nb, Lin, us.merged_in_off0, 1, Lin, 1, 0, Lin, e, opt,
                                err, st));
