@@ -1528,12 +1528,14 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
   static const bool x3_two_streams = getenv("VSG_X3_TWO_STREAMS") != nullptr && getenv("VSG_X3_TWO_STREAMS")[0] == '1';
   const bool one_stream_all = opt.single_stream && !(x3 && x3_two_streams);
   int L = T, ch = UIC;
+  bool prev_planar = false;                   // bf16x3: the stage input is a planar two-plane tensor
   for (int i = 0; i < c.dec_n_ups; ++i) {
     const UpStage& us = P->ups[i];
     const int Lin = L, Cin = ch, Lout = L * us.rate;
     ch = us.Cout; L = Lout;
     const bf* stage_in = io[cur_io];
     bf* stage_out = io[cur_io ^ 1];
+    bool stage_planar_out = false;
     for (int b0 = 0; b0 < B; b0 += pl.sub[i]) {
       const int nb = std::min(pl.sub[i], B - b0);
       const bf* xin = stage_in + (size_t)b0 * Lin * Cin * np;
@@ -1558,21 +1560,31 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       // bf16x3 row-packed stages: the upsampler writes its two planes PLANAR ([2][nb, L, ch]: each plane is then an
       // ordinary one-plane tensor for the resblock kernel's row-packed tensor map), as is the running resblock sum
       const bool planar = x3 && rp_stage;
-      const int up_ld = planar ? ch : 0, up_part = planar ? (int)((size_t)nb * L * ch) : 0;
+      // ... and so do the per-convolution ResBlock1 stages of the bf16x3 mode (every tensor of the stage planar through the
+      // conv kernel's ld / part_stride; the stage output too, unless conv_post reads it): that is what lets them take the
+      // merged-polyphase upsampler as well.  VSG_X3_PLANAR=0 (A/B aid): rows [hi | lo] as before
+      static const bool x3_planar_on = !(getenv("VSG_X3_PLANAR") && getenv("VSG_X3_PLANAR")[0] == '0');
+      const bool stage_planar = x3 && !planar && x3_planar_on && one_stream_all && c.dec_resblock == 1 && !rb_stage && nb == B &&
+                                i + 1 < c.dec_n_ups && (size_t)nb * L * ch < ((size_t)1 << 31);
+      const bool planar_any = planar || stage_planar;
+      stage_planar_out = stage_planar;
+      const int up_ld = planar_any ? ch : 0, up_part = planar_any ? (int)((size_t)nb * L * ch) : 0;
+      // the stage input is planar if the previous stage wrote it so
+      const int in_ld = prev_planar ? Cin : 0, in_part = prev_planar ? (int)((size_t)nb * Lin * Cin) : 0;
       // (split-bf16 planes interleaved per row would come out wrong; PLANAR planes are one-plane tensors each, so the
       // bf16x3 row-packed stages take the merged form too)
       static const bool x3_merge_off = getenv("VSG_X3_NO_MERGED_UPS") != nullptr;   // A/B aid
-      if (opt.merge_ups && (!x3 || (planar && us.merged_x3.has_tmap && !x3_merge_off)) && us.merged_tc.has_tmap &&
+      if (opt.merge_ups && (!x3 || (planar_any && us.merged_x3.has_tmap && !x3_merge_off)) && us.merged_tc.has_tmap &&
           Lout == Lin * us.rate) {
         // ConvTranspose1d (decoder.py:46) as ONE convolution Cin -> rate*Cout over the input rate: its channels-last
         // output [nb, Lin, rate*Cout] is, byte for byte, the upsampled [nb, Lin*rate, Cout] tensor
         EpiTC e;
         e.bias = us.merged_tc.bias;
         e.out_act = bUA;
-        if (planar) { e.ld = us.rate * ch; e.part_stride = up_part; }
+        if (planar_any) { e.ld = us.rate * ch; e.part_stride = up_part; }
         if (!one_stream_all) e.out_raw = bU;
         VSG_TRY(launch_conv_tc(P, W(us.merged_tc, us.merged_x3), xin, nb, Lin, us.merged_in_off0, 1, Lin, 1, 0, Lin, e, opt,
-                               err, st));
+                               err, st, in_ld, in_part));
       } else {
         for (int r = 0; r < us.rate; ++r) {   // one strided launch per polyphase
           EpiTC e;
@@ -1582,7 +1594,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
           if (!one_stream_all) e.out_raw = bU;
           const int Lq = (Lout - r + us.rate - 1) / us.rate;
           VSG_TRY(launch_conv_tc(P, W(us.phases[r].tc, us.phases[r].x3), xin, nb, Lin, us.phases[r].in_off0, 1, Lq, us.rate, r,
-                                 Lout, e, opt, err, st));
+                                 Lout, e, opt, err, st, in_ld, in_part));
         }
       }
       // Only leaky_relu(x) is stored for the running stream; the residual x is recovered from it in the consumer's
@@ -1660,11 +1672,14 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
             bf* nra = in_t ? bTA : bRA;
             EpiTC e1;
             e1.bias = rb.c1_tc[q].bias; e1.out_act = tmp;
-            VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st));
+            if (stage_planar) { e1.ld = ch; e1.part_stride = up_part; e2.ld = ch; e2.part_stride = up_part; }
+            VSG_TRY(launch_conv_tc(P, W(rb.c1_tc[q], rb.c1_x3[q]), curA, nb, L, -((k * d - d) / 2), d, L, 1, 0, L, e1, opt, err, st,
+                                   up_ld, up_part));
             e2.bias = rb.c2_tc[q].bias;
             if (!last) { e2.out_act = nra; if (!one_stream) e2.out_raw = nr; }
             if (sum_wait) VSG_CUDA_TRY(cudaStreamWaitEvent(st, cs->sum_done[j - 1], 0));
-            VSG_TRY(launch_conv_tc(P, W(rb.c2_tc[q], rb.c2_x3[q]), tmp, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st));
+            VSG_TRY(launch_conv_tc(P, W(rb.c2_tc[q], rb.c2_x3[q]), tmp, nb, L, -((k - 1) / 2), 1, L, 1, 0, L, e2, opt, err, st,
+                                   up_ld, up_part));
             cur = one_stream ? nra : nr; curA = nra;
           } else {                           // ResBlock2 (decoder.py:124-133)
             e2.bias = rb.c1_tc[q].bias;
@@ -1695,6 +1710,7 @@ int generator_forward_tc(const VsgPack* P, const float* z, const float* g, float
       VSG_TRY(rc_chains);
     }
     cur_io ^= 1;
+    prev_planar = stage_planar_out;
   }
   {  // wav = tanh(conv_post(leaky_relu(x)))   (decoder.py:55-57); the stage output already holds leaky_relu(x)
     if (!x3 && ch == 16 && P->conv_post_k == 7) {   // the model's shape: sliding-window kernel
